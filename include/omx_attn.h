@@ -1,0 +1,198 @@
+/*
+ * omx_attn.h -- C ABI of the B200-native attention hot path
+ *               (RoPE -> KV-cache append/fetch -> scaled-dot-product attention).
+ *
+ * This is the drop-in boundary for ONE path of OminiX-MLX: the three calls every
+ * model crate makes through mlx-rs-core / mlx-rs.  Each entry point names the
+ * reference interface it replaces (paths relative to the OminiX-MLX checkout):
+ *
+ *   omx_fast_rope                          <- mlx_fast_rope
+ *        mlx-rs/mlx-sys/src/mlx-c/mlx/c/fast.h:169-178 (bound at mlx-rs/src/fast.rs:31-45)
+ *   omx_fast_rope_dynamic                  <- mlx_fast_rope_dynamic          fast.h:179-188
+ *   omx_fast_scaled_dot_product_attention  <- mlx_fast_scaled_dot_product_attention
+ *        fast.h:189-198 (bound at mlx-rs/src/fast.rs:138-150)
+ *   omx_kv_cache_*                         <- KVCache (Rust logic over mlx_zeros /
+ *        mlx_concatenate_axis / mlx_slice_update / mlx_slice): mlx-rs-core/src/cache.rs:92-195
+ *   omx_concat_kv_cache_*                  <- ConcatKeyValueCache            cache.rs:45-85
+ *   omx_attn_decode_fused                  <- the composite Attention::forward decode step
+ *        qwen3-mlx/src/model.rs:186-212 (rope(q), rope(k), update_and_fetch, sdpa) in ONE launch
+ *   omx_dit_rope / omx_dit_joint_attention <- FLUX.2-klein / Z-Image manual attention
+ *        flux-klein-mlx/src/klein_model.rs:124-162,460-483,651-659; zimage-mlx/src/zimage_model.rs:208-235,355-384
+ *   omx_set_error_handler / omx_last_error <- mlx_set_error_handler  mlx-c/mlx/c/error.h
+ *
+ * Differences from mlx-c that a binding must know:
+ *   - EAGER, not lazy: work is enqueued on the given CUDA stream when the call is made
+ *     (asynchronous w.r.t. the host, like async_eval); there is no graph and no eval().
+ *   - Arrays are BORROWED DESCRIPTORS of device memory (pointer + shape + element strides),
+ *     not owning handles.  The caller allocates outputs; only the KV cache owns memory.
+ *   - sm_100a only, no CPU fallback: every entry point fails (status 1) without a B200.
+ *
+ * Conventions (same as mlx-c): every function returns 0 on success, 1 on error; no C++
+ * exception crosses the boundary; the message goes to the registered handler, or, with no
+ * handler registered, into a thread-local slot readable with omx_last_error().
+ */
+#ifndef OMX_ATTN_H
+#define OMX_ATTN_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* the library is built with -fvisibility=hidden; everything declared here is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define OMX_ATTN_VERSION 100
+#define OMX_MAX_NDIM 8
+
+/* Element types; numeric values are those of mlx_dtype (mlx-c/mlx/c/array.h:37-52). */
+typedef enum omx_dtype_ {
+  OMX_BOOL = 0,
+  OMX_INT32 = 7,
+  OMX_FLOAT16 = 9,
+  OMX_FLOAT32 = 10,
+  OMX_BFLOAT16 = 12
+} omx_dtype;
+
+/* Borrowed, strided view of device memory.  Strides are in ELEMENTS (a transposed
+ * [B,L,H,D] -> [B,H,L,D] view or a [..., :offset, :] cache slice is passed as is). */
+typedef struct omx_array_ {
+  void* data;
+  int32_t dtype; /* omx_dtype */
+  int32_t ndim;
+  int64_t shape[OMX_MAX_NDIM];
+  int64_t strides[OMX_MAX_NDIM];
+} omx_array;
+
+/* mlx_optional_float (mlx-c/mlx/c/optional.h:32-35) */
+typedef struct omx_optional_float_ {
+  float value;
+  bool has_value;
+} omx_optional_float;
+
+/* A cudaStream_t (NULL = the legacy default stream). Replaces mlx_stream. */
+typedef void* omx_stream;
+
+/* ---- errors ------------------------------------------------------------- */
+typedef void (*omx_error_handler_func)(const char* msg, void* data);
+void omx_set_error_handler(omx_error_handler_func handler, void* data, void (*dtor)(void*));
+/* Last error message of the calling thread ("" if none); valid until the next failing call. */
+const char* omx_last_error(void);
+int omx_version(void);
+/* 0 and *sm = 100 when the current device can run the kernels; 1 otherwise. */
+int omx_device_check(int* sm);
+
+/* ---- rope --------------------------------------------------------------- */
+/*
+ * out = rope(x): x [..., T, D] (ndim >= 3; T = axis -2), rotate the first `dims` features by
+ * theta(t,i) = (offset + t) * scale * inv_freq[i]; traditional=false pairs (i, i+dims/2),
+ * true pairs (2i, 2i+1); exactly one of base / freqs ([dims/2] float32) must be given.
+ * Same position for every batch row.  out: same shape and dtype as x (any strides).
+ * Numerics: cos/sin tables are computed on the HOST with libm (as the MLX CPU backend does),
+ * cast to x's dtype, and the rotation rounds to x's dtype after every multiply/add.
+ */
+int omx_fast_rope(const omx_array* out, const omx_array* x, int dims, bool traditional,
+                  omx_optional_float base, float scale, int offset,
+                  const omx_array* freqs /* may be null */, omx_stream s);
+/* offset: int32 scalar in DEVICE memory (CUDA-graph friendly). max_position bounds the table. */
+int omx_fast_rope_dynamic(const omx_array* out, const omx_array* x, int dims, bool traditional,
+                          omx_optional_float base, float scale,
+                          const omx_array* offset, int max_position,
+                          const omx_array* freqs /* may be null */, omx_stream s);
+
+/* ---- scaled dot-product attention --------------------------------------- */
+/*
+ * out[B,Hq,Lq,Dv] = softmax(scale * q k^T + mask) v;  q [B,Hq,Lq,D], k [B,Hkv,Lk,D],
+ * v [B,Hkv,Lk,Dv], Hq % Hkv == 0 (GQA: q head h reads kv head h / (Hq/Hkv), K/V not tiled).
+ * mask_mode "" (mask_arr null: none; bool array: true = keep; float array: additive, same
+ * dtype as q) or "causal" (lower-triangular, aligned bottom-right when Lq < Lk).
+ * mask_arr broadcastable to [B,Hq,Lq,Lk].  sinks must be null (mlx-rs never passes any).
+ * Softmax and accumulation in float32.
+ */
+int omx_fast_scaled_dot_product_attention(const omx_array* out, const omx_array* queries,
+                                          const omx_array* keys, const omx_array* values,
+                                          float scale, const char* mask_mode,
+                                          const omx_array* mask_arr /* may be null */,
+                                          const omx_array* sinks /* must be null */,
+                                          omx_stream s);
+
+/* ---- KV caches ---------------------------------------------------------- */
+typedef struct omx_kv_cache_ {
+  void* ctx;
+} omx_kv_cache;
+
+int omx_kv_cache_new(omx_kv_cache* res, int step /* KVCache::new(): 256 */);
+int omx_kv_cache_free(omx_kv_cache c);
+int omx_kv_cache_offset(omx_kv_cache c, int* offset);
+int omx_kv_cache_reset(omx_kv_cache c); /* offset = 0; buffers untouched */
+/*
+ * keys [B,Hkv,n,Dk], values [B,Hkv,n,Dv] (any strides).  Appends at rows [offset, offset+n),
+ * growing by ceil(n/step)*step zero rows (old buffer trimmed to `offset` first when
+ * offset % step != 0) exactly as cache.rs:141-181; then returns VIEWS [.., :offset, :] of
+ * the cache-owned buffers in keys_out / values_out.  Views stay valid until the next growth.
+ */
+int omx_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys, const omx_array* values,
+                                  omx_array* keys_out, omx_array* values_out, omx_stream s);
+/* Whole backing buffers [B,Hkv,cap,D] incl. the zero tail (cap = the reference's keys.shape[2]). */
+int omx_kv_cache_state(omx_kv_cache c, omx_array* keys_buf, omx_array* values_buf);
+/* Extension (mlx-lm's KVCache.trim; the reference only has the stub trim_cache,
+ * mlx-rs-core/src/speculative.rs:165-167): drop the last min(n, offset) rows; buffers untouched. */
+int omx_kv_cache_trim(omx_kv_cache c, int n, int* trimmed);
+/* Extension: pre-size the device allocation (rows) so appends never reallocate.  Does not
+ * change the logical capacity the reference rule produces. */
+int omx_kv_cache_reserve(omx_kv_cache c, int rows);
+
+int omx_concat_kv_cache_new(omx_kv_cache* res);
+int omx_concat_kv_cache_free(omx_kv_cache c);
+int omx_concat_kv_cache_offset(omx_kv_cache c, int* offset);
+int omx_concat_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys,
+                                         const omx_array* values, omx_array* keys_out,
+                                         omx_array* values_out, omx_stream s);
+
+/* ---- fused decode step -------------------------------------------------- */
+/*
+ * One launch for the decode step of Attention::forward (L == 1):
+ *   off = cache.offset; q' = rope(q, off); k' = rope(k_new, off);
+ *   cache.update_and_fetch(k', v_new); out = sdpa(q', K[:off+1], V[:off+1], sm_scale, none)
+ * q [B,Hq,1,D], k_new/v_new [B,Hkv,1,D], out [B,Hq,1,D].  rope_dims == 0 skips the rotation.
+ * keys_out / values_out (may be null) receive the fetched views.  Cache contents are
+ * bit-identical to omx_fast_rope + omx_kv_cache_update_and_fetch.
+ */
+int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                          const omx_array* v_new, omx_kv_cache cache, int rope_dims,
+                          bool traditional, omx_optional_float base, float rope_scale,
+                          const omx_array* freqs /* may be null */, float sm_scale,
+                          omx_array* keys_out, omx_array* values_out, omx_stream s);
+
+/* ---- DiT joint attention ------------------------------------------------ */
+/* Table-driven interleaved rope: x [B,S,H,D], cos/sin [B,S,D/2] (x's dtype);
+ * out0 = x0*c - x1*s, out1 = x1*c + x0*s per adjacent pair, rounding after every op. */
+int omx_dit_rope(const omx_array* out, const omx_array* x, const omx_array* cos,
+                 const omx_array* sin, omx_stream s);
+/* Non-causal joint attention over the concatenated [txt; img] sequence.  q/k/v/out are
+ * [B,H,S,D] views (pass the [B,S,H,D] storage with transposed strides); add_mask optional
+ * float32 [Lq,Lk].  out dtype may be q's dtype or float32 (the reference chain promotes). */
+int omx_dit_joint_attention(const omx_array* out, const omx_array* q, const omx_array* k,
+                            const omx_array* v, float scale, const omx_array* add_mask,
+                            omx_stream s);
+
+/* ---- introspection (tests / bench) -------------------------------------- */
+/* Name of the kernel family the last successful attention call on this thread dispatched to
+ * ("decode_hmma_tma", "decode_simt", "fmha_tcgen05", "sdpa_generic", ...). */
+const char* omx_last_kernel(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+int64_t omx_launch_count(bool reset);
+/* Force a kernel family for subsequent attention calls on this thread (NULL/"" = auto). */
+int omx_force_kernel(const char* name);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMX_ATTN_H */

@@ -1,0 +1,39 @@
+"""The composite decode step of the reference's Attention::forward
+(qwen3-mlx/src/model.rs:186-212) as ONE kernel launch, plus its unfused spelling."""
+import torch
+
+from . import _lib, fast
+from .array import desc, ref, stream_ptr, view
+
+
+def attn_decode_fused(q, k_new, v_new, cache, rope, sm_scale, stream=None, out=None, fetch=False):
+    """off = cache.offset(); q' = rope(q, off); k' = rope(k_new, off);
+    (K, V) = cache.update_and_fetch(k', v_new); out = sdpa(q', K, V, sm_scale)   -- L == 1 only.
+    rope: an nn.Rope (or None to skip the rotation).  Returns out, or (out, K, V) with fetch=True."""
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1], 1, v_new.shape[3]), dtype=q.dtype, device=q.device)
+    dims = rope.dimensions if rope is not None else 0
+    base = _lib.OmxOptionalFloat()
+    base.has_value = rope is not None
+    base.value = rope.base if rope is not None else 0.0
+    ko, vo = _lib.OmxArray(), _lib.OmxArray()
+    qd, kd, vd, od = desc(q), desc(k_new), desc(v_new), desc(out)
+    _lib.check(_lib.lib().omx_attn_decode_fused(
+        ref(od), ref(qd), ref(kd), ref(vd), cache.handle, int(dims),
+        bool(rope.traditional) if rope is not None else False, base,
+        float(rope.scale) if rope is not None else 1.0, None, float(sm_scale), ref(ko), ref(vo),
+        stream_ptr(stream)))
+    if fetch:
+        return out, view(ko, cache, q.device), view(vo, cache, q.device)
+    return out
+
+
+def attn_decode_unfused(q, k_new, v_new, cache, rope, sm_scale, stream=None):
+    """The reference's op sequence, one library call per op (model.rs:186-212)."""
+    off = cache.offset()
+    if rope is not None:
+        q = rope.forward(q, off, stream)
+        k_new = rope.forward(k_new, off, stream)
+    keys, values = cache.update_and_fetch(k_new, v_new, stream)
+    mask = fast.ScaledDotProductAttentionMask.Causal if q.shape[2] > 1 else None
+    return fast.scaled_dot_product_attention(q, keys, values, sm_scale, mask, stream)

@@ -1,0 +1,761 @@
+// decode.cu -- split-K GQA decode attention (Lq == 1), optionally fused with RoPE + KV append.
+//
+// Collapses the decode step of the reference's Attention::forward
+// (qwen3-mlx/src/model.rs:186-212: rope(q, off), rope(k, off), cache.update_and_fetch, sdpa)
+// into ONE launch.  HBM-bandwidth bound: every K/V byte is read exactly once.
+//
+//   grid  = (num_splits, Hkv, B); one CTA streams a contiguous chunk of the keys of ONE
+//           (batch, kv-head) and serves all G = Hq/Hkv query heads of that group from it.
+//   16-bit, D = 128 ("hmma_tma"): a producer warp feeds a 3-stage ring of 64-key K/V tiles with
+//           TMA (cp.async.bulk.tensor, 128 B swizzle, mbarrier completion, L2 evict-first);
+//           4 consumer warps each own whole tiles: S = Q K^T and O += P V on mma.sync m16n8k16
+//           (the G query heads padded to the 16-row M), online softmax with quad shuffles.
+//   float32 / other head dims ("simt"): 8 warps, 128-bit coalesced loads, FFMA dot products,
+//           warp-shuffle reductions.
+//   The per-warp (m, l, O) states are merged in shared memory; with num_splits > 1 partials go
+//   to a workspace and the LAST CTA of the (batch, kv-head) (atomic ticket) combines them, so
+//   there is no second launch.  Counters reset themselves.
+//   Fused mode: every CTA ropes its G query heads on the fly (table lookup, reference
+//   rounding); the CTA owning the last chunk also ropes k_new, stores k'/v_new into the cache
+//   row `position` (bit-identical to the unfused path) and folds that key in from registers,
+//   so the new row is never re-read from HBM.
+#include <algorithm>
+#include <cstdlib>
+
+#include "omx_common.cuh"
+#include "omx_internal.h"
+#include "sm100_utils.cuh"
+
+namespace omx {
+
+namespace {
+
+constexpr int kTile = 64;              // keys per pipeline stage
+constexpr int kBoxBytes = 64 * 64 * 2;  // one TMA box: 64 keys x 64 features x 2 B
+constexpr int kStageBytes = 4 * kBoxBytes;  // K lo/hi + V lo/hi
+constexpr int kQPitch = 136;           // padded q row (elements) -> conflict-free fragment loads
+
+struct DecodeParams {
+  const void* q;
+  void* out;
+  int64_t qs[4], os[4];
+  int B, Hq, Hkv, G;
+  int Lk;     // keys attended (including the new row when fused)
+  int n_mem;  // keys streamed from memory (Lk - 1 when fused)
+  int D;
+  float scale_log2;
+  int num_splits, tiles_per_split;
+  float* ws_o;   // [pair][split][G][D]
+  float* ws_ml;  // [pair][split][G][2]
+  int* counters; // [pair]
+  // simt path reads K/V through plain pointers
+  const void *k, *v;
+  int64_t ks[4], vs[4];
+  // fused new token
+  int fused;
+  const void *k_new, *v_new;
+  int64_t kns[4], vns[4];
+  void *k_row0, *v_row0;  // cache base pointers (row index Lk-1 is written)
+  int64_t kcs[4], vcs[4];
+  int rope_dims, traditional;
+  const float *cos_row, *sin_row;  // table row of the current position, [rope_dims/2]
+};
+
+// roped / copied q heads -> shared memory (as T), used by both kernels
+template <typename T>
+__device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total,
+                                        int first_head, int n_heads, int b, int tid, int nthr) {
+  const T* qg = (const T*)p.q + b * p.qs[0] + (int64_t)first_head * p.qs[1];
+  const int D = p.D;
+  for (int idx = tid; idx < (rows_total - n_heads) * D; idx += nthr)
+    q_s[(n_heads + idx / D) * pitch + idx % D] = Num<T>::from_f(0.f);
+  if (p.fused && p.rope_dims > 0) {
+    const int half = p.rope_dims >> 1;
+    const int per = half + (D - p.rope_dims);
+    for (int idx = tid; idx < n_heads * per; idx += nthr) {
+      const int g = idx / per, u = idx % per;
+      const T* qh = qg + g * p.qs[1];
+      if (u < half) {
+        const int i1 = p.traditional ? 2 * u : u;
+        const int i2 = p.traditional ? 2 * u + 1 : u + half;
+        float o1, o2;
+        rope_pair<T>(Num<T>::to_f(qh[i1 * p.qs[3]]), Num<T>::to_f(qh[i2 * p.qs[3]]),
+                     rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
+        q_s[g * pitch + i1] = Num<T>::from_f(o1);
+        q_s[g * pitch + i2] = Num<T>::from_f(o2);
+      } else {
+        const int d = p.rope_dims + (u - half);
+        q_s[g * pitch + d] = qh[d * p.qs[3]];
+      }
+    }
+  } else {
+    for (int idx = tid; idx < n_heads * D; idx += nthr) {
+      const int g = idx / D, d = idx % D;
+      q_s[g * pitch + d] = qg[g * p.qs[1] + d * p.qs[3]];
+    }
+  }
+}
+
+// One warp: rope k_new, append k'/v_new to the cache row, and score the new key against the
+// staged q heads.  nt_k/nt_v: float[D] scratch, nt_m[g] <- log2-domain score.
+template <typename T>
+__device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
+                                          int b, int hk, int lane, float* nt_k, float* nt_v,
+                                          float* nt_m, bool write_cache = true) {
+  const int D = p.D;
+  const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
+  const T* vn = (const T*)p.v_new + b * p.vns[0] + hk * p.vns[1];
+  T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(p.Lk - 1) * p.kcs[2];
+  T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(p.Lk - 1) * p.vcs[2];
+  const int half = p.rope_dims >> 1;
+  for (int u = lane; u < half; u += 32) {
+    const int i1 = p.traditional ? 2 * u : u;
+    const int i2 = p.traditional ? 2 * u + 1 : u + half;
+    float o1, o2;
+    rope_pair<T>(Num<T>::to_f(kn[i1 * p.kns[3]]), Num<T>::to_f(kn[i2 * p.kns[3]]), rnd<T>(p.cos_row[u]),
+                 rnd<T>(p.sin_row[u]), o1, o2);
+    if (write_cache) {
+      kc[i1 * p.kcs[3]] = Num<T>::from_f(o1);
+      kc[i2 * p.kcs[3]] = Num<T>::from_f(o2);
+    }
+    nt_k[i1] = o1;
+    nt_k[i2] = o2;
+  }
+  for (int d = p.rope_dims + lane; d < D; d += 32) {
+    const T x = kn[d * p.kns[3]];
+    if (write_cache) kc[d * p.kcs[3]] = x;
+    nt_k[d] = Num<T>::to_f(x);
+  }
+  for (int d = lane; d < D; d += 32) {
+    const T x = vn[d * p.vns[3]];
+    if (write_cache) vc[d * p.vcs[3]] = x;
+    nt_v[d] = Num<T>::to_f(x);
+  }
+  __syncwarp();
+  for (int g = 0; g < n_heads; ++g) {
+    float a = 0.f;
+    for (int d = lane; d < D; d += 32) a = fmaf(Num<T>::to_f(q_s[g * pitch + d]), nt_k[d], a);
+    a = warp_sum(a);
+    if (lane == 0) nt_m[g] = a * p.scale_log2;
+  }
+}
+
+// Merge per-warp states -> out (single split) or workspace + last-CTA combine.
+// mo: [n_ent][rows][D] floats, mml: [n_ent][rows][2]; rows = row pitch of the entries.
+template <typename T>
+__device__ __forceinline__ void merge_and_store(const DecodeParams& p, const float* mo, const float* mml,
+                                                int n_ent, int rows, bool has_nt, const float* nt_m,
+                                                const float* nt_v, int first_head, int n_heads, int b,
+                                                int pair, int split, int tid, int nthr, int* s_ticket) {
+  const int D = p.D;
+  T* outp = (T*)p.out + b * p.os[0];
+  for (int idx = tid; idx < n_heads * D; idx += nthr) {
+    const int g = idx / D, d = idx % D;
+    float M = has_nt ? nt_m[g] : -INFINITY;
+    for (int w = 0; w < n_ent; ++w) M = fmaxf(M, mml[(w * rows + g) * 2]);
+    float L = 0.f, O = 0.f;
+    for (int w = 0; w < n_ent; ++w) {
+      const float mw = mml[(w * rows + g) * 2];
+      if (mw > -INFINITY) {
+        const float sc = fast_exp2(mw - M);
+        L = fmaf(mml[(w * rows + g) * 2 + 1], sc, L);
+        O = fmaf(mo[(w * rows + g) * D + d], sc, O);
+      }
+    }
+    if (has_nt) {
+      const float sc = fast_exp2(nt_m[g] - M);
+      L += sc;
+      O = fmaf(nt_v[d], sc, O);
+    }
+    if (p.num_splits == 1) {
+      outp[(int64_t)(first_head + g) * p.os[1] + d * p.os[3]] = Num<T>::from_f(O / L);
+    } else {
+      const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
+      p.ws_o[e * D + d] = O;
+      if (d == 0) {
+        p.ws_ml[e * 2] = M;
+        p.ws_ml[e * 2 + 1] = L;
+      }
+    }
+  }
+  if (p.num_splits == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) *s_ticket = atomicAdd(&p.counters[pair], 1);
+  __syncthreads();
+  if (*s_ticket != p.num_splits - 1) return;
+  __threadfence();
+  for (int idx = tid; idx < n_heads * D; idx += nthr) {
+    const int g = idx / D, d = idx % D;
+    const int64_t e0 = (int64_t)pair * p.num_splits * n_heads + g;
+    float M = -INFINITY;
+    for (int s = 0; s < p.num_splits; ++s) M = fmaxf(M, __ldcg(&p.ws_ml[(e0 + (int64_t)s * n_heads) * 2]));
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < p.num_splits; ++s) {
+      const int64_t e = e0 + (int64_t)s * n_heads;
+      const float ms = __ldcg(&p.ws_ml[e * 2]);
+      if (ms > -INFINITY) {
+        const float sc = fast_exp2(ms - M);
+        L = fmaf(__ldcg(&p.ws_ml[e * 2 + 1]), sc, L);
+        O = fmaf(__ldcg(&p.ws_o[e * D + d]), sc, O);
+      }
+    }
+    outp[(int64_t)(first_head + g) * p.os[1] + d * p.os[3]] = Num<T>::from_f(O / L);
+  }
+  if (tid == 0) p.counters[pair] = 0;  // self-reset for the next launch
+}
+
+// ============================================================ 16-bit, D = 128: TMA + mma.sync
+template <typename T, int NSTAGE, int NW, bool HI, int MINB>
+__global__ void __launch_bounds__((NW + 1) * 32, MINB)
+decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const DecodeParams p) {
+  constexpr int D = 128;
+  constexpr int NTHR = (NW + 1) * 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stages = smem;
+  T* q_s = reinterpret_cast<T*>(smem + NSTAGE * kStageBytes);  // [16][kQPitch]
+  float* nt_k = reinterpret_cast<float*>(q_s + 16 * kQPitch);
+  float* nt_v = nt_k + D;
+  float* nt_m = nt_v + D;
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
+  __shared__ int s_ticket;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int G = p.G;
+  const int pair = b * p.Hkv + hk;
+  const int n_tiles = (p.n_mem + kTile - 1) / kTile;
+  const int tile_begin = split * p.tiles_per_split;
+  const int my_tiles = max(0, min(p.tiles_per_split, n_tiles - tile_begin));
+  const bool has_nt = p.fused && split == p.num_splits - 1;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_fence_init();
+  }
+  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR);
+  __syncthreads();
+
+  // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
+  // that every warp reaches at the same program point)
+  const int g0 = lane >> 2, cq = (lane & 3) * 2;
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  if (warp == NW) {
+    // ------------------------------------------------ producer warp
+    uint64_t pol = 0;
+    if (lane == 0) {
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      pol = policy_evict_first();
+    }
+    auto issue = [&](int t) {
+      const int st = t % NSTAGE;
+      uint8_t* sb = stages + st * kStageBytes;
+      const int key0 = (tile_begin + t) * kTile;
+      mbar_expect_tx(&full_bar[st], kStageBytes);
+      tma_load_4d(sb, &tmK, &full_bar[st], 0, key0, hk, b, pol);
+      tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, b, pol);
+      tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, b, pol);
+      tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, b, pol);
+    };
+    const int first = min(my_tiles, NSTAGE);
+    if (lane == 0)
+      for (int t = 0; t < first; ++t) issue(t);
+    __syncwarp();
+    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m);
+    if (lane == 0) {
+      for (int t = first; t < my_tiles; ++t) {
+        mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
+        issue(t);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ consumer warps
+    using MMA = Mma16816<T>;
+    uint32_t qa[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(&q_s[g0 * kQPitch + ks * 16 + cq]);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(&q_s[g0 * kQPitch + ks * 16 + cq + 8]);
+      qa[ks][1] = HI ? *reinterpret_cast<const uint32_t*>(&q_s[(g0 + 8) * kQPitch + ks * 16 + cq]) : 0u;
+      qa[ks][3] = HI ? *reinterpret_cast<const uint32_t*>(&q_s[(g0 + 8) * kQPitch + ks * 16 + cq + 8]) : 0u;
+    }
+    const int r8 = lane & 7, mi = lane >> 3;
+
+    for (int t = warp; t < my_tiles; t += NW) {
+      const int st = t % NSTAGE;
+      mbar_wait(&full_bar[st], (t / NSTAGE) & 1);
+      const uint32_t sbK = smem_u32(stages + st * kStageBytes);
+      const uint32_t sbV = sbK + 2 * kBoxBytes;
+
+      // S = Q K^T  (16 x 64)
+      float sa[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        sa[nb][0] = sa[nb][1] = sa[nb][2] = sa[nb][3] = 0.f;
+        const uint32_t rowaddr = sbK + (uint32_t)(nb * 8 + r8) * 128u;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int c = kk * 4 + mi;  // 16-byte chunk of the 256-byte key row
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4(b0, b1, b2, b3, rowaddr + (uint32_t)(c >> 3) * kBoxBytes + (uint32_t)(((c & 7) ^ r8) << 4));
+          MMA::run(sa[nb], qa[2 * kk], b0, b1);
+          MMA::run(sa[nb], qa[2 * kk + 1], b2, b3);
+        }
+      }
+
+      // online softmax (log2 domain)
+      const int key_base = (tile_begin + t) * kTile;
+      const bool partial = key_base + kTile > p.n_mem;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool dead = partial && (key_base + nb * 8 + cq + e >= p.n_mem);
+          sa[nb][e] = dead ? -INFINITY : sa[nb][e] * p.scale_log2;
+          mx0 = fmaxf(mx0, sa[nb][e]);
+          if (HI) {
+            sa[nb][2 + e] = dead ? -INFINITY : sa[nb][2 + e] * p.scale_log2;
+            mx1 = fmaxf(mx1, sa[nb][2 + e]);
+          }
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      const float mn0 = fmaxf(m0, mx0);
+      const float c0 = fast_exp2(m0 - mn0);
+      m0 = mn0;
+      float mn1 = 0.f, c1 = 1.f;
+      if (HI) {
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        mn1 = fmaxf(m1, mx1);
+        c1 = fast_exp2(m1 - mn1);
+        m1 = mn1;
+      }
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const float p0 = fast_exp2(sa[nb][0] - mn0), p1 = fast_exp2(sa[nb][1] - mn0);
+        rs0 += p0 + p1;
+        pa[nb >> 1][(nb & 1) * 2] = MMA::pack(p0, p1);
+        if (HI) {
+          const float p2 = fast_exp2(sa[nb][2] - mn1), p3 = fast_exp2(sa[nb][3] - mn1);
+          rs1 += p2 + p3;
+          pa[nb >> 1][(nb & 1) * 2 + 1] = MMA::pack(p2, p3);
+        } else {
+          pa[nb >> 1][(nb & 1) * 2 + 1] = 0u;
+        }
+      }
+      l0 = l0 * c0 + rs0;
+      if (HI) l1 = l1 * c1 + rs1;
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        o[nt][0] *= c0;
+        o[nt][1] *= c0;
+        if (HI) {
+          o[nt][2] *= c1;
+          o[nt][3] *= c1;
+        }
+      }
+
+      // O += P V  (16 x 128)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int key = kk * 16 + (mi & 1) * 8 + r8;
+        const uint32_t rowaddr = sbV + (uint32_t)key * 128u;
+#pragma unroll
+        for (int dp = 0; dp < 8; ++dp) {
+          const int c = dp * 2 + (mi >> 1);
+          uint32_t b0, b1, b2, b3;
+          ldmatrix_x4_trans(b0, b1, b2, b3,
+                            rowaddr + (uint32_t)(c >> 3) * kBoxBytes + (uint32_t)(((c & 7) ^ r8) << 4));
+          MMA::run(o[2 * dp], pa[kk], b0, b1);
+          MMA::run(o[2 * dp + 1], pa[kk], b2, b3);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    if (HI) {
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    }
+  }
+  __syncthreads();  // every stage consumed -> the ring is reused for the merge
+  if (warp < NW) {
+    float* mo = reinterpret_cast<float*>(stages);  // [NW][16][128]
+    float* mml = mo + NW * 16 * D;                 // [NW][16][2]
+    if (g0 < G) {
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt)
+        *reinterpret_cast<float2*>(&mo[(warp * 16 + g0) * D + nt * 8 + cq]) = make_float2(o[nt][0], o[nt][1]);
+      if ((lane & 3) == 0) {
+        mml[(warp * 16 + g0) * 2] = m0;
+        mml[(warp * 16 + g0) * 2 + 1] = l0;
+      }
+    }
+    if (HI && g0 + 8 < G) {
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt)
+        *reinterpret_cast<float2*>(&mo[(warp * 16 + g0 + 8) * D + nt * 8 + cq]) = make_float2(o[nt][2], o[nt][3]);
+      if ((lane & 3) == 0) {
+        mml[(warp * 16 + g0 + 8) * 2] = m1;
+        mml[(warp * 16 + g0 + 8) * 2 + 1] = l1;
+      }
+    }
+  }
+  __syncthreads();  // merge inputs visible
+  const float* mo = reinterpret_cast<const float*>(stages);
+  merge_and_store<T>(p, mo, mo + NW * 16 * D, NW, 16, has_nt, nt_m, nt_v, hk * G, G, b, pair, split, tid,
+                     NTHR, &s_ticket);
+}
+
+// ============================================================ generic: CUDA cores
+// D = Dv = 32*VE, GT query heads per CTA, 8 warps; lane owns features [lane*VE, lane*VE+VE).
+template <typename T, int VE>
+__device__ __forceinline__ void load_row(const T* p, float (&f)[VE]) {
+  if constexpr (sizeof(T) * VE == 16) {
+    union { uint4 r; T t[VE]; } u;
+    u.r = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) f[e] = Num<T>::to_f(u.t[e]);
+  } else if constexpr (sizeof(T) * VE == 8) {
+    union { uint2 r; T t[VE]; } u;
+    u.r = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) f[e] = Num<T>::to_f(u.t[e]);
+  } else if constexpr (sizeof(T) * VE == 32) {
+    union { uint4 r[2]; T t[VE]; } u;
+    u.r[0] = reinterpret_cast<const uint4*>(p)[0];
+    u.r[1] = reinterpret_cast<const uint4*>(p)[1];
+#pragma unroll
+    for (int e = 0; e < VE; ++e) f[e] = Num<T>::to_f(u.t[e]);
+  } else if constexpr (sizeof(T) * VE == 4) {
+    union { uint32_t r; T t[VE]; } u;
+    u.r = *reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) f[e] = Num<T>::to_f(u.t[e]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VE; ++e) f[e] = Num<T>::to_f(p[e]);
+  }
+}
+
+constexpr int kSimtWarps = 8;
+constexpr int kSimtKeys = 4;  // keys in flight per warp iteration
+
+template <typename T, int VE, int GT>
+__global__ void __launch_bounds__(kSimtWarps * 32)
+decode_simt_kernel(const DecodeParams p) {
+  constexpr int D = 32 * VE;
+  constexpr int NTHR = kSimtWarps * 32;
+  extern __shared__ uint8_t smem_raw[];
+  T* q_s = reinterpret_cast<T*>(smem_raw);         // [GT][D] (16-byte aligned rows)
+  float* mo = reinterpret_cast<float*>(q_s + GT * D);  // [warps][GT][D]
+  float* mml = mo + kSimtWarps * GT * D;           // [warps][GT][2]
+  float* nt_k = mml + kSimtWarps * GT * 2;         // [D]
+  float* nt_v = nt_k + D;
+  float* nt_m = nt_v + D;                          // [GT]
+  __shared__ int s_ticket;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x, b = blockIdx.z;
+  const int groups = p.G / GT;
+  const int hk = blockIdx.y / groups, gsub = blockIdx.y % groups;
+  const int first_head = hk * p.G + gsub * GT;
+  const int pair = (b * p.Hkv + hk) * groups + gsub;
+  const int keys_per_split = p.tiles_per_split * kTile;
+  const int kbeg = split * keys_per_split;
+  const int kend = min(p.n_mem, kbeg + keys_per_split);
+  const bool has_nt = p.fused && split == p.num_splits - 1;
+
+  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR);
+  __syncthreads();
+  // the new row is appended once per kv head (gsub == 0 writes it); every group scores it
+  if (has_nt && warp == kSimtWarps - 1)
+    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, /*write_cache=*/gsub == 0);
+
+  float qr[GT][VE], acc[GT][VE], m[GT], l[GT];
+#pragma unroll
+  for (int g = 0; g < GT; ++g) {
+    load_row<T, VE>(q_s + g * D + lane * VE, qr[g]);
+    m[g] = -INFINITY;
+    l[g] = 0.f;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[g][e] = 0.f;
+  }
+  const T* kb = (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + lane * VE;
+  const T* vb = (const T*)p.v + b * p.vs[0] + hk * p.vs[1] + lane * VE;
+
+  for (int j0 = kbeg + warp * kSimtKeys; j0 < kend; j0 += kSimtWarps * kSimtKeys) {
+    float kf[kSimtKeys][VE], vf[kSimtKeys][VE];
+#pragma unroll
+    for (int u = 0; u < kSimtKeys; ++u) {
+      const int j = min(j0 + u, kend - 1);
+      load_row<T, VE>(kb + (int64_t)j * p.ks[2], kf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kSimtKeys; ++u) {
+      const int j = min(j0 + u, kend - 1);
+      load_row<T, VE>(vb + (int64_t)j * p.vs[2], vf[u]);
+    }
+#pragma unroll
+    for (int g = 0; g < GT; ++g) {
+      float s[kSimtKeys];
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) {
+        float a = 0.f;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) a = fmaf(qr[g][e], kf[u][e], a);
+        s[u] = a;
+      }
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) s[u] = warp_sum(s[u]);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) {
+        s[u] = (j0 + u < kend) ? s[u] * p.scale_log2 : -INFINITY;
+        mx = fmaxf(mx, s[u]);
+      }
+      const float mn = fmaxf(m[g], mx);
+      const float c = fast_exp2(m[g] - mn);
+      m[g] = mn;
+      float rs = 0.f;
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) {
+        s[u] = fast_exp2(s[u] - mn);
+        rs += s[u];
+      }
+      l[g] = l[g] * c + rs;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float a = acc[g][e] * c;
+#pragma unroll
+        for (int u = 0; u < kSimtKeys; ++u) a = fmaf(s[u], vf[u][e], a);
+        acc[g][e] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < GT; ++g) {
+#pragma unroll
+    for (int e = 0; e < VE; ++e) mo[(warp * GT + g) * D + lane * VE + e] = acc[g][e];
+    if (lane == 0) {
+      mml[(warp * GT + g) * 2] = m[g];
+      mml[(warp * GT + g) * 2 + 1] = l[g];
+    }
+  }
+  __syncthreads();
+  merge_and_store<T>(p, mo, mml, kSimtWarps, GT, has_nt, nt_m, nt_v, first_head, GT, b, pair, split, tid,
+                     NTHR, &s_ticket);
+}
+
+// ------------------------------------------------------------------ host side
+struct SplitPlan {
+  int num_splits, tiles_per_split;
+};
+
+// Pick the split count that minimises the makespan (in tiles) of a wave model with `slots`
+// concurrently resident CTAs; every split keeps >= min_tiles tiles when possible.
+SplitPlan plan_splits(int64_t pairs, int n_tiles, int slots, int min_tiles) {
+  if (n_tiles <= 0) return {1, 1};
+  int best_s = 1;
+  double best = 1e30;
+  const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), 64));
+  for (int s = 1; s <= max_s; ++s) {
+    const int tps = (n_tiles + s - 1) / s;
+    const int real_s = (n_tiles + tps - 1) / tps;
+    const int64_t waves = (pairs * real_s + slots - 1) / slots;
+    const double cost = (double)waves * (tps + 1.5);  // +1.5 tiles of fixed per-CTA overhead
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_s = real_s;
+    }
+  }
+  const int tps = (n_tiles + best_s - 1) / best_s;
+  return {(n_tiles + tps - 1) / tps, tps};
+}
+
+bool inner_contig(const omx_array* a) { return a->strides[3] == 1 || a->shape[3] == 1; }
+
+template <typename T, int VE>
+void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid) {
+  auto go = [&](auto kern, int gt) {
+    const size_t smem = sizeof(float) * ((size_t)kSimtWarps * gt * (32 * VE + 2) + 2 * 32 * VE + gt) +
+                        sizeof(T) * (size_t)gt * 32 * VE;
+    OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kSimtWarps * 32, smem, stream>>>(p);
+  };
+  switch (Gt) {
+    case 1: go(decode_simt_kernel<T, VE, 1>, 1); break;
+    case 2: go(decode_simt_kernel<T, VE, 2>, 2); break;
+    default: go(decode_simt_kernel<T, VE, 4>, 4); break;
+  }
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
+
+template <typename T>
+void launch_simt_d(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid) {
+  switch (p.D) {
+    case 32: launch_simt<T, 1>(p, stream, Gt, grid); break;
+    case 64: launch_simt<T, 2>(p, stream, Gt, grid); break;
+    case 128: launch_simt<T, 4>(p, stream, Gt, grid); break;
+    default: launch_simt<T, 8>(p, stream, Gt, grid); break;
+  }
+}
+
+}  // namespace
+
+bool decode_supported(const SdpaArgs& a, const char** why) {
+  auto no = [&](const char* w) {
+    if (why) *why = w;
+    return false;
+  };
+  if (a.Lq != 1) return no("Lq != 1");
+  if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) return no("array mask");
+  if (a.D != a.Dv) return no("Dk != Dv");
+  if (!(a.D == 32 || a.D == 64 || a.D == 128 || a.D == 256)) return no("head_dim not in {32,64,128,256}");
+  if (!inner_contig(a.q) || !inner_contig(a.k) || !inner_contig(a.v) || !inner_contig(a.out))
+    return no("innermost axis not contiguous");
+  const size_t es = dtype_size(a.q->dtype);
+  const int64_t v = (int64_t)(16 / es);
+  if (!aligned16(a.k->data) || !aligned16(a.v->data)) return no("K/V base not 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (a.k->strides[i] % v || a.v->strides[i] % v) return no("K/V strides not multiples of 16 bytes");
+  if (a.out->dtype != a.q->dtype) return no("out dtype differs");
+  return true;
+}
+
+void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream) {
+  DecodeParams p{};
+  p.q = a.q->data;
+  p.out = a.out->data;
+  p.k = a.k->data;
+  p.v = a.v->data;
+  for (int i = 0; i < 4; ++i) {
+    p.qs[i] = a.q->strides[i];
+    p.os[i] = a.out->strides[i];
+    p.ks[i] = a.k->strides[i];
+    p.vs[i] = a.v->strides[i];
+  }
+  p.B = a.B; p.Hq = a.Hq; p.Hkv = a.Hkv; p.G = a.Hq / a.Hkv; p.D = a.D;
+  p.Lk = a.Lk;
+  p.fused = f.enabled ? 1 : 0;
+  p.n_mem = f.enabled ? a.Lk - 1 : a.Lk;
+  p.scale_log2 = a.scale * kLog2e;
+  if (f.enabled) {
+    p.k_new = f.k_new->data;
+    p.v_new = f.v_new->data;
+    for (int i = 0; i < 4; ++i) {
+      p.kns[i] = f.k_new->strides[i];
+      p.vns[i] = f.v_new->strides[i];
+      p.kcs[i] = a.k->strides[i];
+      p.vcs[i] = a.v->strides[i];
+    }
+    p.k_row0 = a.k->data;
+    p.v_row0 = a.v->data;
+    p.rope_dims = f.rope_dims;
+    p.traditional = f.traditional ? 1 : 0;
+    if (f.rope_dims > 0) {
+      p.cos_row = f.table.cos + (size_t)f.position * f.table.half;
+      p.sin_row = f.table.sin + (size_t)f.position * f.table.half;
+    }
+  }
+  if (a.B == 0 || a.Hq == 0) return;
+  OMX_CHECK(p.Lk >= 1, "[scaled_dot_product_attention] decode needs at least one key");
+
+  const int sms = sm_count();
+  const int n_tiles = (p.n_mem + kTile - 1) / kTile;
+  const bool b16 = a.q->dtype != OMX_FLOAT32;
+  const bool use_hmma = b16 && a.D == 128 && p.G <= 16 && a.k->strides[2] >= 128 && a.v->strides[2] >= 128;
+
+  if (use_hmma) {
+    // cfg 0: 3 stages x 2 CTAs/SM (default); cfg 1: 6 stages x 1 CTA/SM.  OMX_DECODE_CFG is a
+    // tuning knob for the bench sweeps, not an API.
+    static const int cfg = [] {
+      const char* e = getenv("OMX_DECODE_CFG");
+      return e ? atoi(e) : 0;
+    }();
+    constexpr int NW = 4;
+    const int NSTAGE = cfg == 1 ? 6 : 3;
+    const int occ = cfg == 1 ? 1 : 2;
+    const int64_t pairs = (int64_t)a.B * a.Hkv;
+    SplitPlan sp = plan_splits(pairs, n_tiles, sms * occ, 4);
+    p.num_splits = sp.num_splits;
+    p.tiles_per_split = sp.tiles_per_split;
+    if (p.num_splits > 1) {
+      const size_t no = (size_t)pairs * p.num_splits * p.G * p.D;
+      const size_t nml = (size_t)pairs * p.num_splits * p.G * 2;
+      float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
+      p.ws_o = ws;
+      p.ws_ml = ws + no;
+      p.counters = get_counters((size_t)pairs, stream);
+    }
+    const bool bf = a.q->dtype == OMX_BFLOAT16;
+    const uint64_t rows = (uint64_t)std::max(p.n_mem, 1);
+    CUtensorMap tmK = make_tmap_4d_b16(a.k->data, 128, rows, a.Hkv, a.B, a.k->strides[2], a.k->strides[1],
+                                       a.k->strides[0], 64, 64, bf);
+    CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
+                                       a.v->strides[0], 64, 64, bf);
+    const size_t smem = 1024 + (size_t)NSTAGE * kStageBytes + 16 * kQPitch * 2 + sizeof(float) * (128 + 128 + 16);
+    dim3 grid(p.num_splits, a.Hkv, a.B);
+    auto go = [&](auto kern) {
+      OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, (NW + 1) * 32, smem, stream>>>(tmK, tmV, p);
+    };
+    note_launch("decode_hmma_tma");
+    if (bf) {
+      if (p.G > 8) go(decode_hmma_kernel<__nv_bfloat16, 3, NW, true, 2>);
+      else if (cfg == 1) go(decode_hmma_kernel<__nv_bfloat16, 6, NW, false, 1>);
+      else go(decode_hmma_kernel<__nv_bfloat16, 3, NW, false, 2>);
+    } else {
+      if (p.G > 8) go(decode_hmma_kernel<__half, 3, NW, true, 2>);
+      else go(decode_hmma_kernel<__half, 3, NW, false, 2>);
+    }
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+    return;
+  }
+
+  // ---- CUDA-core path
+  const int Gt = (p.G % 4 == 0) ? 4 : (p.G % 2 == 0 ? 2 : 1);
+  const int groups = p.G / Gt;
+  const int64_t pairs = (int64_t)a.B * a.Hkv * groups;
+  SplitPlan sp = plan_splits(pairs, n_tiles, sms * 2, 2);
+  p.num_splits = sp.num_splits;
+  p.tiles_per_split = sp.tiles_per_split;
+  if (p.num_splits > 1) {
+    const size_t no = (size_t)pairs * p.num_splits * Gt * p.D;
+    const size_t nml = (size_t)pairs * p.num_splits * Gt * 2;
+    float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
+    p.ws_o = ws;
+    p.ws_ml = ws + no;
+    p.counters = get_counters((size_t)pairs, stream);
+  }
+  dim3 grid(p.num_splits, a.Hkv * groups, a.B);
+  note_launch("decode_simt");
+  switch (a.q->dtype) {
+    case OMX_FLOAT32: launch_simt_d<float>(p, stream, Gt, grid); break;
+    case OMX_BFLOAT16: launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid); break;
+    default: launch_simt_d<__half>(p, stream, Gt, grid); break;
+  }
+}
+
+}  // namespace omx

@@ -1,0 +1,276 @@
+// kv_cache.cu -- device-resident KV caches with the reference's growth contract.
+//
+// Replaces the Rust logic of mlx-rs-core/src/cache.rs:
+//   KVCache (step-allocated, :92-195) and ConcatKeyValueCache (:45-85),
+// which the reference builds from mlx_zeros / mlx_concatenate_axis / mlx_slice_update /
+// mlx_slice (mlx-c/mlx/c/ops.h:210,960-989,1220).
+//
+// HBM layout: one allocation per tensor, [B, Hkv, phys_rows, D] row-major; the LOGICAL
+// capacity `cap` (= the reference's keys.shape[2]) follows cache.rs:141-181 exactly, the
+// PHYSICAL row count only ever doubles (or is pre-sized with omx_kv_cache_reserve), so a
+// decode loop re-allocates O(log S) times instead of every `step` tokens.  Fetched views
+// therefore have head stride phys_rows*D (the reference's views have cap*D; both are plain
+// strided views to the consumer).  Rows [offset, cap) hold +0.0 or stale rows after reset(),
+// exactly as in the reference.
+#include <algorithm>
+
+#include "omx_common.cuh"
+#include "omx_internal.h"
+
+namespace omx {
+
+namespace {
+
+template <typename U>
+__global__ void copy4d_kernel(U* __restrict__ dst, const U* __restrict__ src, int64_t n0, int64_t n1,
+                              int64_t n2, int64_t n3, int64_t d0, int64_t d1, int64_t d2, int64_t d3,
+                              int64_t s0, int64_t s1, int64_t s2, int64_t s3) {
+  const int64_t total = n0 * n1 * n2 * n3;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i3 = idx % n3;
+    int64_t r = idx / n3;
+    const int64_t i2 = r % n2;
+    r /= n2;
+    const int64_t i1 = r % n1;
+    const int64_t i0 = r / n1;
+    dst[i0 * d0 + i1 * d1 + i2 * d2 + i3 * d3] = src[i0 * s0 + i1 * s1 + i2 * s2 + i3 * s3];
+  }
+}
+
+template <typename U>
+void launch_copy(void* dst, const void* src, const int64_t n[4], const int64_t d[4],
+                 const int64_t s[4], cudaStream_t stream) {
+  const int64_t total = n[0] * n[1] * n[2] * n[3];
+  if (total == 0) return;
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 32);
+  copy4d_kernel<U><<<blocks, threads, 0, stream>>>((U*)dst, (const U*)src, n[0], n[1], n[2], n[3], d[0],
+                                                   d[1], d[2], d[3], s[0], s[1], s[2], s[3]);
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+void copy4d(const omx_array* dst, const omx_array* src, cudaStream_t stream) {
+  OMX_CHECK(dst->ndim == 4 && src->ndim == 4 && dst->dtype == src->dtype, "[copy4d] bad arguments");
+  const size_t es = dtype_size(src->dtype);
+  int64_t n[4], d[4], s[4];
+  for (int i = 0; i < 4; ++i) {
+    OMX_CHECK(dst->shape[i] == src->shape[i], "[copy4d] shape mismatch");
+    n[i] = src->shape[i];
+    d[i] = dst->strides[i];
+    s[i] = src->strides[i];
+  }
+  // 16-byte path: innermost axis contiguous and everything 16 B aligned
+  const int64_t v = (int64_t)(16 / es);
+  bool vec = d[3] == 1 && s[3] == 1 && n[3] % v == 0 && aligned16(dst->data) && aligned16(src->data);
+  for (int i = 0; i < 3; ++i) vec = vec && d[i] % v == 0 && s[i] % v == 0;
+  if (vec) {
+    int64_t nv[4] = {n[0], n[1], n[2], n[3] / v};
+    int64_t dv[4] = {d[0] / v, d[1] / v, d[2] / v, 1};
+    int64_t sv[4] = {s[0] / v, s[1] / v, s[2] / v, 1};
+    launch_copy<uint4>(dst->data, src->data, nv, dv, sv, stream);
+  } else if (es == 4) {
+    launch_copy<uint32_t>(dst->data, src->data, n, d, s, stream);
+  } else if (es == 2) {
+    launch_copy<uint16_t>(dst->data, src->data, n, d, s, stream);
+  } else {
+    launch_copy<uint8_t>(dst->data, src->data, n, d, s, stream);
+  }
+}
+
+struct KVBuf {
+  void* p = nullptr;
+  int D = 0;
+  int dtype = 0;
+  int64_t phys = 0;  // physical rows
+};
+
+struct KVCacheImpl {
+  bool concat = false;
+  int step = 256;
+  int offset = 0;
+  bool has = false;
+  int64_t cap = 0;  // logical rows (reference's keys.shape[2])
+  int B = 0, H = 0;
+  int64_t reserve_rows = 0;
+  KVBuf k, v;
+  cudaStream_t last_stream = nullptr;
+};
+
+KVCacheImpl* kv_cache_create(int step, bool concat) {
+  OMX_CHECK(concat || step > 0, "[KVCache] step must be positive, got %d", step);
+  auto* c = new KVCacheImpl();
+  c->concat = concat;
+  c->step = step;
+  return c;
+}
+
+void kv_cache_destroy(KVCacheImpl* c) {
+  if (!c) return;
+  if (c->k.p) cudaFreeAsync(c->k.p, c->last_stream);
+  if (c->v.p) cudaFreeAsync(c->v.p, c->last_stream);
+  delete c;
+}
+
+int kv_cache_offset(const KVCacheImpl* c) { return c->offset; }
+bool kv_cache_is_concat(const KVCacheImpl* c) { return c->concat; }
+
+void kv_cache_reset(KVCacheImpl* c) {
+  if (!c->concat) c->offset = 0;  // cache.rs:130-132; the concat cache keeps the trait's no-op
+}
+
+int kv_cache_trim(KVCacheImpl* c, int n) {
+  OMX_CHECK(!c->concat, "[KVCache] trim is not defined for ConcatKeyValueCache");
+  const int t = std::max(0, std::min(n, c->offset));
+  c->offset -= t;
+  return t;
+}
+
+void kv_cache_reserve(KVCacheImpl* c, int rows) {
+  OMX_CHECK(rows >= 0, "[KVCache] reserve rows must be >= 0");
+  c->reserve_rows = rows;
+}
+
+namespace {
+
+// Make `b` hold `new_cap` logical rows: rows [0, keep) preserved, rows [keep, new_cap) zeroed.
+void regrow(KVCacheImpl* c, KVBuf& b, int64_t keep, int64_t new_cap, bool zero_new,
+            cudaStream_t stream) {
+  const size_t es = dtype_size(b.dtype);
+  const size_t row = (size_t)b.D * es;
+  const size_t heads = (size_t)c->B * c->H;
+  if (new_cap > b.phys) {
+    int64_t phys = std::max<int64_t>(new_cap, std::max<int64_t>(c->reserve_rows, 2 * b.phys));
+    void* np = nullptr;
+    OMX_CUDA(cudaMallocAsync(&np, heads * (size_t)phys * row, stream));
+    if (b.p && keep > 0) {
+      OMX_CUDA(cudaMemcpy2DAsync(np, (size_t)phys * row, b.p, (size_t)b.phys * row, (size_t)keep * row,
+                                 heads, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (b.p) OMX_CUDA(cudaFreeAsync(b.p, stream));
+    b.p = np;
+    b.phys = phys;
+  }
+  if (zero_new && new_cap > keep && row > 0 && heads > 0) {
+    OMX_CUDA(cudaMemset2DAsync((char*)b.p + (size_t)keep * row, (size_t)b.phys * row, 0,
+                               (size_t)(new_cap - keep) * row, heads, stream));
+  }
+}
+
+void fill_view(const KVCacheImpl* c, const KVBuf& b, int64_t rows, omx_array* out) {
+  if (!out) return;
+  out->data = b.p;
+  out->dtype = b.dtype;
+  out->ndim = 4;
+  out->shape[0] = c->B;
+  out->shape[1] = c->H;
+  out->shape[2] = rows;
+  out->shape[3] = b.D;
+  out->strides[0] = (int64_t)c->H * b.phys * b.D;
+  out->strides[1] = b.phys * b.D;
+  out->strides[2] = b.D;
+  out->strides[3] = 1;
+}
+
+}  // namespace
+
+void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* values,
+                     omx_array* keys_out, omx_array* values_out, bool skip_copy,
+                     cudaStream_t stream) {
+  OMX_CHECK(keys && values && keys->ndim == 4 && values->ndim == 4,
+            "[KVCache] keys and values must be 4-dimensional [B, n_kv_heads, n, head_dim]");
+  OMX_CHECK(is_float_dtype(keys->dtype) && is_float_dtype(values->dtype),
+            "[KVCache] keys/values must be floating point");
+  for (int i = 0; i < 3; ++i)
+    OMX_CHECK(keys->shape[i] == values->shape[i], "[KVCache] keys/values shape mismatch on axis %d", i);
+  const int prev = c->offset;
+  const int n = (int)keys->shape[2];
+  c->last_stream = stream;
+
+  if (c->has) {
+    OMX_CHECK(keys->shape[0] == c->B && keys->shape[1] == c->H && keys->shape[3] == c->k.D &&
+                  values->shape[3] == c->v.D,
+              "[KVCache] update shape [%lld,%lld,%lld,%lld] does not match the cache [%d,%d,*,%d]",
+              (long long)keys->shape[0], (long long)keys->shape[1], (long long)keys->shape[2],
+              (long long)keys->shape[3], c->B, c->H, c->k.D);
+    OMX_CHECK(keys->dtype == c->k.dtype && values->dtype == c->v.dtype,
+              "[KVCache] update dtype differs from the cache dtype");
+  }
+
+  if (c->concat) {
+    // cache.rs:66-84: keys = concat([old, new], -2); offset = keys.shape[-2]
+    if (!c->has) {
+      c->B = (int)keys->shape[0];
+      c->H = (int)keys->shape[1];
+      c->k.D = (int)keys->shape[3];
+      c->v.D = (int)values->shape[3];
+      c->k.dtype = keys->dtype;
+      c->v.dtype = values->dtype;
+      c->has = true;
+    }
+    const int64_t new_cap = c->cap + n;
+    regrow(c, c->k, c->cap, new_cap, false, stream);
+    regrow(c, c->v, c->cap, new_cap, false, stream);
+    const int64_t at = c->cap;
+    c->cap = new_cap;
+    c->offset = (int)new_cap;
+    if (n > 0 && !skip_copy) {
+      omx_array dk, dv;
+      fill_view(c, c->k, n, &dk);
+      fill_view(c, c->v, n, &dv);
+      dk.data = (char*)c->k.p + (size_t)at * c->k.D * dtype_size(c->k.dtype);
+      dv.data = (char*)c->v.p + (size_t)at * c->v.D * dtype_size(c->v.dtype);
+      copy4d(&dk, keys, stream);
+      copy4d(&dv, values, stream);
+    }
+    fill_view(c, c->k, c->offset, keys_out);
+    fill_view(c, c->v, c->offset, values_out);
+    return;
+  }
+
+  // ---- KVCache::update_and_fetch, cache.rs:134-194 ----
+  const bool needs_grow = !c->has || (int64_t)prev + n > c->cap;  // :141-144
+  if (needs_grow) {
+    const int n_steps = (c->step + n - 1) / c->step;  // :152
+    const int64_t new_size = (int64_t)n_steps * c->step;
+    int64_t keep = 0;
+    if (!c->has) {
+      c->B = (int)keys->shape[0];  // :147-150
+      c->H = (int)keys->shape[1];
+      c->k.D = (int)keys->shape[3];
+      c->v.D = (int)values->shape[3];
+      c->k.dtype = keys->dtype;  // :158-161
+      c->v.dtype = values->dtype;
+      c->has = true;
+    } else {
+      keep = (prev % c->step != 0) ? prev : c->cap;  // :165-172 (trim to prev, else keep whole)
+    }
+    const int64_t new_cap = keep + new_size;  // :173-174 concat([old, zeros])
+    regrow(c, c->k, keep, new_cap, true, stream);
+    regrow(c, c->v, keep, new_cap, true, stream);
+    c->cap = new_cap;
+  }
+  c->offset = prev + n;  // :183
+  if (n > 0 && !skip_copy) {  // :187-188 slice update
+    omx_array dk, dv;
+    fill_view(c, c->k, n, &dk);
+    fill_view(c, c->v, n, &dv);
+    dk.data = (char*)c->k.p + (size_t)prev * c->k.D * dtype_size(c->k.dtype);
+    dv.data = (char*)c->v.p + (size_t)prev * c->v.D * dtype_size(c->v.dtype);
+    copy4d(&dk, keys, stream);
+    copy4d(&dv, values, stream);
+  }
+  fill_view(c, c->k, c->offset, keys_out);  // :190-193
+  fill_view(c, c->v, c->offset, values_out);
+}
+
+void kv_cache_state(const KVCacheImpl* c, omx_array* kbuf, omx_array* vbuf) {
+  OMX_CHECK(c->has, "[KVCache] cache is empty");
+  fill_view(c, c->k, c->cap, kbuf);
+  fill_view(c, c->v, c->cap, vbuf);
+}
+
+}  // namespace omx

@@ -1,0 +1,487 @@
+// omx_api.cu -- the extern "C" boundary of libomx_attn: validation, dispatch, error routing.
+//
+// Mirrors the conventions of mlx-c (mlx-c/mlx/c/fast.cpp:544-633, error.cpp:12-53): every entry
+// point returns 0/1, exceptions never cross the ABI, messages go to the registered handler or a
+// thread-local slot.  Validation messages follow MLX's so that the reference's callers see the
+// same failures (rank, head-dim, GQA divisibility, dtype, mask broadcast / promotion).
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "omx_common.cuh"
+#include "omx_internal.h"
+
+namespace omx {
+
+namespace {
+
+thread_local std::string t_last_error;
+thread_local std::string t_last_kernel;
+thread_local std::string t_forced_kernel;
+thread_local int64_t t_launches = 0;
+
+std::mutex g_handler_mu;
+omx_error_handler_func g_handler = nullptr;
+void* g_handler_data = nullptr;
+void (*g_handler_dtor)(void*) = nullptr;
+
+void report(const char* msg) {
+  t_last_error = msg;
+  std::lock_guard<std::mutex> lk(g_handler_mu);
+  if (g_handler) g_handler(msg, g_handler_data);
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    report(e.what());
+    return 1;
+  } catch (...) {
+    report("unknown error");
+    return 1;
+  }
+}
+
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+std::mutex g_ws_mu;
+std::map<std::pair<int, cudaStream_t>, Scratch> g_ws, g_ctr;
+
+void* grow(std::map<std::pair<int, cudaStream_t>, Scratch>& pool, size_t bytes, cudaStream_t stream,
+           size_t min_bytes) {
+  int dev = 0;
+  OMX_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  Scratch& s = pool[{dev, stream}];
+  if (s.bytes < bytes) {
+    size_t nb = std::max(bytes, std::max(min_bytes, 2 * s.bytes));
+    void* np = nullptr;
+    OMX_CUDA(cudaMallocAsync(&np, nb, stream));
+    OMX_CUDA(cudaMemsetAsync(np, 0, nb, stream));
+    if (s.p) OMX_CUDA(cudaFreeAsync(s.p, stream));  // stream-ordered: earlier kernels finish first
+    s.p = np;
+    s.bytes = nb;
+  }
+  return s.p;
+}
+
+int g_sm_count[64] = {0};
+
+}  // namespace
+
+void note_launch(const char* family) { t_last_kernel = family; }
+void count_launch() { ++t_launches; }
+
+void* get_workspace(size_t bytes, cudaStream_t stream) { return grow(g_ws, bytes, stream, 1 << 20); }
+int* get_counters(size_t count, cudaStream_t stream) {
+  return (int*)grow(g_ctr, count * sizeof(int), stream, 1 << 16);
+}
+
+int sm_count() {
+  int dev = 0;
+  OMX_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && g_sm_count[dev]) return g_sm_count[dev];
+  int n = 0;
+  OMX_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) g_sm_count[dev] = n;
+  return n;
+}
+
+namespace {
+
+void require_device() {
+  int dev = 0;
+  OMX_CUDA(cudaGetDevice(&dev));
+  static thread_local int checked_dev = -1;
+  if (checked_dev == dev) return;
+  int major = 0;
+  OMX_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  OMX_CHECK(major == 10, "libomx_attn is built for sm_100a (B200) only; device %d has compute capability %d.x "
+                         "and there is no fallback path", dev, major);
+  checked_dev = dev;
+}
+
+void check_arr(const omx_array* a, const char* name, int ndim) {
+  OMX_CHECK(a != nullptr, "[omx] %s is null", name);
+  OMX_CHECK(a->ndim == ndim, "[scaled_dot_product_attention] %s must be %d-dimensional, got %d", name, ndim,
+            a->ndim);
+}
+
+// Fill SdpaArgs from the raw arrays with MLX's validation rules.
+SdpaArgs make_sdpa_args(const omx_array* out, const omx_array* q, const omx_array* k, const omx_array* v,
+                        float scale, const char* mask_mode, const omx_array* mask_arr,
+                        const omx_array* sinks) {
+  OMX_CHECK(q && k && v && out, "[scaled_dot_product_attention] null array");
+  for (const omx_array* t : {q, k, v}) {
+    OMX_CHECK(t->ndim == 4,
+              "[scaled_dot_product_attention] input with shape of %d dims is not supported; expected "
+              "[B, N, T, D]", t->ndim);
+  }
+  OMX_CHECK(sinks == nullptr || sinks->data == nullptr,
+            "[scaled_dot_product_attention] attention sinks are not supported");
+  OMX_CHECK(q->shape[0] == k->shape[0] && q->shape[0] == v->shape[0],
+            "[scaled_dot_product_attention] mismatching batch dimension for input");
+  OMX_CHECK(q->shape[3] == k->shape[3],
+            "[scaled_dot_product_attention] query, keys expected to have matching last dimension; found "
+            "%lld and %lld", (long long)q->shape[3], (long long)k->shape[3]);
+  OMX_CHECK(k->shape[1] == v->shape[1],
+            "[scaled_dot_product_attention] keys, values expected to have matching n_kv_heads; found %lld "
+            "and %lld", (long long)k->shape[1], (long long)v->shape[1]);
+  OMX_CHECK(k->shape[2] == v->shape[2],
+            "[scaled_dot_product_attention] keys, values expected to have matching sequence length");
+  OMX_CHECK(k->shape[1] > 0 && q->shape[1] % k->shape[1] == 0,
+            "[scaled_dot_product_attention] n_heads must be a multiple of n_kv_heads, found n_heads %lld "
+            "for n_kv_heads %lld", (long long)q->shape[1], (long long)k->shape[1]);
+  OMX_CHECK(is_float_dtype(q->dtype),
+            "[scaled_dot_product_attention] Received unsupported type %s", dtype_name(q->dtype));
+  OMX_CHECK(q->dtype == k->dtype && q->dtype == v->dtype,
+            "[scaled_dot_product_attention] q, k, v must share one dtype (the reference promotes; this "
+            "boundary does not)");
+  SdpaArgs a{};
+  a.out = out; a.q = q; a.k = k; a.v = v;
+  a.scale = scale;
+  a.B = (int)q->shape[0]; a.Hq = (int)q->shape[1]; a.Lq = (int)q->shape[2]; a.D = (int)q->shape[3];
+  a.Hkv = (int)k->shape[1]; a.Lk = (int)k->shape[2]; a.Dv = (int)v->shape[3];
+  OMX_CHECK(out->ndim == 4 && out->shape[0] == a.B && out->shape[1] == a.Hq && out->shape[2] == a.Lq &&
+                out->shape[3] == a.Dv,
+            "[scaled_dot_product_attention] out must be [B, n_heads, L_q, D_v]");
+  OMX_CHECK(out->dtype == q->dtype || out->dtype == OMX_FLOAT32,
+            "[scaled_dot_product_attention] out dtype must be the input dtype (or float32)");
+  const std::string mode = mask_mode ? mask_mode : "";
+  const bool has_arr = mask_arr && mask_arr->data;
+  if (mode == "causal") {
+    OMX_CHECK(!has_arr, "[scaled_dot_product_attention] Invalid mask_arrs for mask_mode 'causal'. No array "
+                        "masks supported.");
+    a.mask_mode = MASK_CAUSAL;
+  } else if (mode.empty() || mode == "array") {
+    if (has_arr) {
+      OMX_CHECK(mask_arr->ndim <= 4, "[scaled_dot_product_attention] the mask with shape of %d dims is not "
+                                     "supported", mask_arr->ndim);
+      if (mask_arr->dtype == OMX_BOOL) {
+        a.mask_mode = MASK_BOOL;
+      } else {
+        OMX_CHECK(is_float_dtype(mask_arr->dtype) &&
+                      (mask_arr->dtype == q->dtype || (mask_arr->dtype == OMX_FLOAT32 && out->dtype == OMX_FLOAT32)),
+                  "[scaled_dot_product_attention] Mask type must promote to output type %s.",
+                  dtype_name(q->dtype));
+        a.mask_mode = MASK_ADD;
+      }
+      a.mask = mask_arr;
+      const int64_t full[4] = {a.B, a.Hq, a.Lq, a.Lk};
+      const int lead = 4 - mask_arr->ndim;
+      for (int i = 0; i < 4; ++i) {
+        if (i < lead) {
+          a.mask_strides[i] = 0;
+          continue;
+        }
+        const int64_t n = mask_arr->shape[i - lead];
+        OMX_CHECK(n == full[i] || n == 1,
+                  "[scaled_dot_product_attention] Mask with shape axis %d = %lld is not broadcastable to "
+                  "[%d, %d, %d, %d]", i - lead, (long long)n, a.B, a.Hq, a.Lq, a.Lk);
+        a.mask_strides[i] = (n == 1 && full[i] != 1) ? 0 : mask_arr->strides[i - lead];
+      }
+    } else {
+      a.mask_mode = MASK_NONE;
+    }
+  } else {
+    OMX_CHECK(false, "[scaled_dot_product_attention] Invalid mask_mode %s. mask_mode must be 'causal', "
+                     "'array' or ''.", mode.c_str());
+  }
+  return a;
+}
+
+void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
+  if ((int64_t)a.B * a.Hq * a.Lq * a.Dv == 0) return;
+  const std::string& force = t_forced_kernel;
+  const char* why = nullptr;
+  if (force.empty() || force == "decode" || force == "decode_simt" || force == "decode_hmma_tma") {
+    if (a.out->dtype == a.q->dtype && decode_supported(a, &why)) {
+      DecodeFused none;
+      decode_attention(a, none, stream);
+      return;
+    }
+    OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
+  }
+  if (force.empty() || force == "fmha_tcgen05") {
+    if (a.out->dtype == a.q->dtype && fmha_sm100_supported(a, &why)) {
+      fmha_sm100(a, stream);
+      return;
+    }
+    OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
+  }
+  sdpa_generic(a, stream);
+}
+
+}  // namespace
+}  // namespace omx
+
+using namespace omx;
+
+extern "C" {
+
+void omx_set_error_handler(omx_error_handler_func handler, void* data, void (*dtor)(void*)) {
+  std::lock_guard<std::mutex> lk(g_handler_mu);
+  if (g_handler_dtor && g_handler_data) g_handler_dtor(g_handler_data);
+  g_handler = handler;
+  g_handler_data = data;
+  g_handler_dtor = dtor;
+}
+
+const char* omx_last_error(void) { return t_last_error.c_str(); }
+int omx_version(void) { return OMX_ATTN_VERSION; }
+
+int omx_device_check(int* sm) {
+  return guarded([&] {
+    require_device();
+    if (sm) *sm = 100;
+  });
+}
+
+const char* omx_last_kernel(void) { return t_last_kernel.c_str(); }
+
+int64_t omx_launch_count(bool reset) {
+  const int64_t n = t_launches;
+  if (reset) t_launches = 0;
+  return n;
+}
+
+int omx_force_kernel(const char* name) {
+  return guarded([&] {
+    const std::string n = name ? name : "";
+    OMX_CHECK(n.empty() || n == "decode" || n == "decode_simt" || n == "decode_hmma_tma" ||
+                  n == "fmha_tcgen05" || n == "sdpa_generic",
+              "unknown kernel family '%s'", n.c_str());
+    t_forced_kernel = n;
+  });
+}
+
+int omx_fast_rope(const omx_array* out, const omx_array* x, int dims, bool traditional,
+                  omx_optional_float base, float scale, int offset, const omx_array* freqs, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    rope_forward(out, x, dims, traditional, base, scale, offset, nullptr, 0, freqs, (cudaStream_t)s);
+  });
+}
+
+int omx_fast_rope_dynamic(const omx_array* out, const omx_array* x, int dims, bool traditional,
+                          omx_optional_float base, float scale, const omx_array* offset, int max_position,
+                          const omx_array* freqs, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(offset != nullptr, "[rope] offset array is null");
+    rope_forward(out, x, dims, traditional, base, scale, 0, offset, max_position, freqs, (cudaStream_t)s);
+  });
+}
+
+int omx_fast_scaled_dot_product_attention(const omx_array* out, const omx_array* queries,
+                                          const omx_array* keys, const omx_array* values, float scale,
+                                          const char* mask_mode, const omx_array* mask_arr,
+                                          const omx_array* sinks, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    SdpaArgs a = make_sdpa_args(out, queries, keys, values, scale, mask_mode, mask_arr, sinks);
+    dispatch_sdpa(a, (cudaStream_t)s);
+  });
+}
+
+int omx_kv_cache_new(omx_kv_cache* res, int step) {
+  return guarded([&] {
+    OMX_CHECK(res != nullptr, "[KVCache] null result handle");
+    res->ctx = kv_cache_create(step, false);
+  });
+}
+int omx_kv_cache_free(omx_kv_cache c) {
+  return guarded([&] { kv_cache_destroy((KVCacheImpl*)c.ctx); });
+}
+int omx_kv_cache_offset(omx_kv_cache c, int* offset) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx && offset, "[KVCache] null handle");
+    *offset = kv_cache_offset((KVCacheImpl*)c.ctx);
+  });
+}
+int omx_kv_cache_reset(omx_kv_cache c) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    kv_cache_reset((KVCacheImpl*)c.ctx);
+  });
+}
+int omx_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys, const omx_array* values,
+                                  omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    OMX_CHECK(!kv_cache_is_concat((KVCacheImpl*)c.ctx), "[KVCache] handle is a ConcatKeyValueCache");
+    kv_cache_update((KVCacheImpl*)c.ctx, keys, values, keys_out, values_out, false, (cudaStream_t)s);
+  });
+}
+int omx_kv_cache_state(omx_kv_cache c, omx_array* keys_buf, omx_array* values_buf) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    kv_cache_state((KVCacheImpl*)c.ctx, keys_buf, values_buf);
+  });
+}
+int omx_kv_cache_trim(omx_kv_cache c, int n, int* trimmed) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    const int t = kv_cache_trim((KVCacheImpl*)c.ctx, n);
+    if (trimmed) *trimmed = t;
+  });
+}
+int omx_kv_cache_reserve(omx_kv_cache c, int rows) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    kv_cache_reserve((KVCacheImpl*)c.ctx, rows);
+  });
+}
+
+int omx_concat_kv_cache_new(omx_kv_cache* res) {
+  return guarded([&] {
+    OMX_CHECK(res != nullptr, "[ConcatKeyValueCache] null result handle");
+    res->ctx = kv_cache_create(0, true);
+  });
+}
+int omx_concat_kv_cache_free(omx_kv_cache c) { return omx_kv_cache_free(c); }
+int omx_concat_kv_cache_offset(omx_kv_cache c, int* offset) { return omx_kv_cache_offset(c, offset); }
+int omx_concat_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys, const omx_array* values,
+                                         omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(c.ctx, "[ConcatKeyValueCache] null handle");
+    OMX_CHECK(kv_cache_is_concat((KVCacheImpl*)c.ctx), "[ConcatKeyValueCache] handle is a KVCache");
+    kv_cache_update((KVCacheImpl*)c.ctx, keys, values, keys_out, values_out, false, (cudaStream_t)s);
+  });
+}
+
+int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                          const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                          omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
+                          omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    auto* c = (KVCacheImpl*)cache.ctx;
+    OMX_CHECK(c, "[attn_decode_fused] null cache handle");
+    OMX_CHECK(q && k_new && v_new && out, "[attn_decode_fused] null array");
+    OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4,
+              "[attn_decode_fused] q, k_new, v_new, out must be [B, H, 1, D]");
+    OMX_CHECK(q->shape[2] == 1 && k_new->shape[2] == 1 && v_new->shape[2] == 1,
+              "[attn_decode_fused] the fused step handles exactly one new token (L == 1), got L = %lld",
+              (long long)q->shape[2]);
+    OMX_CHECK(k_new->dtype == q->dtype && v_new->dtype == q->dtype, "[attn_decode_fused] dtype mismatch");
+    const int D = (int)q->shape[3];
+    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
+    OMX_CHECK(rope_dims == 0 || base.has_value != (freqs && freqs->data),
+              "[rope] Only one of base or freqs can have a value.");
+    const int position = kv_cache_offset(c);
+    // cache bookkeeping (growth by the reference rule) without copying the new rows: the kernel
+    // ropes k_new and writes row `position` itself.
+    omx_array kview, vview;
+    kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
+    if (keys_out) *keys_out = kview;
+    if (values_out) *values_out = vview;
+    SdpaArgs a = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    const char* why = nullptr;
+    const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
+                      v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
+    if (fast) {
+      DecodeFused f;
+      f.enabled = true;
+      f.k_new = k_new;
+      f.v_new = v_new;
+      f.rope_dims = rope_dims;
+      f.traditional = traditional;
+      f.position = position;
+      if (rope_dims > 0) {
+        std::vector<float> fh;
+        if (!base.has_value) {
+          OMX_CHECK(freqs->ndim == 1 && freqs->shape[0] == rope_dims / 2 && freqs->dtype == OMX_FLOAT32 &&
+                        freqs->strides[0] == 1,
+                    "[rope] freqs must be a contiguous float32 vector of length dims/2");
+          fh.resize(rope_dims / 2);
+          OMX_CUDA(cudaMemcpyAsync(fh.data(), freqs->data, sizeof(float) * fh.size(), cudaMemcpyDeviceToHost,
+                                   stream));
+          OMX_CUDA(cudaStreamSynchronize(stream));
+        }
+        f.table = get_rope_table(rope_dims, base.has_value, base.value, rope_scale,
+                                 fh.empty() ? nullptr : fh.data(), position + 1, stream);
+      }
+      decode_attention(a, f, stream);
+      return;
+    }
+    // Unfused composition for layouts the decode kernels do not take: rope -> row store -> sdpa.
+    omx_array krow = kview, vrow = vview;
+    krow.shape[2] = 1;
+    vrow.shape[2] = 1;
+    krow.data = (char*)kview.data + (size_t)position * kview.strides[2] * dtype_size(kview.dtype);
+    vrow.data = (char*)vview.data + (size_t)position * vview.strides[2] * dtype_size(vview.dtype);
+    if (rope_dims > 0) {
+      rope_forward(&krow, k_new, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+    } else {
+      copy4d(&krow, k_new, stream);
+    }
+    copy4d(&vrow, v_new, stream);
+    if (rope_dims > 0) {
+      const size_t qbytes = (size_t)q->shape[0] * q->shape[1] * D * dtype_size(q->dtype);
+      omx_array qr = *q;
+      qr.data = get_workspace(qbytes, stream);  // sdpa_generic itself uses no scratch
+      qr.strides[0] = q->shape[1] * D;
+      qr.strides[1] = D;
+      qr.strides[2] = D;
+      qr.strides[3] = 1;
+      rope_forward(&qr, q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+      SdpaArgs a2 = make_sdpa_args(out, &qr, &kview, &vview, sm_scale, "", nullptr, nullptr);
+      sdpa_generic(a2, stream);
+    } else {
+      sdpa_generic(a, stream);
+    }
+  });
+}
+
+int omx_dit_rope(const omx_array* out, const omx_array* x, const omx_array* cos, const omx_array* sin,
+                 omx_stream s) {
+  return guarded([&] {
+    require_device();
+    dit_rope_forward(out, x, cos, sin, (cudaStream_t)s);
+  });
+}
+
+int omx_dit_joint_attention(const omx_array* out, const omx_array* q, const omx_array* k, const omx_array* v,
+                            float scale, const omx_array* add_mask, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    const bool has_mask = add_mask && add_mask->data;
+    if (has_mask)
+      OMX_CHECK(add_mask->dtype == OMX_FLOAT32 || add_mask->dtype == q->dtype,
+                "[dit_joint_attention] add_mask must be float32 or the input dtype");
+    // same math as sdpa with mask none / additive; the generic kernel takes f32 masks and outputs
+    SdpaArgs a{};
+    if (has_mask && add_mask->dtype == OMX_FLOAT32 && q->dtype != OMX_FLOAT32) {
+      a = make_sdpa_args(out, q, k, v, scale, "", nullptr, nullptr);
+      a.mask_mode = MASK_ADD;
+      a.mask = add_mask;
+      const int64_t full[4] = {a.B, a.Hq, a.Lq, a.Lk};
+      const int lead = 4 - add_mask->ndim;
+      OMX_CHECK(add_mask->ndim <= 4, "[dit_joint_attention] mask rank > 4");
+      for (int i = 0; i < 4; ++i) {
+        if (i < lead) { a.mask_strides[i] = 0; continue; }
+        const int64_t n = add_mask->shape[i - lead];
+        OMX_CHECK(n == full[i] || n == 1, "[dit_joint_attention] mask not broadcastable");
+        a.mask_strides[i] = (n == 1 && full[i] != 1) ? 0 : add_mask->strides[i - lead];
+      }
+      sdpa_generic(a, (cudaStream_t)s);
+      return;
+    }
+    a = make_sdpa_args(out, q, k, v, scale, "", has_mask ? add_mask : nullptr, nullptr);
+    dispatch_sdpa(a, (cudaStream_t)s);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// omx_internal.h -- cross-translation-unit declarations of libomx_attn (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/omx_attn.h"
+
+namespace omx {
+
+// ---- rope.cu ----
+struct RopeTableRef {
+  const float* cos = nullptr;  // [n_pos, half] float32, device
+  const float* sin = nullptr;
+  int half = 0;
+  int n_pos = 0;
+};
+RopeTableRef get_rope_table(int dims, bool has_base, float base, float scale,
+                            const float* freqs_host, int need_positions, cudaStream_t stream);
+void rope_forward(const omx_array* out, const omx_array* x, int dims, bool traditional,
+                  omx_optional_float base, float scale, int offset, const omx_array* offset_arr,
+                  int max_position, const omx_array* freqs, cudaStream_t stream);
+void dit_rope_forward(const omx_array* out, const omx_array* x, const omx_array* cs,
+                      const omx_array* sn, cudaStream_t stream);
+
+// ---- kv_cache.cu ----
+struct KVCacheImpl;
+KVCacheImpl* kv_cache_create(int step, bool concat);
+void kv_cache_destroy(KVCacheImpl* c);
+int kv_cache_offset(const KVCacheImpl* c);
+void kv_cache_reset(KVCacheImpl* c);
+void kv_cache_reserve(KVCacheImpl* c, int rows);
+int kv_cache_trim(KVCacheImpl* c, int n);
+bool kv_cache_is_concat(const KVCacheImpl* c);
+// Grows if needed (reference rule), copies the n new rows unless `skip_copy` (the fused decode
+// kernel writes them itself), advances the offset and fills the fetched views.
+void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* values,
+                     omx_array* keys_out, omx_array* values_out, bool skip_copy,
+                     cudaStream_t stream);
+void kv_cache_state(const KVCacheImpl* c, omx_array* kbuf, omx_array* vbuf);
+// Strided 4-D copy (dst, src same shape/dtype); used by caches and tests.
+void copy4d(const omx_array* dst, const omx_array* src, cudaStream_t stream);
+
+// ---- workspace (omx_api.cu) ----
+// Per-(device, stream) scratch that only grows; zero-initialised on (re)allocation.
+void* get_workspace(size_t bytes, cudaStream_t stream);
+// A second, separately zero-initialised region for self-resetting arrival counters.
+int* get_counters(size_t count, cudaStream_t stream);
+int sm_count();
+
+// ---- sdpa_generic.cu ----
+enum MaskMode { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_BOOL = 2, MASK_ADD = 3 };
+struct SdpaArgs {
+  const omx_array *out, *q, *k, *v;
+  float scale;
+  int mask_mode;
+  const omx_array* mask;  // broadcastable to [B,Hq,Lq,Lk]
+  int64_t mask_strides[4];  // element strides after broadcasting (0 on broadcast axes)
+  int B, Hq, Hkv, Lq, Lk, D, Dv;
+};
+void sdpa_generic(const SdpaArgs& a, cudaStream_t stream);
+
+// ---- decode.cu ----
+struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
+  bool enabled = false;
+  const omx_array* k_new = nullptr;  // [B,Hkv,1,D] un-roped
+  const omx_array* v_new = nullptr;  // [B,Hkv,1,Dv]
+  int rope_dims = 0;                 // 0: no rotation
+  bool traditional = false;
+  RopeTableRef table;
+  int position = 0;  // = cache offset before the append
+};
+// q [B,Hq,1,D]; k/v views over Lk rows (Lk INCLUDES the new row when fused: the kernel reads
+// rows [0, Lk-1) from memory and takes row Lk-1 from k_new/v_new, writing it to k/v as well).
+bool decode_supported(const SdpaArgs& a, const char** why);
+void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream);
+
+// ---- fmha_sm100.cu ----
+bool fmha_sm100_supported(const SdpaArgs& a, const char** why);
+void fmha_sm100(const SdpaArgs& a, cudaStream_t stream);
+
+}  // namespace omx

@@ -82,3 +82,33 @@ def randn(shape, dtype, seed, device="cpu"):
     import torch
     g = torch.Generator().manual_seed(seed)
     return torch.randn(shape, generator=g, dtype=torch.float32).to(tdt(dtype)).to(device)
+
+
+# ---- parity bars (north_star): fp32 1e-4 relative, bf16 2e-2 max-abs, KV/rope bit-exact ----
+
+def assert_close(got, want, dtype, what=""):
+    """got/want: float32 numpy arrays."""
+    got = np.asarray(got, np.float32)
+    want = np.asarray(want, np.float32)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert np.isfinite(got).all(), f"{what}: non-finite output"
+    err = float(np.abs(got - want).max()) if got.size else 0.0
+    if dtype == "f32":
+        bound = 1e-4 * max(1.0, float(np.abs(want).max()) if want.size else 1.0)
+        assert err <= bound, f"{what}: fp32 max-abs err {err:.3e} > {bound:.3e}"
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5, err_msg=what)
+    else:
+        assert err <= 2e-2, f"{what}: {dtype} max-abs err {err:.3e} > 2e-2"
+
+
+def assert_bits_equal(got_t, want_np, dtype, what=""):
+    """torch tensor vs oracle array, bit for bit."""
+    g = t2n(got_t, dtype)
+    w = np.ascontiguousarray(want_np)
+    if dtype == "f32":
+        g, w = g.view(np.uint32), w.view(np.uint32)
+    elif dtype == "f16":
+        g, w = g.view(np.uint16), w.view(np.uint16)
+    assert g.shape == w.shape, (g.shape, w.shape)
+    bad = int((g != w).sum())
+    assert bad == 0, f"{what}: {bad} of {g.size} elements differ bitwise"

@@ -1,0 +1,197 @@
+"""fast::scaled_dot_product_attention on the B200 vs the CPU oracle (all mask modes, GQA,
+strided views, dtypes) at the north_star tolerances: fp32 1e-4 relative, 16-bit 2e-2 max-abs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_oracle, load_pkg, n2f, randn, t2n
+
+pytestmark = pytest.mark.gpu
+omx = load_pkg()
+orc = load_oracle()
+DEV = "cuda"
+Causal = omx.fast.ScaledDotProductAttentionMask.Causal
+
+
+def _mask(kind, B, Hq, Lq, Lk, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "none":
+        return None, None
+    if kind == "causal":
+        return Causal, "causal"
+    if kind == "bool2d":
+        m = torch.rand((Lq, Lk), generator=g) > 0.3
+        m[:, 0] = True
+        return m.to(DEV), m.numpy()
+    if kind == "bool4d":
+        m = torch.rand((B, 1, Lq, Lk), generator=g) > 0.3
+        m[..., 0] = True
+        return m.to(DEV), m.numpy()
+    if kind == "add":
+        from conftest import tdt
+        m = torch.randn((1, 1, Lq, Lk), generator=g).to(tdt(dtype))
+        return m.to(DEV), t2n(m, dtype)
+    raise ValueError(kind)
+
+
+def _run(shape, dtype, mask_kind, seed=0, qview=None, kvview=None, force=None):
+    B, Hq, Hkv, Lq, Lk, D = shape
+    q = randn((B, Hq, Lq, D), dtype, seed + 1)
+    k = randn((B, Hkv, Lk, D), dtype, seed + 2)
+    v = randn((B, Hkv, Lk, D), dtype, seed + 3)
+    gm, om = _mask(mask_kind, B, Hq, Lq, Lk, dtype, seed + 4)
+    qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+    if qview:
+        qd = qview(qd)
+    if kvview:
+        kd, vd = kvview(kd), kvview(vd)
+    scale = D ** -0.5
+    if force:
+        omx.force_kernel(force)
+    try:
+        got = omx.fast.scaled_dot_product_attention(qd, kd, vd, scale, gm)
+    finally:
+        omx.force_kernel("")
+    assert got.shape == (B, Hq, Lq, D) and got.dtype == qd.dtype
+    want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v, dtype), scale, om, dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, f"sdpa {shape} {dtype} {mask_kind}")
+    return got
+
+
+MASKS = ["none", "causal", "bool2d", "bool4d", "add"]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("mask", MASKS)
+def test_generic_all_masks(dtype, mask):
+    _run((2, 4, 2, 9, 37, 64), dtype, mask, force="sdpa_generic")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 6, 6, 19, 19, 16), (1, 8, 2, 5, 40, 128), (2, 2, 1, 33, 65, 80),
+                                   (1, 2, 2, 3, 130, 256), (1, 3, 1, 7, 7, 24)])
+def test_generic_shapes(dtype, shape):
+    _run(shape, dtype, "causal", force="sdpa_generic")
+    _run(shape, dtype, "none", force="sdpa_generic")
+
+
+@pytest.mark.parametrize("seq_len", [63, 129, 400])
+@pytest.mark.parametrize("dtype", ["f32", "f16"])
+def test_reference_test_fast_sdpa_shapes(seq_len, dtype):
+    # mlx-rs/src/fast.rs:301-331: B2 H24 Dk64, shape + dtype (here with values checked as well)
+    _run((2, 24, 24, seq_len, seq_len, 64), dtype, "none")
+
+
+def test_causal_bottom_right_alignment():
+    shape = (1, 4, 2, 5, 29, 64)
+    a = _run(shape, "f32", "causal")
+    B, Hq, Hkv, Lq, Lk, D = shape
+    q = randn((B, Hq, Lq, D), "f32", 1).to(DEV)
+    k = randn((B, Hkv, Lk, D), "f32", 2).to(DEV)
+    v = randn((B, Hkv, Lk, D), "f32", 3).to(DEV)
+    m = omx.create_causal_mask(Lq, Lk - Lq, device=DEV)  # utils.rs:134-153
+    b = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, m)
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_fully_masked_row_follows_finfo_min_rule():
+    B, H, Lq, Lk, D = 1, 2, 3, 11, 32
+    q, k, v = (randn((B, H, L, D), "f32", s).to(DEV) for L, s in ((Lq, 1), (Lk, 2), (Lk, 3)))
+    m = torch.ones(Lq, Lk, dtype=torch.bool, device=DEV)
+    m[1, :] = False
+    o = omx.fast.scaled_dot_product_attention(q, k, v, 1.0, m)
+    np.testing.assert_allclose(o[0, :, 1].cpu().numpy(), v[0].mean(1).cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_caller_layouts_strided(dtype):
+    # q as transposed [B,L,H,D] storage; k/v as [:, :, :Lk] slices of a larger cache buffer
+    B, Hq, Hkv, Lq, Lk, D = 2, 8, 2, 6, 50, 128
+    q = randn((B, Lq, Hq, D), dtype, 1).to(DEV)
+    kbuf = randn((B, Hkv, 256, D), dtype, 2).to(DEV)
+    vbuf = randn((B, Hkv, 256, D), dtype, 3).to(DEV)
+    qv, kv, vv = q.transpose(1, 2), kbuf[:, :, :Lk], vbuf[:, :, :Lk]
+    got = omx.fast.scaled_dot_product_attention(qv, kv, vv, D ** -0.5, Causal)
+    want = orc.sdpa(t2n(qv, dtype), t2n(kv, dtype), t2n(vv, dtype), D ** -0.5, "causal", dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, "strided")
+    # the caller's epilogue: transpose back + reshape (qwen3-mlx/src/model.rs:211-212) works on it
+    assert got.transpose(1, 2).reshape(B, Lq, Hq * D).shape == (B, Lq, Hq * D)
+
+
+def test_mask_arrays_variant_uses_first():
+    q, k, v = (randn((1, 2, 4, 16), "f32", s).to(DEV) for s in (1, 2, 3))
+    m = torch.rand(4, 4, device=DEV) > 0.5
+    m[:, 0] = True
+    a = omx.fast.scaled_dot_product_attention(q, k, v, 0.25, [m, ~m])
+    b = omx.fast.scaled_dot_product_attention(q, k, v, 0.25, m)
+    assert torch.equal(a, b)
+
+
+def test_wrapper_of_mlx_rs_core_utils():
+    q, k, v = (randn((1, 4, 6, 32), "f32", s).to(DEV) for s in (1, 2, 3))
+    a = omx.scaled_dot_product_attention(q, k, v, None, 0.2, omx.SdpaMask.Causal)
+    b = omx.fast.scaled_dot_product_attention(q, k, v, 0.2, Causal)
+    assert torch.equal(a, b)
+
+
+def test_validation_errors():
+    f = omx.fast.scaled_dot_product_attention
+    q = torch.zeros(1, 4, 3, 16, device=DEV)
+    k = torch.zeros(1, 2, 5, 16, device=DEV)
+    with pytest.raises(omx.Exception, match="matching last dimension"):
+        f(q, torch.zeros(1, 2, 5, 8, device=DEV), torch.zeros(1, 2, 5, 8, device=DEV), 1.0)
+    with pytest.raises(omx.Exception, match="multiple of n_kv_heads"):
+        f(q, torch.zeros(1, 3, 5, 16, device=DEV), torch.zeros(1, 3, 5, 16, device=DEV), 1.0)
+    with pytest.raises(omx.Exception, match="batch dimension"):
+        f(q, torch.zeros(2, 2, 5, 16, device=DEV), torch.zeros(2, 2, 5, 16, device=DEV), 1.0)
+    with pytest.raises(omx.Exception, match="not supported; expected"):
+        f(q[0], k[0], k[0], 1.0)
+    with pytest.raises(omx.Exception, match="unsupported type|Received unsupported"):
+        f(q.int(), k.int(), k.int(), 1.0)
+    with pytest.raises(omx.Exception, match="broadcastable"):
+        f(q, k, k, 1.0, torch.ones(3, 4, dtype=torch.bool, device=DEV))
+    with pytest.raises(omx.Exception, match="promote"):
+        f(q.bfloat16(), k.bfloat16(), k.bfloat16(), 1.0, torch.zeros(3, 5, device=DEV))
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("shape", [(2, 8, 2, 1, 300, 128), (1, 16, 8, 1, 2048, 128), (3, 4, 4, 1, 77, 64),
+                                   (1, 32, 2, 1, 1000, 128), (2, 6, 2, 1, 513, 128), (1, 8, 8, 1, 64, 256)])
+def test_decode_dispatch_lq1(dtype, shape):
+    # Lq == 1 goes to the split-K decode kernels (mask none; "causal" is the same thing at Lq == 1)
+    _run(shape, dtype, "none")
+    assert omx.last_kernel().startswith("decode"), omx.last_kernel()
+    _run(shape, dtype, "causal")
+    assert omx.last_kernel().startswith("decode"), omx.last_kernel()
+
+
+def test_decode_kernel_families():
+    _run((2, 8, 2, 1, 700, 128), "bf16", "none")
+    assert omx.last_kernel() == "decode_hmma_tma"
+    _run((2, 8, 2, 1, 700, 128), "f32", "none")
+    assert omx.last_kernel() == "decode_simt"
+    _run((2, 8, 2, 1, 700, 64), "bf16", "none")
+    assert omx.last_kernel() == "decode_simt"
+    _run((2, 8, 2, 1, 700, 128), "bf16", "bool2d")
+    assert omx.last_kernel() == "sdpa_generic"
+
+
+def test_decode_on_cache_views():
+    # K/V fetched from KVCache are [..., :offset, :] views with head stride cap*D
+    B, Hq, Hkv, S, D = 2, 8, 2, 333, 128
+    c = omx.KVCache()
+    k = randn((B, Hkv, S, D), "bf16", 1).to(DEV)
+    v = randn((B, Hkv, S, D), "bf16", 2).to(DEV)
+    kk, vv = c.update_and_fetch(k, v)
+    assert kk.stride(1) == 512 * D
+    q = randn((B, Hq, 1, D), "bf16", 3).to(DEV)
+    got = omx.fast.scaled_dot_product_attention(q, kk, vv, D ** -0.5)
+    assert omx.last_kernel() == "decode_hmma_tma"
+    want = orc.sdpa(t2n(q, "bf16"), t2n(k, "bf16"), t2n(v, "bf16"), D ** -0.5, None, dtype="bf16")
+    assert_close(got.float().cpu().numpy(), n2f(want, "bf16"), "bf16", "decode on cache views")
+
+
+def test_empty_inputs():
+    q = torch.zeros(0, 4, 3, 16, device=DEV)
+    k = torch.zeros(0, 2, 5, 16, device=DEV)
+    assert omx.fast.scaled_dot_product_attention(q, k, k, 1.0).shape == (0, 4, 3, 16)
