@@ -213,7 +213,11 @@ def main():
     ap.add_argument("--impl", default="omx", choices=["omx", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (parity/debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="replay the steps from a CUDA graph")
+    ap.add_argument("--graph-steps", type=int, default=16, help="steps captured per graph replay")
+    ap.add_argument("--rotate", type=int, default=1,
+                    help="decode: cycle through R distinct KV caches so a working set smaller than L2 "
+                         "is still read from HBM (R x KV bytes should exceed 126 MB)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     kind, cfg = WORKLOADS[args.workload]
@@ -249,17 +253,23 @@ def main():
 
     scale = D ** -0.5
     if kind == "decode":
-        cache = omx.KVCache()
-        CH = 8  # fill in chunks to bound temporary memory
-        for s0 in range(0, S - 1, (S - 1 + CH - 1) // CH):
-            n = min((S - 1 + CH - 1) // CH, S - 1 - s0)
-            cache.update_and_fetch(rn(B, Hkv, n, D), rn(B, Hkv, n, D))
-        assert cache.offset() == S - 1
+        caches = []
+        for _ in range(max(1, args.rotate)):
+            cache = omx.KVCache()
+            CH = 8  # fill in chunks to bound temporary memory
+            for s0 in range(0, S - 1, (S - 1 + CH - 1) // CH):
+                n = min((S - 1 + CH - 1) // CH, S - 1 - s0)
+                cache.update_and_fetch(rn(B, Hkv, n, D), rn(B, Hkv, n, D))
+            assert cache.offset() == S - 1
+            caches.append(cache)
+        turn = [0]
         q, kn, vn = rn(B, Hq, 1, D), rn(B, Hkv, 1, D), rn(B, Hkv, 1, D)
         out = torch.empty((B, Hq, 1, D), dtype=tdt, device=dev)
         rope = omx.nn.Rope(D, False, 1e6, 1.0)
 
         def step():
+            cache = caches[turn[0] % len(caches)]
+            turn[0] += 1
             omx.attn_decode_fused(q, kn, vn, cache, rope, scale, out=out)
             cache.trim(1)
 
@@ -279,6 +289,8 @@ def main():
             q.copy_(hq_pin[0], non_blocking=True)
             kn.copy_(hq_pin[1], non_blocking=True)
             vn.copy_(hq_pin[2], non_blocking=True)
+            cache = caches[turn[0] % len(caches)]
+            turn[0] += 1
             omx.attn_decode_fused(q, kn, vn, cache, rope, scale, out=out)
             cache.trim(1)
             out_pin.copy_(out, non_blocking=True)
@@ -313,21 +325,31 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, graph=False):
+        """Returns the device time (ms) of exactly `steps` steps (max over ranks)."""
         for _ in range(warmup):
             fn()
-        run = fn
+        run, reps = fn, steps
         if graph:
-            torch.cuda.synchronize()
+            per = max(1, min(args.graph_steps, steps))
+            while steps % per:
+                per -= 1
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm the capture stream's scratch before capturing
+                for _ in range(3):
+                    fn()
+            side.synchronize()
             cg = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cg):
-                fn()
-            run = cg.replay
+            with torch.cuda.graph(cg, stream=side):
+                for _ in range(per):
+                    fn()
+            run, reps = cg.replay, steps // per
             for _ in range(3):
                 run()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(reps):
             run()
         e1.record()
         torch.cuda.synchronize()
@@ -385,8 +407,8 @@ def main():
                        "ctx" if kind == "decode" else "seq_len": S, "q_heads": Hq, "kv_heads": Hkv, "head_dim": D,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2_policy": "working set >> 126 MB L2 (streams from HBM every step)"
-                       if alg_bytes > 512e6 else "working set fits L2: warm-L2 number",
-                       "kernel": kernel, "cuda_graph": bool(args.graph)},
+                       if alg_bytes * max(1, args.rotate) > 512e6 else "working set fits L2: warm-L2 number",
+                       "kernel": kernel, "cuda_graph": bool(args.graph), "rotate_caches": args.rotate},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches_timed,

@@ -206,11 +206,16 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
 }
 
 // ============================================================ 16-bit, D = 128: TMA + mma.sync
-template <typename T, int NSTAGE, int NW, bool HI, int MINB>
-__global__ void __launch_bounds__((NW + 1) * 32, MINB)
+// NSTAGE consumer warps + 1 producer warp.  Consumer warp w owns stage w and its full/empty
+// mbarrier pair (tile t -> warp t % NSTAGE -> stage t % NSTAGE): every barrier then has exactly
+// one waiter that consumes its phases in order, which the parity protocol requires (a waiter that
+// skipped ahead to a later phase of a fresh barrier would fall straight through).
+template <typename T, int NSTAGE, bool HI, int MINB>
+__global__ void __launch_bounds__((NSTAGE + 1) * 32, MINB)
 decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const DecodeParams p) {
   constexpr int D = 128;
+  constexpr int NW = NSTAGE;
   constexpr int NTHR = (NW + 1) * 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -575,6 +580,15 @@ struct SplitPlan {
 // concurrently resident CTAs; every split keeps >= min_tiles tiles when possible.
 SplitPlan plan_splits(int64_t pairs, int n_tiles, int slots, int min_tiles) {
   if (n_tiles <= 0) return {1, 1};
+  static const int forced = [] {  // debugging / tuning knob, not an API
+    const char* e = getenv("OMX_DECODE_SPLITS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) {
+    const int s = std::min(forced, n_tiles);
+    const int tps = (n_tiles + s - 1) / s;
+    return {(n_tiles + tps - 1) / tps, tps};
+  }
   int best_s = 1;
   double best = 1e30;
   const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), 64));
@@ -693,8 +707,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       const char* e = getenv("OMX_DECODE_CFG");
       return e ? atoi(e) : 0;
     }();
-    constexpr int NW = 4;
-    const int NSTAGE = cfg == 1 ? 6 : 3;
+    const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
     const int occ = cfg == 1 ? 1 : 2;
     const int64_t pairs = (int64_t)a.B * a.Hkv;
     SplitPlan sp = plan_splits(pairs, n_tiles, sms * occ, 4);
@@ -718,16 +731,25 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     dim3 grid(p.num_splits, a.Hkv, a.B);
     auto go = [&](auto kern) {
       OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, (NW + 1) * 32, smem, stream>>>(tmK, tmV, p);
+      kern<<<grid, (NSTAGE + 1) * 32, smem, stream>>>(tmK, tmV, p);
     };
     note_launch("decode_hmma_tma");
     if (bf) {
-      if (p.G > 8) go(decode_hmma_kernel<__nv_bfloat16, 3, NW, true, 2>);
-      else if (cfg == 1) go(decode_hmma_kernel<__nv_bfloat16, 6, NW, false, 1>);
-      else go(decode_hmma_kernel<__nv_bfloat16, 3, NW, false, 2>);
+      if (cfg == 1) {
+        if (p.G > 8) go(decode_hmma_kernel<__nv_bfloat16, 6, true, 1>);
+        else go(decode_hmma_kernel<__nv_bfloat16, 6, false, 1>);
+      } else {
+        if (p.G > 8) go(decode_hmma_kernel<__nv_bfloat16, 3, true, 2>);
+        else go(decode_hmma_kernel<__nv_bfloat16, 3, false, 2>);
+      }
     } else {
-      if (p.G > 8) go(decode_hmma_kernel<__half, 3, NW, true, 2>);
-      else go(decode_hmma_kernel<__half, 3, NW, false, 2>);
+      if (cfg == 1) {
+        if (p.G > 8) go(decode_hmma_kernel<__half, 6, true, 1>);
+        else go(decode_hmma_kernel<__half, 6, false, 1>);
+      } else {
+        if (p.G > 8) go(decode_hmma_kernel<__half, 3, true, 2>);
+        else go(decode_hmma_kernel<__half, 3, false, 2>);
+      }
     }
     count_launch();
     OMX_CUDA(cudaGetLastError());

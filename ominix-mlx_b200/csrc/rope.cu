@@ -315,7 +315,7 @@ void collapse(const omx_array* a, int64_t shape[4], int64_t strides[4], const ch
 void rope_forward(const omx_array* out, const omx_array* x, int dims, bool traditional,
                   omx_optional_float base, float scale, int offset, const omx_array* offset_arr,
                   int max_position, const omx_array* freqs, cudaStream_t stream) {
-  OMX_CHECK(x && out && x->data && out->data, "[rope] null array");
+  OMX_CHECK(x && out, "[rope] null array");
   OMX_CHECK(x->ndim >= 3 && x->ndim <= OMX_MAX_NDIM,
             "[rope] Input must have at least 3 dimensions but got input with %d dimensions.", x->ndim);
   OMX_CHECK(is_float_dtype(x->dtype), "[rope] Input must be a floating type but got %s.",
@@ -371,6 +371,7 @@ void rope_forward(const omx_array* out, const omx_array* x, int dims, bool tradi
     need = offset + p.T;
   }
   if ((int64_t)p.B * p.N * p.T * D == 0) return;
+  OMX_CHECK(x->data && out->data, "[rope] null data pointer");
   RopeTableRef tb = get_rope_table(dims, base.has_value, base.value, scale,
                                    fh.empty() ? nullptr : fh.data(), need, stream);
   p.cos = tb.cos;

@@ -67,8 +67,11 @@ def scaled_dot_product_attention(queries, keys, values, scale, mask=None, stream
     O = softmax(scale * Q K^T + mask) V, GQA without pre-tiling, f32 softmax; output [B,Hq,Lq,Dv]."""
     mode, m = _mode_and_mask(mask)
     if out is None:
-        out = torch.empty((queries.shape[0], queries.shape[1], queries.shape[2], values.shape[3]),
-                          dtype=queries.dtype, device=queries.device)
+        if queries.dim() == 4 and values.dim() == 4:
+            shape = (queries.shape[0], queries.shape[1], queries.shape[2], values.shape[3])
+        else:  # rank errors are reported by the library, with the reference's message
+            shape = tuple(queries.shape)
+        out = torch.empty(shape, dtype=queries.dtype, device=queries.device)
     q, k, v, o, md = desc(queries), desc(keys), desc(values), desc(out), desc(m)
     _lib.check(_lib.lib().omx_fast_scaled_dot_product_attention(ref(o), ref(q), ref(k), ref(v), float(scale),
                                                                 mode, ref(md), None, stream_ptr(stream)))
