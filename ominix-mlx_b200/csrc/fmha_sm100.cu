@@ -1,16 +1,479 @@
-// fmha_sm100.cu -- tcgen05 / TMEM / TMA flash-attention forward (prefill + DiT joint attention).
-// Placeholder translation unit: the kernel lands in a later commit; until then every call is
-// routed to sdpa_generic by the dispatcher.
+// fmha_sm100.cu -- tcgen05 / TMEM / TMA flash-attention forward for sm_100a.
+//
+// Serves the compute-bound cases of fast::scaled_dot_product_attention (mlx-rs/src/fast.rs:121-151):
+// causal prefill (Qwen3-8B shape, BASELINE C3) and the non-causal DiT joint [txt;img] attention of
+// FLUX.2-klein / Z-Image (C4; flux-klein-mlx/src/klein_model.rs:474-483).  bf16 / f16, D = 128,
+// mask none or "causal" (aligned bottom-right, q_off = max(Lk - Lq, 0)), GQA by head index.
+//
+// One CTA = 256 query rows of one (batch, q-head): two 128-row Q tiles that ping-pong on the tensor
+// core so that the softmax of one overlaps the MMAs of the other.
+//
+//   warp 8     TMA producer: Q tiles once, then K_j / V_j tiles (128 keys x 128 features) into a
+//              5-slot shared-memory ring (cp.async.bulk.tensor, 128-byte swizzle, mbarrier tx).
+//   warp 9     MMA issuer (one elected thread) + TMEM allocator:
+//                S_i = Q_i K_j^T      tcgen05.mma kind::f16, A/B from smem (K-major, SW128)
+//                O_i += P_i V_j       A = P_i from TMEM, B = V_j from smem (MN-major, SW128)
+//              tcgen05.commit -> mbarriers hand S_i / O_i to the softmax warpgroups and free slots.
+//   warps 0-3  softmax warpgroup for Q tile 0, warps 4-7 for Q tile 1: ONE THREAD OWNS ONE ROW
+//              (TMEM lane), so row max / row sum need no shuffles: tcgen05.ld S -> exp2 -> bf16 P
+//              -> tcgen05.st into the columns S occupied; O is rescaled lazily (only when the row
+//              max grew by more than 2^8) and normalised / stored by the same threads at the end.
+//
+// TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512);
+// P_i (packed 16-bit pairs) aliases the first 64 columns of S_i.
+#include <algorithm>
+
 #include "omx_common.cuh"
 #include "omx_internal.h"
+#include "sm100_utils.cuh"
 
 namespace omx {
 
-bool fmha_sm100_supported(const SdpaArgs&, const char** why) {
-  if (why) *why = "tcgen05 kernel not built yet";
-  return false;
+namespace {
+
+constexpr int BM = 128;          // rows per Q tile
+constexpr int BN = 128;          // keys per KV tile
+constexpr int HD = 128;          // head dim
+constexpr int kSlots = 5;        // K/V ring slots
+constexpr int kTileBytes = BN * HD * 2;  // 32 KB: two 64-feature TMA boxes of 16 KB
+constexpr int kBoxBytes = kTileBytes / 2;
+constexpr int kThreads = 320;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+struct FmhaParams {
+  void* out;
+  int64_t os[4];
+  int B, Hq, Hkv, Lq, Lk;
+  float scale_log2;
+  int causal;
+  int q_off;
+};
+
+// ---- tcgen05 wrappers -------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
 }
 
-void fmha_sm100(const SdpaArgs&, cudaStream_t) { OMX_CHECK(false, "fmha_sm100: not available"); }
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 32 columns of 32-bit: thread t of the warp gets lane (base_lane + t), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16, f32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int b_mn_major, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// bounded spin: a protocol bug becomes a launch failure instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+
+template <typename T>
+struct Pack2;
+template <>
+struct Pack2<__nv_bfloat16> {
+  static constexpr int fmt = 1;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <>
+struct Pack2<__half> {
+  static constexpr int fmt = 0;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+struct SharedCtl {
+  uint64_t q_full[2];
+  uint64_t kv_full[kSlots];
+  uint64_t kv_empty[kSlots];
+  uint64_t s_full[2];
+  uint64_t p_full[2];
+  uint32_t tmem_base;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* q_s = smem;                     // 2 x 32 KB
+  uint8_t* kv_s = smem + 2 * kTileBytes;   // kSlots x 32 KB
+  __shared__ SharedCtl ctl;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy tiles first
+  const int hq = blockIdx.y, b = blockIdx.z;
+  const int hk = hq / (p.Hq / p.Hkv);
+  const int m0 = m_blk * 2 * BM;
+
+  // number of KV tiles each Q tile visits
+  int n[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r0 = m0 + i * BM;
+    if (r0 >= p.Lq) {
+      n[i] = 0;
+    } else {
+      const int r1 = min(p.Lq, r0 + BM);
+      const int kmax = p.causal ? min(p.Lk, p.q_off + r1) : p.Lk;
+      n[i] = (kmax + BN - 1) / BN;
+    }
+  }
+  const int N = max(n[0], n[1]);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&ctl.q_full[i], 1);
+      mbar_init(&ctl.s_full[i], 1);
+      mbar_init(&ctl.p_full[i], BM);
+    }
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&ctl.kv_full[s], 1);
+      mbar_init(&ctl.kv_empty[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) {  // TMEM: all 512 columns (1 CTA/SM by shared-memory footprint)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&ctl.tmem_base))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ctl.tmem_base;
+
+  if (warp == 8) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      const uint64_t pol_q = policy_evict_first();
+      const uint64_t pol_kv = policy_evict_last();  // K/V are re-read by the other q heads / m-blocks
+      for (int i = 0; i < 2; ++i) {
+        if (n[i] == 0) continue;
+        mbar_expect_tx(&ctl.q_full[i], kTileBytes);
+        tma_load_4d(q_s + i * kTileBytes, &tmQ, &ctl.q_full[i], 0, m0 + i * BM, hq, b, pol_q);
+        tma_load_4d(q_s + i * kTileBytes + kBoxBytes, &tmQ, &ctl.q_full[i], 64, m0 + i * BM, hq, b, pol_q);
+      }
+      for (int seq = 0; seq < 2 * N; ++seq) {
+        const int slot = seq % kSlots, use = seq / kSlots;
+        if (use > 0) mbar_wait_wd(&ctl.kv_empty[slot], (use - 1) & 1);
+        const int j = seq >> 1;
+        const CUtensorMap* tm = (seq & 1) ? &tmV : &tmK;
+        uint8_t* dst = kv_s + slot * kTileBytes;
+        mbar_expect_tx(&ctl.kv_full[slot], kTileBytes);
+        tma_load_4d(dst, tm, &ctl.kv_full[slot], 0, j * BN, hk, b, pol_kv);
+        tma_load_4d(dst + kBoxBytes, tm, &ctl.kv_full[slot], 64, j * BN, hk, b, pol_kv);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // =========================================================== MMA issuer
+    if (lane == 0 && N > 0) {
+      constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
+      constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
+      const uint32_t q_addr = smem_u32(q_s), kv_addr = smem_u32(kv_s);
+      auto wait_kv = [&](int seq) { mbar_wait_wd(&ctl.kv_full[seq % kSlots], (seq / kSlots) & 1); };
+      auto slot_addr = [&](int seq) { return kv_addr + (uint32_t)(seq % kSlots) * kTileBytes; };
+      // S_i = Q_i K^T : K-major operands, 2 feature blocks x 4 k-steps of 16
+      auto mma_qk = [&](int i, uint32_t k_base) {
+        const uint32_t qa = q_addr + i * kTileBytes;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t off = kb * kBoxBytes + ks * 32;
+            umma_ss(tmem + i * 128, umma_desc(qa + off, 16, 1024), umma_desc(k_base + off, 16, 1024), idesc_qk,
+                    (kb | ks) ? 1u : 0u);
+          }
+        }
+      };
+      // O_i += P_i V : A = P_i in TMEM (16 keys = 8 columns per k-step), B = V MN-major
+      auto mma_pv = [&](int i, uint32_t v_base, bool first) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, umma_desc(v_base + ks * 2048, kBoxBytes, 1024),
+                  idesc_pv, (first && ks == 0) ? 0u : 1u);
+        }
+      };
+      for (int i = 0; i < 2; ++i)
+        if (n[i] > 0) mbar_wait_wd(&ctl.q_full[i], 0);
+      wait_kv(0);
+      tc_fence_after();
+      for (int i = 0; i < 2; ++i) {
+        if (n[i] > 0) {
+          mma_qk(i, slot_addr(0));
+          tc_commit(&ctl.s_full[i]);
+        }
+      }
+      tc_commit(&ctl.kv_empty[0]);
+      for (int j = 0; j < N; ++j) {
+        wait_kv(2 * j + 1);  // V_j
+        bool k_next_ready = false;
+        for (int i = 0; i < 2; ++i) {
+          if (j >= n[i]) continue;
+          mbar_wait_wd(&ctl.p_full[i], j & 1);
+          tc_fence_after();
+          mma_pv(i, slot_addr(2 * j + 1), j == 0);
+          if (j + 1 < n[i]) {
+            if (!k_next_ready) {
+              wait_kv(2 * j + 2);  // K_{j+1}
+              tc_fence_after();
+              k_next_ready = true;
+            }
+            mma_qk(i, slot_addr(2 * j + 2));
+          }
+          tc_commit(&ctl.s_full[i]);
+        }
+        tc_commit(&ctl.kv_empty[(2 * j + 1) % kSlots]);
+        if (j + 1 < N) {
+          if (!k_next_ready) wait_kv(2 * j + 2);  // keep the waiter's phase order even if unused
+          tc_commit(&ctl.kv_empty[(2 * j + 2) % kSlots]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================== softmax warpgroups
+    const int i = warp >> 2;                 // Q tile
+    const int row = (warp & 3) * 32 + lane;  // row within the tile == TMEM lane
+    const int qrow = m0 + i * BM + row;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem + lane_base + i * 128;
+    const uint32_t t_o = tmem + lane_base + 256 + i * 128;
+    const int ni = n[i];
+    float m_run = -INFINITY, l_run = 0.f;
+    const int limit = p.causal ? min(p.Lk, p.q_off + qrow + 1) : p.Lk;  // keys [0, limit) are visible
+
+    for (int j = 0; j < ni; ++j) {
+      mbar_wait_wd(&ctl.s_full[i], j & 1);
+      tc_fence_after();
+      const int key0 = j * BN;
+      const bool need_mask = __any_sync(0xffffffffu, key0 + BN > limit);  // warp-uniform
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]);
+          if (need_mask && key0 + c * 32 + e >= limit) v = -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_tile = mx * p.scale_log2;  // scale > 0: max commutes with the scaling
+      float m_new = fmaxf(m_run, m_tile);
+      // lazy rescale: keep the old reference max unless it grew by more than 2^8 (warp-uniform
+      // decision because the TMEM accesses below are warp-collective)
+      const bool grow = (m_new - m_run) > kRescaleThreshold;  // also true on the first tile (-inf)
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.f;
+      if (grow) {
+        alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
+        m_run = m_new;
+      }
+      if (any_grow && j > 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_o + c * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * alpha);
+          tmem_st32(t_o + c * 32, r);
+        }
+      }
+      l_run *= alpha;
+      // pass 2: P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_s + c * 32, r);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_run));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -m_run));
+          if (need_mask) {
+            if (key0 + c * 32 + e >= limit) p0 = 0.f;
+            if (key0 + c * 32 + e + 1 >= limit) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[e >> 1] = Pack2<T>::pack(p0, p1);
+        }
+        tmem_st16(t_s + c * 16, pk);
+      }
+      l_run += rs;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&ctl.p_full[i]);
+    }
+    if (ni > 0) {
+      // final: O_i / l -> global
+      mbar_wait_wd(&ctl.s_full[i], ni & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_o + c * 32, r);
+        tc_wait_ld();
+        if (qrow < p.Lq) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 v;
+            v.x = Pack2<T>::pack(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+            v.y = Pack2<T>::pack(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+            v.z = Pack2<T>::pack(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+            v.w = Pack2<T>::pack(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c * 32 + e) = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+}  // namespace
+
+bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
+  auto no = [&](const char* w) {
+    if (why) *why = w;
+    return false;
+  };
+  if (a.q->dtype != OMX_BFLOAT16 && a.q->dtype != OMX_FLOAT16) return no("dtype is not bf16/f16");
+  if (a.D != HD || a.Dv != HD) return no("head_dim != 128");
+  if (a.mask_mode != MASK_NONE && a.mask_mode != MASK_CAUSAL) return no("array mask");
+  if (a.Lq < 1 || a.Lk < 1) return no("empty sequence");
+  if (a.out->dtype != a.q->dtype) return no("out dtype differs");
+  const omx_array* ts[4] = {a.q, a.k, a.v, a.out};
+  for (const omx_array* t : ts) {
+    if (t->strides[3] != 1) return no("innermost axis not contiguous");
+    if (!aligned16(t->data)) return no("base pointer not 16-byte aligned");
+    for (int i = 0; i < 3; ++i)
+      if (t->shape[i] > 1 && (t->strides[i] % 8 != 0 || t->strides[i] <= 0)) return no("strides not multiples of 16 bytes");
+  }
+  return true;
+}
+
+void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
+  const bool bf = a.q->dtype == OMX_BFLOAT16;
+  FmhaParams p{};
+  p.out = a.out->data;
+  for (int i = 0; i < 4; ++i) p.os[i] = a.out->strides[i];
+  p.B = a.B; p.Hq = a.Hq; p.Hkv = a.Hkv; p.Lq = a.Lq; p.Lk = a.Lk;
+  p.scale_log2 = a.scale * kLog2e;
+  p.causal = a.mask_mode == MASK_CAUSAL ? 1 : 0;
+  p.q_off = std::max(a.Lk - a.Lq, 0);
+  OMX_CHECK(a.scale > 0.f, "[scaled_dot_product_attention] the tcgen05 path needs scale > 0");
+  CUtensorMap tmQ = make_tmap_4d_b16(a.q->data, HD, a.Lq, a.Hq, a.B, a.q->strides[2], a.q->strides[1],
+                                     a.q->strides[0], 64, BM, bf);
+  CUtensorMap tmK = make_tmap_4d_b16(a.k->data, HD, a.Lk, a.Hkv, a.B, a.k->strides[2], a.k->strides[1],
+                                     a.k->strides[0], 64, BN, bf);
+  CUtensorMap tmV = make_tmap_4d_b16(a.v->data, HD, a.Lk, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
+                                     a.v->strides[0], 64, BN, bf);
+  const size_t smem = 1024 + (size_t)(2 + kSlots) * kTileBytes;
+  dim3 grid((a.Lq + 2 * BM - 1) / (2 * BM), a.Hq, a.B);
+  note_launch("fmha_tcgen05");
+  if (bf) {
+    OMX_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fmha_fwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    OMX_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fmha_fwd_kernel<__half><<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  }
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
 
 }  // namespace omx

@@ -211,7 +211,8 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
     OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
   }
   if (force.empty() || force == "fmha_tcgen05") {
-    if (a.out->dtype == a.q->dtype && fmha_sm100_supported(a, &why)) {
+    // small query blocks waste the 256-row CTA tile: leave them to the CUDA-core kernel unless forced
+    if (a.out->dtype == a.q->dtype && fmha_sm100_supported(a, &why) && (a.Lq >= 32 || !force.empty())) {
       fmha_sm100(a, stream);
       return;
     }

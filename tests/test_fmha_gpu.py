@@ -1,0 +1,124 @@
+"""tcgen05/TMEM/TMA flash-attention forward (causal prefill + non-causal DiT) vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, load_oracle, load_pkg, n2f, randn, t2n
+
+pytestmark = pytest.mark.gpu
+omx = load_pkg()
+orc = load_oracle()
+DEV = "cuda"
+Causal = omx.fast.ScaledDotProductAttentionMask.Causal
+
+
+def _run(B, Hq, Hkv, Lq, Lk, dtype="bf16", causal=True, seed=0, qview=False, kvslice=False, tol_check=True):
+    D = 128
+    if qview:  # [B, L, H, D] storage viewed [B, H, L, D]
+        q = randn((B, Lq, Hq, D), dtype, seed + 1).transpose(1, 2)
+    else:
+        q = randn((B, Hq, Lq, D), dtype, seed + 1)
+    cap = Lk + 77 if kvslice else Lk
+    kbuf = randn((B, Hkv, cap, D), dtype, seed + 2)
+    vbuf = randn((B, Hkv, cap, D), dtype, seed + 3)
+    qd, kd, vd = q.to(DEV), kbuf.to(DEV)[:, :, :Lk], vbuf.to(DEV)[:, :, :Lk]
+    scale = D ** -0.5
+    omx.force_kernel("fmha_tcgen05")
+    try:
+        got = omx.fast.scaled_dot_product_attention(qd, kd, vd, scale, Causal if causal else None)
+    finally:
+        omx.force_kernel("")
+    torch.cuda.synchronize()
+    assert omx.last_kernel() == "fmha_tcgen05"
+    assert got.shape == (B, Hq, Lq, D)
+    want = orc.sdpa(t2n(q, dtype), t2n(kbuf[:, :, :Lk], dtype), t2n(vbuf[:, :, :Lk], dtype), scale,
+                    "causal" if causal else None, dtype=dtype)
+    if tol_check:
+        assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype,
+                     f"fmha B{B} Hq{Hq} Hkv{Hkv} Lq{Lq} Lk{Lk} causal={causal}")
+    return got, want
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_single_tile(causal):
+    _run(1, 1, 1, 128, 128, causal=causal)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_two_q_tiles_two_kv_tiles(causal):
+    _run(1, 2, 2, 256, 256, causal=causal)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("L", [384, 1024])
+def test_square_gqa(causal, L):
+    _run(2, 8, 2, L, L, causal=causal)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("Lq,Lk", [(100, 100), (129, 257), (300, 300), (511, 777), (64, 1000), (257, 130)])
+def test_ragged_lengths(causal, Lq, Lk):
+    # partial Q / KV tiles; causal is bottom-right aligned when Lq < Lk, top-left when Lq > Lk
+    _run(1, 4, 2, Lq, Lk, causal=causal)
+
+
+def test_f16():
+    _run(1, 4, 4, 256, 384, dtype="f16", causal=True)
+    _run(1, 4, 4, 256, 384, dtype="f16", causal=False)
+
+
+def test_caller_layouts():
+    _run(2, 8, 2, 300, 300, causal=True, qview=True, kvslice=True)
+
+
+def test_long_kv_many_ring_wraps():
+    _run(1, 2, 1, 256, 4096, causal=False)
+    _run(1, 2, 1, 512, 4096, causal=True)
+
+
+def test_c4_dit_shape_reduced_batch():
+    # FLUX.2-klein: 24 heads x 128, 512 txt + 4096 img tokens (C4), one batch item, 4 heads checked
+    got, want = _run(1, 4, 4, 4608, 4608, causal=False)
+
+
+def test_c3_prefill_shape_slice():
+    # Qwen3-8B prefill geometry (GQA 4:1, seq 8192) on one kv head group
+    _run(1, 4, 1, 8192, 8192, causal=True)
+
+
+def test_auto_dispatch_and_bool_mask_equivalence():
+    B, Hq, Hkv, L, D = 1, 8, 2, 512, 128
+    q, k, v = (randn((B, h, L, D), "bf16", s).to(DEV) for h, s in ((Hq, 1), (Hkv, 2), (Hkv, 3)))
+    a = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, Causal)
+    assert omx.last_kernel() == "fmha_tcgen05"
+    m = omx.create_causal_mask(L, 0, device=DEV)  # the array mask the LLM crates build (utils.rs:134-153)
+    b = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, m)
+    assert omx.last_kernel() == "sdpa_generic"
+    assert (a.float() - b.float()).abs().max().item() <= 1e-2
+
+
+def test_full_size_properties_c3():
+    # BASELINE C3 at full size (B8, 32q/8kv, seq 8192, bf16): size-independent properties
+    B, Hq, Hkv, L, D = 8, 32, 8, 8192, 128
+    g = torch.Generator(device=DEV).manual_seed(1237)
+    q = torch.randn((B, Hq, L, D), generator=g, device=DEV).bfloat16()
+    k = torch.randn((B, Hkv, L, D), generator=g, device=DEV).bfloat16()
+    v = torch.randn((B, Hkv, L, D), generator=g, device=DEV).bfloat16()
+    o = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, Causal)
+    assert omx.last_kernel() == "fmha_tcgen05"
+    assert torch.isfinite(o.float()).all()
+    # (1) row 0 attends to key 0 only: O[:, h, 0] == V[:, h/4, 0]
+    assert torch.equal(o[:, :, 0], v[:, :, 0].repeat_interleave(Hq // Hkv, 1))
+    # (2) causality: perturbing the future does not change the past
+    k2, v2 = k.clone(), v.clone()
+    k2[:, :, 4096:] = -k2[:, :, 4096:]
+    v2[:, :, 4096:] = 0
+    o2 = omx.fast.scaled_dot_product_attention(q, k2, v2, D ** -0.5, Causal)
+    assert torch.equal(o[:, :, :4096], o2[:, :, :4096])
+    # (3) linearity in V
+    o3 = omx.fast.scaled_dot_product_attention(q, k, (v.float() * 2).bfloat16(), D ** -0.5, Causal)
+    assert (o3.float() - 2 * o.float()).abs().max().item() <= 2e-2
+    # (4) one (batch, kv-group) slice against the oracle
+    want = orc.sdpa(t2n(q[3:4, 8:12], "bf16"), t2n(k[3:4, 2:3], "bf16"), t2n(v[3:4, 2:3], "bf16"), D ** -0.5,
+                    "causal", dtype="bf16")
+    assert_close(o[3:4, 8:12].float().cpu().numpy(), n2f(want, "bf16"), "bf16", "C3 slice")
