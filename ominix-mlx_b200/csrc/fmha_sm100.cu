@@ -37,7 +37,9 @@ constexpr int HD = 128;          // head dim
 constexpr int kSlots = 5;        // K/V ring slots
 constexpr int kTileBytes = BN * HD * 2;  // 32 KB: two 64-feature TMA boxes of 16 KB
 constexpr int kBoxBytes = kTileBytes / 2;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;   // 2 softmax warpgroups + 1 warpgroup {TMA, MMA, 2 idle}
+constexpr int kRegsSoftmax = 216;  // setmaxnreg budgets: 8 warps x 216 + 4 warps x 72 <= 64K registers
+constexpr int kRegsOther = 72;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct FmhaParams {
@@ -128,6 +130,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int b_mn_major, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // bounded spin: a protocol bug becomes a launch failure instead of a hung GPU
@@ -221,6 +229,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 8) {
     // =========================================================== TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -247,6 +256,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else if (warp == 9) {
     // =========================================================== MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
     if (lane == 0 && N > 0) {
       constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
       constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
@@ -311,8 +321,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 8) {
     // =========================================================== softmax warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     const int i = warp >> 2;                 // Q tile
     const int row = (warp & 3) * 32 + lane;  // row within the tile == TMEM lane
     const int qrow = m0 + i * BM + row;
@@ -322,31 +333,40 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int ni = n[i];
     float m_run = -INFINITY, l_run = 0.f;
     const int limit = p.causal ? min(p.Lk, p.q_off + qrow + 1) : p.Lk;  // keys [0, limit) are visible
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 
     for (int j = 0; j < ni; ++j) {
       mbar_wait_wd(&ctl.s_full[i], j & 1);
       tc_fence_after();
       const int key0 = j * BN;
-      const bool need_mask = __any_sync(0xffffffffu, key0 + BN > limit);  // warp-uniform
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
+      // the whole S row of this thread: 128 fp32 scores, one TMEM round trip
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(t_s, s0);
+      tmem_ld32(t_s + 32, s1);
+      tmem_ld32(t_s + 64, s2);
+      tmem_ld32(t_s + 96, s3);
+      tc_wait_ld();
+      if (__any_sync(0xffffffffu, key0 + BN > limit)) {  // diagonal / tail tile (warp-uniform branch)
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          float v = __uint_as_float(r[e]);
-          if (need_mask && key0 + c * 32 + e >= limit) v = -INFINITY;
-          mx = fmaxf(mx, v);
+          if (key0 + e >= limit) s0[e] = 0xff800000u;
+          if (key0 + 32 + e >= limit) s1[e] = 0xff800000u;
+          if (key0 + 64 + e >= limit) s2[e] = 0xff800000u;
+          if (key0 + 96 + e >= limit) s3[e] = 0xff800000u;
         }
       }
-      const float m_tile = mx * p.scale_log2;  // scale > 0: max commutes with the scaling
-      float m_new = fmaxf(m_run, m_tile);
-      // lazy rescale: keep the old reference max unless it grew by more than 2^8 (warp-uniform
-      // decision because the TMEM accesses below are warp-collective)
-      const bool grow = (m_new - m_run) > kRescaleThreshold;  // also true on the first tile (-inf)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        mx = fmax3(mx, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+        mx = fmax3(mx, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+        mx = fmax3(mx, __uint_as_float(s2[e]), __uint_as_float(s2[e + 1]));
+        mx = fmax3(mx, __uint_as_float(s3[e]), __uint_as_float(s3[e + 1]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);  // scale > 0: max commutes with scaling
+      // lazy rescale: keep the old reference max unless it grew by more than 2^8 (the decision to
+      // touch O is warp-uniform because TMEM accesses are warp-collective)
+      const bool grow = (m_new - m_run) > kRescaleThreshold;  // true on the first tile (m_run = -inf)
       const bool any_grow = __any_sync(0xffffffffu, grow);
       float alpha = 1.f;
       if (grow) {
@@ -364,29 +384,25 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st32(t_o + c * 32, r);
         }
       }
-      l_run *= alpha;
-      // pass 2: P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(t_s + c * 32, r);
-        tc_wait_ld();
+      // P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
+      const float2 nm2 = make_float2(-m_run, -m_run);
+      float2 acc2 = make_float2(0.f, 0.f);
+      auto chunk = [&](const uint32_t (&sv)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[e]), p.scale_log2, -m_run));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[e + 1]), p.scale_log2, -m_run));
-          if (need_mask) {
-            if (key0 + c * 32 + e >= limit) p0 = 0.f;
-            if (key0 + c * 32 + e + 1 >= limit) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[e >> 1] = Pack2<T>::pack(p0, p1);
+          const float2 a = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sc2, nm2);
+          const float2 pe = make_float2(fast_exp2(a.x), fast_exp2(a.y));
+          acc2 = __fadd2_rn(acc2, pe);
+          pk[e >> 1] = Pack2<T>::pack(pe.x, pe.y);
         }
         tmem_st16(t_s + c * 16, pk);
-      }
-      l_run += rs;
+      };
+      chunk(s0, 0);
+      chunk(s1, 1);
+      chunk(s2, 2);
+      chunk(s3, 3);
+      l_run = l_run * alpha + (acc2.x + acc2.y);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&ctl.p_full[i]);
@@ -415,6 +431,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));  // idle warps of warpgroup 2
   }
   tc_fence_before();
   __syncthreads();
