@@ -1,0 +1,93 @@
+//! Raw declarations of include/omx_attn.h (what bindgen produces for mlx-c in mlx-sys).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const OMX_MAX_NDIM: usize = 8;
+
+/// Values equal mlx_dtype (mlx-c/mlx/c/array.h:37-52).
+#[repr(i32)]
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+pub enum omx_dtype {
+    Bool = 0,
+    Int32 = 7,
+    Float16 = 9,
+    Float32 = 10,
+    Bfloat16 = 12,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct omx_array {
+    pub data: *mut c_void,
+    pub dtype: i32,
+    pub ndim: i32,
+    pub shape: [i64; OMX_MAX_NDIM],
+    pub strides: [i64; OMX_MAX_NDIM],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct omx_optional_float {
+    pub value: f32,
+    pub has_value: bool,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct omx_kv_cache {
+    pub ctx: *mut c_void,
+}
+
+pub type omx_stream = *mut c_void; // cudaStream_t
+pub type omx_error_handler_func = Option<unsafe extern "C" fn(msg: *const c_char, data: *mut c_void)>;
+
+extern "C" {
+    pub fn omx_set_error_handler(handler: omx_error_handler_func, data: *mut c_void,
+                                 dtor: Option<unsafe extern "C" fn(*mut c_void)>);
+    pub fn omx_last_error() -> *const c_char;
+    pub fn omx_version() -> c_int;
+    pub fn omx_device_check(sm: *mut c_int) -> c_int;
+
+    pub fn omx_fast_rope(out: *const omx_array, x: *const omx_array, dims: c_int, traditional: bool,
+                         base: omx_optional_float, scale: f32, offset: c_int, freqs: *const omx_array,
+                         s: omx_stream) -> c_int;
+    pub fn omx_fast_rope_dynamic(out: *const omx_array, x: *const omx_array, dims: c_int, traditional: bool,
+                                 base: omx_optional_float, scale: f32, offset: *const omx_array,
+                                 max_position: c_int, freqs: *const omx_array, s: omx_stream) -> c_int;
+    pub fn omx_fast_scaled_dot_product_attention(out: *const omx_array, queries: *const omx_array,
+                                                 keys: *const omx_array, values: *const omx_array,
+                                                 scale: f32, mask_mode: *const c_char,
+                                                 mask_arr: *const omx_array, sinks: *const omx_array,
+                                                 s: omx_stream) -> c_int;
+
+    pub fn omx_kv_cache_new(res: *mut omx_kv_cache, step: c_int) -> c_int;
+    pub fn omx_kv_cache_free(c: omx_kv_cache) -> c_int;
+    pub fn omx_kv_cache_offset(c: omx_kv_cache, offset: *mut c_int) -> c_int;
+    pub fn omx_kv_cache_reset(c: omx_kv_cache) -> c_int;
+    pub fn omx_kv_cache_update_and_fetch(c: omx_kv_cache, keys: *const omx_array, values: *const omx_array,
+                                         keys_out: *mut omx_array, values_out: *mut omx_array,
+                                         s: omx_stream) -> c_int;
+    pub fn omx_kv_cache_state(c: omx_kv_cache, keys_buf: *mut omx_array, values_buf: *mut omx_array) -> c_int;
+    pub fn omx_kv_cache_trim(c: omx_kv_cache, n: c_int, trimmed: *mut c_int) -> c_int;
+    pub fn omx_kv_cache_reserve(c: omx_kv_cache, rows: c_int) -> c_int;
+    pub fn omx_concat_kv_cache_new(res: *mut omx_kv_cache) -> c_int;
+    pub fn omx_concat_kv_cache_free(c: omx_kv_cache) -> c_int;
+    pub fn omx_concat_kv_cache_offset(c: omx_kv_cache, offset: *mut c_int) -> c_int;
+    pub fn omx_concat_kv_cache_update_and_fetch(c: omx_kv_cache, keys: *const omx_array,
+                                                values: *const omx_array, keys_out: *mut omx_array,
+                                                values_out: *mut omx_array, s: omx_stream) -> c_int;
+
+    pub fn omx_attn_decode_fused(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                 v_new: *const omx_array, cache: omx_kv_cache, rope_dims: c_int,
+                                 traditional: bool, base: omx_optional_float, rope_scale: f32,
+                                 freqs: *const omx_array, sm_scale: f32, keys_out: *mut omx_array,
+                                 values_out: *mut omx_array, s: omx_stream) -> c_int;
+    pub fn omx_dit_rope(out: *const omx_array, x: *const omx_array, cos: *const omx_array,
+                        sin: *const omx_array, s: omx_stream) -> c_int;
+    pub fn omx_dit_joint_attention(out: *const omx_array, q: *const omx_array, k: *const omx_array,
+                                   v: *const omx_array, scale: f32, add_mask: *const omx_array,
+                                   s: omx_stream) -> c_int;
+    pub fn omx_last_kernel() -> *const c_char;
+    pub fn omx_launch_count(reset: bool) -> i64;
+    pub fn omx_force_kernel(name: *const c_char) -> c_int;
+}
