@@ -215,6 +215,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", action="store_true", help="replay the steps from a CUDA graph")
     ap.add_argument("--graph-steps", type=int, default=16, help="steps captured per graph replay")
+    ap.add_argument("--gather", default="peer", choices=["peer", "collective"],
+                    help="c5 with --gpus > 1 (kv-head-sharded single sequence): exchange of the output heads "
+                         "by peer stores fused into the decode kernel, or by an NCCL all-gather")
     ap.add_argument("--rotate", type=int, default=1,
                     help="decode: cycle through R distinct KV caches so a working set smaller than L2 "
                          "is still read from HBM (R x KV bytes should exceed 126 MB)")
@@ -252,7 +255,46 @@ def main():
         return torch.randn(shape, generator=g, device=dev, dtype=torch.float32).to(tdt)
 
     scale = D ** -0.5
-    if kind == "decode":
+    sharded = kind == "decode" and args.workload == "c5" and world > 1
+    if sharded:
+        # C5: ONE sequence; rank r holds kv heads [r*Hkv/N, ...) and computes their q heads; the full
+        # [B,Hq,1,D] output lands on every rank (strong scaling: total work is fixed).
+        g0 = torch.Generator(device=dev).manual_seed(1234)  # replicated step inputs
+        def rn0(*shape):
+            return torch.randn(shape, generator=g0, device=dev, dtype=torch.float32).to(tdt)
+        rope = omx.nn.Rope(D, False, 1e6, 1.0)
+        eng = omx.parallel.HeadShardedDecode(Hq, Hkv, D, tdt, rope, scale, batch=B, gather=args.gather)
+        for s0 in range(0, S - 1, 4096):
+            n = min(4096, S - 1 - s0)
+            kk, vv = rn0(B, Hkv, n, D), rn0(B, Hkv, n, D)
+            eng.prefill(kk, vv)
+        assert eng.cache.offset() == S - 1
+        q, kn, vn = rn0(B, Hq, 1, D), rn0(B, Hkv, 1, D), rn0(B, Hkv, 1, D)
+
+        def step():
+            eng.step(q, kn, vn)
+            eng.rewind(1)
+
+        units = B
+        alg_bytes = (2 * B * Hkv * S * D * es + 2 * (2 * B * Hkv * D * es)) // world + 2 * B * Hq * D * es
+        alg_flops = 4.0 * B * Hq * S * D / world
+        metric, unit = "attn_decode_tokens_per_s", "tokens/s"
+        bound, peak, peak_unit = "hbm", pk["hbm"], "GB/s"
+        hq_pin = [torch.empty_like(t, device="cpu").pin_memory() for t in (q, kn, vn)]
+        for hp, t in zip(hq_pin, (q, kn, vn)):
+            hp.copy_(t)
+        out_pin = torch.empty((B, Hq, 1, D), dtype=tdt).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in hq_pin)
+        d2h = out_pin.numel() * out_pin.element_size()
+
+        def step_e2e():
+            q.copy_(hq_pin[0], non_blocking=True)
+            kn.copy_(hq_pin[1], non_blocking=True)
+            vn.copy_(hq_pin[2], non_blocking=True)
+            o = eng.step(q, kn, vn)
+            eng.rewind(1)
+            out_pin.copy_(o, non_blocking=True)
+    elif kind == "decode":
         caches = []
         for _ in range(max(1, args.rotate)):
             cache = omx.KVCache()
@@ -372,7 +414,11 @@ def main():
     ms_step = total_ms / args.steps
     e2e_ms = timed(step_e2e, max(3, min(args.steps, 200)), 3) / max(3, min(args.steps, 200))
 
-    if kind == "decode":
+    if sharded:
+        value = units / (ms_step / 1e3)
+        e2e_value = units / (e2e_ms / 1e3)
+        achieved = alg_bytes / (ms_step / 1e3) / 1e9
+    elif kind == "decode":
         value = units * world / (ms_step / 1e3)
         e2e_value = units * world / (e2e_ms / 1e3)
         achieved = alg_bytes / (ms_step / 1e3) / 1e9
@@ -401,11 +447,15 @@ def main():
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-            "config": {"workload": cfg["label"], "per_gpu_batch": B, "global_batch": B * world,
+            "config": {"workload": cfg["label"], "per_gpu_batch": B, "global_batch": B if sharded else B * world,
                        "ctx" if kind == "decode" else "seq_len": S, "q_heads": Hq, "kv_heads": Hkv, "head_dim": D,
-                       "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "parallelism": (f"kv-head-sharded x{world}, output heads exchanged by "
+                                       + ("peer stores fused into the decode kernel" if args.gather == "peer"
+                                          else "NCCL all-gather")) if sharded
+                       else f"batch-sharded x{world}, no data-path collective",
                        "l2_policy": "working set >> 126 MB L2 (streams from HBM every step)"
                        if alg_bytes * max(1, args.rotate) > 512e6 else "working set fits L2: warm-L2 number",
                        "kernel": kernel, "cuda_graph": bool(args.graph), "rotate_caches": args.rotate},

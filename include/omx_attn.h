@@ -48,6 +48,7 @@ extern "C" {
 
 #define OMX_ATTN_VERSION 100
 #define OMX_MAX_NDIM 8
+#define OMX_MAX_PEERS 8
 
 /* Element types; numeric values are those of mlx_dtype (mlx-c/mlx/c/array.h:37-52). */
 typedef enum omx_dtype_ {
@@ -167,6 +168,35 @@ int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_ar
                           bool traditional, omx_optional_float base, float rope_scale,
                           const omx_array* freqs /* may be null */, float sm_scale,
                           omx_array* keys_out, omx_array* values_out, omx_stream s);
+
+/* ---- head-sharded single-sequence decode (BASELINE C5) -------------------- */
+/*
+ * The reference has no multi-device path (MLX is single-GPU); this is the exchange step the
+ * kv-head-sharded layout of SURVEY 8(e) needs.  Rank r owns kv heads [r*Hkv/world, ...) and the
+ * q heads that read them; every rank must end the step holding the full [B,Hq,1,D] output.
+ * Instead of a separate all-gather, the decode kernel's final store writes this rank's head slice
+ * straight into EVERY rank's output buffer through NVLink peer mappings, and the last CTA of the
+ * launch bumps one arrival counter per rank (system-scope fence, then atomic).  omx_peer_wait
+ * enqueues a one-warp kernel that returns once all `world` counters of the local rank reached
+ * `expected` (= number of sharded steps issued so far).
+ */
+typedef struct omx_peer_group_ {
+  int32_t world; /* <= OMX_MAX_PEERS */
+  int32_t rank;
+  void* out[OMX_MAX_PEERS];       /* rank r's FULL output buffer, mapped into this process (out[rank] = local) */
+  uint32_t* flags[OMX_MAX_PEERS]; /* rank r's uint32[world] arrival counters (zero-initialised), mapped likewise */
+} omx_peer_group;
+/* Same contract as omx_attn_decode_fused for the LOCAL heads (q [B,Hq_local,1,D], k_new/v_new
+ * [B,Hkv_local,1,D], cache = this rank's shard).  out_full describes the full [B,Hq_total,1,D]
+ * buffer (same strides on every rank); rows [head_offset, head_offset + Hq_local) are written on
+ * every rank. */
+int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q,
+                                  const omx_array* k_new, const omx_array* v_new,
+                                  omx_kv_cache cache, int rope_dims, bool traditional,
+                                  omx_optional_float base, float rope_scale,
+                                  const omx_array* freqs /* may be null */, float sm_scale,
+                                  const omx_peer_group* peers, int head_offset, omx_stream s);
+int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s);
 
 /* ---- DiT joint attention ------------------------------------------------ */
 /* Table-driven interleaved rope: x [B,S,H,D], cos/sin [B,S,D/2] (x's dtype);

@@ -15,7 +15,7 @@ Layout
 The package name has a hyphen (it is the repo's name); import it with
 importlib.import_module("ominix-mlx_b200").
 """
-from . import _lib, array, attention, cache, dit, fast, nn, utils  # noqa: F401
+from . import _lib, array, attention, cache, dit, fast, nn, parallel, utils  # noqa: F401
 from ._lib import Exception_ as Exception  # noqa: A001,F401
 from ._lib import EXPORTED_SYMBOLS, LIB_PATH, build, force_kernel, last_kernel, launch_count, lib  # noqa: F401
 from .attention import attn_decode_fused, attn_decode_unfused  # noqa: F401

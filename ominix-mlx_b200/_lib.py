@@ -29,6 +29,14 @@ class OmxKVCache(ctypes.Structure):
     _fields_ = [("ctx", ctypes.c_void_p)]
 
 
+OMX_MAX_PEERS = 8
+
+
+class OmxPeerGroup(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("out", ctypes.c_void_p * OMX_MAX_PEERS), ("flags", ctypes.c_void_p * OMX_MAX_PEERS)]
+
+
 class Exception_(RuntimeError):
     """Counterpart of mlx_rs::error::Exception {what} (mlx-rs/src/error.rs)."""
 
@@ -61,6 +69,10 @@ _SIGS = {
     "omx_attn_decode_fused": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                              OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float, _AP, _AP,
                                              ctypes.c_void_p]),
+    "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
+                                                     OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
+                                                     ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),
+    "omx_peer_wait": (ctypes.c_int, [ctypes.POINTER(OmxPeerGroup), ctypes.c_uint32, ctypes.c_void_p]),
     "omx_dit_rope": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_void_p]),
     "omx_dit_joint_attention": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_float, _AP, ctypes.c_void_p]),
     "omx_last_kernel": (ctypes.c_char_p, []),

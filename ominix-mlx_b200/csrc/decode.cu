@@ -34,6 +34,7 @@ constexpr int kTile = 64;              // keys per pipeline stage
 constexpr int kBoxBytes = 64 * 64 * 2;  // one TMA box: 64 keys x 64 features x 2 B
 constexpr int kStageBytes = 4 * kBoxBytes;  // K lo/hi + V lo/hi
 constexpr int kQPitch = 136;           // padded q row (elements) -> conflict-free fragment loads
+constexpr int kMaxPeers = OMX_MAX_PEERS;
 
 struct DecodeParams {
   const void* q;
@@ -59,7 +60,41 @@ struct DecodeParams {
   int64_t kcs[4], vcs[4];
   int rope_dims, traditional;
   const float *cos_row, *sin_row;  // table row of the current position, [rope_dims/2]
+  // head-sharded output (C5): the final store goes to every rank's full buffer over NVLink peer
+  // mappings; the last finishing CTA of the launch bumps one arrival counter per rank.
+  int n_peers;                // 0: plain local store through `out`
+  int peer_rank;
+  int peer_total;             // CTAs that perform a final store in this launch
+  void* peer_out[kMaxPeers];  // pre-offset to this rank's first global q head
+  unsigned* peer_flag[kMaxPeers];  // rank r's counters live in rank r's memory: [world]
+  int* peer_done;             // local, self-resetting
 };
+
+template <typename T>
+__device__ __forceinline__ void store_out(const DecodeParams& p, int64_t off, float v) {
+  const T x = Num<T>::from_f(v);
+  if (p.n_peers == 0) {
+    ((T*)p.out)[off] = x;
+    return;
+  }
+  for (int r = 0; r < p.n_peers; ++r) ((T*)p.peer_out[r])[off] = x;
+}
+
+// After the final stores of one CTA (called by all its threads).  Writers fence their peer stores
+// at system scope, the CTA takes a ticket, and the launch's last ticket publishes the arrival.
+__device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
+  if (p.n_peers == 0) return;
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const int t = atomicAdd(p.peer_done, 1);
+    if (t == p.peer_total - 1) {
+      *p.peer_done = 0;  // self-reset for the next launch (stream-ordered)
+      __threadfence_system();
+      for (int r = 0; r < p.n_peers; ++r) atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u);
+    }
+  }
+}
 
 // roped / copied q heads -> shared memory (as T), used by both kernels
 template <typename T>
@@ -148,7 +183,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
                                                 const float* nt_v, int first_head, int n_heads, int b,
                                                 int pair, int split, int tid, int nthr, int* s_ticket) {
   const int D = p.D;
-  T* outp = (T*)p.out + b * p.os[0];
+  const int64_t ob = b * p.os[0];
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
     const int g = idx / D, d = idx % D;
     float M = has_nt ? nt_m[g] : -INFINITY;
@@ -168,7 +203,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
       O = fmaf(nt_v[d], sc, O);
     }
     if (p.num_splits == 1) {
-      outp[(int64_t)(first_head + g) * p.os[1] + d * p.os[3]] = Num<T>::from_f(O / L);
+      store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
     } else {
       const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
       p.ws_o[e * D + d] = O;
@@ -178,7 +213,10 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
       }
     }
   }
-  if (p.num_splits == 1) return;
+  if (p.num_splits == 1) {
+    peer_signal(p, tid);
+    return;
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) *s_ticket = atomicAdd(&p.counters[pair], 1);
@@ -200,9 +238,10 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
         O = fmaf(__ldcg(&p.ws_o[e * D + d]), sc, O);
       }
     }
-    outp[(int64_t)(first_head + g) * p.os[1] + d * p.os[3]] = Num<T>::from_f(O / L);
+    store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
   }
   if (tid == 0) p.counters[pair] = 0;  // self-reset for the next launch
+  peer_signal(p, tid);
 }
 
 // ============================================================ 16-bit, D = 128: TMA + mma.sync
@@ -635,7 +674,25 @@ void launch_simt_d(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid) {
   }
 }
 
+__global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expected) {
+  if ((int)threadIdx.x >= world) return;
+  const volatile unsigned* f = flags + threadIdx.x;
+  unsigned spins = 0;
+  // counters only grow; the signed difference tolerates wrap-around
+  while ((int)(*f - expected) < 0) {
+    __nanosleep(64);
+    if (++spins > (1u << 25)) __trap();  // a lost peer becomes a launch failure, not a hung GPU
+  }
+  __threadfence_system();
+}
+
 }  // namespace
+
+void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream) {
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, expected);
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
 
 bool decode_supported(const SdpaArgs& a, const char** why) {
   auto no = [&](const char* w) {
@@ -694,6 +751,14 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   }
   if (a.B == 0 || a.Hq == 0) return;
   OMX_CHECK(p.Lk >= 1, "[scaled_dot_product_attention] decode needs at least one key");
+  if (f.peers) {
+    p.n_peers = f.peers->world;
+    p.peer_rank = f.peers->rank;
+    for (int r = 0; r < p.n_peers; ++r) {  // already shifted to this rank's first head by the caller
+      p.peer_out[r] = f.peers->out[r];
+      p.peer_flag[r] = f.peers->flags[r];
+    }
+  }
 
   const int sms = sm_count();
   const int n_tiles = (p.n_mem + kTile - 1) / kTile;
@@ -719,7 +784,11 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
       p.ws_o = ws;
       p.ws_ml = ws + no;
-      p.counters = get_counters((size_t)pairs, stream);
+    }
+    if (p.num_splits > 1 || p.n_peers) {
+      p.counters = get_counters((size_t)pairs + 1, stream);
+      p.peer_done = p.counters + pairs;
+      p.peer_total = (int)pairs;
     }
     const bool bf = a.q->dtype == OMX_BFLOAT16;
     const uint64_t rows = (uint64_t)std::max(p.n_mem, 1);
@@ -769,7 +838,11 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
     p.ws_o = ws;
     p.ws_ml = ws + no;
-    p.counters = get_counters((size_t)pairs, stream);
+  }
+  if (p.num_splits > 1 || p.n_peers) {
+    p.counters = get_counters((size_t)pairs + 1, stream);
+    p.peer_done = p.counters + pairs;
+    p.peer_total = (int)pairs;
   }
   dim3 grid(p.num_splits, a.Hkv * groups, a.B);
   note_launch("decode_simt");

@@ -361,88 +361,145 @@ int omx_concat_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys, 
   });
 }
 
+namespace {
+// Shared body of the fused decode step; `peers` != null selects the head-sharded output.
+void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                       const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                       omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
+                       omx_array* keys_out, omx_array* values_out, const omx_peer_group* peers,
+                       int head_offset, cudaStream_t stream) {
+  require_device();
+  auto* c = (KVCacheImpl*)cache.ctx;
+  OMX_CHECK(c, "[attn_decode_fused] null cache handle");
+  OMX_CHECK(q && k_new && v_new && out, "[attn_decode_fused] null array");
+  OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4,
+            "[attn_decode_fused] q, k_new, v_new, out must be [B, H, 1, D]");
+  OMX_CHECK(q->shape[2] == 1 && k_new->shape[2] == 1 && v_new->shape[2] == 1,
+            "[attn_decode_fused] the fused step handles exactly one new token (L == 1), got L = %lld",
+            (long long)q->shape[2]);
+  OMX_CHECK(k_new->dtype == q->dtype && v_new->dtype == q->dtype, "[attn_decode_fused] dtype mismatch");
+  const int D = (int)q->shape[3];
+  OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
+  OMX_CHECK(rope_dims == 0 || base.has_value != (freqs && freqs->data),
+            "[rope] Only one of base or freqs can have a value.");
+  omx_array out_local = *out;  // the rows of `out` this call writes
+  if (peers) {
+    OMX_CHECK(peers->world >= 1 && peers->world <= OMX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
+              "[attn_decode_fused_sharded] bad peer group (world %d, rank %d)", peers->world, peers->rank);
+    for (int r = 0; r < peers->world; ++r)
+      OMX_CHECK(peers->out[r] && peers->flags[r], "[attn_decode_fused_sharded] peer %d is not mapped", r);
+    OMX_CHECK(head_offset >= 0 && head_offset + q->shape[1] <= out->shape[1],
+              "[attn_decode_fused_sharded] heads [%d, %lld) do not fit the full output (%lld heads)", head_offset,
+              (long long)(head_offset + q->shape[1]), (long long)out->shape[1]);
+    OMX_CHECK(peers->out[peers->rank] == out->data,
+              "[attn_decode_fused_sharded] out_full must be this rank's buffer of the peer group");
+    out_local.shape[1] = q->shape[1];
+    out_local.data = (char*)out->data + (size_t)head_offset * out->strides[1] * dtype_size(out->dtype);
+  }
+  const int position = kv_cache_offset(c);
+  // cache bookkeeping (growth by the reference rule) without copying the new rows: the kernel
+  // ropes k_new and writes row `position` itself.
+  omx_array kview, vview;
+  kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
+  if (keys_out) *keys_out = kview;
+  if (values_out) *values_out = vview;
+  SdpaArgs a = make_sdpa_args(&out_local, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+  const char* why = nullptr;
+  const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
+                    v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
+  OMX_CHECK(fast || !peers, "[attn_decode_fused_sharded] layout not supported by the decode kernels: %s",
+            why ? why : "strided k_new/v_new");
+  if (fast) {
+    DecodeFused f;
+    f.enabled = true;
+    f.k_new = k_new;
+    f.v_new = v_new;
+    f.rope_dims = rope_dims;
+    f.traditional = traditional;
+    f.position = position;
+    f.peers = peers;
+    f.head_offset = 0;  // out_local already starts at this rank's first head
+    if (rope_dims > 0) {
+      std::vector<float> fh;
+      if (!base.has_value) {
+        OMX_CHECK(freqs->ndim == 1 && freqs->shape[0] == rope_dims / 2 && freqs->dtype == OMX_FLOAT32 &&
+                      freqs->strides[0] == 1,
+                  "[rope] freqs must be a contiguous float32 vector of length dims/2");
+        fh.resize(rope_dims / 2);
+        OMX_CUDA(cudaMemcpyAsync(fh.data(), freqs->data, sizeof(float) * fh.size(), cudaMemcpyDeviceToHost,
+                                 stream));
+        OMX_CUDA(cudaStreamSynchronize(stream));
+      }
+      f.table = get_rope_table(rope_dims, base.has_value, base.value, rope_scale,
+                               fh.empty() ? nullptr : fh.data(), position + 1, stream);
+    }
+    omx_peer_group shifted;
+    if (peers) {  // peer pointers address the same head slice in every rank's buffer
+      shifted = *peers;
+      const size_t shift = (size_t)head_offset * out->strides[1] * dtype_size(out->dtype);
+      for (int r = 0; r < peers->world; ++r) shifted.out[r] = (char*)peers->out[r] + shift;
+      f.peers = &shifted;
+    }
+    decode_attention(a, f, stream);
+    return;
+  }
+  // Unfused composition for layouts the decode kernels do not take: rope -> row store -> sdpa.
+  omx_array krow = kview, vrow = vview;
+  krow.shape[2] = 1;
+  vrow.shape[2] = 1;
+  krow.data = (char*)kview.data + (size_t)position * kview.strides[2] * dtype_size(kview.dtype);
+  vrow.data = (char*)vview.data + (size_t)position * vview.strides[2] * dtype_size(vview.dtype);
+  if (rope_dims > 0) {
+    rope_forward(&krow, k_new, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+  } else {
+    copy4d(&krow, k_new, stream);
+  }
+  copy4d(&vrow, v_new, stream);
+  if (rope_dims > 0) {
+    const size_t qbytes = (size_t)q->shape[0] * q->shape[1] * D * dtype_size(q->dtype);
+    omx_array qr = *q;
+    qr.data = get_workspace(qbytes, stream);  // sdpa_generic itself uses no scratch
+    qr.strides[0] = q->shape[1] * D;
+    qr.strides[1] = D;
+    qr.strides[2] = D;
+    qr.strides[3] = 1;
+    rope_forward(&qr, q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+    SdpaArgs a2 = make_sdpa_args(out, &qr, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    sdpa_generic(a2, stream);
+  } else {
+    sdpa_generic(a, stream);
+  }
+}
+}  // namespace
+
 int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
                           const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
                           omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
                           omx_array* keys_out, omx_array* values_out, omx_stream s) {
   return guarded([&] {
+    decode_fused_impl(out, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs, sm_scale,
+                      keys_out, values_out, nullptr, 0, (cudaStream_t)s);
+  });
+}
+
+int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q, const omx_array* k_new,
+                                  const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                                  omx_optional_float base, float rope_scale, const omx_array* freqs,
+                                  float sm_scale, const omx_peer_group* peers, int head_offset, omx_stream s) {
+  return guarded([&] {
+    OMX_CHECK(peers != nullptr, "[attn_decode_fused_sharded] null peer group");
+    decode_fused_impl(out_full, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs,
+                      sm_scale, nullptr, nullptr, peers, head_offset, (cudaStream_t)s);
+  });
+}
+
+int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s) {
+  return guarded([&] {
     require_device();
-    cudaStream_t stream = (cudaStream_t)s;
-    auto* c = (KVCacheImpl*)cache.ctx;
-    OMX_CHECK(c, "[attn_decode_fused] null cache handle");
-    OMX_CHECK(q && k_new && v_new && out, "[attn_decode_fused] null array");
-    OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4,
-              "[attn_decode_fused] q, k_new, v_new, out must be [B, H, 1, D]");
-    OMX_CHECK(q->shape[2] == 1 && k_new->shape[2] == 1 && v_new->shape[2] == 1,
-              "[attn_decode_fused] the fused step handles exactly one new token (L == 1), got L = %lld",
-              (long long)q->shape[2]);
-    OMX_CHECK(k_new->dtype == q->dtype && v_new->dtype == q->dtype, "[attn_decode_fused] dtype mismatch");
-    const int D = (int)q->shape[3];
-    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
-    OMX_CHECK(rope_dims == 0 || base.has_value != (freqs && freqs->data),
-              "[rope] Only one of base or freqs can have a value.");
-    const int position = kv_cache_offset(c);
-    // cache bookkeeping (growth by the reference rule) without copying the new rows: the kernel
-    // ropes k_new and writes row `position` itself.
-    omx_array kview, vview;
-    kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
-    if (keys_out) *keys_out = kview;
-    if (values_out) *values_out = vview;
-    SdpaArgs a = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
-    const char* why = nullptr;
-    const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
-                      v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
-    if (fast) {
-      DecodeFused f;
-      f.enabled = true;
-      f.k_new = k_new;
-      f.v_new = v_new;
-      f.rope_dims = rope_dims;
-      f.traditional = traditional;
-      f.position = position;
-      if (rope_dims > 0) {
-        std::vector<float> fh;
-        if (!base.has_value) {
-          OMX_CHECK(freqs->ndim == 1 && freqs->shape[0] == rope_dims / 2 && freqs->dtype == OMX_FLOAT32 &&
-                        freqs->strides[0] == 1,
-                    "[rope] freqs must be a contiguous float32 vector of length dims/2");
-          fh.resize(rope_dims / 2);
-          OMX_CUDA(cudaMemcpyAsync(fh.data(), freqs->data, sizeof(float) * fh.size(), cudaMemcpyDeviceToHost,
-                                   stream));
-          OMX_CUDA(cudaStreamSynchronize(stream));
-        }
-        f.table = get_rope_table(rope_dims, base.has_value, base.value, rope_scale,
-                                 fh.empty() ? nullptr : fh.data(), position + 1, stream);
-      }
-      decode_attention(a, f, stream);
-      return;
-    }
-    // Unfused composition for layouts the decode kernels do not take: rope -> row store -> sdpa.
-    omx_array krow = kview, vrow = vview;
-    krow.shape[2] = 1;
-    vrow.shape[2] = 1;
-    krow.data = (char*)kview.data + (size_t)position * kview.strides[2] * dtype_size(kview.dtype);
-    vrow.data = (char*)vview.data + (size_t)position * vview.strides[2] * dtype_size(vview.dtype);
-    if (rope_dims > 0) {
-      rope_forward(&krow, k_new, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
-    } else {
-      copy4d(&krow, k_new, stream);
-    }
-    copy4d(&vrow, v_new, stream);
-    if (rope_dims > 0) {
-      const size_t qbytes = (size_t)q->shape[0] * q->shape[1] * D * dtype_size(q->dtype);
-      omx_array qr = *q;
-      qr.data = get_workspace(qbytes, stream);  // sdpa_generic itself uses no scratch
-      qr.strides[0] = q->shape[1] * D;
-      qr.strides[1] = D;
-      qr.strides[2] = D;
-      qr.strides[3] = 1;
-      rope_forward(&qr, q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
-      SdpaArgs a2 = make_sdpa_args(out, &qr, &kview, &vview, sm_scale, "", nullptr, nullptr);
-      sdpa_generic(a2, stream);
-    } else {
-      sdpa_generic(a, stream);
-    }
+    OMX_CHECK(peers && peers->world >= 1 && peers->world <= OMX_MAX_PEERS && peers->rank >= 0 &&
+                  peers->rank < peers->world && peers->flags[peers->rank],
+              "[peer_wait] bad peer group");
+    peer_wait(peers->flags[peers->rank], peers->world, expected, (cudaStream_t)s);
   });
 }
 

@@ -70,11 +70,16 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   bool traditional = false;
   RopeTableRef table;
   int position = 0;  // = cache offset before the append
+  // head-sharded output: store this rank's heads into every rank's full [B,Hq_total,1,D] buffer
+  const omx_peer_group* peers = nullptr;  // out pointers already shifted to this rank's first head
+  int head_offset = 0;
 };
 // q [B,Hq,1,D]; k/v views over Lk rows (Lk INCLUDES the new row when fused: the kernel reads
 // rows [0, Lk-1) from memory and takes row Lk-1 from k_new/v_new, writing it to k/v as well).
 bool decode_supported(const SdpaArgs& a, const char** why);
 void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream);
+// One thread per rank spins (bounded) until flags[r] has reached `expected` for every r.
+void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream);
 
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);

@@ -1,0 +1,166 @@
+"""Sharding of the attention path over 1..8 B200 (one process per GPU).
+
+The reference is single-device (MLX); these helpers are what a multi-GPU deployment of the same
+path needs and nothing more:
+
+* C2 / C3 / C4 shard the BATCH: every (batch, kv-head group) is independent, so there is no
+  data-path collective at all -- `batch_shard` only computes who owns what.
+* C5 (one sequence, ctx 32768) shards the KV HEADS: rank r keeps kv heads
+  [r*Hkv/N, (r+1)*Hkv/N) of the cache and computes the q heads that read them.  The step needs one
+  exchange so that every rank ends up with the full [B,Hq,1,D] output (the caller's o_proj wants
+  all heads).  Two spellings:
+    - `gather="collective"`: the local decode launch followed by dist.all_gather_into_tensor
+      (NCCL over NVLink on the GPU box; gloo in the CPU tests) -- the baseline;
+    - `gather="peer"`: ONE launch -- the decode kernel's final store writes the rank's head slice
+      into every rank's output buffer through NVLink peer mappings and bumps an arrival counter
+      (omx_attn_decode_fused_sharded), then a one-warp wait kernel (omx_peer_wait).  Buffers come
+      from torch's symmetric-memory allocator (plumbing only).
+torch.distributed is used for rendezvous / the baseline collective only.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .array import desc, ref, stream_ptr
+from .attention import attn_decode_fused
+
+
+def batch_shard(batch, world, rank):
+    """Contiguous block of batch rows owned by `rank`: (start, count).  Remainders go to the
+    first ranks, so counts differ by at most one."""
+    if world < 1 or not (0 <= rank < world):
+        raise _lib.Exception_(f"bad rank {rank} for world size {world}")
+    base, rem = divmod(int(batch), world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def kv_head_shard(n_heads, n_kv_heads, world, rank):
+    """kv-head sharding: (kv_start, kv_count, q_start, q_count).  Needs Hkv % world == 0 so that every
+    q head finds its kv head on the same rank (q head h reads kv head h // (Hq/Hkv))."""
+    if n_heads % n_kv_heads:
+        raise _lib.Exception_(f"n_heads {n_heads} must be a multiple of n_kv_heads {n_kv_heads}")
+    if n_kv_heads % world:
+        raise _lib.Exception_(f"n_kv_heads {n_kv_heads} is not divisible by the world size {world}")
+    if not (0 <= rank < world):
+        raise _lib.Exception_(f"bad rank {rank} for world size {world}")
+    per = n_kv_heads // world
+    g = n_heads // n_kv_heads
+    return rank * per, per, rank * per * g, per * g
+
+
+def shard_heads(x, start, count):
+    """[B,H,L,D] -> view of heads [start, start+count) (no copy)."""
+    return x[:, start:start + count]
+
+
+def all_gather_heads(out_local, n_heads, group=None, out=None):
+    """Baseline exchange: every rank contributes [B,Hl,L,D]; returns [B,n_heads,L,D] in rank order.
+    Works on any backend (NCCL on the GPU box, gloo in the CPU tests)."""
+    world = dist.get_world_size(group)
+    B, Hl, L, D = out_local.shape
+    if Hl * world != n_heads:
+        raise _lib.Exception_(f"{world} ranks x {Hl} local heads != {n_heads} heads")
+    if world == 1:
+        return out_local
+    # gather as [world, B, Hl, L, D] (rank-major, what the collective produces), then view heads
+    flat = torch.empty((world, B, Hl, L, D), dtype=out_local.dtype, device=out_local.device)
+    src = out_local.contiguous()
+    if out_local.is_cuda:
+        dist.all_gather_into_tensor(flat, src, group=group)
+    else:  # gloo moves bytes: it has neither bf16 nor all_gather_into_tensor for every dtype
+        raw = src.view(torch.uint8)
+        parts = [torch.empty_like(raw) for _ in range(world)]
+        dist.all_gather(parts, raw, group=group)
+        flat = torch.stack(parts).view(src.dtype).view(world, B, Hl, L, D)
+    full = flat.permute(1, 0, 2, 3, 4).reshape(B, n_heads, L, D)
+    if out is not None:
+        out.copy_(full)
+        return out
+    return full
+
+
+class HeadShardedDecode:
+    """The C5 decode step on `world` GPUs: rank r owns a KVCache holding only its kv heads.
+
+    step(q, k_new, v_new) takes the FULL-head inputs of the step (what the caller's q/k/v
+    projections produce, replicated on every rank), runs rope + append + attention for the local
+    heads in one launch and returns the full [B,Hq,1,D] output on every rank."""
+
+    def __init__(self, n_heads, n_kv_heads, head_dim, dtype, rope, sm_scale, batch=1, group=None,
+                 gather="collective", device=None):
+        from .cache import KVCache
+        if gather not in ("collective", "peer"):
+            raise _lib.Exception_(f"unknown gather mode {gather!r}")
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_heads, self.n_kv_heads, self.head_dim = n_heads, n_kv_heads, head_dim
+        self.kv0, self.nkv, self.q0, self.nq = kv_head_shard(n_heads, n_kv_heads, self.world, self.rank)
+        self.rope, self.sm_scale, self.gather = rope, sm_scale, gather
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.cache = KVCache()
+        self.steps = 0
+        self._peer = None
+        if gather == "peer":
+            self._init_peer(batch, dtype)
+        else:
+            self.out_full = torch.empty((batch, n_heads, 1, head_dim), dtype=dtype, device=self.device)
+
+    # -- symmetric memory plumbing (allocation + pointer exchange only)
+    def _init_peer(self, batch, dtype):
+        try:
+            import torch.distributed._symmetric_memory as symm
+        except Exception as e:  # pragma: no cover
+            raise _lib.Exception_(f"gather='peer' needs torch symmetric memory: {e}")
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self.out_full = symm.empty((batch, self.n_heads, 1, self.head_dim), dtype=dtype, device=self.device)
+        self._flags = symm.empty((_lib.OMX_MAX_PEERS,), dtype=torch.int32, device=self.device)
+        self._flags.zero_()
+        h_out = symm.rendezvous(self.out_full, group=grp)
+        h_flg = symm.rendezvous(self._flags, group=grp)
+        pg = _lib.OmxPeerGroup()
+        pg.world, pg.rank = self.world, self.rank
+        for r in range(self.world):
+            pg.out[r] = int(h_out.buffer_ptrs[r])
+            pg.flags[r] = int(h_flg.buffer_ptrs[r])
+        if pg.out[self.rank] != self.out_full.data_ptr():
+            raise _lib.Exception_("symmetric memory handle does not map the local buffer at its own address")
+        self._handles = (h_out, h_flg)
+        self._peer = pg
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=grp)  # every rank's counters are zero before anyone signals
+
+    def prefill(self, keys, values):
+        """Append the local kv heads of full-head [B,Hkv,n,D] keys / values (already roped)."""
+        return self.cache.update_and_fetch(shard_heads(keys, self.kv0, self.nkv),
+                                           shard_heads(values, self.kv0, self.nkv))
+
+    def step(self, q, k_new, v_new, stream=None):
+        ql = shard_heads(q, self.q0, self.nq)
+        kl = shard_heads(k_new, self.kv0, self.nkv)
+        vl = shard_heads(v_new, self.kv0, self.nkv)
+        self.steps += 1
+        if self._peer is None:
+            out_local = attn_decode_fused(ql, kl, vl, self.cache, self.rope, self.sm_scale, stream=stream)
+            if self.world == 1:
+                return out_local
+            return all_gather_heads(out_local, self.n_heads, self.group, out=self.out_full)
+        rope = self.rope
+        base = _lib.OmxOptionalFloat()
+        base.has_value = rope is not None
+        base.value = rope.base if rope is not None else 0.0
+        qd, kd, vd, od = desc(ql), desc(kl), desc(vl), desc(self.out_full)
+        sp = stream_ptr(stream)
+        _lib.check(_lib.lib().omx_attn_decode_fused_sharded(
+            ref(od), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
+            bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0, None,
+            float(self.sm_scale), ctypes.byref(self._peer), int(self.q0), sp))
+        _lib.check(_lib.lib().omx_peer_wait(ctypes.byref(self._peer), ctypes.c_uint32(self.steps & 0xFFFFFFFF), sp))
+        return self.out_full
+
+    def rewind(self, n=1):
+        """Bench helper: drop the last n rows so that every step does identical work."""
+        return self.cache.trim(n)

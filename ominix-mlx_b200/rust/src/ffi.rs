@@ -38,6 +38,18 @@ pub struct omx_kv_cache {
     pub ctx: *mut c_void,
 }
 
+pub const OMX_MAX_PEERS: usize = 8;
+
+/// Peer mappings of the head-sharded decode step (include/omx_attn.h: omx_peer_group).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct omx_peer_group {
+    pub world: i32,
+    pub rank: i32,
+    pub out: [*mut c_void; OMX_MAX_PEERS],
+    pub flags: [*mut u32; OMX_MAX_PEERS],
+}
+
 pub type omx_stream = *mut c_void; // cudaStream_t
 pub type omx_error_handler_func = Option<unsafe extern "C" fn(msg: *const c_char, data: *mut c_void)>;
 
@@ -82,6 +94,13 @@ extern "C" {
                                  traditional: bool, base: omx_optional_float, rope_scale: f32,
                                  freqs: *const omx_array, sm_scale: f32, keys_out: *mut omx_array,
                                  values_out: *mut omx_array, s: omx_stream) -> c_int;
+    pub fn omx_attn_decode_fused_sharded(out_full: *const omx_array, q: *const omx_array,
+                                         k_new: *const omx_array, v_new: *const omx_array,
+                                         cache: omx_kv_cache, rope_dims: c_int, traditional: bool,
+                                         base: omx_optional_float, rope_scale: f32, freqs: *const omx_array,
+                                         sm_scale: f32, peers: *const omx_peer_group, head_offset: c_int,
+                                         s: omx_stream) -> c_int;
+    pub fn omx_peer_wait(peers: *const omx_peer_group, expected: u32, s: omx_stream) -> c_int;
     pub fn omx_dit_rope(out: *const omx_array, x: *const omx_array, cos: *const omx_array,
                         sin: *const omx_array, s: omx_stream) -> c_int;
     pub fn omx_dit_joint_attention(out: *const omx_array, q: *const omx_array, k: *const omx_array,

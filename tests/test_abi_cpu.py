@@ -87,3 +87,13 @@ def test_host_side_helpers_without_gpu():
     assert (m.numpy() == orc.create_causal_mask(3, 2)).all()
     w = omx.create_causal_mask(4, 1, window_size=2, device="cpu")
     assert (w.numpy() == orc.create_causal_mask(4, 1, 2)).all()
+
+
+def test_rust_ffi_declares_the_same_symbols():
+    # the Rust crate cannot be compiled in this image (no cargo); at least its extern block must
+    # name exactly the functions the header exports
+    src = open(os.path.join(ROOT, "ominix-mlx_b200", "rust", "src", "ffi.rs")).read()
+    rust = set(re.findall(r"pub fn (omx_[a-z0-9_]+)\s*\(", src))
+    assert rust == set(_declared()), sorted(rust ^ set(_declared()))
+    for mod in ("fast", "cache", "utils", "array", "error", "ffi"):
+        assert os.path.exists(os.path.join(ROOT, "ominix-mlx_b200", "rust", "src", mod + ".rs")), mod

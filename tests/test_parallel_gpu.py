@@ -1,0 +1,123 @@
+"""Head-sharded decode (BASELINE C5 layout) on the GPU: the peer-store output path of the decode
+kernel on one device (world 1 through the raw C ABI), and, when the box has >= 2 GPUs, both
+exchange spellings (NCCL all-gather baseline, fused peer stores) across 2 ranks against the
+oracle's unsharded answer."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_bits_equal, assert_close, load_oracle, load_pkg, n2f, randn, t2n
+
+pytestmark = pytest.mark.gpu
+omx = load_pkg()
+orc = load_oracle()
+ROPE = (128, False, 1e6, 1.0)
+
+
+def _oracle_full(k, v, q, kn, vn, dtype, S):
+    oc = orc.KVCache()
+    oc.update_and_fetch(t2n(k, dtype), t2n(v, dtype))
+    qo = orc.rope(t2n(q, dtype), *ROPE, S, dtype=dtype)
+    ko = orc.rope(t2n(kn, dtype), *ROPE, S, dtype=dtype)
+    K, V = oc.update_and_fetch(ko, t2n(vn, dtype))
+    want = orc.sdpa(qo, np.ascontiguousarray(K), np.ascontiguousarray(V), 128 ** -0.5, None, dtype=dtype)
+    return n2f(want, dtype), oc
+
+
+@pytest.mark.parametrize("dtype,S", [("bf16", 777), ("bf16", 5000), ("f32", 300)])
+def test_peer_store_path_world1_raw_abi(dtype, S):
+    """world = 1: the kernel's final store goes through the peer table (here: the local buffer,
+    at a head offset inside a larger output) and the arrival counter reaches the step count."""
+    L = omx._lib
+    B, Hq, Hkv, D, Htot, h0 = 2, 8, 2, 128, 24, 8
+    k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
+    q, kn, vn = randn((B, Hq, 1, D), dtype, 3), randn((B, Hkv, 1, D), dtype, 4), randn((B, Hkv, 1, D), dtype, 5)
+    want, oc = _oracle_full(k, v, q, kn, vn, dtype, S)
+    cache = omx.KVCache()
+    cache.update_and_fetch(k.cuda(), v.cuda())
+    out_full = torch.full((B, Htot, 1, D), 7.0, dtype=q.dtype, device="cuda")
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    pg = L.OmxPeerGroup()
+    pg.world, pg.rank = 1, 0
+    pg.out[0], pg.flags[0] = out_full.data_ptr(), flags.data_ptr()
+    base = L.OmxOptionalFloat()
+    base.has_value, base.value = True, ROPE[2]
+    A = omx.array
+    qd, kd, vd, od = A.desc(q.cuda()), A.desc(kn.cuda()), A.desc(vn.cuda()), A.desc(out_full)
+    sp = A.stream_ptr()
+    for step in (1, 2):
+        L.check(L.lib().omx_attn_decode_fused_sharded(A.ref(od), A.ref(qd), A.ref(kd), A.ref(vd), cache.handle,
+                                                      128, False, base, 1.0, None, 128 ** -0.5,
+                                                      ctypes.byref(pg), h0, sp))
+        L.check(L.lib().omx_peer_wait(ctypes.byref(pg), step, sp))
+        torch.cuda.synchronize()
+        assert int(flags[0]) == step
+        assert_close(out_full[:, h0:h0 + Hq].float().cpu().numpy(), want, dtype, "peer-store output slice")
+        assert bool((out_full[:, :h0] == 7).all()) and bool((out_full[:, h0 + Hq:] == 7).all()), \
+            "rows outside this rank's head slice were touched"
+        if step == 1:
+            sk, sv = cache.state()
+            assert_bits_equal(sk, oc.keys, dtype, "KV keys (sharded step)")
+            assert_bits_equal(sv, oc.values, dtype, "KV values (sharded step)")
+            cache.trim(1)
+    # validation: a head slice that does not fit
+    assert L.lib().omx_attn_decode_fused_sharded(A.ref(od), A.ref(qd), A.ref(kd), A.ref(vd), cache.handle, 128,
+                                                 False, base, 1.0, None, 0.1, ctypes.byref(pg), Htot - 2, sp) == 1
+    assert b"do not fit" in L.lib().omx_last_error()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, gather, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dtype, B, Hq, Hkv, D, S = "bf16", 1, 32, 8, 128, 4099
+        k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
+        qq, kn, vn = randn((B, Hq, 1, D), dtype, 3), randn((B, Hkv, 1, D), dtype, 4), randn((B, Hkv, 1, D), dtype, 5)
+        want, oc = _oracle_full(k, v, qq, kn, vn, dtype, S)
+        rope = omx.nn.Rope(*ROPE)
+        eng = omx.parallel.HeadShardedDecode(Hq, Hkv, D, torch.bfloat16, rope, D ** -0.5, batch=B, gather=gather)
+        eng.prefill(k.cuda(), v.cuda())
+        errs = []
+        for _ in range(3):
+            out = eng.step(qq.cuda(), kn.cuda(), vn.cuda())
+            torch.cuda.synchronize()
+            errs.append(float(np.abs(out.float().cpu().numpy() - want).max()))
+            dist.barrier()  # nobody overwrites a buffer a slower rank is still reading
+            eng.rewind(1)
+        sk, _ = eng.cache.state()
+        kv_ok = bool((t2n(sk, dtype) == oc.keys[:, eng.kv0:eng.kv0 + eng.nkv]).all())
+        q.put((rank, max(errs), kv_ok, omx.last_kernel()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("gather", ["collective", "peer"])
+def test_head_sharded_decode_two_ranks(gather):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, gather, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0, f"rank process exited with {p.exitcode}"
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    for rank, err, kv_ok, kern in res:
+        assert err <= 2e-2, (rank, err)
+        assert kv_ok, f"rank {rank}: KV shard not bit-exact"
+        assert kern == "decode_hmma_tma"
