@@ -22,6 +22,7 @@
 // TMEM (512 columns x 128 lanes x 32 bit): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512);
 // P_i (packed 16-bit pairs) aliases the first 64 columns of S_i.
 #include <algorithm>
+#include <cstdlib>
 
 #include "omx_common.cuh"
 #include "omx_internal.h"
@@ -41,6 +42,8 @@ constexpr int kThreads = 384;   // 2 softmax warpgroups + 1 warpgroup {TMA, MMA,
 constexpr int kRegsSoftmax = 216;  // setmaxnreg budgets: 8 warps x 216 + 4 warps x 72 <= 64K registers
 constexpr int kRegsOther = 72;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr int kDefaultCfg = 1;             // kEmu = 0 (all exp2 on MUFU), split hand-off (measured best)
+constexpr int kSplitKeys = 96;             // keys of P handed over first when the hand-off is split
 
 struct FmhaParams {
   void* out;
@@ -132,10 +135,44 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// MUFU exp2 without `volatile`: the scheduler may interleave it with the FMA-pipe work
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp2 of two values on the FMA/ALU pipes (Cody-Waite split + degree-3 polynomial, max relative
+// error 7.5e-5 -- far below the 2^-9 rounding of the 16-bit P it feeds).  Takes load off the MUFU
+// unit, which at 16 ex2/clk/SM is exactly as loaded as the tensor pipe in this kernel.
+__device__ __forceinline__ float2 ex2_emu2(float2 x) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: low mantissa bits of (x + magic) hold round(x)
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 xr = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(xr, make_float2(-kMagic, -kMagic));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));  // in [-0.5, 0.5]
+  float2 p = __ffma2_rn(f, make_float2(0.0551716685f, 0.0551716685f), make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  // 2^n by adding n to the exponent field ((magic + n) << 23 == n << 23 mod 2^32)
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(xr.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(xr.y) << 23));
+  return p;
+}
+
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+
+// one lane of the (converged) warp; the rest skip the guarded statement
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // bounded spin: a protocol bug becomes a launch failure instead of a hung GPU
@@ -170,11 +207,15 @@ struct SharedCtl {
   uint64_t kv_full[kSlots];
   uint64_t kv_empty[kSlots];
   uint64_t s_full[2];
-  uint64_t p_full[2];
+  uint64_t p_full[2];   // first kSplitKeys keys of P_i written (whole tile when the hand-off is not split)
+  uint64_t p_full2[2];  // remaining keys of P_i written
   uint32_t tmem_base;
 };
 
-template <typename T>
+// kEmu: of every 4 packed pairs of scores, kEmu take the polynomial exp2 (0..4 -> 0..100 %).
+// kSplit: hand P to the MMA warp in two pieces (first 96 keys, then the last 32) so that O += P V
+// starts while the softmax warpgroup is still exponentiating the tail.
+template <typename T, int kEmu, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -184,7 +225,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* kv_s = smem + 2 * kTileBytes;   // kSlots x 32 KB
   __shared__ SharedCtl ctl;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role index
   const int m_blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy tiles first
   const int hq = blockIdx.y, b = blockIdx.z;
   const int hk = hq / (p.Hq / p.Hkv);
@@ -210,6 +252,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&ctl.q_full[i], 1);
       mbar_init(&ctl.s_full[i], 1);
       mbar_init(&ctl.p_full[i], BM);
+      mbar_init(&ctl.p_full2[i], BM);
     }
     for (int s = 0; s < kSlots; ++s) {
       mbar_init(&ctl.kv_full[s], 1);
@@ -225,7 +268,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = ctl.tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl.tmem_base, 0);  // warp-uniform for the UTCHMMA operands
 
   if (warp == 8) {
     // =========================================================== TMA producer
@@ -256,71 +299,94 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     __syncwarp();
   } else if (warp == 9) {
     // =========================================================== MMA issuer
+    // The whole warp runs this loop convergently and only the tcgen05 instructions sit under
+    // elect.sync: every operand is then a warp-uniform value that lives in uniform registers, and
+    // one MMA costs ~3 issue slots.  (Issuing from inside `if (lane == 0)` made ptxas wrap each
+    // UTCHMMA in a divergence loop with the descriptor rebuilt from scratch: ~90 cycles per
+    // 64-cycle MMA, i.e. the tensor pipe could not exceed ~70 %.)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
-    if (lane == 0 && N > 0) {
+    if (N > 0) {
       constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
       constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
-      const uint32_t q_addr = smem_u32(q_s), kv_addr = smem_u32(kv_s);
+      constexpr uint32_t kTile16 = kTileBytes >> 4, kBox16 = kBoxBytes >> 4;
+      // descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (smem < 256 KB)
+      const uint64_t q_desc = umma_desc(smem_u32(q_s), 16, 1024);             // K-major
+      const uint64_t k_desc0 = umma_desc(smem_u32(kv_s), 16, 1024);           // K-major
+      const uint64_t v_desc0 = umma_desc(smem_u32(kv_s), kBoxBytes, 1024);    // MN-major
       auto wait_kv = [&](int seq) { mbar_wait_wd(&ctl.kv_full[seq % kSlots], (seq / kSlots) & 1); };
-      auto slot_addr = [&](int seq) { return kv_addr + (uint32_t)(seq % kSlots) * kTileBytes; };
-      // S_i = Q_i K^T : K-major operands, 2 feature blocks x 4 k-steps of 16
-      auto mma_qk = [&](int i, uint32_t k_base) {
-        const uint32_t qa = q_addr + i * kTileBytes;
+      auto slot16 = [&](int seq) { return (uint64_t)((uint32_t)(seq % kSlots) * kTile16); };
+      // S_i = Q_i K^T : 2 feature blocks x 4 k-steps of 16
+      auto mma_qk = [&](int i, uint64_t k_desc) {
+        const uint64_t qa = q_desc + (uint64_t)(i * kTile16);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t off = kb * kBoxBytes + ks * 32;
-            umma_ss(tmem + i * 128, umma_desc(qa + off, 16, 1024), umma_desc(k_base + off, 16, 1024), idesc_qk,
-                    (kb | ks) ? 1u : 0u);
+            const uint32_t off = kb * kBox16 + ks * 2;
+            umma_ss(tmem + i * 128, qa + off, k_desc + off, idesc_qk, (kb | ks) ? 1u : 0u);
           }
         }
       };
       // O_i += P_i V : A = P_i in TMEM (16 keys = 8 columns per k-step), B = V MN-major
-      auto mma_pv = [&](int i, uint32_t v_base, bool first) {
+      auto mma_pv = [&](int i, uint64_t v_desc, bool first, int ks0, int ks1) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, umma_desc(v_base + ks * 2048, kBoxBytes, 1024),
-                  idesc_pv, (first && ks == 0) ? 0u : 1u);
+        for (int ks = ks0; ks < ks1; ++ks) {
+          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, v_desc + (uint64_t)(ks * (2048 >> 4)), idesc_pv,
+                  (first && ks == 0) ? 0u : 1u);
         }
       };
+#pragma unroll
       for (int i = 0; i < 2; ++i)
         if (n[i] > 0) mbar_wait_wd(&ctl.q_full[i], 0);
       wait_kv(0);
       tc_fence_after();
-      for (int i = 0; i < 2; ++i) {
-        if (n[i] > 0) {
-          mma_qk(i, slot_addr(0));
-          tc_commit(&ctl.s_full[i]);
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (n[i] > 0) {
+            mma_qk(i, k_desc0 + slot16(0));
+            tc_commit(&ctl.s_full[i]);
+          }
         }
+        tc_commit(&ctl.kv_empty[0]);
       }
-      tc_commit(&ctl.kv_empty[0]);
+      __syncwarp();
       for (int j = 0; j < N; ++j) {
         wait_kv(2 * j + 1);  // V_j
-        bool k_next_ready = false;
+        if (j + 1 < N) wait_kv(2 * j + 2);  // K_{j+1}: in flight since long (5-slot ring)
+        const uint64_t v_desc = v_desc0 + slot16(2 * j + 1);
+        const uint64_t k_desc = k_desc0 + slot16(2 * j + 2);
+#pragma unroll
         for (int i = 0; i < 2; ++i) {
           if (j >= n[i]) continue;
           mbar_wait_wd(&ctl.p_full[i], j & 1);
           tc_fence_after();
-          mma_pv(i, slot_addr(2 * j + 1), j == 0);
-          if (j + 1 < n[i]) {
-            if (!k_next_ready) {
-              wait_kv(2 * j + 2);  // K_{j+1}
-              tc_fence_after();
-              k_next_ready = true;
+          if (kSplit) {
+            if (elect_one()) mma_pv(i, v_desc, j == 0, 0, kSplitKeys / 16);
+            __syncwarp();
+            mbar_wait_wd(&ctl.p_full2[i], j & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              mma_pv(i, v_desc, j == 0, kSplitKeys / 16, 8);
+              if (j + 1 < n[i]) mma_qk(i, k_desc);
+              tc_commit(&ctl.s_full[i]);
             }
-            mma_qk(i, slot_addr(2 * j + 2));
+          } else {
+            if (elect_one()) {
+              mma_pv(i, v_desc, j == 0, 0, 8);
+              if (j + 1 < n[i]) mma_qk(i, k_desc);
+              tc_commit(&ctl.s_full[i]);
+            }
           }
-          tc_commit(&ctl.s_full[i]);
+          __syncwarp();
         }
-        tc_commit(&ctl.kv_empty[(2 * j + 1) % kSlots]);
-        if (j + 1 < N) {
-          if (!k_next_ready) wait_kv(2 * j + 2);  // keep the waiter's phase order even if unused
-          tc_commit(&ctl.kv_empty[(2 * j + 2) % kSlots]);
+        if (elect_one()) {
+          tc_commit(&ctl.kv_empty[(2 * j + 1) % kSlots]);
+          if (j + 1 < N) tc_commit(&ctl.kv_empty[(2 * j + 2) % kSlots]);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp < 8) {
     // =========================================================== softmax warpgroups
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
@@ -355,14 +421,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (key0 + 96 + e >= limit) s3[e] = 0xff800000u;
         }
       }
-      float mx = -INFINITY;
+      // four independent max chains (one per 32-column chunk) instead of one 64-deep dependency
+      float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        mx = fmax3(mx, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
-        mx = fmax3(mx, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
-        mx = fmax3(mx, __uint_as_float(s2[e]), __uint_as_float(s2[e + 1]));
-        mx = fmax3(mx, __uint_as_float(s3[e]), __uint_as_float(s3[e + 1]));
+        mxa = fmax3(mxa, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+        mxb = fmax3(mxb, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+        mxc = fmax3(mxc, __uint_as_float(s2[e]), __uint_as_float(s2[e + 1]));
+        mxd = fmax3(mxd, __uint_as_float(s3[e]), __uint_as_float(s3[e + 1]));
       }
+      const float mx = fmaxf(fmax3(mxa, mxb, mxc), mxd);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);  // scale > 0: max commutes with scaling
       // lazy rescale: keep the old reference max unless it grew by more than 2^8 (the decision to
       // touch O is warp-uniform because TMEM accesses are warp-collective)
@@ -386,14 +454,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
       const float2 nm2 = make_float2(-m_run, -m_run);
-      float2 acc2 = make_float2(0.f, 0.f);
+      float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
       auto chunk = [&](const uint32_t (&sv)[32], int c) {
         uint32_t pk[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
           const float2 a = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sc2, nm2);
-          const float2 pe = make_float2(fast_exp2(a.x), fast_exp2(a.y));
-          acc2 = __fadd2_rn(acc2, pe);
+          float2 pe;
+          if (((e >> 1) & 3) < kEmu) {
+            pe = ex2_emu2(a);
+          } else {
+            pe = make_float2(ex2_mufu(a.x), ex2_mufu(a.y));
+          }
+          if (e & 2) acc_b = __fadd2_rn(acc_b, pe);
+          else acc_a = __fadd2_rn(acc_a, pe);
           pk[e >> 1] = Pack2<T>::pack(pe.x, pe.y);
         }
         tmem_st16(t_s + c * 16, pk);
@@ -401,11 +475,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       chunk(s0, 0);
       chunk(s1, 1);
       chunk(s2, 2);
+      if (kSplit) {  // keys [0, 96) are in TMEM: let O += P V start on them
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&ctl.p_full[i]);
+      }
       chunk(s3, 3);
+      const float2 acc2 = __fadd2_rn(acc_a, acc_b);
       l_run = l_run * alpha + (acc2.x + acc2.y);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&ctl.p_full[i]);
+      mbar_arrive(kSplit ? &ctl.p_full2[i] : &ctl.p_full[i]);
     }
     if (ni > 0) {
       // final: O_i / l -> global
@@ -483,13 +563,32 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   const size_t smem = 1024 + (size_t)(2 + kSlots) * kTileBytes;
   dim3 grid((a.Lq + 2 * BM - 1) / (2 * BM), a.Hq, a.B);
   note_launch("fmha_tcgen05");
-  if (bf) {
-    OMX_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fmha_fwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
-  } else {
-    OMX_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fmha_fwd_kernel<__half><<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  auto go = [&](auto kern) {
+    OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
+  };
+  // OMX_FMHA_CFG = 10 * kEmu + kSplit is a tuning knob for the bench sweeps, not an API.
+  static const int cfg = [] {
+    const char* e = getenv("OMX_FMHA_CFG");
+    return e ? atoi(e) : kDefaultCfg;
+  }();
+#define OMX_FMHA_CASE(EMU, SPLIT)                                  \
+  case EMU * 10 + SPLIT:                                           \
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT != 0>);   \
+    else go(fmha_fwd_kernel<__half, EMU, SPLIT != 0>);             \
+    break;
+  switch (cfg) {
+    OMX_FMHA_CASE(0, 0)
+    OMX_FMHA_CASE(0, 1)
+    OMX_FMHA_CASE(1, 0)
+    OMX_FMHA_CASE(1, 1)
+    OMX_FMHA_CASE(2, 0)
+    OMX_FMHA_CASE(2, 1)
+    OMX_FMHA_CASE(3, 1)
+    default:
+      OMX_CHECK(false, "OMX_FMHA_CFG=%d is not an instantiated variant", cfg);
   }
+#undef OMX_FMHA_CASE
   count_launch();
   OMX_CUDA(cudaGetLastError());
 }

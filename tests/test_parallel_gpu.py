@@ -47,7 +47,8 @@ def test_peer_store_path_world1_raw_abi(dtype, S):
     base = L.OmxOptionalFloat()
     base.has_value, base.value = True, ROPE[2]
     A = omx.array
-    qd, kd, vd, od = A.desc(q.cuda()), A.desc(kn.cuda()), A.desc(vn.cuda()), A.desc(out_full)
+    qg, kg, vg = q.cuda(), kn.cuda(), vn.cuda()  # descriptors borrow: keep the tensors alive
+    qd, kd, vd, od = A.desc(qg), A.desc(kg), A.desc(vg), A.desc(out_full)
     sp = A.stream_ptr()
     for step in (1, 2):
         L.check(L.lib().omx_attn_decode_fused_sharded(A.ref(od), A.ref(qd), A.ref(kd), A.ref(vd), cache.handle,
