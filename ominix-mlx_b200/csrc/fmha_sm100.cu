@@ -42,8 +42,7 @@ constexpr int kThreads = 384;   // 2 softmax warpgroups + 1 warpgroup {TMA, MMA,
 constexpr int kRegsSoftmax = 216;  // setmaxnreg budgets: 8 warps x 216 + 4 warps x 72 <= 64K registers
 constexpr int kRegsOther = 72;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
-constexpr int kDefaultCfg = 1;             // kEmu = 0 (all exp2 on MUFU), split hand-off (measured best)
-constexpr int kSplitKeys = 96;             // keys of P handed over first when the hand-off is split
+constexpr int kDefaultCfg = 1;             // kEmu = 0 (all exp2 on MUFU), split hand-off at 96 keys (measured best)
 
 struct FmhaParams {
   void* out;
@@ -106,6 +105,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
       "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
       "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -213,9 +218,9 @@ struct SharedCtl {
 };
 
 // kEmu: of every 4 packed pairs of scores, kEmu take the polynomial exp2 (0..4 -> 0..100 %).
-// kSplit: hand P to the MMA warp in two pieces (first 96 keys, then the last 32) so that O += P V
-// starts while the softmax warpgroup is still exponentiating the tail.
-template <typename T, int kEmu, bool kSplit>
+// kSplitKeys: hand P to the MMA warp in two pieces (the first kSplitKeys keys, then the rest) so
+// that O += P V starts while the softmax warpgroup is still exponentiating the tail; 0 = one piece.
+template <typename T, int kEmu, int kSplitKeys>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -309,6 +314,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
       constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
       constexpr uint32_t kTile16 = kTileBytes >> 4, kBox16 = kBoxBytes >> 4;
+      constexpr bool kSplit = kSplitKeys > 0;
       // descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (smem < 256 KB)
       const uint64_t q_desc = umma_desc(smem_u32(q_s), 16, 1024);             // K-major
       const uint64_t k_desc0 = umma_desc(smem_u32(kv_s), 16, 1024);           // K-major
@@ -421,16 +427,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (key0 + 96 + e >= limit) s3[e] = 0xff800000u;
         }
       }
-      // four independent max chains (one per 32-column chunk) instead of one 64-deep dependency
-      float mxa = -INFINITY, mxb = -INFINITY, mxc = -INFINITY, mxd = -INFINITY;
+      // eight independent max chains instead of one 64-deep dependency
+      float mxs[8];
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        mxa = fmax3(mxa, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
-        mxb = fmax3(mxb, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
-        mxc = fmax3(mxc, __uint_as_float(s2[e]), __uint_as_float(s2[e + 1]));
-        mxd = fmax3(mxd, __uint_as_float(s3[e]), __uint_as_float(s3[e + 1]));
+      for (int c = 0; c < 8; ++c) mxs[c] = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        mxs[0] = fmax3(mxs[0], __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+        mxs[1] = fmax3(mxs[1], __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
+        mxs[2] = fmax3(mxs[2], __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+        mxs[3] = fmax3(mxs[3], __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
+        mxs[4] = fmax3(mxs[4], __uint_as_float(s2[e]), __uint_as_float(s2[e + 1]));
+        mxs[5] = fmax3(mxs[5], __uint_as_float(s2[e + 2]), __uint_as_float(s2[e + 3]));
+        mxs[6] = fmax3(mxs[6], __uint_as_float(s3[e]), __uint_as_float(s3[e + 1]));
+        mxs[7] = fmax3(mxs[7], __uint_as_float(s3[e + 2]), __uint_as_float(s3[e + 3]));
       }
-      const float mx = fmaxf(fmax3(mxa, mxb, mxc), mxd);
+      const float mx = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);  // scale > 0: max commutes with scaling
       // lazy rescale: keep the old reference max unless it grew by more than 2^8 (the decision to
       // touch O is warp-uniform because TMEM accesses are warp-collective)
@@ -455,10 +467,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
       const float2 nm2 = make_float2(-m_run, -m_run);
       float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
-      auto chunk = [&](const uint32_t (&sv)[32], int c) {
+      // elements [lo, hi) of 32-column chunk c (lo, hi multiples of 16) -> packed P columns
+      auto chunk = [&](const uint32_t (&sv)[32], int c, int lo, int hi) {
         uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
+        for (int e = lo; e < hi; e += 2) {
           const float2 a = __ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sc2, nm2);
           float2 pe;
           if (((e >> 1) & 3) < kEmu) {
@@ -470,22 +483,30 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           else acc_a = __fadd2_rn(acc_a, pe);
           pk[e >> 1] = Pack2<T>::pack(pe.x, pe.y);
         }
-        tmem_st16(t_s + c * 16, pk);
+        if (hi - lo == 32) tmem_st16(t_s + c * 16, pk);
+        else tmem_st8(t_s + c * 16 + (lo >> 1), pk + (lo >> 1));
       };
-      chunk(s0, 0);
-      chunk(s1, 1);
-      chunk(s2, 2);
-      if (kSplit) {  // keys [0, 96) are in TMEM: let O += P V start on them
+      auto hand_over_first = [&] {  // keys [0, kSplitKeys) are in TMEM: let O += P V start on them
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(&ctl.p_full[i]);
+      };
+      chunk(s0, 0, 0, 32);
+      chunk(s1, 1, 0, 32);
+      chunk(s2, 2, 0, 32);
+      if (kSplitKeys == 96) hand_over_first();
+      if (kSplitKeys == 112) {
+        chunk(s3, 3, 0, 16);
+        hand_over_first();
+        chunk(s3, 3, 16, 32);
+      } else {
+        chunk(s3, 3, 0, 32);
       }
-      chunk(s3, 3);
       const float2 acc2 = __fadd2_rn(acc_a, acc_b);
       l_run = l_run * alpha + (acc2.x + acc2.y);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(kSplit ? &ctl.p_full2[i] : &ctl.p_full[i]);
+      mbar_arrive(kSplitKeys > 0 ? &ctl.p_full2[i] : &ctl.p_full[i]);
     }
     if (ni > 0) {
       // final: O_i / l -> global
@@ -567,24 +588,24 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   };
-  // OMX_FMHA_CFG = 10 * kEmu + kSplit is a tuning knob for the bench sweeps, not an API.
+  // OMX_FMHA_CFG = 10 * kEmu + {0: one-piece hand-off, 1: split at 96 keys, 2: split at 112} is a
+  // tuning knob for the bench sweeps, not an API.
   static const int cfg = [] {
     const char* e = getenv("OMX_FMHA_CFG");
     return e ? atoi(e) : kDefaultCfg;
   }();
 #define OMX_FMHA_CASE(EMU, SPLIT)                                  \
   case EMU * 10 + SPLIT:                                           \
-    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT != 0>);   \
-    else go(fmha_fwd_kernel<__half, EMU, SPLIT != 0>);             \
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112)>);   \
+    else go(fmha_fwd_kernel<__half, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112)>);             \
     break;
   switch (cfg) {
     OMX_FMHA_CASE(0, 0)
     OMX_FMHA_CASE(0, 1)
-    OMX_FMHA_CASE(1, 0)
+    OMX_FMHA_CASE(0, 2)
     OMX_FMHA_CASE(1, 1)
-    OMX_FMHA_CASE(2, 0)
+    OMX_FMHA_CASE(1, 2)
     OMX_FMHA_CASE(2, 1)
-    OMX_FMHA_CASE(3, 1)
     default:
       OMX_CHECK(false, "OMX_FMHA_CFG=%d is not an instantiated variant", cfg);
   }
