@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "collective"],
                     help="c5 with --gpus > 1 (kv-head-sharded single sequence): exchange of the output heads "
                          "by peer stores fused into the decode kernel, or by an NCCL all-gather")
+    ap.add_argument("--mask", default="string", choices=["string", "array"],
+                    help="c3: pass the causal mask as the \"causal\" mode string or as the bool [T,T] array the LLM "
+                         "crates build with create_causal_mask (classified per tile, same tiles skipped)")
     ap.add_argument("--rotate", type=int, default=1,
                     help="decode: cycle through R distinct KV caches so a working set smaller than L2 "
                          "is still read from HBM (R x KV bytes should exceed 126 MB)")
@@ -340,6 +343,8 @@ def main():
         q, k, v = rn(B, Hq, S, D), rn(B, Hkv, S, D), rn(B, Hkv, S, D)
         out = torch.empty_like(q)
         mask = omx.fast.ScaledDotProductAttentionMask.Causal if cfg["causal"] else None
+        if cfg["causal"] and args.mask == "array":
+            mask = omx.create_causal_mask(S, 0, device=dev)
 
         def step():
             omx.fast.scaled_dot_product_attention(q, k, v, scale, mask, out=out)
@@ -458,7 +463,8 @@ def main():
                        else f"batch-sharded x{world}, no data-path collective",
                        "l2_policy": "working set >> 126 MB L2 (streams from HBM every step)"
                        if alg_bytes * max(1, args.rotate) > 512e6 else "working set fits L2: warm-L2 number",
-                       "kernel": kernel, "cuda_graph": bool(args.graph), "rotate_caches": args.rotate},
+                       "kernel": kernel, "cuda_graph": bool(args.graph), "rotate_caches": args.rotate,
+                       "mask": args.mask if kind == "prefill" and cfg.get("causal") else None},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches_timed,

@@ -51,7 +51,17 @@ struct FmhaParams {
   float scale_log2;
   int causal;
   int q_off;
+  // array masks (kArr kernels): element strides after broadcasting, innermost (key) stride 1
+  int mask_kind;  // 1 bool (true = keep), 2 additive in the q/k/v dtype
+  const void* mask;
+  int64_t ms[3];       // batch, head, query-row strides (0 on broadcast axes)
+  const uint8_t* tmap; // tile classes [Bm][Hm][n_qt][n_kt]: 0 all masked, 1 all kept, 2 mixed
+  int64_t tms[2];      // batch, head strides of tmap (0 on broadcast axes)
+  int n_kt;
+  float inv_scale;
 };
+
+constexpr int kMaxSteps = 896;  // KV tiles a CTA of an array-mask launch can visit (static smem budget)
 
 // ---- tcgen05 wrappers -------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -215,12 +225,20 @@ struct SharedCtl {
   uint64_t p_full[2];   // first kSplitKeys keys of P_i written (whole tile when the hand-off is not split)
   uint64_t p_full2[2];  // remaining keys of P_i written
   uint32_t tmem_base;
+  int n_steps;          // kArr: length of the step list
 };
 
 // kEmu: of every 4 packed pairs of scores, kEmu take the polynomial exp2 (0..4 -> 0..100 %).
 // kSplitKeys: hand P to the MMA warp in two pieces (the first kSplitKeys keys, then the rest) so
 // that O += P V starts while the softmax warpgroup is still exponentiating the tail; 0 = one piece.
-template <typename T, int kEmu, int kSplitKeys>
+//
+// kArr: boolean / additive ARRAY masks (what create_causal_mask hands the reference's prefill,
+// mlx-rs-core/src/utils.rs:134-188).  A pre-pass classifies every 128 x 128 tile of the mask
+// (mask_tile_classify_kernel); an idle warp compacts the KV tiles that are not fully masked for this
+// CTA's 256 query rows into a step list in shared memory, and the three roles walk that list, so a
+// causal- or window-shaped array mask costs what the structured mask costs.  Mixed tiles read their
+// mask rows (128-bit loads) in the softmax threads.
+template <typename T, int kEmu, int kSplitKeys, bool kArr>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
@@ -229,6 +247,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* q_s = smem;                     // 2 x 32 KB
   uint8_t* kv_s = smem + 2 * kTileBytes;   // kSlots x 32 KB
   __shared__ SharedCtl ctl;
+  __shared__ uint16_t jlist[kArr ? kMaxSteps : 1];  // entry: KV tile | tile-0 needs mask << 12 | tile-1 << 13
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role index
@@ -250,7 +269,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       n[i] = (kmax + BN - 1) / BN;
     }
   }
-  const int N = max(n[0], n[1]);
+  int N = max(n[0], n[1]);
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -270,10 +289,38 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (kArr && warp == 10) {
+    // step list: KV tiles with at least one visible element for either Q tile of this CTA
+    const int t0 = m_blk * 2;
+    const uint8_t* r0 = p.tmap + b * p.tms[0] + hq * p.tms[1] + (int64_t)t0 * p.n_kt;
+    const bool has1 = n[1] > 0;
+    int cnt = 0;
+    for (int base = 0; base < p.n_kt; base += 32) {
+      const int jt = base + lane;
+      int c0 = 0, c1 = 0;
+      if (jt < p.n_kt) {
+        c0 = r0[jt];
+        c1 = has1 ? r0[p.n_kt + jt] : 0;
+      }
+      const bool act = (c0 | c1) != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (pos < kMaxSteps) jlist[pos] = (uint16_t)(jt | ((c0 != 1) << 12) | ((c1 != 1) << 13));
+      }
+      cnt += __popc(bal);
+    }
+    if (lane == 0) ctl.n_steps = min(cnt, kMaxSteps);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, ctl.tmem_base, 0);  // warp-uniform for the UTCHMMA operands
+  if (kArr) {
+    N = __shfl_sync(0xffffffffu, ctl.n_steps, 0);
+    n[0] = n[0] > 0 ? N : 0;
+    n[1] = n[1] > 0 ? N : 0;
+  }
 
   if (warp == 8) {
     // =========================================================== TMA producer
@@ -293,7 +340,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int seq = 0; seq < 2 * N; ++seq) {
         const int slot = seq % kSlots, use = seq / kSlots;
         if (use > 0) mbar_wait_wd(&ctl.kv_empty[slot], (use - 1) & 1);
-        const int j = seq >> 1;
+        const int j = kArr ? (jlist[seq >> 1] & 0xfff) : (seq >> 1);
         const CUtensorMap* tm = (seq & 1) ? &tmV : &tmK;
         uint8_t* dst = kv_s + slot * kTileBytes;
         mbar_expect_tx(&ctl.kv_full[slot], kTileBytes);
@@ -407,8 +454,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int limit = p.causal ? min(p.Lk, p.q_off + qrow + 1) : p.Lk;  // keys [0, limit) are visible
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 
-    for (int j = 0; j < ni; ++j) {
-      mbar_wait_wd(&ctl.s_full[i], j & 1);
+    for (int st = 0; st < ni; ++st) {
+      const int ent = kArr ? jlist[st] : st;
+      const int j = kArr ? (ent & 0xfff) : st;  // KV tile index
+      mbar_wait_wd(&ctl.s_full[i], st & 1);
       tc_fence_after();
       const int key0 = j * BN;
       // the whole S row of this thread: 128 fp32 scores, one TMEM round trip
@@ -425,6 +474,51 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (key0 + 32 + e >= limit) s1[e] = 0xff800000u;
           if (key0 + 64 + e >= limit) s2[e] = 0xff800000u;
           if (key0 + 96 + e >= limit) s3[e] = 0xff800000u;
+        }
+      }
+      if (kArr && ((ent >> (12 + i)) & 1)) {  // mixed tile: fold this row's mask segment into the scores
+        const int64_t moff = b * p.ms[0] + hq * p.ms[1] + (int64_t)min(qrow, p.Lq - 1) * p.ms[2] + key0;
+        const int nk = min(BN, p.Lk - key0);  // keys of this tile that exist
+        if (p.mask_kind == 1) {
+          const uint8_t* mrow = (const uint8_t*)p.mask + moff;
+          const bool vec = ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {  // 16 keys per 128-bit load
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            if (vec && g * 16 + 16 <= nk) {
+              const uint4 v = __ldg(reinterpret_cast<const uint4*>(mrow) + g);
+              w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else {
+              for (int t = 0; t < 16; ++t)
+                if (g * 16 + t < nk && mrow[g * 16 + t]) w[t >> 2] |= 1u << ((t & 3) * 8);
+            }
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const bool keep = (w[t >> 2] >> ((t & 3) * 8)) & 0xffu;
+              const int e = (g & 1) * 16 + t;
+              uint32_t& dst = (g >> 1) == 0 ? s0[e] : (g >> 1) == 1 ? s1[e] : (g >> 1) == 2 ? s2[e] : s3[e];
+              if (!keep) dst = 0xff800000u;
+            }
+          }
+        } else {
+          const T* mrow = (const T*)p.mask + moff;
+          const bool vec = ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {  // 8 keys per 128-bit load
+            union { uint4 v; T t[8]; } u;
+            if (vec && g * 8 + 8 <= nk) {
+              u.v = __ldg(reinterpret_cast<const uint4*>(mrow) + g);
+            } else {
+              for (int t = 0; t < 8; ++t) u.t[t] = (g * 8 + t < nk) ? mrow[g * 8 + t] : Num<T>::from_f(0.f);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const int e = (g & 3) * 8 + t;
+              uint32_t& dst = (g >> 2) == 0 ? s0[e] : (g >> 2) == 1 ? s1[e] : (g >> 2) == 2 ? s2[e] : s3[e];
+              // score + mask / scale: the later multiply by scale restores scale * s + mask
+              dst = __float_as_uint(fmaf(Num<T>::to_f(u.t[t]), p.inv_scale, __uint_as_float(dst)));
+            }
+          }
         }
       }
       // eight independent max chains instead of one 64-deep dependency
@@ -453,7 +547,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         alpha = fast_exp2(m_run - m_new);  // 0 on the first tile
         m_run = m_new;
       }
-      if (any_grow && j > 0) {
+      if (any_grow && st > 0) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
@@ -465,7 +559,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       // P = exp2(S * scale - m_run) -> 16-bit pairs over the first 64 columns of S
-      const float2 nm2 = make_float2(-m_run, -m_run);
+      // (array masks can hide every key a row has seen so far: keep exp2(-inf - m) = 0, not NaN)
+      const float m_use = (kArr && m_run == -INFINITY) ? 0.f : m_run;
+      const float2 nm2 = make_float2(-m_use, -m_use);
       float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
       // elements [lo, hi) of 32-column chunk c (lo, hi multiples of 16) -> packed P columns
       auto chunk = [&](const uint32_t (&sv)[32], int c, int lo, int hi) {
@@ -512,7 +608,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // final: O_i / l -> global
       mbar_wait_wd(&ctl.s_full[i], ni & 1);
       tc_fence_after();
-      const float inv = 1.0f / l_run;
+      const float inv = (kArr && !(l_run > 0.f)) ? 0.f : 1.0f / l_run;  // rows with no visible key -> 0
       T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -531,6 +627,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
+    } else if (kArr && qrow < p.Lq) {  // every KV tile masked for this CTA: defined output (zeros)
+      T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+#pragma unroll
+      for (int e = 0; e < HD; e += 8) *reinterpret_cast<uint4*>(orow + e) = make_uint4(0u, 0u, 0u, 0u);
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));  // idle warps of warpgroup 2
@@ -543,6 +643,34 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// One CTA per 128 x 128 tile of the (broadcast-collapsed) mask: 0 = nothing visible, 1 = everything
+// visible (bool: all true; additive: all zero), 2 = mixed.  Additive entries <= -1e8 count as masked.
+template <typename M>
+__global__ void mask_tile_classify_kernel(const M* mask, int64_t s0, int64_t s1, int64_t s2, int64_t s3, int Lq,
+                                          int Lk, int Hm, uint8_t* out, int kind) {
+  const int kt = blockIdx.x, qt = blockIdx.y, bh = blockIdx.z;
+  const M* base = mask + (int64_t)(bh / Hm) * s0 + (int64_t)(bh % Hm) * s1;
+  const int r_end = min(Lq, qt * BM + BM), k_end = min(Lk, kt * BN + BN);
+  bool any_keep = false, any_drop = false, any_other = false;
+  for (int r = qt * BM + (threadIdx.x >> 5); r < r_end; r += blockDim.x >> 5) {
+    for (int k = kt * BN + (threadIdx.x & 31); k < k_end; k += 32) {
+      const M v = base[(int64_t)r * s2 + (int64_t)k * s3];
+      if (kind == 1) {
+        if (v != M(0)) any_keep = true;
+        else any_drop = true;
+      } else {
+        const float f = (float)v;
+        if (f == 0.f) any_keep = true;
+        else if (f <= -1e8f) any_drop = true;
+        else any_other = true;
+      }
+    }
+  }
+  const int keep = __syncthreads_or(any_keep), drop = __syncthreads_or(any_drop), other = __syncthreads_or(any_other);
+  if (threadIdx.x == 0)
+    out[((int64_t)bh * gridDim.y + qt) * gridDim.x + kt] = other || (keep && drop) ? 2 : (keep ? 1 : 0);
+}
+
 }  // namespace
 
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
@@ -552,7 +680,11 @@ bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
   };
   if (a.q->dtype != OMX_BFLOAT16 && a.q->dtype != OMX_FLOAT16) return no("dtype is not bf16/f16");
   if (a.D != HD || a.Dv != HD) return no("head_dim != 128");
-  if (a.mask_mode != MASK_NONE && a.mask_mode != MASK_CAUSAL) return no("array mask");
+  if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) {
+    if (a.mask_mode == MASK_ADD && a.mask->dtype != a.q->dtype) return no("additive mask dtype differs from q");
+    if (a.Lk > 1 && a.mask_strides[3] != 1) return no("mask key axis not contiguous");
+    if ((a.Lk + BN - 1) / BN > kMaxSteps) return no("array mask over more than 896 KV tiles");
+  }
   if (a.Lq < 1 || a.Lk < 1) return no("empty sequence");
   if (a.out->dtype != a.q->dtype) return no("out dtype differs");
   const omx_array* ts[4] = {a.q, a.k, a.v, a.out};
@@ -583,11 +715,44 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
                                      a.v->strides[0], 64, BN, bf);
   const size_t smem = 1024 + (size_t)(2 + kSlots) * kTileBytes;
   dim3 grid((a.Lq + 2 * BM - 1) / (2 * BM), a.Hq, a.B);
-  note_launch("fmha_tcgen05");
   auto go = [&](auto kern) {
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   };
+  if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) {
+    // ---- array mask: classify the mask's tiles, then the step-list kernel
+    const int n_qt = (a.Lq + BM - 1) / BM, n_kt = (a.Lk + BN - 1) / BN;
+    const int Bm = a.mask_strides[0] ? a.B : 1, Hm = a.mask_strides[1] ? a.Hq : 1;
+    uint8_t* tmap = (uint8_t*)get_workspace((size_t)Bm * Hm * n_qt * n_kt, stream);
+    p.mask_kind = a.mask_mode == MASK_BOOL ? 1 : 2;
+    p.mask = a.mask->data;
+    for (int i = 0; i < 3; ++i) p.ms[i] = a.mask_strides[i];
+    p.tmap = tmap;
+    p.tms[0] = a.mask_strides[0] ? (int64_t)Hm * n_qt * n_kt : 0;
+    p.tms[1] = a.mask_strides[1] ? (int64_t)n_qt * n_kt : 0;
+    p.n_kt = n_kt;
+    p.inv_scale = 1.0f / a.scale;
+    dim3 cgrid(n_kt, n_qt, Bm * Hm);
+    const int64_t* ms = a.mask_strides;
+    if (a.mask_mode == MASK_BOOL)
+      mask_tile_classify_kernel<uint8_t><<<cgrid, 256, 0, stream>>>((const uint8_t*)a.mask->data, ms[0], ms[1], ms[2],
+                                                                     ms[3], a.Lq, a.Lk, Hm, tmap, 1);
+    else if (bf)
+      mask_tile_classify_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a.mask->data, ms[0],
+                                                                           ms[1], ms[2], ms[3], a.Lq, a.Lk, Hm, tmap, 2);
+    else
+      mask_tile_classify_kernel<__half><<<cgrid, 256, 0, stream>>>((const __half*)a.mask->data, ms[0], ms[1], ms[2],
+                                                                    ms[3], a.Lq, a.Lk, Hm, tmap, 2);
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+    note_launch("fmha_tcgen05_arraymask");
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 0, 96, true>);
+    else go(fmha_fwd_kernel<__half, 0, 96, true>);
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+    return;
+  }
+  note_launch("fmha_tcgen05");
   // OMX_FMHA_CFG = 10 * kEmu + {0: one-piece hand-off, 1: split at 96 keys, 2: split at 112} is a
   // tuning knob for the bench sweeps, not an API.
   static const int cfg = [] {
@@ -596,8 +761,8 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   }();
 #define OMX_FMHA_CASE(EMU, SPLIT)                                  \
   case EMU * 10 + SPLIT:                                           \
-    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112)>);   \
-    else go(fmha_fwd_kernel<__half, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112)>);             \
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);   \
+    else go(fmha_fwd_kernel<__half, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);             \
     break;
   switch (cfg) {
     OMX_FMHA_CASE(0, 0)
