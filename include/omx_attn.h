@@ -105,6 +105,16 @@ int omx_fast_rope_dynamic(const omx_array* out, const omx_array* x, int dims, bo
                           const omx_array* offset, int max_position,
                           const omx_array* freqs /* may be null */, omx_stream s);
 
+/* ---- rms_norm ----------------------------------------------------------- */
+/*
+ * out = rms_norm(x, weight, eps) over the last axis  <- mlx_fast_rms_norm (fast.h:163-168, bound at
+ * mlx-rs/src/fast.rs:163-180; on this path: the per-head q_norm / k_norm, qwen3-mlx/src/model.rs:172-181).
+ * weight: [D] in x's dtype, or null.  Same op order and rounding as the MLX CPU backend (f32 sum
+ * left to right, 1/sqrt, round to dtype, then * weight), so downstream KV-cache bits are unchanged.
+ */
+int omx_fast_rms_norm(const omx_array* out, const omx_array* x, const omx_array* weight /* may be null */,
+                      float eps, omx_stream s);
+
 /* ---- scaled dot-product attention --------------------------------------- */
 /*
  * out[B,Hq,Lq,Dv] = softmax(scale * q k^T + mask) v;  q [B,Hq,Lq,D], k [B,Hkv,Lk,D],
@@ -168,6 +178,20 @@ int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_ar
                           bool traditional, omx_optional_float base, float rope_scale,
                           const omx_array* freqs /* may be null */, float sm_scale,
                           omx_array* keys_out, omx_array* values_out, omx_stream s);
+
+/*
+ * The same step with the per-head RMSNorm prologue of the Qwen3-family crates folded in
+ * (qwen3-mlx/src/model.rs:172-212: q_norm(q), k_norm(k), rope, rope, update_and_fetch, sdpa):
+ *   q' = rope(rms_norm(q, q_norm_weight, norm_eps), off); k' = rope(rms_norm(k_new, k_norm_weight, norm_eps), off)
+ * q_norm_weight / k_norm_weight: [D] in q's dtype (either may be null = no norm on that side).
+ */
+int omx_attn_decode_fused_norm(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                               const omx_array* v_new, omx_kv_cache cache,
+                               const omx_array* q_norm_weight, const omx_array* k_norm_weight,
+                               float norm_eps, int rope_dims, bool traditional,
+                               omx_optional_float base, float rope_scale,
+                               const omx_array* freqs /* may be null */, float sm_scale,
+                               omx_array* keys_out, omx_array* values_out, omx_stream s);
 
 /* ---- head-sharded single-sequence decode (BASELINE C5) -------------------- */
 /*

@@ -48,6 +48,7 @@ _SIGS = {
     "omx_last_error": (ctypes.c_char_p, []),
     "omx_version": (ctypes.c_int, []),
     "omx_device_check": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "omx_fast_rms_norm": (ctypes.c_int, [_AP, _AP, _AP, ctypes.c_float, ctypes.c_void_p]),
     "omx_fast_rope": (ctypes.c_int, [_AP, _AP, ctypes.c_int, ctypes.c_bool, OmxOptionalFloat, ctypes.c_float,
                                      ctypes.c_int, _AP, ctypes.c_void_p]),
     "omx_fast_rope_dynamic": (ctypes.c_int, [_AP, _AP, ctypes.c_int, ctypes.c_bool, OmxOptionalFloat,
@@ -69,6 +70,9 @@ _SIGS = {
     "omx_attn_decode_fused": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                              OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float, _AP, _AP,
                                              ctypes.c_void_p]),
+    "omx_attn_decode_fused_norm": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, _AP, _AP, ctypes.c_float,
+                                                  ctypes.c_int, ctypes.c_bool, OmxOptionalFloat, ctypes.c_float, _AP,
+                                                  ctypes.c_float, _AP, _AP, ctypes.c_void_p]),
     "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                      OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                      ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),

@@ -60,6 +60,9 @@ struct DecodeParams {
   int64_t kcs[4], vcs[4];
   int rope_dims, traditional;
   const float *cos_row, *sin_row;  // table row of the current position, [rope_dims/2]
+  // fused per-head RMSNorm of q / k_new before the rotation (null = none); [D] contiguous
+  const void *q_norm_w, *k_norm_w;
+  float norm_eps, norm_inv_n;
   // head-sharded output (C5): the final store goes to every rank's full buffer over NVLink peer
   // mappings; the last finishing CTA of the launch bumps one arrival counter per rank.
   int n_peers;                // 0: plain local store through `out`
@@ -97,11 +100,33 @@ __device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
 }
 
 // roped / copied q heads -> shared memory (as T), used by both kernels
+// 1/rms of the staged q heads (rs[0..n_heads)) and of the new k row (rs[16]) when the fused
+// q_norm / k_norm prologue is on.  One thread per row: the left-to-right f32 sum is the contract.
+template <typename T>
+__device__ __forceinline__ void stage_norms(const DecodeParams& p, float* rs, int first_head, int n_heads,
+                                            int b, int hk, bool has_nt, int tid) {
+  if (p.q_norm_w && tid < n_heads) {
+    const T* qh = (const T*)p.q + b * p.qs[0] + (int64_t)(first_head + tid) * p.qs[1];
+    rs[tid] = rms_rsqrt_row<T>(qh, p.qs[3], p.D, p.norm_eps, p.norm_inv_n);
+  }
+  if (p.k_norm_w && has_nt && tid == 32) {
+    const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
+    rs[16] = rms_rsqrt_row<T>(kn, p.kns[3], p.D, p.norm_eps, p.norm_inv_n);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total,
-                                        int first_head, int n_heads, int b, int tid, int nthr) {
+                                        int first_head, int n_heads, int b, int tid, int nthr,
+                                        const float* rs) {
   const T* qg = (const T*)p.q + b * p.qs[0] + (int64_t)first_head * p.qs[1];
   const int D = p.D;
+  const T* nw = (const T*)p.q_norm_w;
+  // element d of staged head g, after the optional RMSNorm (value already rounded to T)
+  auto qval = [&](const T* qh, int g, int d) -> float {
+    const float x = Num<T>::to_f(qh[d * p.qs[3]]);
+    return nw ? rms_apply<T>(x, rs[g], Num<T>::to_f(nw[d]), true) : x;
+  };
   for (int idx = tid; idx < (rows_total - n_heads) * D; idx += nthr)
     q_s[(n_heads + idx / D) * pitch + idx % D] = Num<T>::from_f(0.f);
   if (p.fused && p.rope_dims > 0) {
@@ -114,19 +139,18 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
         const int i1 = p.traditional ? 2 * u : u;
         const int i2 = p.traditional ? 2 * u + 1 : u + half;
         float o1, o2;
-        rope_pair<T>(Num<T>::to_f(qh[i1 * p.qs[3]]), Num<T>::to_f(qh[i2 * p.qs[3]]),
-                     rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
+        rope_pair<T>(qval(qh, g, i1), qval(qh, g, i2), rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
         q_s[g * pitch + i1] = Num<T>::from_f(o1);
         q_s[g * pitch + i2] = Num<T>::from_f(o2);
       } else {
         const int d = p.rope_dims + (u - half);
-        q_s[g * pitch + d] = qh[d * p.qs[3]];
+        q_s[g * pitch + d] = Num<T>::from_f(qval(qh, g, d));
       }
     }
   } else {
     for (int idx = tid; idx < n_heads * D; idx += nthr) {
       const int g = idx / D, d = idx % D;
-      q_s[g * pitch + d] = qg[g * p.qs[1] + d * p.qs[3]];
+      q_s[g * pitch + d] = Num<T>::from_f(qval(qg + g * p.qs[1], g, d));
     }
   }
 }
@@ -136,9 +160,14 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
 template <typename T>
 __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
                                           int b, int hk, int lane, float* nt_k, float* nt_v,
-                                          float* nt_m, bool write_cache = true) {
+                                          float* nt_m, const float* rs, bool write_cache = true) {
   const int D = p.D;
   const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
+  const T* nw = (const T*)p.k_norm_w;
+  auto kval = [&](int d) -> float {  // k_new element after the optional RMSNorm (rounded to T)
+    const float x = Num<T>::to_f(kn[d * p.kns[3]]);
+    return nw ? rms_apply<T>(x, rs[16], Num<T>::to_f(nw[d]), true) : x;
+  };
   const T* vn = (const T*)p.v_new + b * p.vns[0] + hk * p.vns[1];
   T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(p.Lk - 1) * p.kcs[2];
   T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(p.Lk - 1) * p.vcs[2];
@@ -147,8 +176,7 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
     const int i1 = p.traditional ? 2 * u : u;
     const int i2 = p.traditional ? 2 * u + 1 : u + half;
     float o1, o2;
-    rope_pair<T>(Num<T>::to_f(kn[i1 * p.kns[3]]), Num<T>::to_f(kn[i2 * p.kns[3]]), rnd<T>(p.cos_row[u]),
-                 rnd<T>(p.sin_row[u]), o1, o2);
+    rope_pair<T>(kval(i1), kval(i2), rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
     if (write_cache) {
       kc[i1 * p.kcs[3]] = Num<T>::from_f(o1);
       kc[i2 * p.kcs[3]] = Num<T>::from_f(o2);
@@ -157,9 +185,9 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
     nt_k[i2] = o2;
   }
   for (int d = p.rope_dims + lane; d < D; d += 32) {
-    const T x = kn[d * p.kns[3]];
-    if (write_cache) kc[d * p.kcs[3]] = x;
-    nt_k[d] = Num<T>::to_f(x);
+    const float x = kval(d);
+    if (write_cache) kc[d * p.kcs[3]] = Num<T>::from_f(x);
+    nt_k[d] = x;
   }
   for (int d = lane; d < D; d += 32) {
     const T x = vn[d * p.vns[3]];
@@ -265,6 +293,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   float* nt_m = nt_v + D;
   __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
   __shared__ int s_ticket;
+  __shared__ float s_rs[17];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -283,7 +312,11 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     }
     mbar_fence_init();
   }
-  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR);
+  if (p.q_norm_w || p.k_norm_w) {
+    stage_norms<T>(p, s_rs, hk * G, G, b, hk, has_nt, tid);
+    __syncthreads();
+  }
+  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR, s_rs);
   __syncthreads();
 
   // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
@@ -316,7 +349,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     if (lane == 0)
       for (int t = 0; t < first; ++t) issue(t);
     __syncwarp();
-    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m);
+    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_rs);
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
         mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
@@ -517,6 +550,7 @@ decode_simt_kernel(const DecodeParams p) {
   float* nt_v = nt_k + D;
   float* nt_m = nt_v + D;                          // [GT]
   __shared__ int s_ticket;
+  __shared__ float s_rs[17];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, b = blockIdx.z;
@@ -529,11 +563,15 @@ decode_simt_kernel(const DecodeParams p) {
   const int kend = min(p.n_mem, kbeg + keys_per_split);
   const bool has_nt = p.fused && split == p.num_splits - 1;
 
-  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR);
+  if (p.q_norm_w || p.k_norm_w) {
+    stage_norms<T>(p, s_rs, first_head, GT, b, hk, has_nt, tid);
+    __syncthreads();
+  }
+  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR, s_rs);
   __syncthreads();
   // the new row is appended once per kv head (gsub == 0 writes it); every group scores it
   if (has_nt && warp == kSimtWarps - 1)
-    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, /*write_cache=*/gsub == 0);
+    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_rs, /*write_cache=*/gsub == 0);
 
   float qr[GT][VE], acc[GT][VE], m[GT], l[GT];
 #pragma unroll
@@ -748,6 +786,10 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       p.cos_row = f.table.cos + (size_t)f.position * f.table.half;
       p.sin_row = f.table.sin + (size_t)f.position * f.table.half;
     }
+    p.q_norm_w = f.q_norm_w;
+    p.k_norm_w = f.k_norm_w;
+    p.norm_eps = f.norm_eps;
+    p.norm_inv_n = 1.0f / (float)a.D;
   }
   if (a.B == 0 || a.Hq == 0) return;
   OMX_CHECK(p.Lk >= 1, "[scaled_dot_product_attention] decode needs at least one key");

@@ -264,6 +264,13 @@ int omx_force_kernel(const char* name) {
   });
 }
 
+int omx_fast_rms_norm(const omx_array* out, const omx_array* x, const omx_array* weight, float eps, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    rms_norm_forward(out, x, weight, eps, (cudaStream_t)s);
+  });
+}
+
 int omx_fast_rope(const omx_array* out, const omx_array* x, int dims, bool traditional,
                   omx_optional_float base, float scale, int offset, const omx_array* freqs, omx_stream s) {
   return guarded([&] {
@@ -367,7 +374,8 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
                        const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
                        omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
                        omx_array* keys_out, omx_array* values_out, const omx_peer_group* peers,
-                       int head_offset, cudaStream_t stream) {
+                       int head_offset, cudaStream_t stream, const omx_array* q_norm_w = nullptr,
+                       const omx_array* k_norm_w = nullptr, float norm_eps = 0.f) {
   require_device();
   auto* c = (KVCacheImpl*)cache.ctx;
   OMX_CHECK(c, "[attn_decode_fused] null cache handle");
@@ -382,6 +390,12 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
   OMX_CHECK(rope_dims == 0 || base.has_value != (freqs && freqs->data),
             "[rope] Only one of base or freqs can have a value.");
+  const bool qn = q_norm_w && q_norm_w->data, kn = k_norm_w && k_norm_w->data;
+  for (const omx_array* w : {qn ? q_norm_w : nullptr, kn ? k_norm_w : nullptr}) {
+    if (!w) continue;
+    OMX_CHECK(w->ndim == 1 && w->shape[0] == D && w->dtype == q->dtype && (w->strides[0] == 1 || D == 1),
+              "[attn_decode_fused_norm] norm weights must be contiguous [%d] vectors in the q dtype", D);
+  }
   omx_array out_local = *out;  // the rows of `out` this call writes
   if (peers) {
     OMX_CHECK(peers->world >= 1 && peers->world <= OMX_MAX_PEERS && peers->rank >= 0 && peers->rank < peers->world,
@@ -419,6 +433,9 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     f.position = position;
     f.peers = peers;
     f.head_offset = 0;  // out_local already starts at this rank's first head
+    f.q_norm_w = qn ? q_norm_w->data : nullptr;
+    f.k_norm_w = kn ? k_norm_w->data : nullptr;
+    f.norm_eps = norm_eps;
     if (rope_dims > 0) {
       std::vector<float> fh;
       if (!base.has_value) {
@@ -443,7 +460,31 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     decode_attention(a, f, stream);
     return;
   }
-  // Unfused composition for layouts the decode kernels do not take: rope -> row store -> sdpa.
+  // Unfused composition for layouts the decode kernels do not take: (norm) -> rope -> row store -> sdpa.
+  const size_t es = dtype_size(q->dtype);
+  const size_t qbytes = ((size_t)q->shape[0] * q->shape[1] * D * es + 255) & ~(size_t)255;
+  const size_t kbytes = ((size_t)k_new->shape[0] * k_new->shape[1] * D * es + 255) & ~(size_t)255;
+  char* ws = (qn || kn || rope_dims > 0) ? (char*)get_workspace(2 * qbytes + kbytes, stream) : nullptr;
+  auto dense = [&](const omx_array* like, char* mem) {  // contiguous [B,H,1,D] scratch array
+    omx_array t = *like;
+    t.data = mem;
+    t.strides[0] = like->shape[1] * D;
+    t.strides[1] = D;
+    t.strides[2] = D;
+    t.strides[3] = 1;
+    return t;
+  };
+  omx_array qn_arr, kn_arr;
+  if (qn) {
+    qn_arr = dense(q, ws);
+    rms_norm_forward(&qn_arr, q, q_norm_w, norm_eps, stream);
+    q = &qn_arr;
+  }
+  if (kn) {
+    kn_arr = dense(k_new, ws + 2 * qbytes);
+    rms_norm_forward(&kn_arr, k_new, k_norm_w, norm_eps, stream);
+    k_new = &kn_arr;
+  }
   omx_array krow = kview, vrow = vview;
   krow.shape[2] = 1;
   vrow.shape[2] = 1;
@@ -456,18 +497,13 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   }
   copy4d(&vrow, v_new, stream);
   if (rope_dims > 0) {
-    const size_t qbytes = (size_t)q->shape[0] * q->shape[1] * D * dtype_size(q->dtype);
-    omx_array qr = *q;
-    qr.data = get_workspace(qbytes, stream);  // sdpa_generic itself uses no scratch
-    qr.strides[0] = q->shape[1] * D;
-    qr.strides[1] = D;
-    qr.strides[2] = D;
-    qr.strides[3] = 1;
+    omx_array qr = dense(q, ws + qbytes);  // sdpa_generic itself uses no scratch
     rope_forward(&qr, q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
     SdpaArgs a2 = make_sdpa_args(out, &qr, &kview, &vview, sm_scale, "", nullptr, nullptr);
     sdpa_generic(a2, stream);
   } else {
-    sdpa_generic(a, stream);
+    SdpaArgs a2 = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    sdpa_generic(a2, stream);
   }
 }
 }  // namespace
@@ -479,6 +515,17 @@ int omx_attn_decode_fused(const omx_array* out, const omx_array* q, const omx_ar
   return guarded([&] {
     decode_fused_impl(out, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs, sm_scale,
                       keys_out, values_out, nullptr, 0, (cudaStream_t)s);
+  });
+}
+
+int omx_attn_decode_fused_norm(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                               const omx_array* v_new, omx_kv_cache cache, const omx_array* q_norm_weight,
+                               const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,
+                               omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
+                               omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    decode_fused_impl(out, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs, sm_scale,
+                      keys_out, values_out, nullptr, 0, (cudaStream_t)s, q_norm_weight, k_norm_weight, norm_eps);
   });
 }
 

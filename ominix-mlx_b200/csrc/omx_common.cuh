@@ -132,6 +132,24 @@ __device__ __forceinline__ void rope_pair(float x1, float x2, float c, float s, 
   o2 = rnd<T>(__fadd_rn(e, f));
 }
 
+// rms_norm with the reference's per-primitive rounding (MLX CPU fallback graph, see norm.cu):
+// r = 1 / sqrt(sum_d(x_d^2, left to right) * (1/D) + eps), all IEEE-rounded f32 operations.
+template <typename T>
+__device__ __forceinline__ float rms_rsqrt_row(const T* x, int64_t stride, int D, float eps, float inv_n) {
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float v = Num<T>::to_f(x[d * stride]);
+    acc = __fadd_rn(acc, __fmul_rn(v, v));
+  }
+  return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fmul_rn(acc, inv_n), eps)));
+}
+// y = T(x * r); out = T(w * y)  (value returned as float, already rounded to T)
+template <typename T>
+__device__ __forceinline__ float rms_apply(float x, float r, float w, bool has_w) {
+  const float y = rnd<T>(__fmul_rn(x, r));
+  return has_w ? rnd<T>(__fmul_rn(w, y)) : y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

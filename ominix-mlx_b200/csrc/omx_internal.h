@@ -24,6 +24,10 @@ void rope_forward(const omx_array* out, const omx_array* x, int dims, bool tradi
 void dit_rope_forward(const omx_array* out, const omx_array* x, const omx_array* cs,
                       const omx_array* sn, cudaStream_t stream);
 
+// ---- norm.cu ----
+void rms_norm_forward(const omx_array* out, const omx_array* x, const omx_array* weight, float eps,
+                      cudaStream_t stream);
+
 // ---- kv_cache.cu ----
 struct KVCacheImpl;
 KVCacheImpl* kv_cache_create(int step, bool concat);
@@ -73,6 +77,11 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   // head-sharded output: store this rank's heads into every rank's full [B,Hq_total,1,D] buffer
   const omx_peer_group* peers = nullptr;  // out pointers already shifted to this rank's first head
   int head_offset = 0;
+  // per-head RMSNorm of q / k_new before the rotation (Qwen3 q_norm / k_norm): [D] weights in the
+  // q dtype, contiguous; null = no norm
+  const void* q_norm_w = nullptr;
+  const void* k_norm_w = nullptr;
+  float norm_eps = 0.f;
 };
 // q [B,Hq,1,D]; k/v views over Lk rows (Lk INCLUDES the new row when fused: the kernel reads
 // rows [0, Lk-1) from memory and takes row Lk-1 from k_new/v_new, writing it to k/v as well).

@@ -24,6 +24,16 @@ def _opt_float(x):
     return o
 
 
+def rms_norm(x, weight, eps, stream=None, out=None):
+    """fast::rms_norm (mlx-rs/src/fast.rs:163-180): normalisation over the last axis, `weight` [D] in x's
+    dtype (None for no scaling, as mlx_fast_rms_norm allows)."""
+    if out is None:
+        out = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    xd, od, wd = desc(x), desc(out), desc(weight)
+    _lib.check(_lib.lib().omx_fast_rms_norm(ref(od), ref(xd), ref(wd), float(eps), stream_ptr(stream)))
+    return out
+
+
 def rope(array, dimensions, traditional, base, scale, offset, freqs=None, stream=None, out=None):
     """fast::rope (mlx-rs/src/fast.rs:15-46).  `offset` may be an int or an int32 CUDA scalar tensor
     (mlx_fast_rope_dynamic); in the latter case pass `max_position` via `rope_dynamic`."""

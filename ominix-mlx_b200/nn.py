@@ -44,3 +44,18 @@ class RopeBuilder:
 
     def build(self):
         return Rope(**self._d)
+
+
+class RmsNorm:
+    """nn::RmsNorm {weight [dims], eps = 1e-5} (mlx-rs/src/nn/normalization.rs:209-270): forward = fast::rms_norm."""
+
+    DEFAULT_EPS = 1e-5
+
+    def __init__(self, weight, eps=DEFAULT_EPS):
+        self.weight = weight
+        self.eps = float(eps)
+
+    def forward(self, x, stream=None):
+        return fast.rms_norm(x, self.weight, self.eps, stream)
+
+    __call__ = forward

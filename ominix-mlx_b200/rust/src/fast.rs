@@ -46,6 +46,18 @@ pub fn rope<'a>(
     rope_device(array, dimensions, traditional, base, scale, offset, freqs, Stream::default())
 }
 
+/// fast.rs:163-180: RMS normalisation over the last axis (`weight`: `[D]` in `x`'s dtype).
+pub fn rms_norm_device(x: impl AsRef<Array>, weight: impl AsRef<Array>, eps: f32, stream: Stream) -> Result<Array> {
+    let x = x.as_ref();
+    let out = Array::empty(x.shape(), x.dtype())?;
+    check(unsafe { ffi::omx_fast_rms_norm(out.as_ptr(), x.as_ptr(), weight.as_ref().as_ptr(), eps, stream.0) })?;
+    Ok(out)
+}
+
+pub fn rms_norm(x: impl AsRef<Array>, weight: impl AsRef<Array>, eps: f32) -> Result<Array> {
+    rms_norm_device(x, weight, eps, Stream::default())
+}
+
 /// fast.rs:53-62.
 #[derive(Debug, Clone)]
 pub enum ScaledDotProductAttentionMask<'a> {

@@ -60,6 +60,8 @@ extern "C" {
     pub fn omx_version() -> c_int;
     pub fn omx_device_check(sm: *mut c_int) -> c_int;
 
+    pub fn omx_fast_rms_norm(out: *const omx_array, x: *const omx_array, weight: *const omx_array, eps: f32,
+                             s: omx_stream) -> c_int;
     pub fn omx_fast_rope(out: *const omx_array, x: *const omx_array, dims: c_int, traditional: bool,
                          base: omx_optional_float, scale: f32, offset: c_int, freqs: *const omx_array,
                          s: omx_stream) -> c_int;
@@ -94,6 +96,13 @@ extern "C" {
                                  traditional: bool, base: omx_optional_float, rope_scale: f32,
                                  freqs: *const omx_array, sm_scale: f32, keys_out: *mut omx_array,
                                  values_out: *mut omx_array, s: omx_stream) -> c_int;
+    pub fn omx_attn_decode_fused_norm(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                      v_new: *const omx_array, cache: omx_kv_cache,
+                                      q_norm_weight: *const omx_array, k_norm_weight: *const omx_array,
+                                      norm_eps: f32, rope_dims: c_int, traditional: bool,
+                                      base: omx_optional_float, rope_scale: f32, freqs: *const omx_array,
+                                      sm_scale: f32, keys_out: *mut omx_array, values_out: *mut omx_array,
+                                      s: omx_stream) -> c_int;
     pub fn omx_attn_decode_fused_sharded(out_full: *const omx_array, q: *const omx_array,
                                          k_new: *const omx_array, v_new: *const omx_array,
                                          cache: omx_kv_cache, rope_dims: c_int, traditional: bool,

@@ -189,6 +189,44 @@ void omx_oracle_rope(const void* x, void* out, int dt, int B, int N, int T,
   free(s);
 }
 
+/* ---- rms_norm -------------------------------------------------------------- */
+
+/*
+ * fast::rms_norm CPU fallback graph (MLX v0.30.1 mlx/fast.cpp, reached from
+ * mlx-c fast.cpp via mlx_fast_rms_norm, fast.h:163-168; Rust entry
+ * mlx-rs/src/fast.rs:163-180; callers: q_norm / k_norm per head,
+ * qwen3-mlx/src/model.rs:172-181):
+ *   xf  = astype(x, float32)
+ *   m   = mean(square(xf), -1, keepdims) = sum(xf*xf) * float32(1/D)
+ *         (ops.cpp mean: multiply(sum, 1/n); the contiguous CPU reduce walks
+ *          the row left to right -- on x86 simd::max_size is 1, base_simd.h)
+ *   n   = xf * rsqrt(m + eps)          rsqrt = 1.0f / sqrtf(.) on the CPU backend
+ *   y   = astype(n, dtype)
+ *   out = weight * y                   (in dtype; skipped without a weight)
+ * x [rows, D] contiguous, weight [D] in the same dtype or NULL.
+ */
+void omx_oracle_rms_norm(const void* x, const void* w, void* out, int dt,
+                         long rows, int D, float eps) {
+  const float inv_n = 1.0f / (float)D;
+#pragma omp parallel for schedule(static)
+  for (long r = 0; r < rows; ++r) {
+    size_t o = (size_t)r * D;
+    float acc = 0.0f;
+    for (int d = 0; d < D; ++d) {
+      float v = ld(x, dt, o + d);
+      float sq = v * v;
+      acc = acc + sq;
+    }
+    float m = acc * inv_n;
+    float rs = 1.0f / sqrtf(m + eps);
+    for (int d = 0; d < D; ++d) {
+      float y = rnd(ld(x, dt, o + d) * rs, dt);
+      if (w) y = ld(w, dt, (size_t)d) * y;
+      st(out, dt, o + d, y);
+    }
+  }
+}
+
 /* ---- scaled_dot_product_attention ---------------------------------------- */
 
 enum { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_BOOL = 2, MASK_ADD = 3 };

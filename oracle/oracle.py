@@ -134,6 +134,21 @@ def rope(x, dims, traditional, base, scale, offset, freqs=None, dtype="f32"):
     return out
 
 
+# -------------------------------------------------------------------- rms_norm
+
+def rms_norm(x, weight, eps, dtype="f32"):
+    """mlx_rs::fast::rms_norm (mlx-rs/src/fast.rs:163-180) over the last axis; weight [D] or None."""
+    x = _c(x, dtype)
+    D = x.shape[-1]
+    out = np.empty_like(x)
+    w = None if weight is None else _c(weight, dtype)
+    if w is not None and w.shape != (D,):
+        raise ValueError("[rms_norm] weight must be one-dimensional with the size of the last axis of x")
+    lib().omx_oracle_rms_norm(_ptr(x), None if w is None else _ptr(w), _ptr(out), ctypes.c_int(DT[dtype]),
+                              ctypes.c_long(x.size // D if D else 0), ctypes.c_int(D), ctypes.c_float(eps))
+    return out
+
+
 # ------------------------------------------------------------------------ sdpa
 
 def _mask_args(mask, B, Hq, Lq, Lk, dtype):

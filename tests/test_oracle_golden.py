@@ -36,6 +36,36 @@ def test_reference_rope_golden_vector():
     assert abs(float(alt.sum(dtype=np.float64)) - 116.80096435546875) > 0.1
 
 
+# --- reference golden vector: mlx-rs/src/fast.rs:253-274 (seed 103, uniform(0,1,[2,8,16]), weight = ones, eps 1e-5)
+
+def test_reference_rms_norm_golden_vector():
+    a = mlx_random.uniform_f32(mlx_random.RandomState(103), (2, 8, 16))
+    out = orc.rms_norm(a, np.ones(16, np.float32), 1e-5, dtype="f32")
+    assert out.shape == (2, 8, 16) and out.dtype == np.float32
+    assert abs(float(out.mean(dtype=np.float64)) - 0.87293875) < 5e-7   # reference tolerance: 1.7e-2
+    assert abs(float(out.sum(dtype=np.float64)) - 223.47232) < 1e-4     # reference tolerance: 4.5
+    x64 = a.astype(np.float64)
+    np.testing.assert_allclose(out, x64 / np.sqrt((x64 ** 2).mean(-1, keepdims=True) + 1e-5), rtol=3e-7)
+
+
+def test_rms_norm_weight_and_16bit_rounding_chain():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 5, 128)).astype(np.float32)
+    w = rng.standard_normal(128).astype(np.float32)
+    o = orc.rms_norm(x, w, 1e-6, dtype="f32")
+    x64 = x.astype(np.float64)
+    np.testing.assert_allclose(o, w * (x64 / np.sqrt((x64 ** 2).mean(-1, keepdims=True) + 1e-6)), rtol=2e-6, atol=1e-6)
+    np.testing.assert_array_equal(orc.rms_norm(x, None, 1e-6, dtype="f32"),
+                                  orc.rms_norm(x, np.ones(128, np.float32), 1e-6, dtype="f32"))
+    # bf16: normalised value is rounded to bf16 BEFORE the weight multiply (astype, then multiply)
+    xb, wb = orc.f32_to_bf16_bits(x), orc.f32_to_bf16_bits(w)
+    ob = orc.bf16_bits_to_f32(orc.rms_norm(xb, wb, 1e-6, dtype="bf16"))
+    xf, wf = orc.bf16_bits_to_f32(xb).astype(np.float64), orc.bf16_bits_to_f32(wb).astype(np.float64)
+    y = orc.bf16_bits_to_f32(orc.f32_to_bf16_bits((xf / np.sqrt((xf ** 2).mean(-1, keepdims=True) + 1e-6)).astype(np.float32)))
+    want = orc.bf16_bits_to_f32(orc.f32_to_bf16_bits((wf * y).astype(np.float32)))
+    assert (ob != want).mean() < 0.01  # identical except where the f32 sum order flips a bf16 rounding
+
+
 def test_rope_tail_copied_and_norm_preserved():
     rng = np.random.default_rng(0)
     x = rng.standard_normal((2, 3, 5, 16)).astype(np.float32)
