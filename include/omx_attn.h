@@ -193,6 +193,23 @@ int omx_attn_decode_fused_norm(const omx_array* out, const omx_array* q, const o
                                const omx_array* freqs /* may be null */, float sm_scale,
                                omx_array* keys_out, omx_array* values_out, omx_stream s);
 
+/*
+ * The prefill spelling of the same composite (L >= 1 new tokens; Attention::forward with L > 1,
+ * qwen3-mlx/src/model.rs:172-212): k' = rope(norm(k_new)) is written straight into the cache rows
+ * [offset, offset+L) (no intermediate k' array, no second copy), v_new is copied into its rows, q' goes
+ * to library scratch, then attention over the fetched K/V with the caller's mask rule
+ * (mask_mode / mask_arr exactly as omx_fast_scaled_dot_product_attention: "causal", a bool array from
+ * create_causal_mask, an additive array, or none).  Cache bits = the unfused op chain's.
+ */
+int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                           const omx_array* v_new, omx_kv_cache cache,
+                           const omx_array* q_norm_weight /* may be null */,
+                           const omx_array* k_norm_weight /* may be null */, float norm_eps,
+                           int rope_dims, bool traditional, omx_optional_float base, float rope_scale,
+                           const omx_array* freqs /* may be null */, float sm_scale,
+                           const char* mask_mode, const omx_array* mask_arr /* may be null */,
+                           omx_array* keys_out, omx_array* values_out, omx_stream s);
+
 /* ---- head-sharded single-sequence decode (BASELINE C5) -------------------- */
 /*
  * The reference has no multi-device path (MLX is single-GPU); this is the exchange step the

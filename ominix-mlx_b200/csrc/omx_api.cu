@@ -53,7 +53,7 @@ struct Scratch {
   size_t bytes = 0;
 };
 std::mutex g_ws_mu;
-std::map<std::pair<int, cudaStream_t>, Scratch> g_ws, g_ctr;
+std::map<std::pair<int, cudaStream_t>, Scratch> g_ws, g_ws_outer, g_ctr;
 
 void* grow(std::map<std::pair<int, cudaStream_t>, Scratch>& pool, size_t bytes, cudaStream_t stream,
            size_t min_bytes) {
@@ -81,6 +81,7 @@ void note_launch(const char* family) { t_last_kernel = family; }
 void count_launch() { ++t_launches; }
 
 void* get_workspace(size_t bytes, cudaStream_t stream) { return grow(g_ws, bytes, stream, 1 << 20); }
+void* get_outer_workspace(size_t bytes, cudaStream_t stream) { return grow(g_ws_outer, bytes, stream, 1 << 20); }
 int* get_counters(size_t count, cudaStream_t stream) {
   return (int*)grow(g_ctr, count * sizeof(int), stream, 1 << 16);
 }
@@ -526,6 +527,81 @@ int omx_attn_decode_fused_norm(const omx_array* out, const omx_array* q, const o
   return guarded([&] {
     decode_fused_impl(out, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs, sm_scale,
                       keys_out, values_out, nullptr, 0, (cudaStream_t)s, q_norm_weight, k_norm_weight, norm_eps);
+  });
+}
+
+int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                           const omx_array* v_new, omx_kv_cache cache, const omx_array* q_norm_weight,
+                           const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,
+                           omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
+                           const char* mask_mode, const omx_array* mask_arr, omx_array* keys_out,
+                           omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    auto* c = (KVCacheImpl*)cache.ctx;
+    OMX_CHECK(c, "[attn_prefill_fused] null cache handle");
+    OMX_CHECK(q && k_new && v_new && out, "[attn_prefill_fused] null array");
+    OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4,
+              "[attn_prefill_fused] q, k_new, v_new, out must be [B, H, L, D]");
+    OMX_CHECK(k_new->dtype == q->dtype && v_new->dtype == q->dtype, "[attn_prefill_fused] dtype mismatch");
+    OMX_CHECK(q->shape[2] == k_new->shape[2] && q->shape[2] == v_new->shape[2],
+              "[attn_prefill_fused] q, k_new, v_new must carry the same number of new tokens");
+    const int D = (int)q->shape[3];
+    const int64_t L = q->shape[2];
+    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
+    const bool qn = q_norm_weight && q_norm_weight->data, kn = k_norm_weight && k_norm_weight->data;
+    const int position = kv_cache_offset(c);
+    // cache bookkeeping by the reference rule; the rows are written below, straight into the cache
+    omx_array kview, vview;
+    kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
+    if (keys_out) *keys_out = kview;
+    if (values_out) *values_out = vview;
+    if ((int64_t)q->shape[0] * L == 0) return;
+    auto rows = [&](const omx_array& view) {  // rows [position, position + L) of a fetched view
+      omx_array r = view;
+      r.shape[2] = L;
+      r.data = (char*)view.data + (size_t)position * view.strides[2] * dtype_size(view.dtype);
+      return r;
+    };
+    omx_array krows = rows(kview), vrows = rows(vview);
+    const size_t es = dtype_size(q->dtype);
+    const size_t qbytes = ((size_t)q->shape[0] * q->shape[1] * L * D * es + 255) & ~(size_t)255;
+    const size_t kbytes = ((size_t)k_new->shape[0] * k_new->shape[1] * L * D * es + 255) & ~(size_t)255;
+    char* ws = (char*)get_outer_workspace(qbytes + (kn && rope_dims > 0 ? kbytes : 0), stream);
+    auto dense = [&](const omx_array* like, char* mem) {
+      omx_array t = *like;
+      t.data = mem;
+      t.strides[3] = 1;
+      t.strides[2] = D;
+      t.strides[1] = L * D;
+      t.strides[0] = like->shape[1] * L * D;
+      return t;
+    };
+    // k: (norm) -> rope -> cache rows; v: copy -> cache rows; q: (norm) -> rope -> scratch
+    if (kn && rope_dims > 0) {
+      omx_array kt = dense(k_new, ws + qbytes);
+      rms_norm_forward(&kt, k_new, k_norm_weight, norm_eps, stream);
+      rope_forward(&krows, &kt, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+    } else if (kn) {
+      rms_norm_forward(&krows, k_new, k_norm_weight, norm_eps, stream);
+    } else if (rope_dims > 0) {
+      rope_forward(&krows, k_new, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+    } else {
+      copy4d(&krows, k_new, stream);
+    }
+    copy4d(&vrows, v_new, stream);
+    const omx_array* qa = q;
+    omx_array qt;
+    if (qn || rope_dims > 0) {
+      qt = dense(q, ws);
+      if (qn) rms_norm_forward(&qt, q, q_norm_weight, norm_eps, stream);
+      if (rope_dims > 0)
+        rope_forward(&qt, qn ? &qt : q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
+      qa = &qt;
+    }
+    SdpaArgs a = make_sdpa_args(out, qa, &kview, &vview, sm_scale, mask_mode, mask_arr, nullptr);
+    dispatch_sdpa(a, stream);
   });
 }
 

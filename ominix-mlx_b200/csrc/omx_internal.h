@@ -49,6 +49,8 @@ void copy4d(const omx_array* dst, const omx_array* src, cudaStream_t stream);
 // ---- workspace (omx_api.cu) ----
 // Per-(device, stream) scratch that only grows; zero-initialised on (re)allocation.
 void* get_workspace(size_t bytes, cudaStream_t stream);
+// Scratch of the composite entry points (kept apart from the kernels' own workspace above).
+void* get_outer_workspace(size_t bytes, cudaStream_t stream);
 // A second, separately zero-initialised region for self-resetting arrival counters.
 int* get_counters(size_t count, cudaStream_t stream);
 int sm_count();

@@ -103,6 +103,13 @@ extern "C" {
                                       base: omx_optional_float, rope_scale: f32, freqs: *const omx_array,
                                       sm_scale: f32, keys_out: *mut omx_array, values_out: *mut omx_array,
                                       s: omx_stream) -> c_int;
+    pub fn omx_attn_prefill_fused(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                  v_new: *const omx_array, cache: omx_kv_cache, q_norm_weight: *const omx_array,
+                                  k_norm_weight: *const omx_array, norm_eps: f32, rope_dims: c_int,
+                                  traditional: bool, base: omx_optional_float, rope_scale: f32,
+                                  freqs: *const omx_array, sm_scale: f32, mask_mode: *const c_char,
+                                  mask_arr: *const omx_array, keys_out: *mut omx_array,
+                                  values_out: *mut omx_array, s: omx_stream) -> c_int;
     pub fn omx_attn_decode_fused_sharded(out_full: *const omx_array, q: *const omx_array,
                                          k_new: *const omx_array, v_new: *const omx_array,
                                          cache: omx_kv_cache, rope_dims: c_int, traditional: bool,
