@@ -59,6 +59,8 @@ struct FmhaParams {
   int64_t tms[2];      // batch, head strides of tmap (0 on broadcast axes)
   int n_kt;
   float inv_scale;
+  // work items (256 query rows of one (batch, q head)), walked by persistent CTAs
+  int n_mblk, n_items;
 };
 
 constexpr int kMaxSteps = 896;  // KV tiles a CTA of an array-mask launch can visit (static smem budget)
@@ -219,6 +221,7 @@ struct Pack2<__half> {
 
 struct SharedCtl {
   uint64_t q_full[2];
+  uint64_t q_empty[2];  // last QK of the work item has read Q_i: the producer may load the next item's Q_i
   uint64_t kv_full[kSlots];
   uint64_t kv_empty[kSlots];
   uint64_t s_full[2];
@@ -251,29 +254,51 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role index
-  const int m_blk = p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;  // heavy tiles first
-  const int hq = blockIdx.y, b = blockIdx.z;
-  const int hk = hq / (p.Hq / p.Hkv);
-  const int m0 = m_blk * 2 * BM;
 
-  // number of KV tiles each Q tile visits
-  int n[2];
+  // ---- work items.  A CTA is persistent: it walks items z_0, z_1, ... of the list ordered
+  // (batch, q head, query block) -- query blocks fastest, heaviest first under a causal mask, so the
+  // CTAs running at any moment share K/V tiles in L2 -- in snake order over the grid, which balances
+  // the static partition to ~1 % without any communication (C3: max/mean load 1.012); every role
+  // derives the same sequence on its own.  While
+  // the softmax warps run item k's epilogue, the producer is already loading item k+1's Q / K / V
+  // and the MMA warp issues its first QK.  (Array-mask launches use one item per CTA.)
+  struct Item {
+    int m_blk, hq, b, hk, m0, n[2], N;
+  };
+  auto item_index = [&](int r) {  // r-th item of this CTA, or -1
+    const int G = (int)gridDim.x;
+    const int z = r * G + ((r & 1) ? G - 1 - (int)blockIdx.x : (int)blockIdx.x);
+    return z < p.n_items ? z : -1;
+  };
+  auto decode_item = [&](int z, int n_steps_arr) {
+    Item it;
+    const int mz = z % p.n_mblk, rem = z / p.n_mblk;
+    it.m_blk = p.causal ? p.n_mblk - 1 - mz : mz;
+    it.hq = rem % p.Hq;
+    it.b = rem / p.Hq;
+    it.hk = it.hq / (p.Hq / p.Hkv);
+    it.m0 = it.m_blk * 2 * BM;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r0 = m0 + i * BM;
-    if (r0 >= p.Lq) {
-      n[i] = 0;
-    } else {
-      const int r1 = min(p.Lq, r0 + BM);
-      const int kmax = p.causal ? min(p.Lk, p.q_off + r1) : p.Lk;
-      n[i] = (kmax + BN - 1) / BN;
+    for (int i = 0; i < 2; ++i) {
+      const int r0 = it.m0 + i * BM;
+      if (r0 >= p.Lq) {
+        it.n[i] = 0;
+      } else if (kArr) {
+        it.n[i] = n_steps_arr;
+      } else {
+        const int r1 = min(p.Lq, r0 + BM);
+        const int kmax = p.causal ? min(p.Lk, p.q_off + r1) : p.Lk;
+        it.n[i] = (kmax + BN - 1) / BN;
+      }
     }
-  }
-  int N = max(n[0], n[1]);
+    it.N = max(it.n[0], it.n[1]);
+    return it;
+  };
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&ctl.q_full[i], 1);
+      mbar_init(&ctl.q_empty[i], 1);
       mbar_init(&ctl.s_full[i], 1);
       mbar_init(&ctl.p_full[i], BM);
       mbar_init(&ctl.p_full2[i], BM);
@@ -290,10 +315,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (kArr && warp == 10) {
-    // step list: KV tiles with at least one visible element for either Q tile of this CTA
-    const int t0 = m_blk * 2;
-    const uint8_t* r0 = p.tmap + b * p.tms[0] + hq * p.tms[1] + (int64_t)t0 * p.n_kt;
-    const bool has1 = n[1] > 0;
+    // step list: KV tiles with at least one visible element for either Q tile of this CTA's item
+    const Item it = decode_item((int)blockIdx.x, 1);
+    const int t0 = it.m_blk * 2;
+    const uint8_t* r0 = p.tmap + it.b * p.tms[0] + it.hq * p.tms[1] + (int64_t)t0 * p.n_kt;
+    const bool has1 = it.n[1] > 0;
     int cnt = 0;
     for (int base = 0; base < p.n_kt; base += 32) {
       const int jt = base + lane;
@@ -316,11 +342,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, ctl.tmem_base, 0);  // warp-uniform for the UTCHMMA operands
-  if (kArr) {
-    N = __shfl_sync(0xffffffffu, ctl.n_steps, 0);
-    n[0] = n[0] > 0 ? N : 0;
-    n[1] = n[1] > 0 ? N : 0;
-  }
+  const int n_steps_arr = kArr ? __shfl_sync(0xffffffffu, ctl.n_steps, 0) : 0;
 
   if (warp == 8) {
     // =========================================================== TMA producer
@@ -331,21 +353,31 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_prefetch_desc(&tmV);
       const uint64_t pol_q = policy_evict_first();
       const uint64_t pol_kv = policy_evict_last();  // K/V are re-read by the other q heads / m-blocks
-      for (int i = 0; i < 2; ++i) {
-        if (n[i] == 0) continue;
-        mbar_expect_tx(&ctl.q_full[i], kTileBytes);
-        tma_load_4d(q_s + i * kTileBytes, &tmQ, &ctl.q_full[i], 0, m0 + i * BM, hq, b, pol_q);
-        tma_load_4d(q_s + i * kTileBytes + kBoxBytes, &tmQ, &ctl.q_full[i], 64, m0 + i * BM, hq, b, pol_q);
-      }
-      for (int seq = 0; seq < 2 * N; ++seq) {
-        const int slot = seq % kSlots, use = seq / kSlots;
-        if (use > 0) mbar_wait_wd(&ctl.kv_empty[slot], (use - 1) & 1);
-        const int j = kArr ? (jlist[seq >> 1] & 0xfff) : (seq >> 1);
-        const CUtensorMap* tm = (seq & 1) ? &tmV : &tmK;
-        uint8_t* dst = kv_s + slot * kTileBytes;
-        mbar_expect_tx(&ctl.kv_full[slot], kTileBytes);
-        tma_load_4d(dst, tm, &ctl.kv_full[slot], 0, j * BN, hk, b, pol_kv);
-        tma_load_4d(dst + kBoxBytes, tm, &ctl.kv_full[slot], 64, j * BN, hk, b, pol_kv);
+      int seq = 0;  // running position in the K/V ring across items
+      for (int r = 0;; ++r) {
+        const int z = item_index(r);
+        if (z < 0) break;
+        const Item it = decode_item(z, n_steps_arr);
+        for (int i = 0; i < 2; ++i) {
+          if (r > 0) mbar_wait_wd(&ctl.q_empty[i], (r - 1) & 1);
+          if (it.n[i] == 0) {
+            mbar_arrive(&ctl.q_full[i]);
+            continue;
+          }
+          mbar_expect_tx(&ctl.q_full[i], kTileBytes);
+          tma_load_4d(q_s + i * kTileBytes, &tmQ, &ctl.q_full[i], 0, it.m0 + i * BM, it.hq, it.b, pol_q);
+          tma_load_4d(q_s + i * kTileBytes + kBoxBytes, &tmQ, &ctl.q_full[i], 64, it.m0 + i * BM, it.hq, it.b, pol_q);
+        }
+        for (int t = 0; t < 2 * it.N; ++t, ++seq) {
+          const int slot = seq % kSlots, use = seq / kSlots;
+          if (use > 0) mbar_wait_wd(&ctl.kv_empty[slot], (use - 1) & 1);
+          const int j = kArr ? (jlist[t >> 1] & 0xfff) : (t >> 1);
+          const CUtensorMap* tm = (t & 1) ? &tmV : &tmK;
+          uint8_t* dst = kv_s + slot * kTileBytes;
+          mbar_expect_tx(&ctl.kv_full[slot], kTileBytes);
+          tma_load_4d(dst, tm, &ctl.kv_full[slot], 0, j * BN, it.hk, it.b, pol_kv);
+          tma_load_4d(dst + kBoxBytes, tm, &ctl.kv_full[slot], 64, j * BN, it.hk, it.b, pol_kv);
+        }
       }
     }
     __syncwarp();
@@ -357,107 +389,135 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // UTCHMMA in a divergence loop with the descriptor rebuilt from scratch: ~90 cycles per
     // 64-cycle MMA, i.e. the tensor pipe could not exceed ~70 %.)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));
-    if (N > 0) {
-      constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
-      constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
-      constexpr uint32_t kTile16 = kTileBytes >> 4, kBox16 = kBoxBytes >> 4;
-      constexpr bool kSplit = kSplitKeys > 0;
-      // descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (smem < 256 KB)
-      const uint64_t q_desc = umma_desc(smem_u32(q_s), 16, 1024);             // K-major
-      const uint64_t k_desc0 = umma_desc(smem_u32(kv_s), 16, 1024);           // K-major
-      const uint64_t v_desc0 = umma_desc(smem_u32(kv_s), kBoxBytes, 1024);    // MN-major
-      auto wait_kv = [&](int seq) { mbar_wait_wd(&ctl.kv_full[seq % kSlots], (seq / kSlots) & 1); };
-      auto slot16 = [&](int seq) { return (uint64_t)((uint32_t)(seq % kSlots) * kTile16); };
-      // S_i = Q_i K^T : 2 feature blocks x 4 k-steps of 16
-      auto mma_qk = [&](int i, uint64_t k_desc) {
-        const uint64_t qa = q_desc + (uint64_t)(i * kTile16);
+    constexpr uint32_t idesc_qk = umma_idesc(Pack2<T>::fmt, 0, BM, BN);
+    constexpr uint32_t idesc_pv = umma_idesc(Pack2<T>::fmt, 1, BM, HD);
+    constexpr uint32_t kTile16 = kTileBytes >> 4, kBox16 = kBoxBytes >> 4;
+    constexpr bool kSplit = kSplitKeys > 0;
+    // descriptors advance by adding (bytes >> 4) to the 14-bit start-address field (smem < 256 KB)
+    const uint64_t q_desc = umma_desc(smem_u32(q_s), 16, 1024);             // K-major
+    const uint64_t k_desc0 = umma_desc(smem_u32(kv_s), 16, 1024);           // K-major
+    const uint64_t v_desc0 = umma_desc(smem_u32(kv_s), kBoxBytes, 1024);    // MN-major
+    auto wait_kv = [&](int seq) { mbar_wait_wd(&ctl.kv_full[seq % kSlots], (seq / kSlots) & 1); };
+    auto slot16 = [&](int seq) { return (uint64_t)((uint32_t)(seq % kSlots) * kTile16); };
+    // S_i = Q_i K^T : 2 feature blocks x 4 k-steps of 16
+    auto mma_qk = [&](int i, uint64_t k_desc) {
+      const uint64_t qa = q_desc + (uint64_t)(i * kTile16);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t off = kb * kBox16 + ks * 2;
-            umma_ss(tmem + i * 128, qa + off, k_desc + off, idesc_qk, (kb | ks) ? 1u : 0u);
-          }
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t off = kb * kBox16 + ks * 2;
+          umma_ss(tmem + i * 128, qa + off, k_desc + off, idesc_qk, (kb | ks) ? 1u : 0u);
         }
-      };
-      // O_i += P_i V : A = P_i in TMEM (16 keys = 8 columns per k-step), B = V MN-major
-      auto mma_pv = [&](int i, uint64_t v_desc, bool first, int ks0, int ks1) {
-#pragma unroll
-        for (int ks = ks0; ks < ks1; ++ks) {
-          umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, v_desc + (uint64_t)(ks * (2048 >> 4)), idesc_pv,
-                  (first && ks == 0) ? 0u : 1u);
-        }
-      };
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-        if (n[i] > 0) mbar_wait_wd(&ctl.q_full[i], 0);
-      wait_kv(0);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (n[i] > 0) {
-            mma_qk(i, k_desc0 + slot16(0));
-            tc_commit(&ctl.s_full[i]);
-          }
-        }
-        tc_commit(&ctl.kv_empty[0]);
       }
-      __syncwarp();
-      for (int j = 0; j < N; ++j) {
-        wait_kv(2 * j + 1);  // V_j
-        if (j + 1 < N) wait_kv(2 * j + 2);  // K_{j+1}: in flight since long (5-slot ring)
-        const uint64_t v_desc = v_desc0 + slot16(2 * j + 1);
-        const uint64_t k_desc = k_desc0 + slot16(2 * j + 2);
+    };
+    // O_i += P_i V : A = P_i in TMEM (16 keys = 8 columns per k-step), B = V MN-major
+    auto mma_pv = [&](int i, uint64_t v_desc, bool first, int ks0, int ks1) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (j >= n[i]) continue;
-          mbar_wait_wd(&ctl.p_full[i], j & 1);
-          tc_fence_after();
-          if (kSplit) {
-            if (elect_one()) mma_pv(i, v_desc, j == 0, 0, kSplitKeys / 16);
-            __syncwarp();
-            mbar_wait_wd(&ctl.p_full2[i], j & 1);
+      for (int ks = ks0; ks < ks1; ++ks) {
+        umma_ts(tmem + 256 + i * 128, tmem + i * 128 + ks * 8, v_desc + (uint64_t)(ks * (2048 >> 4)), idesc_pv,
+                (first && ks == 0) ? 0u : 1u);
+      }
+    };
+    int seq0 = 0;           // ring position of this item's K_0
+    int cp[2] = {0, 0};     // p_full / p_full2 phases consumed per tile
+    for (int r = 0;; ++r) {
+      const int z = item_index(r);
+      if (z < 0) break;
+      const Item it = decode_item(z, n_steps_arr);
+      const int N = it.N;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) mbar_wait_wd(&ctl.q_full[i], r & 1);
+      if (N > 0) {
+        wait_kv(seq0);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (it.n[i] > 0) {
+              mma_qk(i, k_desc0 + slot16(seq0));
+              tc_commit(&ctl.s_full[i]);
+            }
+            if (it.n[i] <= 1) tc_commit(&ctl.q_empty[i]);  // that was this item's only QK for tile i
+          }
+          tc_commit(&ctl.kv_empty[seq0 % kSlots]);
+        }
+        __syncwarp();
+        for (int st = 0; st < N; ++st) {
+          const int sv = seq0 + 2 * st + 1, sk = seq0 + 2 * st + 2;
+          wait_kv(sv);                   // V of this step
+          if (st + 1 < N) wait_kv(sk);   // K of the next step: in flight since long (5-slot ring)
+          const uint64_t v_desc = v_desc0 + slot16(sv);
+          const uint64_t k_desc = k_desc0 + slot16(sk);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (st >= it.n[i]) continue;
+            const bool more = st + 1 < it.n[i];
+            const bool last_qk = st + 2 == it.n[i];
+            mbar_wait_wd(&ctl.p_full[i], cp[i] & 1);
             tc_fence_after();
-            if (elect_one()) {
-              mma_pv(i, v_desc, j == 0, kSplitKeys / 16, 8);
-              if (j + 1 < n[i]) mma_qk(i, k_desc);
-              tc_commit(&ctl.s_full[i]);
+            if (kSplit) {
+              if (elect_one()) mma_pv(i, v_desc, st == 0, 0, kSplitKeys / 16);
+              __syncwarp();
+              mbar_wait_wd(&ctl.p_full2[i], cp[i] & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                mma_pv(i, v_desc, st == 0, kSplitKeys / 16, 8);
+                if (more) mma_qk(i, k_desc);
+                tc_commit(&ctl.s_full[i]);
+                if (last_qk) tc_commit(&ctl.q_empty[i]);
+              }
+            } else {
+              if (elect_one()) {
+                mma_pv(i, v_desc, st == 0, 0, 8);
+                if (more) mma_qk(i, k_desc);
+                tc_commit(&ctl.s_full[i]);
+                if (last_qk) tc_commit(&ctl.q_empty[i]);
+              }
             }
-          } else {
-            if (elect_one()) {
-              mma_pv(i, v_desc, j == 0, 0, 8);
-              if (j + 1 < n[i]) mma_qk(i, k_desc);
-              tc_commit(&ctl.s_full[i]);
-            }
+            __syncwarp();
+            ++cp[i];
+          }
+          if (elect_one()) {
+            tc_commit(&ctl.kv_empty[sv % kSlots]);
+            if (st + 1 < N) tc_commit(&ctl.kv_empty[sk % kSlots]);
           }
           __syncwarp();
         }
+      } else {
         if (elect_one()) {
-          tc_commit(&ctl.kv_empty[(2 * j + 1) % kSlots]);
-          if (j + 1 < N) tc_commit(&ctl.kv_empty[(2 * j + 2) % kSlots]);
+          tc_commit(&ctl.q_empty[0]);
+          tc_commit(&ctl.q_empty[1]);
         }
         __syncwarp();
       }
+      seq0 += 2 * N;
     }
   } else if (warp < 8) {
     // =========================================================== softmax warpgroups
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsSoftmax));
     const int i = warp >> 2;                 // Q tile
     const int row = (warp & 3) * 32 + lane;  // row within the tile == TMEM lane
-    const int qrow = m0 + i * BM + row;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t t_s = tmem + lane_base + i * 128;
     const uint32_t t_o = tmem + lane_base + 256 + i * 128;
-    const int ni = n[i];
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    int cs = 0;  // s_full phases consumed by this tile
+
+    for (int r = 0;; ++r) {
+    const int z = item_index(r);
+    if (z < 0) break;
+    const Item it = decode_item(z, n_steps_arr);
+    const int b = it.b, hq = it.hq;
+    const int qrow = it.m0 + i * BM + row;
+    const int ni = it.n[i];
     float m_run = -INFINITY, l_run = 0.f;
     const int limit = p.causal ? min(p.Lk, p.q_off + qrow + 1) : p.Lk;  // keys [0, limit) are visible
-    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-
     for (int st = 0; st < ni; ++st) {
       const int ent = kArr ? jlist[st] : st;
       const int j = kArr ? (ent & 0xfff) : st;  // KV tile index
-      mbar_wait_wd(&ctl.s_full[i], st & 1);
+      mbar_wait_wd(&ctl.s_full[i], cs & 1);
+      ++cs;
       tc_fence_after();
       const int key0 = j * BN;
       // the whole S row of this thread: 128 fp32 scores, one TMEM round trip
@@ -606,7 +666,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (ni > 0) {
       // final: O_i / l -> global
-      mbar_wait_wd(&ctl.s_full[i], ni & 1);
+      mbar_wait_wd(&ctl.s_full[i], cs & 1);
+      ++cs;
       tc_fence_after();
       const float inv = (kArr && !(l_run > 0.f)) ? 0.f : 1.0f / l_run;  // rows with no visible key -> 0
       T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
@@ -632,6 +693,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int e = 0; e < HD; e += 8) *reinterpret_cast<uint4*>(orow + e) = make_uint4(0u, 0u, 0u, 0u);
     }
+    }  // work items
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsOther));  // idle warps of warpgroup 2
   }
@@ -714,7 +776,15 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   CUtensorMap tmV = make_tmap_4d_b16(a.v->data, HD, a.Lk, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
                                      a.v->strides[0], 64, BN, bf);
   const size_t smem = 1024 + (size_t)(2 + kSlots) * kTileBytes;
-  dim3 grid((a.Lq + 2 * BM - 1) / (2 * BM), a.Hq, a.B);
+  p.n_mblk = (a.Lq + 2 * BM - 1) / (2 * BM);
+  p.n_items = p.n_mblk * a.Hq * a.B;
+  // persistent CTAs (one per SM) walk the work items; array-mask launches keep one item per CTA
+  const bool arr = a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD;
+  static const int persist = [] {  // OMX_FMHA_PERSIST=0: one item per CTA (A/B knob for the bench sweeps)
+    const char* e = getenv("OMX_FMHA_PERSIST");
+    return e ? atoi(e) : 1;
+  }();
+  dim3 grid((arr || !persist) ? p.n_items : std::min(p.n_items, sm_count()));
   auto go = [&](auto kern) {
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
