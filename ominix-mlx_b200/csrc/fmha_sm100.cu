@@ -61,6 +61,7 @@ struct FmhaParams {
   float inv_scale;
   // work items (256 query rows of one (batch, q head)), walked by persistent CTAs
   int n_mblk, n_items;
+  int early_next;  // issue the next item's first QK for tile 0 under the causal tail step
 };
 
 constexpr int kMaxSteps = 896;  // KV tiles a CTA of an array-mask launch can visit (static smem budget)
@@ -421,27 +422,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     int seq0 = 0;           // ring position of this item's K_0
     int cp[2] = {0, 0};     // p_full / p_full2 phases consumed per tile
+    bool early0 = false;    // tile 0's first QK of this item was already issued during the previous item
+    // first QK of an item for tile i (K_0 in ring position sq); returns after issuing, no kv_empty commit
+    auto first_qk = [&](const Item& it, int i, int sq) {
+      if (elect_one()) {
+        if (it.n[i] > 0) {
+          mma_qk(i, k_desc0 + slot16(sq));
+          tc_commit(&ctl.s_full[i]);
+        }
+        if (it.n[i] <= 1) tc_commit(&ctl.q_empty[i]);  // that was this item's only QK for tile i
+      }
+      __syncwarp();
+    };
     for (int r = 0;; ++r) {
       const int z = item_index(r);
       if (z < 0) break;
       const Item it = decode_item(z, n_steps_arr);
       const int N = it.N;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) mbar_wait_wd(&ctl.q_full[i], r & 1);
+      const int zn = item_index(r + 1);
+      if (!early0) mbar_wait_wd(&ctl.q_full[0], r & 1);
+      mbar_wait_wd(&ctl.q_full[1], r & 1);
       if (N > 0) {
         wait_kv(seq0);
         tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (it.n[i] > 0) {
-              mma_qk(i, k_desc0 + slot16(seq0));
-              tc_commit(&ctl.s_full[i]);
-            }
-            if (it.n[i] <= 1) tc_commit(&ctl.q_empty[i]);  // that was this item's only QK for tile i
-          }
-          tc_commit(&ctl.kv_empty[seq0 % kSlots]);
-        }
+        if (!early0) first_qk(it, 0, seq0);
+        first_qk(it, 1, seq0);
+        early0 = false;
+        if (elect_one()) tc_commit(&ctl.kv_empty[seq0 % kSlots]);
         __syncwarp();
         for (int st = 0; st < N; ++st) {
           const int sv = seq0 + 2 * st + 1, sk = seq0 + 2 * st + 2;
@@ -449,6 +456,19 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (st + 1 < N) wait_kv(sk);   // K of the next step: in flight since long (5-slot ring)
           const uint64_t v_desc = v_desc0 + slot16(sv);
           const uint64_t k_desc = k_desc0 + slot16(sk);
+          if (!kArr && p.early_next && st + 1 == N && st >= it.n[0] && zn >= 0) {
+            // causal tail: tile 1 has one more KV tile than tile 0.  Tile 0's half of the machine would
+            // idle through this step, so give it the NEXT item's first QK now (its Q_0 and K_0 are
+            // already in flight): softmax warpgroup 0 runs step 0 of the next item under this step.
+            const Item nx = decode_item(zn, n_steps_arr);
+            if (nx.N > 0) {
+              mbar_wait_wd(&ctl.q_full[0], (r + 1) & 1);
+              wait_kv(seq0 + 2 * N);
+              tc_fence_after();
+              first_qk(nx, 0, seq0 + 2 * N);
+              early0 = true;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             if (st >= it.n[i]) continue;
@@ -784,6 +804,11 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     const char* e = getenv("OMX_FMHA_PERSIST");
     return e ? atoi(e) : 1;
   }();
+  static const int early = [] {  // OMX_FMHA_EARLY=0 disables the causal-tail overlap (A/B knob)
+    const char* e = getenv("OMX_FMHA_EARLY");
+    return e ? atoi(e) : 1;
+  }();
+  p.early_next = early;
   dim3 grid((arr || !persist) ? p.n_items : std::min(p.n_items, sm_count()));
   auto go = [&](auto kern) {
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
