@@ -35,6 +35,7 @@ constexpr int kBoxBytes = 64 * 64 * 2;  // one TMA box: 64 keys x 64 features x 
 constexpr int kStageBytes = 4 * kBoxBytes;  // K lo/hi + V lo/hi
 constexpr int kQPitch = 136;           // padded q row (elements) -> conflict-free fragment loads
 constexpr int kMaxPeers = OMX_MAX_PEERS;
+constexpr int kMaxSplits = 64;         // split-K upper bound (plan_splits), sizes the combine scratch
 
 struct DecodeParams {
   const void* q;
@@ -251,22 +252,42 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   __syncthreads();
   if (*s_ticket != p.num_splits - 1) return;
   __threadfence();
+  // ---- last CTA of this (batch, kv-head): combine the split partials.  Three short phases so that
+  // no thread walks the splits through dependent L2 round trips: (A) all (split, head) running
+  // max / sum pairs -> shared memory, coalesced; (B) one thread per head turns them into weights
+  // 2^(m_s - M) / L; (C) every (head, feature) accumulates its splits with independent loads.
+  float* sm_w = const_cast<float*>(mo);            // [num_splits][rows]  (the merge inputs are dead)
+  float* sm_l = sm_w + kMaxSplits * rows;          // [num_splits][rows]
+  const int64_t e0p = (int64_t)pair * p.num_splits * n_heads;
+  for (int idx = tid; idx < p.num_splits * n_heads; idx += nthr) {
+    const int sp = idx / n_heads, g = idx % n_heads;
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + idx) * 2]));
+    sm_w[sp * rows + g] = ml.x;
+    sm_l[sp * rows + g] = ml.y;
+  }
+  __syncthreads();
+  if (tid < n_heads) {
+    float M = -INFINITY;
+    for (int sp = 0; sp < p.num_splits; ++sp) M = fmaxf(M, sm_w[sp * rows + tid]);
+    float L = 0.f;
+    for (int sp = 0; sp < p.num_splits; ++sp) {
+      const float ms = sm_w[sp * rows + tid];
+      const float sc = ms > -INFINITY ? fast_exp2(ms - M) : 0.f;
+      L = fmaf(sm_l[sp * rows + tid], sc, L);
+      sm_w[sp * rows + tid] = sc;
+    }
+    const float inv = 1.0f / L;
+    for (int sp = 0; sp < p.num_splits; ++sp) sm_w[sp * rows + tid] *= inv;
+  }
+  __syncthreads();
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
     const int g = idx / D, d = idx % D;
-    const int64_t e0 = (int64_t)pair * p.num_splits * n_heads + g;
-    float M = -INFINITY;
-    for (int s = 0; s < p.num_splits; ++s) M = fmaxf(M, __ldcg(&p.ws_ml[(e0 + (int64_t)s * n_heads) * 2]));
-    float L = 0.f, O = 0.f;
-    for (int s = 0; s < p.num_splits; ++s) {
-      const int64_t e = e0 + (int64_t)s * n_heads;
-      const float ms = __ldcg(&p.ws_ml[e * 2]);
-      if (ms > -INFINITY) {
-        const float sc = fast_exp2(ms - M);
-        L = fmaf(__ldcg(&p.ws_ml[e * 2 + 1]), sc, L);
-        O = fmaf(__ldcg(&p.ws_o[e * D + d]), sc, O);
-      }
-    }
-    store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
+    const float* po = p.ws_o + (e0p + g) * D + d;
+    float O = 0.f;
+#pragma unroll 8
+    for (int sp = 0; sp < p.num_splits; ++sp)
+      O = fmaf(__ldcg(po + (int64_t)sp * n_heads * D), sm_w[sp * rows + g], O);
+    store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O);
   }
   if (tid == 0) p.counters[pair] = 0;  // self-reset for the next launch
   peer_signal(p, tid);
@@ -304,13 +325,32 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int my_tiles = max(0, min(p.tiles_per_split, n_tiles - tile_begin));
   const bool has_nt = p.fused && split == p.num_splits - 1;
 
-  if (tid == 0) {
+  // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight BEFORE the
+  // CTA stages q: the K/V stream does not depend on q, and with only a dozen tiles per CTA (single
+  // sequence, many splits) the q round trip would otherwise sit in front of the whole pipeline.
+  uint64_t pol = 0;
+  auto issue = [&](int t) {
+    const int st = t % NSTAGE;
+    uint8_t* sb = stages + st * kStageBytes;
+    const int key0 = (tile_begin + t) * kTile;
+    mbar_expect_tx(&full_bar[st], kStageBytes);
+    tma_load_4d(sb, &tmK, &full_bar[st], 0, key0, hk, b, pol);
+    tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, b, pol);
+    tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, b, pol);
+    tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, b, pol);
+  };
+  const int first = min(my_tiles, NSTAGE);
+  if (tid == NW * 32) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_fence_init();
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    pol = policy_evict_first();
+    for (int t = 0; t < first; ++t) issue(t);
   }
   if (p.q_norm_w || p.k_norm_w) {
     stage_norms<T>(p, s_rs, hk * G, G, b, hk, has_nt, tid);
@@ -328,27 +368,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 
   if (warp == NW) {
-    // ------------------------------------------------ producer warp
-    uint64_t pol = 0;
-    if (lane == 0) {
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      pol = policy_evict_first();
-    }
-    auto issue = [&](int t) {
-      const int st = t % NSTAGE;
-      uint8_t* sb = stages + st * kStageBytes;
-      const int key0 = (tile_begin + t) * kTile;
-      mbar_expect_tx(&full_bar[st], kStageBytes);
-      tma_load_4d(sb, &tmK, &full_bar[st], 0, key0, hk, b, pol);
-      tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, b, pol);
-      tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, b, pol);
-      tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, b, pol);
-    };
-    const int first = min(my_tiles, NSTAGE);
-    if (lane == 0)
-      for (int t = 0; t < first; ++t) issue(t);
-    __syncwarp();
+    // ------------------------------------------------ producer warp (first tiles already in flight)
     if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_rs);
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
@@ -653,33 +673,21 @@ struct SplitPlan {
   int num_splits, tiles_per_split;
 };
 
-// Pick the split count that minimises the makespan (in tiles) of a wave model with `slots`
-// concurrently resident CTAs; every split keeps >= min_tiles tiles when possible.
-SplitPlan plan_splits(int64_t pairs, int n_tiles, int slots, int min_tiles) {
+// Split-K plan.  HBM bandwidth is a chip-wide resource, so what matters is (a) enough CTAs in flight
+// to cover it -- about one per SM, each with >= 96 KB of TMA loads outstanding -- and (b) as little
+// per-CTA overhead (q staging, partial write, combine) as possible.  Measured on B200
+// (gpurun_out/s19_sweep.log): C2 (512 (batch, kv-head) pairs) is fastest with NO split (299 us vs 315 us
+// with 4); C5 (8 pairs) is fastest with one CTA per SM (18 splits: 31 us; 37 splits: 40 us; 9: 33 us).
+SplitPlan plan_splits(int64_t pairs, int n_tiles, int sms, int min_tiles) {
   if (n_tiles <= 0) return {1, 1};
   static const int forced = [] {  // debugging / tuning knob, not an API
     const char* e = getenv("OMX_DECODE_SPLITS");
     return e ? atoi(e) : 0;
   }();
-  if (forced > 0) {
-    const int s = std::min(forced, n_tiles);
-    const int tps = (n_tiles + s - 1) / s;
-    return {(n_tiles + tps - 1) / tps, tps};
-  }
-  int best_s = 1;
-  double best = 1e30;
-  const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), 64));
-  for (int s = 1; s <= max_s; ++s) {
-    const int tps = (n_tiles + s - 1) / s;
-    const int real_s = (n_tiles + tps - 1) / tps;
-    const int64_t waves = (pairs * real_s + slots - 1) / slots;
-    const double cost = (double)waves * (tps + 1.5);  // +1.5 tiles of fixed per-CTA overhead
-    if (cost < best - 1e-9) {
-      best = cost;
-      best_s = real_s;
-    }
-  }
-  const int tps = (n_tiles + best_s - 1) / best_s;
+  int want = forced > 0 ? forced : (pairs >= sms ? 1 : (int)(sms / pairs));
+  const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), kMaxSplits));
+  want = std::max(1, std::min(want, forced > 0 ? std::min(n_tiles, kMaxSplits) : max_s));
+  const int tps = (n_tiles + want - 1) / want;
   return {(n_tiles + tps - 1) / tps, tps};
 }
 
@@ -810,14 +818,17 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   if (use_hmma) {
     // cfg 0: 3 stages x 2 CTAs/SM (default); cfg 1: 6 stages x 1 CTA/SM.  OMX_DECODE_CFG is a
     // tuning knob for the bench sweeps, not an API.
-    static const int cfg = [] {
+    static const int cfg_env = [] {
       const char* e = getenv("OMX_DECODE_CFG");
-      return e ? atoi(e) : 0;
+      return e ? atoi(e) : -1;
     }();
-    const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
-    const int occ = cfg == 1 ? 1 : 2;
     const int64_t pairs = (int64_t)a.B * a.Hkv;
-    SplitPlan sp = plan_splits(pairs, n_tiles, sms * occ, 4);
+    SplitPlan sp = plan_splits(pairs, n_tiles, sms, 4);
+    // a grid that fits one CTA per SM runs the 6-stage / 1-CTA-per-SM variant (deeper TMA pipeline per
+    // CTA: C5 31 us vs 34 us); larger grids the 3-stage / 2-CTA-per-SM one (C2 299 us vs 307 us)
+    const bool deep = cfg_env == 1 || (cfg_env < 0 && pairs * sp.num_splits <= sms);
+    const int cfg = deep ? 1 : 0;
+    const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
     p.num_splits = sp.num_splits;
     p.tiles_per_split = sp.tiles_per_split;
     if (p.num_splits > 1) {
@@ -871,7 +882,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   const int Gt = (p.G % 4 == 0) ? 4 : (p.G % 2 == 0 ? 2 : 1);
   const int groups = p.G / Gt;
   const int64_t pairs = (int64_t)a.B * a.Hkv * groups;
-  SplitPlan sp = plan_splits(pairs, n_tiles, sms * 2, 2);
+  SplitPlan sp = plan_splits(pairs, n_tiles, sms, 2);
   p.num_splits = sp.num_splits;
   p.tiles_per_split = sp.tiles_per_split;
   if (p.num_splits > 1) {
