@@ -220,3 +220,27 @@ def test_full_size_properties_c3():
     want = orc.sdpa(t2n(q[3:4, 8:12], "bf16"), t2n(k[3:4, 2:3], "bf16"), t2n(v[3:4, 2:3], "bf16"), D ** -0.5,
                     "causal", dtype="bf16")
     assert_close(o[3:4, 8:12].float().cpu().numpy(), n2f(want, "bf16"), "bf16", "C3 slice")
+
+
+def test_full_size_properties_c4():
+    # BASELINE C4 at full size (FLUX.2-klein joint attention: B4, 24 heads, 512 txt + 4096 img tokens, bf16)
+    B, H, S, D = 4, 24, 4608, 128
+    g = torch.Generator(device=DEV).manual_seed(1238)
+    # [B, S, H, D] storage viewed [B, H, S, D], the crates' layout (klein_model.rs:465-468)
+    q, k, v = (torch.randn((B, S, H, D), generator=g, device=DEV).bfloat16().transpose(1, 2) for _ in range(3))
+    o = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, None)
+    assert omx.last_kernel() == "fmha_tcgen05" and torch.isfinite(o.float()).all()
+    # (1) non-causal attention does not care about the order of the keys: permute [txt; img] rows of K and V together
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(3)).to(DEV)
+    o_p = omx.fast.scaled_dot_product_attention(q, k[:, :, perm], v[:, :, perm], D ** -0.5, None)
+    assert (o.float() - o_p.float()).abs().max().item() <= 2e-2
+    # (2) a query block's result does not depend on which other query rows ride in the launch
+    o_txt = omx.fast.scaled_dot_product_attention(q[:, :, :512], k, v, D ** -0.5, None)
+    assert torch.equal(o_txt, o[:, :, :512])
+    # (3) convexity: every output lies inside the per-feature range of V
+    vmin, vmax = v.float().amin(2, keepdim=True), v.float().amax(2, keepdim=True)
+    assert bool(((o.float() >= vmin - 1e-2) & (o.float() <= vmax + 1e-2)).all())
+    # (4) two heads of one batch item against the oracle
+    want = orc.sdpa(t2n(q[2:3, 5:7], "bf16"), t2n(k[2:3, 5:7], "bf16"), t2n(v[2:3, 5:7], "bf16"), D ** -0.5, None,
+                    dtype="bf16")
+    assert_close(o[2:3, 5:7].float().cpu().numpy(), n2f(want, "bf16"), "bf16", "C4 slice")
