@@ -221,6 +221,10 @@ def main():
     ap.add_argument("--mask", default="string", choices=["string", "array"],
                     help="c3: pass the causal mask as the \"causal\" mode string or as the bool [T,T] array the LLM "
                          "crates build with create_causal_mask (classified per tile, same tiles skipped)")
+    ap.add_argument("--composite", action="store_true",
+                    help="c3 / c4: time the whole composite entry point (q_norm/k_norm + rope + KV append / [txt;img] "
+                         "concat in ONE prologue launch, then attention) instead of the attention call alone; FLOPs "
+                         "counted are still the attention's")
     ap.add_argument("--rotate", type=int, default=1,
                     help="decode: cycle through R distinct KV caches so a working set smaller than L2 "
                          "is still read from HBM (R x KV bytes should exceed 126 MB)")
@@ -378,6 +382,30 @@ def main():
         def step():
             omx.fast.scaled_dot_product_attention(q, k, v, scale, mask, out=out)
 
+        if args.composite and cfg["causal"]:
+            # Attention::forward for L = S new tokens (qwen3-mlx/src/model.rs:172-212), caller layouts:
+            # projections [B,L,H,D] viewed [B,H,L,D], merged-head output
+            qc, kc, vc = (rn(B, S, h, D).transpose(1, 2) for h in (Hq, Hkv, Hkv))
+            qn = omx.nn.RmsNorm((1 + 0.1 * rn(D).float()).to(tdt), 1e-6)
+            kn_ = omx.nn.RmsNorm((1 + 0.1 * rn(D).float()).to(tdt), 1e-6)
+            rope = omx.nn.Rope(D, False, 1e6, 1.0)
+            pcache = omx.KVCache()
+            merged = torch.empty((B, S, Hq, D), dtype=tdt, device=dev).transpose(1, 2)
+
+            def step():
+                pcache.reset()
+                omx.attn_prefill_fused(qc, kc, vc, pcache, rope, scale, mask, out=merged, q_norm=qn, k_norm=kn_)
+        elif args.composite:
+            # one FLUX.2-klein double-stream block's attention (klein_model.rs:443-489): 512 txt + 4096 img tokens
+            lens = (512, S - 512)
+            qs, ks, vs = ([rn(B, n, h, D) for n in lens] for h in (Hq, Hkv, Hkv))
+            ang = torch.rand((B, S, D // 2), generator=g, device=dev) * 6.28
+            ct, st = ang.cos().to(tdt), ang.sin().to(tdt)
+            nw = [omx.nn.RmsNorm((1 + 0.1 * rn(D).float()).to(tdt), 1e-6) for _ in range(4)]
+
+            def step():
+                omx.dit.attn_fused(qs, ks, vs, scale, cos=ct, sin=st, q_norm=nw[:2], k_norm=nw[2:])
+
         units = B * S
         alg_flops = 4.0 * B * Hq * S * S * D * (0.5 if cfg["causal"] else 1.0)
         alg_bytes = (2 * B * Hq * S * D + 2 * B * Hkv * S * D) * es
@@ -496,7 +524,8 @@ def main():
                        "l2_policy": "working set >> 126 MB L2 (streams from HBM every step)"
                        if alg_bytes * max(1, args.rotate) > 512e6 else "working set fits L2: warm-L2 number",
                        "kernel": kernel, "cuda_graph": bool(args.graph), "rotate_caches": args.rotate,
-                       "mask": args.mask if kind == "prefill" and cfg.get("causal") else None},
+                       "mask": args.mask if kind == "prefill" and cfg.get("causal") else None,
+                       "composite": bool(args.composite) if kind == "prefill" else None},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches_timed,

@@ -16,8 +16,8 @@
  *   omx_concat_kv_cache_*                  <- ConcatKeyValueCache            cache.rs:45-85
  *   omx_attn_decode_fused                  <- the composite Attention::forward decode step
  *        qwen3-mlx/src/model.rs:186-212 (rope(q), rope(k), update_and_fetch, sdpa) in ONE launch
- *   omx_dit_rope / omx_dit_joint_attention <- FLUX.2-klein / Z-Image manual attention
- *        flux-klein-mlx/src/klein_model.rs:124-162,460-483,651-659; zimage-mlx/src/zimage_model.rs:208-235,355-384
+ *   omx_dit_rope / omx_dit_joint_attention / omx_dit_attn_fused <- FLUX.2-klein / Z-Image manual attention
+ *        flux-klein-mlx/src/klein_model.rs:124-162,443-489,641-663; zimage-mlx/src/zimage_model.rs:208-235,345-388
  *   omx_set_error_handler / omx_last_error <- mlx_set_error_handler  mlx-c/mlx/c/error.h
  *
  * Differences from mlx-c that a binding must know:
@@ -250,6 +250,23 @@ int omx_dit_rope(const omx_array* out, const omx_array* x, const omx_array* cos,
 int omx_dit_joint_attention(const omx_array* out, const omx_array* q, const omx_array* k,
                             const omx_array* v, float scale, const omx_array* add_mask,
                             omx_stream s);
+
+/*
+ * One DiT attention block's attention, prologue included (klein_model.rs:443-489 double stream,
+ * :641-663 single stream; zimage_model.rs:345-388): for each of the n_streams (1 or 2; FLUX's
+ * [txt, img] in that order) q_i, k_i, v_i [B,S_i,H,D] are normalised per head (RMSNorm weights
+ * q_norm_weight[i] / k_norm_weight[i], [D]; the list or an entry may be null), rotated with rows
+ * [sum S_<i, ...) of the per-token tables cos / sin [B,S_total,D/2] (null = no rotation) and
+ * concatenated along the sequence -- ONE launch for all of it -- then
+ * out[B,S_total,H,Dv] = softmax(scale q k^T [+ add_mask]) v over the joint sequence (k/v may carry
+ * fewer heads than q: Z-Image's repeat_axis GQA).  The caller slices out[:, :S_0] / out[:, S_0:].
+ */
+int omx_dit_attn_fused(const omx_array* out, int n_streams, const omx_array* const* q,
+                       const omx_array* const* k, const omx_array* const* v,
+                       const omx_array* const* q_norm_weight /* may be null */,
+                       const omx_array* const* k_norm_weight /* may be null */, float norm_eps,
+                       const omx_array* cos /* may be null */, const omx_array* sin /* may be null */,
+                       float scale, const omx_array* add_mask /* may be null */, omx_stream s);
 
 /* ---- introspection (tests / bench) -------------------------------------- */
 /* Name of the kernel family the last successful attention call on this thread dispatched to

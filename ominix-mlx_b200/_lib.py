@@ -82,6 +82,9 @@ _SIGS = {
     "omx_peer_wait": (ctypes.c_int, [ctypes.POINTER(OmxPeerGroup), ctypes.c_uint32, ctypes.c_void_p]),
     "omx_dit_rope": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_void_p]),
     "omx_dit_joint_attention": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_float, _AP, ctypes.c_void_p]),
+    "omx_dit_attn_fused": (ctypes.c_int, [_AP, ctypes.c_int, ctypes.POINTER(_AP), ctypes.POINTER(_AP),
+                                          ctypes.POINTER(_AP), ctypes.POINTER(_AP), ctypes.POINTER(_AP),
+                                          ctypes.c_float, _AP, _AP, ctypes.c_float, _AP, ctypes.c_void_p]),
     "omx_last_kernel": (ctypes.c_char_p, []),
     "omx_launch_count": (ctypes.c_int64, [ctypes.c_bool]),
     "omx_force_kernel": (ctypes.c_int, [ctypes.c_char_p]),

@@ -578,6 +578,42 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
       t.strides[0] = like->shape[1] * L * D;
       return t;
     };
+    // One launch for the whole prologue when the layout allows (prologue.cu): k' -> cache rows,
+    // v -> cache rows, q' -> scratch.  Otherwise the standalone ops below, same results.
+    const bool has_freqs = freqs && freqs->data;
+    bool fused_prologue = false;
+    if (!has_freqs && (rope_dims == 0 || base.has_value)) {
+      PrologueCall pc;
+      pc.dims = rope_dims;
+      pc.traditional = traditional;
+      pc.mode = 1;
+      pc.eps = norm_eps;
+      if (rope_dims > 0)
+        pc.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, position + (int)L, stream);
+      int n = 0;
+      omx_array qt0{};
+      if (qn || rope_dims > 0) {
+        qt0 = dense(q, ws);
+        pc.seg[n].x = q; pc.seg[n].out = qt0; pc.seg[n].w = qn ? q_norm_weight : nullptr;
+        pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+      }
+      pc.seg[n].x = k_new; pc.seg[n].out = krows; pc.seg[n].w = kn ? k_norm_weight : nullptr;
+      pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+      const bool v_in = v_new->shape[3] == D;
+      if (v_in) {
+        pc.seg[n].x = v_new; pc.seg[n].out = vrows; pc.seg[n].w = nullptr; pc.seg[n].rope = false; ++n;
+      }
+      pc.nseg = n;
+      note_launch("qkv_prologue");
+      if (qkv_prologue(pc, stream)) {
+        fused_prologue = true;
+        if (!v_in) copy4d(&vrows, v_new, stream);
+        const omx_array* qa = (qn || rope_dims > 0) ? &qt0 : q;
+        SdpaArgs a = make_sdpa_args(out, qa, &kview, &vview, sm_scale, mask_mode, mask_arr, nullptr);
+        dispatch_sdpa(a, stream);
+      }
+    }
+    if (fused_prologue) return;
     // k: (norm) -> rope -> cache rows; v: copy -> cache rows; q: (norm) -> rope -> scratch
     if (kn && rope_dims > 0) {
       omx_array kt = dense(k_new, ws + qbytes);
@@ -634,34 +670,198 @@ int omx_dit_rope(const omx_array* out, const omx_array* x, const omx_array* cos,
   });
 }
 
+// softmax(scale q k^T [+ mask]) v for the DiT callers; an f32 mask with 16-bit inputs goes to the
+// generic kernel (the reference chain promotes there), everything else through the dispatcher.
+static void dit_attention_impl(const omx_array* out, const omx_array* q, const omx_array* k, const omx_array* v,
+                               float scale, const omx_array* add_mask, cudaStream_t stream) {
+  const bool has_mask = add_mask && add_mask->data;
+  if (has_mask)
+    OMX_CHECK(add_mask->dtype == OMX_FLOAT32 || add_mask->dtype == q->dtype,
+              "[dit_joint_attention] add_mask must be float32 or the input dtype");
+  SdpaArgs a{};
+  if (has_mask && add_mask->dtype == OMX_FLOAT32 && q->dtype != OMX_FLOAT32) {
+    a = make_sdpa_args(out, q, k, v, scale, "", nullptr, nullptr);
+    a.mask_mode = MASK_ADD;
+    a.mask = add_mask;
+    const int64_t full[4] = {a.B, a.Hq, a.Lq, a.Lk};
+    const int lead = 4 - add_mask->ndim;
+    OMX_CHECK(add_mask->ndim <= 4, "[dit_joint_attention] mask rank > 4");
+    for (int i = 0; i < 4; ++i) {
+      if (i < lead) { a.mask_strides[i] = 0; continue; }
+      const int64_t n = add_mask->shape[i - lead];
+      OMX_CHECK(n == full[i] || n == 1, "[dit_joint_attention] mask not broadcastable");
+      a.mask_strides[i] = (n == 1 && full[i] != 1) ? 0 : add_mask->strides[i - lead];
+    }
+    sdpa_generic(a, stream);
+    return;
+  }
+  a = make_sdpa_args(out, q, k, v, scale, "", has_mask ? add_mask : nullptr, nullptr);
+  dispatch_sdpa(a, stream);
+}
+
 int omx_dit_joint_attention(const omx_array* out, const omx_array* q, const omx_array* k, const omx_array* v,
                             float scale, const omx_array* add_mask, omx_stream s) {
   return guarded([&] {
     require_device();
-    const bool has_mask = add_mask && add_mask->data;
-    if (has_mask)
-      OMX_CHECK(add_mask->dtype == OMX_FLOAT32 || add_mask->dtype == q->dtype,
-                "[dit_joint_attention] add_mask must be float32 or the input dtype");
-    // same math as sdpa with mask none / additive; the generic kernel takes f32 masks and outputs
-    SdpaArgs a{};
-    if (has_mask && add_mask->dtype == OMX_FLOAT32 && q->dtype != OMX_FLOAT32) {
-      a = make_sdpa_args(out, q, k, v, scale, "", nullptr, nullptr);
-      a.mask_mode = MASK_ADD;
-      a.mask = add_mask;
-      const int64_t full[4] = {a.B, a.Hq, a.Lq, a.Lk};
-      const int lead = 4 - add_mask->ndim;
-      OMX_CHECK(add_mask->ndim <= 4, "[dit_joint_attention] mask rank > 4");
-      for (int i = 0; i < 4; ++i) {
-        if (i < lead) { a.mask_strides[i] = 0; continue; }
-        const int64_t n = add_mask->shape[i - lead];
-        OMX_CHECK(n == full[i] || n == 1, "[dit_joint_attention] mask not broadcastable");
-        a.mask_strides[i] = (n == 1 && full[i] != 1) ? 0 : add_mask->strides[i - lead];
-      }
-      sdpa_generic(a, (cudaStream_t)s);
-      return;
+    dit_attention_impl(out, q, k, v, scale, add_mask, (cudaStream_t)s);
+  });
+}
+
+// [B,S,H,D] storage -> the [B,H,S,D] view the kernels take
+static omx_array bshd_as_bhsd(const omx_array& a) {
+  omx_array t = a;
+  t.shape[1] = a.shape[2]; t.shape[2] = a.shape[1];
+  t.strides[1] = a.strides[2]; t.strides[2] = a.strides[1];
+  return t;
+}
+// rows [t0, t0 + n) along axis 1 of a [B,S,...] array
+static omx_array rows_axis1(const omx_array& a, int64_t t0, int64_t n) {
+  omx_array t = a;
+  t.shape[1] = n;
+  t.data = (char*)a.data + (size_t)t0 * a.strides[1] * dtype_size(a.dtype);
+  return t;
+}
+
+int omx_dit_attn_fused(const omx_array* out, int n_streams, const omx_array* const* q, const omx_array* const* k,
+                       const omx_array* const* v, const omx_array* const* q_norm_weight,
+                       const omx_array* const* k_norm_weight, float norm_eps, const omx_array* cos,
+                       const omx_array* sin, float scale, const omx_array* add_mask, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    OMX_CHECK(n_streams == 1 || n_streams == 2, "[dit_attn_fused] n_streams must be 1 or 2, got %d", n_streams);
+    OMX_CHECK(out && q && k && v, "[dit_attn_fused] null array list");
+    int64_t S = 0;
+    for (int i = 0; i < n_streams; ++i) {
+      OMX_CHECK(q[i] && k[i] && v[i], "[dit_attn_fused] null array in stream %d", i);
+      OMX_CHECK(q[i]->ndim == 4 && k[i]->ndim == 4 && v[i]->ndim == 4, "[dit_attn_fused] q, k, v must be [B,S,H,D]");
+      OMX_CHECK(is_float_dtype(q[i]->dtype) && k[i]->dtype == q[0]->dtype && v[i]->dtype == q[0]->dtype &&
+                    q[i]->dtype == q[0]->dtype,
+                "[dit_attn_fused] q, k, v of all streams must share one floating dtype");
+      OMX_CHECK(q[i]->shape[0] == q[0]->shape[0] && k[i]->shape[0] == q[0]->shape[0] &&
+                    v[i]->shape[0] == q[0]->shape[0],
+                "[dit_attn_fused] mismatching batch dimension");
+      OMX_CHECK(q[i]->shape[1] == k[i]->shape[1] && q[i]->shape[1] == v[i]->shape[1],
+                "[dit_attn_fused] q, k, v of stream %d must have the same number of tokens", i);
+      OMX_CHECK(q[i]->shape[2] == q[0]->shape[2] && k[i]->shape[2] == k[0]->shape[2] &&
+                    v[i]->shape[2] == k[0]->shape[2] && q[i]->shape[3] == q[0]->shape[3] &&
+                    k[i]->shape[3] == q[0]->shape[3] && v[i]->shape[3] == v[0]->shape[3],
+                "[dit_attn_fused] head counts / head dims differ between streams");
+      S += q[i]->shape[1];
     }
-    a = make_sdpa_args(out, q, k, v, scale, "", has_mask ? add_mask : nullptr, nullptr);
-    dispatch_sdpa(a, (cudaStream_t)s);
+    const int dt = q[0]->dtype;
+    const int64_t B = q[0]->shape[0], H = q[0]->shape[2], Hkv = k[0]->shape[2], D = q[0]->shape[3],
+                  Dv = v[0]->shape[3];
+    OMX_CHECK(out->ndim == 4 && out->shape[0] == B && out->shape[1] == S && out->shape[2] == H &&
+                  out->shape[3] == Dv,
+              "[dit_attn_fused] out must be [B, S_total, H, Dv]");
+    const bool has_rope = cos && cos->data && sin && sin->data;
+    int64_t tcs[3] = {0, 0, 0}, tss[3] = {0, 0, 0};
+    if (has_rope) {
+      OMX_CHECK(D % 2 == 0, "[dit_attn_fused] head_dim must be even");
+      auto tbl = [&](const omx_array* a, int64_t st[3], const char* nm) {
+        OMX_CHECK(a->dtype == dt, "[dit_attn_fused] %s must have the q dtype", nm);
+        if (a->ndim == 3) {
+          OMX_CHECK(a->shape[0] == B && a->shape[1] == S && a->shape[2] == D / 2,
+                    "[dit_attn_fused] %s must be [B, S_total, D/2]", nm);
+          st[0] = a->strides[0]; st[1] = a->strides[1]; st[2] = a->strides[2];
+        } else {
+          OMX_CHECK(a->ndim == 4 && a->shape[0] == B && a->shape[1] == S && a->shape[2] == 1 &&
+                        a->shape[3] == D / 2,
+                    "[dit_attn_fused] %s must be [B, S_total, D/2] or [B, S_total, 1, D/2]", nm);
+          st[0] = a->strides[0]; st[1] = a->strides[1]; st[2] = a->strides[3];
+        }
+      };
+      tbl(cos, tcs, "cos");
+      tbl(sin, tss, "sin");
+    }
+    auto wt = [&](const omx_array* const* list, int i) -> const omx_array* {
+      return (list && list[i] && list[i]->data) ? list[i] : nullptr;
+    };
+    bool any_norm = false;
+    for (int i = 0; i < n_streams; ++i) any_norm = any_norm || wt(q_norm_weight, i) || wt(k_norm_weight, i);
+    if (B * S * H == 0) return;
+    // joint [txt; img] buffers (K/V order = the order of the streams, klein_model.rs:461-462)
+    const size_t es = dtype_size(dt);
+    auto al = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const bool in_place_qk = n_streams == 1 && !any_norm && !has_rope;
+    const bool in_place_v = n_streams == 1;
+    const size_t qb = in_place_qk ? 0 : al((size_t)B * S * H * D * es);
+    const size_t kb = in_place_qk ? 0 : al((size_t)B * S * Hkv * D * es);
+    const size_t vb = in_place_v ? 0 : al((size_t)B * S * Hkv * Dv * es);
+    char* ws = (qb + kb + vb) ? (char*)get_outer_workspace(qb + kb + vb, stream) : nullptr;
+    auto dense = [&](char* mem, int64_t heads, int64_t d) {
+      omx_array t{};
+      t.data = mem; t.dtype = dt; t.ndim = 4;
+      t.shape[0] = B; t.shape[1] = S; t.shape[2] = heads; t.shape[3] = d;
+      t.strides[3] = 1; t.strides[2] = d; t.strides[1] = heads * d; t.strides[0] = S * heads * d;
+      return t;
+    };
+    omx_array Qj = in_place_qk ? *q[0] : dense(ws, H, D);
+    omx_array Kj = in_place_qk ? *k[0] : dense(ws + qb, Hkv, D);
+    omx_array Vj = in_place_v ? *v[0] : dense(ws + qb + kb, Hkv, Dv);
+    if (!in_place_qk || !in_place_v) {
+      PrologueCall pc;
+      pc.mode = 2;
+      pc.dims = (int)D;
+      pc.eps = norm_eps;
+      pc.tcos = has_rope ? cos : nullptr;
+      pc.tsin = has_rope ? sin : nullptr;
+      for (int j = 0; j < 3; ++j) { pc.tcs[j] = tcs[j]; pc.tss[j] = tss[j]; }
+      omx_array xin[6];
+      int n = 0;
+      int64_t t0 = 0;
+      for (int i = 0; i < n_streams; ++i) {
+        const int64_t Si = q[i]->shape[1];
+        if (!in_place_qk) {
+          xin[n] = bshd_as_bhsd(*q[i]);
+          pc.seg[n].x = &xin[n]; pc.seg[n].out = bshd_as_bhsd(rows_axis1(Qj, t0, Si));
+          pc.seg[n].w = wt(q_norm_weight, i); pc.seg[n].rope = has_rope; pc.seg[n].tok0 = (int)t0; ++n;
+          xin[n] = bshd_as_bhsd(*k[i]);
+          pc.seg[n].x = &xin[n]; pc.seg[n].out = bshd_as_bhsd(rows_axis1(Kj, t0, Si));
+          pc.seg[n].w = wt(k_norm_weight, i); pc.seg[n].rope = has_rope; pc.seg[n].tok0 = (int)t0; ++n;
+        }
+        if (!in_place_v && Dv == D) {
+          xin[n] = bshd_as_bhsd(*v[i]);
+          pc.seg[n].x = &xin[n]; pc.seg[n].out = bshd_as_bhsd(rows_axis1(Vj, t0, Si));
+          pc.seg[n].w = nullptr; pc.seg[n].rope = false; ++n;
+        }
+        t0 += Si;
+      }
+      pc.nseg = n;
+      note_launch("qkv_prologue");
+      const bool fused = n > 0 && qkv_prologue(pc, stream);
+      t0 = 0;
+      for (int i = 0; i < n_streams; ++i) {  // whatever the one-launch kernel did not cover
+        const int64_t Si = q[i]->shape[1];
+        if (!fused && !in_place_qk) {
+          const omx_array* src[2] = {q[i], k[i]};
+          omx_array dst[2] = {rows_axis1(Qj, t0, Si), rows_axis1(Kj, t0, Si)};
+          const omx_array* w[2] = {wt(q_norm_weight, i), wt(k_norm_weight, i)};
+          for (int j = 0; j < 2; ++j) {
+            const omx_array* cur = src[j];
+            if (w[j]) {
+              rms_norm_forward(&dst[j], cur, w[j], norm_eps, stream);
+              cur = &dst[j];
+            }
+            if (has_rope) {
+              omx_array c = rows_axis1(*cos, t0, Si), sn = rows_axis1(*sin, t0, Si);
+              dit_rope_forward(&dst[j], cur, &c, &sn, stream);
+            } else if (!w[j]) {
+              omx_array d4 = bshd_as_bhsd(dst[j]), s4 = bshd_as_bhsd(*cur);
+              copy4d(&d4, &s4, stream);
+            }
+          }
+        }
+        if (!in_place_v && (!fused || Dv != D)) {
+          omx_array d4 = bshd_as_bhsd(rows_axis1(Vj, t0, Si)), s4 = bshd_as_bhsd(*v[i]);
+          copy4d(&d4, &s4, stream);
+        }
+        t0 += Si;
+      }
+    }
+    omx_array qv = bshd_as_bhsd(Qj), kv = bshd_as_bhsd(Kj), vv = bshd_as_bhsd(Vj), ov = bshd_as_bhsd(*out);
+    dit_attention_impl(&ov, &qv, &kv, &vv, scale, add_mask, stream);
   });
 }
 

@@ -28,6 +28,30 @@ void dit_rope_forward(const omx_array* out, const omx_array* x, const omx_array*
 void rms_norm_forward(const omx_array* out, const omx_array* x, const omx_array* weight, float eps,
                       cudaStream_t stream);
 
+// ---- prologue.cu ----
+// One launch for the row-wise ops in front of the attention kernel: per segment, out = rope(norm(x)).
+struct PrologueSeg {
+  const omx_array* x = nullptr;  // [B,H,L,D] logical view (any leading strides, feature axis contiguous)
+  omx_array out{};               // same shape; may point into the KV cache / a joint buffer
+  const omx_array* w = nullptr;  // RMSNorm weight [D] or null
+  bool rope = false;             // rotate (true) or copy
+  int tok0 = 0;                  // table row of token l == 0
+};
+struct PrologueCall {
+  PrologueSeg seg[6];
+  int nseg = 0;
+  int dims = 0;  // rotated features (mode 1); mode 2 rotates all D
+  bool traditional = false;
+  int mode = 1;  // 1: fast::rope position table; 2: per-token tables in the array dtype (DiT)
+  RopeTableRef table;
+  const omx_array *tcos = nullptr, *tsin = nullptr;  // mode 2
+  int64_t tcs[3] = {0, 0, 0}, tss[3] = {0, 0, 0};    // element strides of (b, token, pair)
+  float eps = 0.f;
+};
+// false: shape / layout outside the kernel's coverage (nothing launched) -- the caller composes the
+// standalone ops instead.
+bool qkv_prologue(const PrologueCall& c, cudaStream_t stream);
+
 // ---- kv_cache.cu ----
 struct KVCacheImpl;
 KVCacheImpl* kv_cache_create(int step, bool concat);

@@ -429,9 +429,32 @@ void dit_rope_forward(const omx_array* out, const omx_array* x, const omx_array*
   tbl(sn, p.ss, "sin");
   const int64_t total = (int64_t)p.B * p.S * p.H * (p.D / 2);
   if (total == 0) return;
+  note_launch("dit_rope");
+  {  // whole rows in registers, 128-bit accesses (prologue.cu) when the layout allows
+    auto bhsd = [](const omx_array& a) {
+      omx_array t = a;
+      t.shape[1] = a.shape[2]; t.shape[2] = a.shape[1];
+      t.strides[1] = a.strides[2]; t.strides[2] = a.strides[1];
+      return t;
+    };
+    PrologueCall pc;
+    const omx_array xv = bhsd(*x);
+    pc.seg[0].x = &xv;
+    pc.seg[0].out = bhsd(*out);
+    pc.seg[0].rope = true;
+    pc.nseg = 1;
+    pc.mode = 2;
+    pc.dims = p.D;
+    pc.tcos = cs;
+    pc.tsin = sn;
+    for (int j = 0; j < 3; ++j) {
+      pc.tcs[j] = p.cs[j];
+      pc.tss[j] = p.ss[j];
+    }
+    if (x->data != out->data && qkv_prologue(pc, stream)) return;
+  }
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, 148 * 16);
-  note_launch("dit_rope");
   switch (x->dtype) {
     case OMX_FLOAT32: dit_rope_kernel<float><<<blocks, threads, 0, stream>>>(p); break;
     case OMX_BFLOAT16: dit_rope_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(p); break;

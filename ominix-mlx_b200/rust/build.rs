@@ -8,7 +8,7 @@ fn main() {
     let csrc = manifest.join("../csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let sources = ["omx_api.cu", "rope.cu", "norm.cu", "kv_cache.cu", "sdpa_generic.cu", "decode.cu", "fmha_sm100.cu"];
+    let sources = ["omx_api.cu", "rope.cu", "norm.cu", "prologue.cu", "kv_cache.cu", "sdpa_generic.cu", "decode.cu", "fmha_sm100.cu"];
     let mut objects = Vec::new();
     for src in sources {
         let obj = out.join(src.replace(".cu", ".o"));

@@ -122,6 +122,12 @@ extern "C" {
     pub fn omx_dit_joint_attention(out: *const omx_array, q: *const omx_array, k: *const omx_array,
                                    v: *const omx_array, scale: f32, add_mask: *const omx_array,
                                    s: omx_stream) -> c_int;
+    pub fn omx_dit_attn_fused(out: *const omx_array, n_streams: c_int, q: *const *const omx_array,
+                              k: *const *const omx_array, v: *const *const omx_array,
+                              q_norm_weight: *const *const omx_array,
+                              k_norm_weight: *const *const omx_array, norm_eps: f32,
+                              cos: *const omx_array, sin: *const omx_array, scale: f32,
+                              add_mask: *const omx_array, s: omx_stream) -> c_int;
     pub fn omx_last_kernel() -> *const c_char;
     pub fn omx_launch_count(reset: bool) -> i64;
     pub fn omx_force_kernel(name: *const c_char) -> c_int;
