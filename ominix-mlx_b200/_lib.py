@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libomx_attn.so")
+LIB_PATH = os.environ.get("OMX_ATTN_LIB") or os.path.join(_HERE, "libomx_attn.so")  # env: A/B builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 OMX_MAX_NDIM = 8

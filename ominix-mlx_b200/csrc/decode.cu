@@ -72,7 +72,23 @@ struct DecodeParams {
   void* peer_out[kMaxPeers];  // pre-offset to this rank's first global q head
   unsigned* peer_flag[kMaxPeers];  // rank r's counters live in rank r's memory: [world]
   int* peer_done;             // local, self-resetting
+  // array mask over the keys (unfused calls only): bool (true = keep) or additive in the q dtype,
+  // broadcast [B,Hq,1,Lk] with element strides (batch, head, key)
+  const void* mask;
+  int mask_kind;  // 0 none, 1 bool, 2 additive
+  int64_t mks[3];
+  uint8_t* dead;  // [B][Hq]: 1 = the mask hid every key (masked_rows_fixup rewrites the row)
 };
+
+// score (log2 domain) of `key` for query head `h` after the array mask.  Additive entries <= -1e8
+// (the callers' -1e9 / -inf spelling of "hidden") hide the key outright, like the prefill kernel.
+template <typename T>
+__device__ __forceinline__ float mask_score(const DecodeParams& p, float s, int b, int h, int key) {
+  const int64_t mi = b * p.mks[0] + h * p.mks[1] + key * p.mks[2];
+  if (p.mask_kind == 1) return ((const uint8_t*)p.mask)[mi] ? s : -INFINITY;
+  const float mf = Num<T>::to_f(((const T*)p.mask)[mi]);
+  return mf <= -1e8f ? -INFINITY : fmaf(mf, kLog2e, s);
+}
 
 template <typename T>
 __device__ __forceinline__ void store_out(const DecodeParams& p, int64_t off, float v) {
@@ -233,6 +249,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     }
     if (p.num_splits == 1) {
       store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
+      if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
     } else {
       const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
       p.ws_o[e * D + d] = O;
@@ -278,6 +295,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     }
     const float inv = 1.0f / L;
     for (int sp = 0; sp < p.num_splits; ++sp) sm_w[sp * rows + tid] *= inv;
+    if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + tid] = L > 0.f ? 0 : 1;
   }
   __syncthreads();
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
@@ -420,27 +438,33 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const bool dead = partial && (key_base + nb * 8 + cq + e >= p.n_mem);
+          const int key = key_base + nb * 8 + cq + e;
+          const bool dead = partial && (key >= p.n_mem);
           sa[nb][e] = dead ? -INFINITY : sa[nb][e] * p.scale_log2;
-          mx0 = fmaxf(mx0, sa[nb][e]);
-          if (HI) {
-            sa[nb][2 + e] = dead ? -INFINITY : sa[nb][2 + e] * p.scale_log2;
-            mx1 = fmaxf(mx1, sa[nb][2 + e]);
+          if (HI) sa[nb][2 + e] = dead ? -INFINITY : sa[nb][2 + e] * p.scale_log2;
+          if (p.mask_kind && !dead) {  // launch-uniform
+            if (g0 < G) sa[nb][e] = mask_score<T>(p, sa[nb][e], b, hk * G + g0, key);
+            if (HI && g0 + 8 < G) sa[nb][2 + e] = mask_score<T>(p, sa[nb][2 + e], b, hk * G + g0 + 8, key);
           }
+          mx0 = fmaxf(mx0, sa[nb][e]);
+          if (HI) mx1 = fmaxf(mx1, sa[nb][2 + e]);
         }
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      const float mn0 = fmaxf(m0, mx0);
-      const float c0 = fast_exp2(m0 - mn0);
-      m0 = mn0;
+      const float m0o = m0;
+      // (a masked row can have seen no key yet: subtract 0 instead of -inf so that 2^(-inf - m) = 0)
+      m0 = fmaxf(m0, mx0);
+      const float mn0 = m0 == -INFINITY ? 0.f : m0;
+      const float c0 = fast_exp2(m0o - mn0);
       float mn1 = 0.f, c1 = 1.f;
       if (HI) {
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
         mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        mn1 = fmaxf(m1, mx1);
-        c1 = fast_exp2(m1 - mn1);
-        m1 = mn1;
+        const float m1o = m1;
+        m1 = fmaxf(m1, mx1);
+        mn1 = m1 == -INFINITY ? 0.f : m1;
+        c1 = fast_exp2(m1o - mn1);
       }
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pa[4][4];
@@ -633,11 +657,13 @@ decode_simt_kernel(const DecodeParams p) {
 #pragma unroll
       for (int u = 0; u < kSimtKeys; ++u) {
         s[u] = (j0 + u < kend) ? s[u] * p.scale_log2 : -INFINITY;
+        if (p.mask_kind && j0 + u < kend) s[u] = mask_score<T>(p, s[u], b, first_head + g, j0 + u);
         mx = fmaxf(mx, s[u]);
       }
-      const float mn = fmaxf(m[g], mx);
-      const float c = fast_exp2(m[g] - mn);
-      m[g] = mn;
+      const float mo_ = m[g];
+      m[g] = fmaxf(m[g], mx);
+      const float mn = m[g] == -INFINITY ? 0.f : m[g];  // masked rows may have seen no key yet
+      const float c = fast_exp2(mo_ - mn);
       float rs = 0.f;
 #pragma unroll
       for (int u = 0; u < kSimtKeys; ++u) {
@@ -746,7 +772,7 @@ bool decode_supported(const SdpaArgs& a, const char** why) {
     return false;
   };
   if (a.Lq != 1) return no("Lq != 1");
-  if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) return no("array mask");
+  if (a.mask_mode == MASK_ADD && a.mask->dtype != a.q->dtype) return no("additive mask dtype differs from q");
   if (a.D != a.Dv) return no("Dk != Dv");
   if (!(a.D == 32 || a.D == 64 || a.D == 128 || a.D == 256)) return no("head_dim not in {32,64,128,256}");
   if (!inner_contig(a.q) || !inner_contig(a.k) || !inner_contig(a.v) || !inner_contig(a.out))
@@ -810,6 +836,27 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     }
   }
 
+  const bool masked = a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD;
+  if (masked) {
+    OMX_CHECK(!f.enabled, "the fused decode step takes no array mask");
+    p.mask = a.mask->data;
+    p.mask_kind = a.mask_mode == MASK_BOOL ? 1 : 2;
+    p.mks[0] = a.mask_strides[0];
+    p.mks[1] = a.mask_strides[1];
+    p.mks[2] = a.mask_strides[3];
+  }
+  // one workspace request per call (a second one could move the first): split-K partials, then flags
+  auto carve_workspace = [&](size_t no, size_t nml) {
+    const size_t fl = masked ? (size_t)a.B * a.Hq : 0;
+    if (no + nml + fl == 0) return;
+    float* ws = (float*)get_workspace(sizeof(float) * (no + nml) + fl, stream);
+    if (no) {
+      p.ws_o = ws;
+      p.ws_ml = ws + no;
+    }
+    if (fl) p.dead = reinterpret_cast<uint8_t*>(ws + no + nml);
+  };
+
   const int sms = sm_count();
   const int n_tiles = (p.n_mem + kTile - 1) / kTile;
   const bool b16 = a.q->dtype != OMX_FLOAT32;
@@ -831,13 +878,8 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
     p.num_splits = sp.num_splits;
     p.tiles_per_split = sp.tiles_per_split;
-    if (p.num_splits > 1) {
-      const size_t no = (size_t)pairs * p.num_splits * p.G * p.D;
-      const size_t nml = (size_t)pairs * p.num_splits * p.G * 2;
-      float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
-      p.ws_o = ws;
-      p.ws_ml = ws + no;
-    }
+    carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
+                    p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0);
     if (p.num_splits > 1 || p.n_peers) {
       p.counters = get_counters((size_t)pairs + 1, stream);
       p.peer_done = p.counters + pairs;
@@ -875,6 +917,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     }
     count_launch();
     OMX_CUDA(cudaGetLastError());
+    if (masked) masked_rows_fixup(a, p.dead, stream);
     return;
   }
 
@@ -885,13 +928,8 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   SplitPlan sp = plan_splits(pairs, n_tiles, sms, 2);
   p.num_splits = sp.num_splits;
   p.tiles_per_split = sp.tiles_per_split;
-  if (p.num_splits > 1) {
-    const size_t no = (size_t)pairs * p.num_splits * Gt * p.D;
-    const size_t nml = (size_t)pairs * p.num_splits * Gt * 2;
-    float* ws = (float*)get_workspace(sizeof(float) * (no + nml), stream);
-    p.ws_o = ws;
-    p.ws_ml = ws + no;
-  }
+  carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * p.D : 0,
+                  p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * 2 : 0);
   if (p.num_splits > 1 || p.n_peers) {
     p.counters = get_counters((size_t)pairs + 1, stream);
     p.peer_done = p.counters + pairs;
@@ -904,6 +942,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     case OMX_BFLOAT16: launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid); break;
     default: launch_simt_d<__half>(p, stream, Gt, grid); break;
   }
+  if (masked) masked_rows_fixup(a, p.dead, stream);
 }
 
 }  // namespace omx

@@ -2,8 +2,10 @@
 //
 // Serves the compute-bound cases of fast::scaled_dot_product_attention (mlx-rs/src/fast.rs:121-151):
 // causal prefill (Qwen3-8B shape, BASELINE C3) and the non-causal DiT joint [txt;img] attention of
-// FLUX.2-klein / Z-Image (C4; flux-klein-mlx/src/klein_model.rs:474-483).  bf16 / f16, D = 128,
-// mask none or "causal" (aligned bottom-right, q_off = max(Lk - Lq, 0)), GQA by head index.
+// FLUX.2-klein / Z-Image (C4; flux-klein-mlx/src/klein_model.rs:474-483).  bf16 / f16, D = 128 (or 64:
+// the Qwen3-ASR audio encoder, qwen3-asr-mlx/src/encoder.rs:133, and the reference's own sdpa test
+// shapes, mlx-rs/src/fast.rs:301-331), mask none, "causal" (aligned bottom-right,
+// q_off = max(Lk - Lq, 0)) or a bool / additive array, GQA by head index.
 //
 // One CTA = 256 query rows of one (batch, q-head): two 128-row Q tiles that ping-pong on the tensor
 // core so that the softmax of one overlaps the MMAs of the other.
@@ -34,10 +36,8 @@ namespace {
 
 constexpr int BM = 128;          // rows per Q tile
 constexpr int BN = 128;          // keys per KV tile
-constexpr int HD = 128;          // head dim
 constexpr int kSlots = 5;        // K/V ring slots
-constexpr int kTileBytes = BN * HD * 2;  // 32 KB: two 64-feature TMA boxes of 16 KB
-constexpr int kBoxBytes = kTileBytes / 2;
+constexpr int kBoxBytes = BN * 64 * 2;   // one TMA box: 128 rows x 64 features (one 128-byte swizzle row each)
 constexpr int kThreads = 384;   // 2 softmax warpgroups + 1 warpgroup {TMA, MMA, 2 idle}
 constexpr int kRegsSoftmax = 216;  // setmaxnreg budgets: 8 warps x 216 + 4 warps x 72 <= 64K registers
 constexpr int kRegsOther = 72;
@@ -56,6 +56,7 @@ struct FmhaParams {
   const void* mask;
   int64_t ms[3];       // batch, head, query-row strides (0 on broadcast axes)
   const uint8_t* tmap; // tile classes [Bm][Hm][n_qt][n_kt]: 0 all masked, 1 all kept, 2 mixed
+  uint8_t* dead;       // [B][Hq][Lq]: 1 = the mask hides every key of the row (masked_rows_fixup rewrites it)
   int64_t tms[2];      // batch, head strides of tmap (0 on broadcast axes)
   int n_kt;
   float inv_scale;
@@ -210,6 +211,9 @@ struct Pack2<__nv_bfloat16> {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
   }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+  }
 };
 template <>
 struct Pack2<__half> {
@@ -217,6 +221,9 @@ struct Pack2<__half> {
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
   }
 };
 
@@ -242,14 +249,16 @@ struct SharedCtl {
 // CTA's 256 query rows into a step list in shared memory, and the three roles walk that list, so a
 // causal- or window-shaped array mask costs what the structured mask costs.  Mixed tiles read their
 // mask rows (128-bit loads) in the softmax threads.
-template <typename T, int kEmu, int kSplitKeys, bool kArr>
+template <typename T, int HD, int kEmu, int kSplitKeys, bool kArr>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* q_s = smem;                     // 2 x 32 KB
-  uint8_t* kv_s = smem + 2 * kTileBytes;   // kSlots x 32 KB
+  constexpr int kBoxes = HD / 64;               // 64-feature TMA boxes per tile
+  constexpr int kTileBytes = kBoxes * kBoxBytes;  // 32 KB at D = 128
+  uint8_t* q_s = smem;                     // 2 tiles
+  uint8_t* kv_s = smem + 2 * kTileBytes;   // kSlots tiles
   __shared__ SharedCtl ctl;
   __shared__ uint16_t jlist[kArr ? kMaxSteps : 1];  // entry: KV tile | tile-0 needs mask << 12 | tile-1 << 13
 
@@ -366,8 +375,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             continue;
           }
           mbar_expect_tx(&ctl.q_full[i], kTileBytes);
-          tma_load_4d(q_s + i * kTileBytes, &tmQ, &ctl.q_full[i], 0, it.m0 + i * BM, it.hq, it.b, pol_q);
-          tma_load_4d(q_s + i * kTileBytes + kBoxBytes, &tmQ, &ctl.q_full[i], 64, it.m0 + i * BM, it.hq, it.b, pol_q);
+#pragma unroll
+          for (int bx = 0; bx < kBoxes; ++bx)
+            tma_load_4d(q_s + i * kTileBytes + bx * kBoxBytes, &tmQ, &ctl.q_full[i], bx * 64, it.m0 + i * BM, it.hq,
+                        it.b, pol_q);
         }
         for (int t = 0; t < 2 * it.N; ++t, ++seq) {
           const int slot = seq % kSlots, use = seq / kSlots;
@@ -376,8 +387,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const CUtensorMap* tm = (t & 1) ? &tmV : &tmK;
           uint8_t* dst = kv_s + slot * kTileBytes;
           mbar_expect_tx(&ctl.kv_full[slot], kTileBytes);
-          tma_load_4d(dst, tm, &ctl.kv_full[slot], 0, j * BN, it.hk, it.b, pol_kv);
-          tma_load_4d(dst + kBoxBytes, tm, &ctl.kv_full[slot], 64, j * BN, it.hk, it.b, pol_kv);
+#pragma unroll
+          for (int bx = 0; bx < kBoxes; ++bx)
+            tma_load_4d(dst + bx * kBoxBytes, tm, &ctl.kv_full[slot], bx * 64, j * BN, it.hk, it.b, pol_kv);
         }
       }
     }
@@ -400,11 +412,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t v_desc0 = umma_desc(smem_u32(kv_s), kBoxBytes, 1024);    // MN-major
     auto wait_kv = [&](int seq) { mbar_wait_wd(&ctl.kv_full[seq % kSlots], (seq / kSlots) & 1); };
     auto slot16 = [&](int seq) { return (uint64_t)((uint32_t)(seq % kSlots) * kTile16); };
-    // S_i = Q_i K^T : 2 feature blocks x 4 k-steps of 16
+    // S_i = Q_i K^T : HD / 64 feature blocks x 4 k-steps of 16
     auto mma_qk = [&](int i, uint64_t k_desc) {
       const uint64_t qa = q_desc + (uint64_t)(i * kTile16);
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < kBoxes; ++kb) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t off = kb * kBox16 + ks * 2;
@@ -595,8 +607,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int t = 0; t < 8; ++t) {
               const int e = (g & 3) * 8 + t;
               uint32_t& dst = (g >> 2) == 0 ? s0[e] : (g >> 2) == 1 ? s1[e] : (g >> 2) == 2 ? s2[e] : s3[e];
-              // score + mask / scale: the later multiply by scale restores scale * s + mask
-              dst = __float_as_uint(fmaf(Num<T>::to_f(u.t[t]), p.inv_scale, __uint_as_float(dst)));
+              // score + mask / scale: the later multiply by scale restores scale * s + mask.  Entries
+              // <= -1e8 (the callers' "-1e9" / -inf spelling of "hidden") hide the key outright, as
+              // the tile classifier assumes, so that a row without any visible key ends with l == 0.
+              const float mf = Num<T>::to_f(u.t[t]);
+              dst = mf <= -1e8f ? 0xff800000u : __float_as_uint(fmaf(mf, p.inv_scale, __uint_as_float(dst)));
             }
           }
         }
@@ -629,7 +644,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       if (any_grow && st > 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < HD / 32; ++c) {
           uint32_t r[32];
           tmem_ld32(t_o + c * 32, r);
           tc_wait_ld();
@@ -655,9 +670,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           } else {
             pe = make_float2(ex2_mufu(a.x), ex2_mufu(a.y));
           }
+          // (summing the ROUNDED P instead -- OMX_FMHA_L_FROM_P -- measured no accuracy gain against
+          // float64 and -4 % throughput: scripts/exp_fmha_err.py, gpurun_out/exp_lp.log)
+          pk[e >> 1] = Pack2<T>::pack(pe.x, pe.y);
+#ifdef OMX_FMHA_L_FROM_P
+          pe = Pack2<T>::unpack(pk[e >> 1]);
+#endif
           if (e & 2) acc_b = __fadd2_rn(acc_b, pe);
           else acc_a = __fadd2_rn(acc_a, pe);
-          pk[e >> 1] = Pack2<T>::pack(pe.x, pe.y);
         }
         if (hi - lo == 32) tmem_st16(t_s + c * 16, pk);
         else tmem_st8(t_s + c * 16 + (lo >> 1), pk + (lo >> 1));
@@ -689,10 +709,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait_wd(&ctl.s_full[i], cs & 1);
       ++cs;
       tc_fence_after();
-      const float inv = (kArr && !(l_run > 0.f)) ? 0.f : 1.0f / l_run;  // rows with no visible key -> 0
+      // rows with no visible key: 0 here, flagged for masked_rows_fixup (the reference's uniform average)
+      const float inv = (kArr && !(l_run > 0.f)) ? 0.f : 1.0f / l_run;
+      if (kArr && qrow < p.Lq) p.dead[((int64_t)b * p.Hq + hq) * p.Lq + qrow] = l_run > 0.f ? 0 : 1;
       T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < HD / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(t_o + c * 32, r);
         tc_wait_ld();
@@ -708,7 +730,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-    } else if (kArr && qrow < p.Lq) {  // every KV tile masked for this CTA: defined output (zeros)
+    } else if (kArr && qrow < p.Lq) {  // every KV tile masked for this CTA: all its rows are flagged
+      p.dead[((int64_t)b * p.Hq + hq) * p.Lq + qrow] = 1;
       T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
 #pragma unroll
       for (int e = 0; e < HD; e += 8) *reinterpret_cast<uint4*>(orow + e) = make_uint4(0u, 0u, 0u, 0u);
@@ -761,7 +784,7 @@ bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
     return false;
   };
   if (a.q->dtype != OMX_BFLOAT16 && a.q->dtype != OMX_FLOAT16) return no("dtype is not bf16/f16");
-  if (a.D != HD || a.Dv != HD) return no("head_dim != 128");
+  if (!((a.D == 128 && a.Dv == 128) || (a.D == 64 && a.Dv == 64))) return no("head_dim not 64 or 128");
   if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) {
     if (a.mask_mode == MASK_ADD && a.mask->dtype != a.q->dtype) return no("additive mask dtype differs from q");
     if (a.Lk > 1 && a.mask_strides[3] != 1) return no("mask key axis not contiguous");
@@ -781,6 +804,8 @@ bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
 
 void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   const bool bf = a.q->dtype == OMX_BFLOAT16;
+  const int HD = a.D;  // 64 or 128 (fmha_sm100_supported)
+  const int tile_bytes = (HD / 64) * kBoxBytes;
   FmhaParams p{};
   p.out = a.out->data;
   for (int i = 0; i < 4; ++i) p.os[i] = a.out->strides[i];
@@ -795,7 +820,7 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
                                      a.k->strides[0], 64, BN, bf);
   CUtensorMap tmV = make_tmap_4d_b16(a.v->data, HD, a.Lk, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
                                      a.v->strides[0], 64, BN, bf);
-  const size_t smem = 1024 + (size_t)(2 + kSlots) * kTileBytes;
+  const size_t smem = 1024 + (size_t)(2 + kSlots) * tile_bytes;
   p.n_mblk = (a.Lq + 2 * BM - 1) / (2 * BM);
   p.n_items = p.n_mblk * a.Hq * a.B;
   // persistent CTAs (one per SM) walk the work items; array-mask launches keep one item per CTA
@@ -814,15 +839,17 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   };
-  if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) {
-    // ---- array mask: classify the mask's tiles, then the step-list kernel
+  if (arr) {
+    // ---- array mask: classify the mask's tiles, run the step-list kernel, rewrite fully hidden rows
     const int n_qt = (a.Lq + BM - 1) / BM, n_kt = (a.Lk + BN - 1) / BN;
     const int Bm = a.mask_strides[0] ? a.B : 1, Hm = a.mask_strides[1] ? a.Hq : 1;
-    uint8_t* tmap = (uint8_t*)get_workspace((size_t)Bm * Hm * n_qt * n_kt, stream);
+    const size_t tmap_bytes = (((size_t)Bm * Hm * n_qt * n_kt) + 255) & ~(size_t)255;
+    uint8_t* tmap = (uint8_t*)get_workspace(tmap_bytes + (size_t)a.B * a.Hq * a.Lq, stream);
     p.mask_kind = a.mask_mode == MASK_BOOL ? 1 : 2;
     p.mask = a.mask->data;
     for (int i = 0; i < 3; ++i) p.ms[i] = a.mask_strides[i];
     p.tmap = tmap;
+    p.dead = tmap + tmap_bytes;
     p.tms[0] = a.mask_strides[0] ? (int64_t)Hm * n_qt * n_kt : 0;
     p.tms[1] = a.mask_strides[1] ? (int64_t)n_qt * n_kt : 0;
     p.n_kt = n_kt;
@@ -841,13 +868,26 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     count_launch();
     OMX_CUDA(cudaGetLastError());
     note_launch("fmha_tcgen05_arraymask");
-    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 0, 96, true>);
-    else go(fmha_fwd_kernel<__half, 0, 96, true>);
+    if (HD == 128) {
+      if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 128, 0, 96, true>);
+      else go(fmha_fwd_kernel<__half, 128, 0, 96, true>);
+    } else {
+      if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 64, 0, 96, true>);
+      else go(fmha_fwd_kernel<__half, 64, 0, 96, true>);
+    }
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+    masked_rows_fixup(a, p.dead, stream);
+    return;
+  }
+  note_launch("fmha_tcgen05");
+  if (HD == 64) {
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 64, 0, 96, false>);
+    else go(fmha_fwd_kernel<__half, 64, 0, 96, false>);
     count_launch();
     OMX_CUDA(cudaGetLastError());
     return;
   }
-  note_launch("fmha_tcgen05");
   // OMX_FMHA_CFG = 10 * kEmu + {0: one-piece hand-off, 1: split at 96 keys, 2: split at 112} is a
   // tuning knob for the bench sweeps, not an API.
   static const int cfg = [] {
@@ -856,8 +896,8 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   }();
 #define OMX_FMHA_CASE(EMU, SPLIT)                                  \
   case EMU * 10 + SPLIT:                                           \
-    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);   \
-    else go(fmha_fwd_kernel<__half, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);             \
+    if (bf) go(fmha_fwd_kernel<__nv_bfloat16, 128, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);   \
+    else go(fmha_fwd_kernel<__half, 128, EMU, SPLIT == 0 ? 0 : (SPLIT == 1 ? 96 : 112), false>);             \
     break;
   switch (cfg) {
     OMX_FMHA_CASE(0, 0)

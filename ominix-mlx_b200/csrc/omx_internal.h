@@ -90,6 +90,9 @@ struct SdpaArgs {
   int B, Hq, Hkv, Lq, Lk, D, Dv;
 };
 void sdpa_generic(const SdpaArgs& a, cudaStream_t stream);
+// Rewrites the rows flagged in dead[B][Hq][Lq] (array mask hides every key) with the reference's
+// uniform average over all Lk rows of V; launched by the tile-skipping kernels after their own pass.
+void masked_rows_fixup(const SdpaArgs& a, const uint8_t* dead, cudaStream_t stream);
 
 // ---- decode.cu ----
 struct DecodeFused {  // optional fused rope + append of the new token (L == 1)

@@ -11,6 +11,7 @@
 // finfo(dtype).min (so a fully masked row degrades to a uniform average, not NaN); additive
 // masks are added to the scaled scores.
 #include <algorithm>
+#include <type_traits>
 
 #include "omx_common.cuh"
 #include "omx_internal.h"
@@ -144,7 +145,65 @@ void launch(const GenParams& p, cudaStream_t s) {
   OMX_CUDA(cudaGetLastError());
 }
 
+// Rows whose array mask hides EVERY key.  The reference's CPU chain fills masked scores with
+// finfo(dtype).min (bool masks) or adds ~-1e9 (the callers' additive masks), so such a row's
+// softmax is uniform and its output is sum_k T(1/Lk) * V[k] -- an average over ALL Lk keys.  The
+// tile-skipping kernels (fmha_sm100.cu, decode.cu) never visit masked keys; they flag those rows
+// (dead[b][h][row] = 1) and this pass rewrites them.  One CTA per 128 query rows of one (b, h):
+// a block without a flagged row exits after one byte load per thread.
+template <typename T>
+__global__ void __launch_bounds__(128)
+masked_rows_fixup_kernel(const uint8_t* __restrict__ dead, const T* __restrict__ v, int64_t vs0, int64_t vs1,
+                         int64_t vs2, int64_t vs3, void* out, int64_t os0, int64_t os1, int64_t os2, int64_t os3,
+                         int Hq, int Hkv, int Lq, int Lk, int Dv, int out_is_f32) {
+  __shared__ float mean[256];
+  __shared__ uint8_t fl[128];
+  const int tid = threadIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row = blockIdx.x * 128 + tid;
+  const int flag = row < Lq ? dead[((int64_t)b * Hq + h) * Lq + row] : 0;
+  if (!__syncthreads_or(flag)) return;
+  const T* vb = v + b * vs0 + (int64_t)(h / (Hq / Hkv)) * vs1;
+  const float w = Num<T>::to_f(Num<T>::from_f(1.0f / (float)Lk));
+  for (int d = tid; d < Dv; d += 128) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < Lk; ++k) acc = fmaf(w, Num<T>::to_f(vb[(int64_t)k * vs2 + d * vs3]), acc);
+    mean[d] = acc;
+  }
+  fl[tid] = (uint8_t)flag;
+  __syncthreads();
+  for (int r = 0; r < 128; ++r) {
+    if (!fl[r]) continue;
+    const int64_t oo = b * os0 + h * os1 + (int64_t)(blockIdx.x * 128 + r) * os2;
+    for (int d = tid; d < Dv; d += 128) {
+      if (out_is_f32) ((float*)out)[oo + d * os3] = mean[d];
+      else ((T*)out)[oo + d * os3] = Num<T>::from_f(mean[d]);
+    }
+  }
+}
+
 }  // namespace
+
+void masked_rows_fixup(const SdpaArgs& a, const uint8_t* dead, cudaStream_t stream) {
+  if ((int64_t)a.B * a.Hq * a.Lq == 0 || a.Lk == 0) return;
+  OMX_CHECK(a.Dv <= 256, "[scaled_dot_product_attention] head_dim > 256 is not supported");
+  dim3 grid((a.Lq + 127) / 128, a.Hq, a.B);
+  const int64_t* vs = a.v->strides;
+  const int64_t* os = a.out->strides;
+  const int f32o = a.out->dtype == OMX_FLOAT32 ? 1 : 0;
+  auto go = [&](auto* vp) {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(vp)>>;
+    masked_rows_fixup_kernel<T><<<grid, 128, 0, stream>>>(dead, vp, vs[0], vs[1], vs[2], vs[3], a.out->data, os[0],
+                                                          os[1], os[2], os[3], a.Hq, a.Hkv, a.Lq, a.Lk, a.Dv, f32o);
+  };
+  switch (a.q->dtype) {
+    case OMX_FLOAT32: go((const float*)a.v->data); break;
+    case OMX_BFLOAT16: go((const __nv_bfloat16*)a.v->data); break;
+    default: go((const __half*)a.v->data); break;
+  }
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
 
 void sdpa_generic(const SdpaArgs& a, cudaStream_t stream) {
   OMX_CHECK(a.D <= 256 && a.Dv <= 256, "[scaled_dot_product_attention] head_dim > 256 is not supported");

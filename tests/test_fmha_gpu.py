@@ -12,8 +12,7 @@ DEV = "cuda"
 Causal = omx.fast.ScaledDotProductAttentionMask.Causal
 
 
-def _run(B, Hq, Hkv, Lq, Lk, dtype="bf16", causal=True, seed=0, qview=False, kvslice=False, tol_check=True):
-    D = 128
+def _run(B, Hq, Hkv, Lq, Lk, dtype="bf16", causal=True, seed=0, qview=False, kvslice=False, tol_check=True, D=128):
     if qview:  # [B, L, H, D] storage viewed [B, H, L, D]
         q = randn((B, Lq, Hq, D), dtype, seed + 1).transpose(1, 2)
     else:
@@ -100,8 +99,7 @@ def test_auto_dispatch_and_bool_mask_equivalence():
 # ---- array masks on the tcgen05 path (what the LLM crates' prefill actually passes: qwen3-mlx/src/model.rs:401,
 # mixtral-mlx/src/model.rs:388 call create_attention_mask(h, cache, Some(true)) -> a bool [T, offset+T] array)
 
-def _run_arr(B, Hq, Hkv, Lq, Lk, mask_t, dtype="bf16", seed=0, expect="fmha_tcgen05_arraymask"):
-    D = 128
+def _run_arr(B, Hq, Hkv, Lq, Lk, mask_t, dtype="bf16", seed=0, expect="fmha_tcgen05_arraymask", D=128):
     q = randn((B, Hq, Lq, D), dtype, seed + 1)
     k = randn((B, Hkv, Lk, D), dtype, seed + 2)
     v = randn((B, Hkv, Lk, D), dtype, seed + 3)
@@ -168,20 +166,40 @@ def test_array_mask_unaligned_rows_and_fully_masked_tiles():
     _run_arr(1, 2, 2, Lq, Lk, m)
 
 
-def test_rows_without_visible_keys_are_finite():
-    # degenerate rows (no visible key): the reference's CPU path averages V uniformly; the tensor-core path
-    # returns zeros -- documented deviation, asserted finite here; all other rows must still match
+def test_rows_without_visible_keys_average_v_like_the_reference():
+    # degenerate rows (no visible key): the reference's CPU chain fills with finfo.min, so the softmax is
+    # uniform over ALL keys; the tile-skipping kernel flags such rows and masked_rows_fixup rewrites them
     Lq = Lk = 256
     m = omx.create_causal_mask(Lq, 0, device="cpu").clone()
     m[10] = False
-    D = 128
-    q, k, v = (randn((1, 2, Lq, D), "bf16", s) for s in (1, 2, 3))
-    got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, m.to(DEV))
-    assert torch.isfinite(got.float()).all()
-    want = n2f(orc.sdpa(t2n(q, "bf16"), t2n(k, "bf16"), t2n(v, "bf16"), D ** -0.5, m.numpy(), dtype="bf16"), "bf16")
-    keep = np.ones(Lq, bool)
-    keep[10] = False
-    assert_close(got.float().cpu().numpy()[:, :, keep], want[:, :, keep], "bf16", "rows with visible keys")
+    m[200:] = False   # a whole 128-row tile's worth of rows and more
+    _run_arr(1, 2, 2, Lq, Lk, m)
+    m4 = m[None, None].repeat(2, 4, 1, 1).clone()
+    m4[1, 2] = True   # per-(batch, head) pattern: one head sees everything
+    m4[0, 0] = False  # one head sees nothing: every KV tile skipped for its CTAs
+    _run_arr(2, 4, 2, Lq, Lk, m4)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_additive_mask_rows_without_visible_keys(dtype):
+    # left-padded batch the way flux-klein's text encoder masks it (qwen3_encoder.rs:173-200):
+    # causal AND key-not-padding, as (1 - keep) * -1e9 in the q dtype; padded query rows see no key at all
+    from conftest import tdt
+    L, pad = 300, 37
+    keep = omx.create_causal_mask(L, 0, device="cpu").clone()
+    keep[:, :pad] = False
+    add = ((~keep).float() * -1e9).to(tdt(dtype))[None, None]
+    if dtype == "bf16":
+        _run_arr(1, 4, 2, L, L, add, dtype=dtype)
+        return
+    # f16 cannot hold -1e9: the mask is -inf and the reference's softmax of an all -inf row is NaN.  This
+    # library returns the uniform average there too (finite); every other row must match.
+    q, k, v = (randn((1, h, L, 128), dtype, s) for h, s in ((4, 1), (2, 2), (2, 3)))
+    got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), 128 ** -0.5, add.to(DEV))
+    assert omx.last_kernel() == "fmha_tcgen05_arraymask"
+    want = n2f(orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v, dtype), 128 ** -0.5, t2n(add, dtype), dtype=dtype), dtype)
+    assert np.isnan(want[:, :, :pad]).all() and torch.isfinite(got.float()).all()
+    assert_close(got.float().cpu().numpy()[:, :, pad:], want[:, :, pad:], dtype, "rows with visible keys")
 
 
 def test_c3_shape_bool_array_mask_matches_causal_string():
@@ -244,3 +262,32 @@ def test_full_size_properties_c4():
     want = orc.sdpa(t2n(q[2:3, 5:7], "bf16"), t2n(k[2:3, 5:7], "bf16"), t2n(v[2:3, 5:7], "bf16"), D ** -0.5, None,
                     dtype="bf16")
     assert_close(o[2:3, 5:7].float().cpu().numpy(), n2f(want, "bf16"), "bf16", "C4 slice")
+
+
+# ---- head_dim 64 on the same kernel (Qwen3-ASR audio encoder: embed_dim / heads = 64, non-causal,
+# qwen3-asr-mlx/src/encoder.rs:133-180; and the shapes of the reference's own sdpa tests, mlx-rs/src/fast.rs:301-331)
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("Lq,Lk", [(128, 128), (256, 384), (63, 63), (129, 129), (400, 400), (300, 1000)])
+def test_head_dim_64(causal, Lq, Lk):
+    _run(2, 4, 2, Lq, Lk, causal=causal, D=64)
+
+
+def test_head_dim_64_reference_test_shape_f16():
+    # fast.rs:301-331: B2, H24, D64, f16
+    for L in (63, 129, 400):
+        _run(2, 24, 24, L, L, dtype="f16", causal=False, D=64, seed=L)
+
+
+def test_head_dim_64_caller_layouts_and_long_kv():
+    _run(2, 8, 2, 300, 300, causal=True, qview=True, kvslice=True, D=64)
+    _run(1, 2, 1, 512, 4096, causal=True, D=64)
+    _run(1, 20, 20, 1500, 1500, causal=False, D=64)   # audio-encoder-sized window
+
+
+def test_head_dim_64_array_masks():
+    m = omx.create_causal_mask(512, 256, window_size=200, device="cpu")
+    _run_arr(1, 4, 2, 512, 768, m, D=64)
+    m2 = omx.create_causal_mask(300, 0, device="cpu").clone()
+    m2[17] = False
+    _run_arr(1, 2, 2, 300, 300, m2, D=64)

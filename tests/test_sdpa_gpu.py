@@ -173,7 +173,9 @@ def test_decode_kernel_families():
     _run((2, 8, 2, 1, 700, 64), "bf16", "none")
     assert omx.last_kernel() == "decode_simt"
     _run((2, 8, 2, 1, 700, 128), "bf16", "bool2d")
-    assert omx.last_kernel() == "sdpa_generic"
+    assert omx.last_kernel() == "decode_hmma_tma"   # array masks stay on the split-K decode kernels
+    _run((2, 8, 2, 1, 700, 96), "bf16", "bool2d")
+    assert omx.last_kernel() == "sdpa_generic"      # head dims outside {32, 64, 128, 256}
 
 
 def test_decode_on_cache_views():
@@ -195,3 +197,66 @@ def test_empty_inputs():
     q = torch.zeros(0, 4, 3, 16, device=DEV)
     k = torch.zeros(0, 2, 5, 16, device=DEV)
     assert omx.fast.scaled_dot_product_attention(q, k, k, 1.0).shape == (0, 4, 3, 16)
+
+
+# ---- decode (Lq == 1) with array masks stays on the split-K decode kernels (sliding windows,
+# padding masks); rows whose mask hides every key follow the reference's finfo.min rule (uniform average)
+
+def _decode_masked(B, Hq, Hkv, Lk, D, dtype, mask_t, expect):
+    q = randn((B, Hq, 1, D), dtype, 1)
+    k = randn((B, Hkv, Lk, D), dtype, 2)
+    v = randn((B, Hkv, Lk, D), dtype, 3)
+    scale = D ** -0.5
+    got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), scale, mask_t.to(DEV))
+    torch.cuda.synchronize()
+    assert omx.last_kernel() == expect, omx.last_kernel()
+    om = mask_t.numpy() if mask_t.dtype == torch.bool else t2n(mask_t, dtype)
+    want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v, dtype), scale, om, dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, f"masked decode {dtype} D{D} Lk{Lk}")
+
+
+@pytest.mark.parametrize("dtype,D,expect", [("bf16", 128, "decode_hmma_tma"), ("f16", 128, "decode_hmma_tma"),
+                                            ("f32", 128, "decode_simt"), ("bf16", 64, "decode_simt"),
+                                            ("f32", 64, "decode_simt")])
+def test_decode_sliding_window_bool_mask(dtype, D, expect):
+    Lk = 1500
+    m = omx.create_causal_mask(1, Lk - 1, window_size=300, device="cpu")  # [1, Lk]: last 301 keys visible
+    assert m.shape == (1, Lk) and int(m.sum()) == 301
+    _decode_masked(2, 8, 2, Lk, D, dtype, m, expect)
+
+
+@pytest.mark.parametrize("dtype,expect", [("bf16", "decode_hmma_tma"), ("f32", "decode_simt")])
+def test_decode_per_batch_head_masks_and_hidden_rows(dtype, expect):
+    g = torch.Generator().manual_seed(9)
+    B, Hq, Hkv, Lk, D = 3, 8, 2, 777, 128
+    m = torch.rand((B, Hq, 1, Lk), generator=g) > 0.6
+    m[0, 3] = False          # one (batch, head) row sees nothing -> uniform average of V
+    m[2] = False             # a whole batch item sees nothing
+    m[1, :, :, :700] = False  # first tiles hidden entirely
+    m[1, :, :, 701] = True
+    _decode_masked(B, Hq, Hkv, Lk, D, dtype, m, expect)
+    mb = torch.rand((B, 1, 1, Lk), generator=g) > 0.5   # padding-style [B,1,1,Lk]
+    mb[..., 0] = True
+    _decode_masked(B, Hq, Hkv, Lk, D, dtype, mb, expect)
+
+
+@pytest.mark.parametrize("dtype,expect", [("bf16", "decode_hmma_tma"), ("f32", "decode_simt")])
+def test_decode_additive_masks(dtype, expect):
+    from conftest import tdt
+    g = torch.Generator().manual_seed(10)
+    B, Hq, Hkv, Lk, D = 2, 4, 4, 390, 128
+    bias = (0.25 * torch.randn((1, Hq, 1, Lk), generator=g)).to(tdt(dtype))
+    _decode_masked(B, Hq, Hkv, Lk, D, dtype, bias, expect)
+    keep = torch.rand((B, 1, 1, Lk), generator=g) > 0.5
+    keep[1] = False   # padded-out batch item
+    add = ((~keep).float() * -1e9).to(tdt(dtype))
+    _decode_masked(B, Hq, Hkv, Lk, D, dtype, add, expect)
+
+
+def test_decode_mask_long_context_split_k():
+    # single sequence, long context: the split-K plan with the last-CTA combine, masked
+    Lk = 20000
+    m = omx.create_causal_mask(1, Lk - 1, window_size=4095, device="cpu")
+    _decode_masked(1, 32, 8, Lk, 128, "bf16", m, "decode_hmma_tma")
+    none = torch.zeros((1, Lk), dtype=torch.bool)
+    _decode_masked(1, 32, 8, Lk, 128, "bf16", none, "decode_hmma_tma")
