@@ -168,6 +168,30 @@ static float max_abs_diff(const std::vector<uint16_t>& a, const std::vector<uint
   return m;
 }
 
+// float64 causal attention [B,H,L,D] (same q/k/v heads): the yardstick for the reference chain's own rounding noise
+static std::vector<double> sdpa_causal_f64(const std::vector<uint16_t>& q, const std::vector<uint16_t>& k,
+                                           const std::vector<uint16_t>& v, int B, int H, int L, int D, float scale) {
+  std::vector<double> out((size_t)B * H * L * D, 0.0), p(L);
+  for (int bh = 0; bh < B * H; ++bh) {
+    const size_t base = (size_t)bh * L * D;
+    for (int i = 0; i < L; ++i) {
+      double mx = -1e300, sum = 0.0;
+      for (int j = 0; j <= i; ++j) {
+        double s = 0.0;
+        for (int d = 0; d < D; ++d) s += (double)bf2f(q[base + (size_t)i * D + d]) * (double)bf2f(k[base + (size_t)j * D + d]);
+        p[j] = s * (double)scale;
+        mx = std::max(mx, p[j]);
+      }
+      for (int j = 0; j <= i; ++j) sum += (p[j] = std::exp(p[j] - mx));
+      for (int j = 0; j <= i; ++j) {
+        const double w = p[j] / sum;
+        for (int d = 0; d < D; ++d) out[base + (size_t)i * D + d] += w * (double)bf2f(v[base + (size_t)j * D + d]);
+      }
+    }
+  }
+  return out;
+}
+
 static void test_sdpa_shapes_like_the_reference_test() {
   printf("test_sdpa_shapes_like_the_reference_test\n");
   // mlx-rs/src/fast.rs:301-331 checks shape and dtype for B2, H24, L in {63, 129, 400}, D64; here values too
@@ -183,20 +207,26 @@ static void test_sdpa_shapes_like_the_reference_test() {
     std::vector<uint16_t> want(q.size());
     omx_oracle_sdpa(q.data(), k.data(), v.data(), want.data(), OMX_BFLOAT16, B, H, H, L, L, D, D, scale, 1, nullptr, 0,
                     nullptr, 0);
-    // 2e-2 max-abs (north_star).  One carve-out: where |reference| >= 2 one bf16 ulp is already 0.0156 and the
-    // reference chain's own distance from the float64 result reaches 0.02 on the short causal rows of these
-    // 48 heads (scripts/exp_fmha_err.py: kernel-vs-exact 0.009, oracle-vs-exact 0.020), so there the bound is
-    // 2 ulps of the reference value.
+    // 2e-2 max-abs against the reference chain (north_star).  That chain rounds q*scale, the scores and the
+    // probabilities to bf16, so on the short causal rows of these 48 heads (1-3 keys: nothing averages out) it
+    // sits up to 0.020 from the float64 answer itself, while the kernel (f32 scores, one final rounding) stays
+    // within 0.009 (scripts/exp_fmha_err.py).  An element may therefore exceed 2e-2 against the chain ONLY where
+    // the kernel is at least as close to the float64 answer as the chain is; everywhere else the bar is 2e-2.
     const std::vector<uint16_t> got = download(out);
-    float err = 0.f, err_big = 0.f;
+    const std::vector<double> exact = sdpa_causal_f64(q, k, v, B, H, L, D, scale);
+    float err = 0.f;
+    size_t excused = 0;
     for (size_t i = 0; i < got.size(); ++i) {
       const float r = bf2f(want[i]), g = bf2f(got[i]), d = std::fabs(g - r);
-      const float big = std::max(std::fabs(r), std::fabs(g));  // (1.992 vs 2.016 straddles the binade edge)
-      if (big >= 2.f) err_big = std::max(err_big, d / std::ldexp(1.f, std::ilogb(big) - 7));
-      else err = std::max(err, d);
+      if (d > 2e-2f && std::fabs((double)g - exact[i]) <= std::fabs((double)r - exact[i])) {
+        ++excused;
+        continue;
+      }
+      err = std::max(err, d);
     }
     EXPECT(err <= 2e-2f, "sdpa L=%d max-abs err %g > 2e-2", L, err);
-    EXPECT(err_big <= 2.f, "sdpa L=%d: %g bf16 ulps off where |ref| >= 2", L, err_big);
+    EXPECT(excused <= got.size() / 100000 + 2, "sdpa L=%d: %zu elements beyond 2e-2 of the chain (closer to float64)", L,
+           excused);
   }
   bool threw = false;
   try {  // n_heads % n_kv_heads
