@@ -210,6 +210,39 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
                            const char* mask_mode, const omx_array* mask_arr /* may be null */,
                            omx_array* keys_out, omx_array* values_out, omx_stream s);
 
+/* ---- CUDA-graph decode loop -------------------------------- */
+/*
+ * The reference hides per-op launch cost behind MLX's lazy graph + async_eval double buffering
+ * (qwen3-mlx/src/model.rs:798-844: Generate::next evaluates token t while building t+1).  The
+ * eager equivalent on CUDA is to capture the per-layer launches of one decode step ONCE and replay
+ * the graph per token.  A captured launch cannot take the position as a host argument, so:
+ *   - omx_kv_cache_prepare_graph pins the cache buffers (and a cache-owned split-K scratch) for
+ *     positions [0, max_rows) -- addresses then stay fixed until the cache grows past max_rows or
+ *     prepare_graph is called again (re-capture after either).  n_q_heads = Hq of the launches;
+ *   - omx_attn_decode_fused_dynamic is omx_attn_decode_fused_norm with `off` read by the KERNEL
+ *     from *position (device int32, shared by all layers of the model): row *position is written,
+ *     keys [0, *position] are attended.  It does NOT touch the host-side offset;
+ *   - omx_device_counter_add bumps the device position (one 1-thread launch per token step);
+ *   - omx_kv_cache_advance(c, n) is the host bookkeeping after n such steps (offset += n, logical
+ *     capacity by the cache.rs:141-181 rule, no copy), so offset()/state()/update_and_fetch agree
+ *     with what the launches did.
+ * Every launch is capture-safe once the same call has run eagerly (rope table and scratch exist).
+ * Same kernels and arithmetic as omx_attn_decode_fused_norm: the appended cache rows are always
+ * bit-identical, the outputs are bit-identical whenever the split-K plan coincides (it is fixed at
+ * capture from max_rows instead of following the current length) and differ by f32 summation
+ * order otherwise.
+ */
+int omx_kv_cache_prepare_graph(omx_kv_cache c, int max_rows, int n_q_heads, omx_stream s);
+int omx_kv_cache_advance(omx_kv_cache c, int n, omx_stream s);
+int omx_attn_decode_fused_dynamic(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                                  const omx_array* v_new, omx_kv_cache cache,
+                                  const omx_array* q_norm_weight /* may be null */,
+                                  const omx_array* k_norm_weight /* may be null */, float norm_eps,
+                                  int rope_dims, bool traditional, omx_optional_float base,
+                                  float rope_scale, float sm_scale,
+                                  const int32_t* position /* device */, omx_stream s);
+int omx_device_counter_add(int32_t* counter /* device */, int delta, omx_stream s);
+
 /* ---- head-sharded single-sequence decode (BASELINE C5) -------------------- */
 /*
  * The reference has no multi-device path (MLX is single-GPU); this is the exchange step the

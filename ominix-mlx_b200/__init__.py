@@ -18,7 +18,8 @@ importlib.import_module("ominix-mlx_b200").
 from . import _lib, array, attention, cache, dit, fast, nn, parallel, utils  # noqa: F401
 from ._lib import Exception_ as Exception  # noqa: A001,F401
 from ._lib import EXPORTED_SYMBOLS, LIB_PATH, build, force_kernel, last_kernel, launch_count, lib  # noqa: F401
-from .attention import attn_decode_fused, attn_decode_unfused, attn_prefill_fused  # noqa: F401
+from .attention import (DecodeLoopGraph, attn_decode_fused, attn_decode_fused_dynamic,  # noqa: F401
+                        attn_decode_unfused, attn_prefill_fused, device_counter_add)
 from .cache import ConcatKeyValueCache, KeyValueCache, KVCache  # noqa: F401
 from .utils import (AttentionMask, SdpaMask, create_attention_mask, create_causal_mask,  # noqa: F401
                     initialize_rope, scaled_dot_product_attention)

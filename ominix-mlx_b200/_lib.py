@@ -76,6 +76,12 @@ _SIGS = {
     "omx_attn_prefill_fused": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, _AP, _AP, ctypes.c_float, ctypes.c_int,
                                               ctypes.c_bool, OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                               ctypes.c_char_p, _AP, _AP, _AP, ctypes.c_void_p]),
+    "omx_kv_cache_prepare_graph": (ctypes.c_int, [OmxKVCache, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "omx_kv_cache_advance": (ctypes.c_int, [OmxKVCache, ctypes.c_int, ctypes.c_void_p]),
+    "omx_attn_decode_fused_dynamic": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, _AP, _AP, ctypes.c_float,
+                                                     ctypes.c_int, ctypes.c_bool, OmxOptionalFloat, ctypes.c_float,
+                                                     ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
+    "omx_device_counter_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                      OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                      ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),

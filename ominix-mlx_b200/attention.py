@@ -41,6 +41,92 @@ def attn_decode_fused(q, k_new, v_new, cache, rope, sm_scale, stream=None, out=N
     return out
 
 
+def attn_decode_fused_dynamic(q, k_new, v_new, cache, rope, sm_scale, position, stream=None, out=None,
+                              q_norm=None, k_norm=None):
+    """attn_decode_fused with the position read by the kernel from `position` (int32 CUDA tensor, one
+    element, shared by all layers) -- capturable into a CUDA graph and replayable for every token.
+    The cache must have been pinned with cache.prepare_graph(max_rows, Hq); the host offset is NOT
+    advanced here (cache.advance(n) after the step / replays)."""
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1], 1, v_new.shape[3]), dtype=q.dtype, device=q.device)
+    if position.dtype != torch.int32 or not position.is_cuda or position.numel() != 1:
+        raise _lib.Exception_("position must be a one-element int32 CUDA tensor")
+    base = _lib.OmxOptionalFloat()
+    base.has_value = rope is not None
+    base.value = rope.base if rope is not None else 0.0
+    eps = (q_norm or k_norm).eps if (q_norm is not None or k_norm is not None) else 0.0
+    if q_norm is not None and k_norm is not None and q_norm.eps != k_norm.eps:
+        raise _lib.Exception_("q_norm and k_norm must share one eps in the fused step")
+    qd, kd, vd, od = desc(q), desc(k_new), desc(v_new), desc(out)
+    qw = desc(q_norm.weight) if q_norm is not None else None
+    kw = desc(k_norm.weight) if k_norm is not None else None
+    _lib.check(_lib.lib().omx_attn_decode_fused_dynamic(
+        ref(od), ref(qd), ref(kd), ref(vd), cache.handle, ref(qw), ref(kw), float(eps),
+        int(rope.dimensions if rope is not None else 0), bool(rope.traditional) if rope is not None else False,
+        base, float(rope.scale) if rope is not None else 1.0, float(sm_scale), position.data_ptr(),
+        stream_ptr(stream)))
+    return out
+
+
+def device_counter_add(counter, delta=1, stream=None):
+    """counter (int32 CUDA tensor) += delta on the stream: the per-token position bump of a graph loop."""
+    _lib.check(_lib.lib().omx_device_counter_add(counter.data_ptr(), int(delta), stream_ptr(stream)))
+
+
+class DecodeLoopGraph:
+    """One decode step of an n-layer model's attention -- per layer the one-launch fused step
+    (q_norm/k_norm, rope, KV append, GQA attention), then the position bump -- captured ONCE into a CUDA
+    graph and replayed per token: what MLX's lazy graph + async_eval gave the reference's decode loop
+    (qwen3-mlx/src/model.rs:798-844), without re-tracing.
+
+    q / k_new / v_new / out are STATIC per-layer buffers (lists of tensors): the projections of the
+    surrounding model write into them before each replay, as with any CUDA graph.  `caches`: one
+    prefilled KVCache per layer, all at the same offset."""
+
+    def __init__(self, q, k_new, v_new, caches, rope, sm_scale, max_rows, q_norm=None, k_norm=None, out=None):
+        n = len(caches)
+        self.caches, self.q, self.k_new, self.v_new = caches, q, k_new, v_new
+        dev = q[0].device
+        off = caches[0].offset()
+        if any(c.offset() != off for c in caches):
+            raise _lib.Exception_("all layer caches must be at the same offset")
+        self.max_rows = int(max_rows)
+        self.out = out or [torch.empty((t.shape[0], t.shape[1], 1, v.shape[3]), dtype=t.dtype, device=dev)
+                           for t, v in zip(q, v_new)]
+        self.position = torch.full((1,), off, dtype=torch.int32, device=dev)
+        qn = q_norm if isinstance(q_norm, (list, tuple)) else [q_norm] * n
+        kn = k_norm if isinstance(k_norm, (list, tuple)) else [k_norm] * n
+        for c, t in zip(caches, q):
+            c.prepare_graph(max_rows, t.shape[1])
+
+        def step(stream=None):
+            for i in range(n):
+                attn_decode_fused_dynamic(q[i], k_new[i], v_new[i], caches[i], rope, sm_scale, self.position,
+                                          stream=stream, out=self.out[i], q_norm=qn[i], k_norm=kn[i])
+            device_counter_add(self.position, 1, stream=stream)
+        # eager warm-up on a side stream builds the rope table and proves the launch configuration; its
+        # effects are rolled back (same row is rewritten by the first replay, position restored)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+            device_counter_add(self.position, -1)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            step()
+        self.launches_per_step = n + 1
+
+    def step(self):
+        """Replay one token step (asynchronous) and advance the host-side offsets."""
+        if self.caches[0].offset() + 1 > self.max_rows:
+            raise _lib.Exception_(f"decode loop graph was pinned for {self.max_rows} rows")
+        self.graph.replay()
+        for c in self.caches:
+            c.advance(1)
+        return self.out
+
+
 def attn_prefill_fused(q, k_new, v_new, cache, rope, sm_scale, mask=None, stream=None, out=None, fetch=False,
                        q_norm=None, k_norm=None):
     """Attention::forward for L >= 1 new tokens (model.rs:172-212) with the minimum of memory passes:

@@ -71,6 +71,15 @@ class KVCache(KeyValueCache):
         _lib.check(_lib.lib().omx_kv_cache_trim(self._h, int(n), ctypes.byref(t)))
         return t.value
 
+    def prepare_graph(self, max_rows, n_q_heads, stream=None):
+        """Extension (CUDA-graph decode loop, include/omx_attn.h): pin the buffers and the cache-owned
+        split-K scratch for positions [0, max_rows); addresses stay fixed until the cache outgrows them."""
+        _lib.check(_lib.lib().omx_kv_cache_prepare_graph(self._h, int(max_rows), int(n_q_heads), stream_ptr(stream)))
+
+    def advance(self, n=1, stream=None):
+        """Host bookkeeping for n rows appended by dynamic-position launches / graph replays."""
+        _lib.check(_lib.lib().omx_kv_cache_advance(self._h, int(n), stream_ptr(stream)))
+
     def update_and_fetch(self, keys, values, stream=None):
         k, v = desc(keys), desc(values)
         ko, vo = _lib.OmxArray(), _lib.OmxArray()

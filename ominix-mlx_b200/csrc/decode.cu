@@ -78,7 +78,37 @@ struct DecodeParams {
   int mask_kind;  // 0 none, 1 bool, 2 additive
   int64_t mks[3];
   uint8_t* dead;  // [B][Hq]: 1 = the mask hid every key (masked_rows_fixup rewrites the row)
+  // graph mode (omx_attn_decode_fused_dynamic): the position (= keys already cached) is read from device
+  // memory at run time, so ONE captured launch serves every step of a decode loop.  Lk / n_mem /
+  // tiles_per_split above then hold the values of the LAST admissible position (max_rows - 1) and
+  // cos_row / sin_row the table base; the grid (num_splits) is fixed at capture.
+  const int* pos_dev;
+  int max_rows;
 };
+
+// The launch's key count, split size and rope row: kernel arguments, or derived from *pos_dev.
+struct DecodeDyn {
+  int Lk, n_mem, tps;
+  const float *cos_row, *sin_row;
+};
+
+__device__ __forceinline__ DecodeDyn load_dyn(const DecodeParams& p) {
+  DecodeDyn d{p.Lk, p.n_mem, p.tiles_per_split, p.cos_row, p.sin_row};
+  if (p.pos_dev) {
+    // clamped: a loop driven past the reserved rows rewrites the last row instead of leaving the buffer
+    // (omx_kv_cache_advance reports the overflow to the host)
+    const int pos = min(max(__ldg(p.pos_dev), 0), p.max_rows - 1);
+    d.n_mem = pos;
+    d.Lk = pos + 1;
+    const int n_tiles = (pos + kTile - 1) / kTile;
+    d.tps = max(1, (n_tiles + p.num_splits - 1) / p.num_splits);
+    if (p.rope_dims > 0) {
+      d.cos_row = p.cos_row + (size_t)pos * (p.rope_dims >> 1);
+      d.sin_row = p.sin_row + (size_t)pos * (p.rope_dims >> 1);
+    }
+  }
+  return d;
+}
 
 // score (log2 domain) of `key` for query head `h` after the array mask.  Additive entries <= -1e8
 // (the callers' -1e9 / -inf spelling of "hidden") hide the key outright, like the prefill kernel.
@@ -135,7 +165,7 @@ __device__ __forceinline__ void stage_norms(const DecodeParams& p, float* rs, in
 template <typename T>
 __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total,
                                         int first_head, int n_heads, int b, int tid, int nthr,
-                                        const float* rs) {
+                                        const float* rs, const DecodeDyn& dy) {
   const T* qg = (const T*)p.q + b * p.qs[0] + (int64_t)first_head * p.qs[1];
   const int D = p.D;
   const T* nw = (const T*)p.q_norm_w;
@@ -156,7 +186,7 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
         const int i1 = p.traditional ? 2 * u : u;
         const int i2 = p.traditional ? 2 * u + 1 : u + half;
         float o1, o2;
-        rope_pair<T>(qval(qh, g, i1), qval(qh, g, i2), rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
+        rope_pair<T>(qval(qh, g, i1), qval(qh, g, i2), rnd<T>(dy.cos_row[u]), rnd<T>(dy.sin_row[u]), o1, o2);
         q_s[g * pitch + i1] = Num<T>::from_f(o1);
         q_s[g * pitch + i2] = Num<T>::from_f(o2);
       } else {
@@ -177,7 +207,8 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
 template <typename T>
 __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
                                           int b, int hk, int lane, float* nt_k, float* nt_v,
-                                          float* nt_m, const float* rs, bool write_cache = true) {
+                                          float* nt_m, const float* rs, const DecodeDyn& dy,
+                                          bool write_cache = true) {
   const int D = p.D;
   const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
   const T* nw = (const T*)p.k_norm_w;
@@ -186,14 +217,14 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
     return nw ? rms_apply<T>(x, rs[16], Num<T>::to_f(nw[d]), true) : x;
   };
   const T* vn = (const T*)p.v_new + b * p.vns[0] + hk * p.vns[1];
-  T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(p.Lk - 1) * p.kcs[2];
-  T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(p.Lk - 1) * p.vcs[2];
+  T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(dy.Lk - 1) * p.kcs[2];
+  T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(dy.Lk - 1) * p.vcs[2];
   const int half = p.rope_dims >> 1;
   for (int u = lane; u < half; u += 32) {
     const int i1 = p.traditional ? 2 * u : u;
     const int i2 = p.traditional ? 2 * u + 1 : u + half;
     float o1, o2;
-    rope_pair<T>(kval(i1), kval(i2), rnd<T>(p.cos_row[u]), rnd<T>(p.sin_row[u]), o1, o2);
+    rope_pair<T>(kval(i1), kval(i2), rnd<T>(dy.cos_row[u]), rnd<T>(dy.sin_row[u]), o1, o2);
     if (write_cache) {
       kc[i1 * p.kcs[3]] = Num<T>::from_f(o1);
       kc[i2 * p.kcs[3]] = Num<T>::from_f(o2);
@@ -338,9 +369,10 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
-  const int n_tiles = (p.n_mem + kTile - 1) / kTile;
-  const int tile_begin = split * p.tiles_per_split;
-  const int my_tiles = max(0, min(p.tiles_per_split, n_tiles - tile_begin));
+  const DecodeDyn dy = load_dyn(p);
+  const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
+  const int tile_begin = split * dy.tps;
+  const int my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
   const bool has_nt = p.fused && split == p.num_splits - 1;
 
   // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight BEFORE the
@@ -374,7 +406,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     stage_norms<T>(p, s_rs, hk * G, G, b, hk, has_nt, tid);
     __syncthreads();
   }
-  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR, s_rs);
+  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR, s_rs, dy);
   __syncthreads();
 
   // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
@@ -387,7 +419,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   if (warp == NW) {
     // ------------------------------------------------ producer warp (first tiles already in flight)
-    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_rs);
+    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_rs, dy);
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
         mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
@@ -432,14 +464,14 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
       // online softmax (log2 domain)
       const int key_base = (tile_begin + t) * kTile;
-      const bool partial = key_base + kTile > p.n_mem;
+      const bool partial = key_base + kTile > dy.n_mem;
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = key_base + nb * 8 + cq + e;
-          const bool dead = partial && (key >= p.n_mem);
+          const bool dead = partial && (key >= dy.n_mem);
           sa[nb][e] = dead ? -INFINITY : sa[nb][e] * p.scale_log2;
           if (HI) sa[nb][2 + e] = dead ? -INFINITY : sa[nb][2 + e] * p.scale_log2;
           if (p.mask_kind && !dead) {  // launch-uniform
@@ -602,20 +634,21 @@ decode_simt_kernel(const DecodeParams p) {
   const int hk = blockIdx.y / groups, gsub = blockIdx.y % groups;
   const int first_head = hk * p.G + gsub * GT;
   const int pair = (b * p.Hkv + hk) * groups + gsub;
-  const int keys_per_split = p.tiles_per_split * kTile;
+  const DecodeDyn dy = load_dyn(p);
+  const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
-  const int kend = min(p.n_mem, kbeg + keys_per_split);
+  const int kend = min(dy.n_mem, kbeg + keys_per_split);
   const bool has_nt = p.fused && split == p.num_splits - 1;
 
   if (p.q_norm_w || p.k_norm_w) {
     stage_norms<T>(p, s_rs, first_head, GT, b, hk, has_nt, tid);
     __syncthreads();
   }
-  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR, s_rs);
+  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR, s_rs, dy);
   __syncthreads();
   // the new row is appended once per kv head (gsub == 0 writes it); every group scores it
   if (has_nt && warp == kSimtWarps - 1)
-    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_rs, /*write_cache=*/gsub == 0);
+    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_rs, dy, /*write_cache=*/gsub == 0);
 
   float qr[GT][VE], acc[GT][VE], m[GT], l[GT];
 #pragma unroll
@@ -766,6 +799,23 @@ void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t
   OMX_CUDA(cudaGetLastError());
 }
 
+size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int max_rows) {
+  // mirrors the two plans of decode_attention at the largest position the launch may see
+  const int sms = sm_count();
+  const int n_tiles = (std::max(max_rows - 1, 0) + kTile - 1) / kTile;
+  const int G = Hq / std::max(Hkv, 1);
+  size_t worst = 0;
+  for (int simt = 0; simt < 2; ++simt) {
+    if (!simt && !(dtype != OMX_FLOAT32 && D == 128 && G <= 16)) continue;
+    const int Gt = simt ? ((G % 4 == 0) ? 4 : (G % 2 == 0 ? 2 : 1)) : G;
+    const int64_t pairs = (int64_t)B * Hkv * (simt ? G / Gt : 1);
+    const SplitPlan sp = plan_splits(pairs, n_tiles, sms, simt ? 2 : 4);
+    const size_t part = sp.num_splits > 1 ? (size_t)pairs * sp.num_splits * Gt * (D + 2) : 0;
+    worst = std::max(worst, sizeof(float) * part + sizeof(int) * ((size_t)pairs + 1));
+  }
+  return worst;
+}
+
 bool decode_supported(const SdpaArgs& a, const char** why) {
   auto no = [&](const char* w) {
     if (why) *why = w;
@@ -845,16 +895,43 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     p.mks[1] = a.mask_strides[1];
     p.mks[2] = a.mask_strides[3];
   }
-  // one workspace request per call (a second one could move the first): split-K partials, then flags
-  auto carve_workspace = [&](size_t no, size_t nml) {
-    const size_t fl = masked ? (size_t)a.B * a.Hq : 0;
-    if (no + nml + fl == 0) return;
-    float* ws = (float*)get_workspace(sizeof(float) * (no + nml) + fl, stream);
-    if (no) {
+  const bool dyn = f.enabled && f.pos_dev != nullptr;
+  if (dyn) {
+    OMX_CHECK(!f.peers && !masked, "the dynamic-position decode step takes no peer group and no array mask");
+    OMX_CHECK(f.max_rows >= 1 && a.Lk == f.max_rows, "dynamic-position decode: K/V views must span max_rows");
+    p.pos_dev = f.pos_dev;
+    p.max_rows = f.max_rows;
+  }
+  // one workspace request per call (a second one could move the first): split-K partials, then flags.
+  // Graph mode carves the same layout (+ the counters) out of the cache-owned scratch instead, whose
+  // address never changes under a captured launch.
+  auto carve_workspace = [&](size_t no, size_t nml, size_t n_ctr) {
+    if (dyn) {
+      const size_t need = sizeof(float) * (no + nml) + sizeof(int) * n_ctr;
+      OMX_CHECK(need <= f.scratch_bytes, "dynamic-position decode: scratch too small (%zu > %zu bytes); call "
+                "omx_kv_cache_prepare_graph with this launch's head count first", need, f.scratch_bytes);
+      float* ws = (float*)f.scratch;
       p.ws_o = ws;
       p.ws_ml = ws + no;
+      if (n_ctr) {
+        p.counters = reinterpret_cast<int*>(ws + no + nml);
+        p.peer_done = p.counters + n_ctr - 1;
+      }
+      return;
     }
-    if (fl) p.dead = reinterpret_cast<uint8_t*>(ws + no + nml);
+    const size_t fl = masked ? (size_t)a.B * a.Hq : 0;
+    if (no + nml + fl) {
+      float* ws = (float*)get_workspace(sizeof(float) * (no + nml) + fl, stream);
+      if (no) {
+        p.ws_o = ws;
+        p.ws_ml = ws + no;
+      }
+      if (fl) p.dead = reinterpret_cast<uint8_t*>(ws + no + nml);
+    }
+    if (n_ctr) {
+      p.counters = get_counters(n_ctr, stream);
+      p.peer_done = p.counters + n_ctr - 1;
+    }
   };
 
   const int sms = sm_count();
@@ -879,14 +956,12 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     p.num_splits = sp.num_splits;
     p.tiles_per_split = sp.tiles_per_split;
     carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
-                    p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0);
-    if (p.num_splits > 1 || p.n_peers) {
-      p.counters = get_counters((size_t)pairs + 1, stream);
-      p.peer_done = p.counters + pairs;
-      p.peer_total = (int)pairs;
-    }
+                    p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
+                    (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
+    p.peer_total = (int)pairs;
     const bool bf = a.q->dtype == OMX_BFLOAT16;
-    const uint64_t rows = (uint64_t)std::max(p.n_mem, 1);
+    // graph mode: the map spans every reserved row (the tail beyond the position is masked in the kernel)
+    const uint64_t rows = (uint64_t)std::max(dyn ? p.max_rows : p.n_mem, 1);
     CUtensorMap tmK = make_tmap_4d_b16(a.k->data, 128, rows, a.Hkv, a.B, a.k->strides[2], a.k->strides[1],
                                        a.k->strides[0], 64, 64, bf);
     CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
@@ -929,12 +1004,9 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   p.num_splits = sp.num_splits;
   p.tiles_per_split = sp.tiles_per_split;
   carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * p.D : 0,
-                  p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * 2 : 0);
-  if (p.num_splits > 1 || p.n_peers) {
-    p.counters = get_counters((size_t)pairs + 1, stream);
-    p.peer_done = p.counters + pairs;
-    p.peer_total = (int)pairs;
-  }
+                  p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * 2 : 0,
+                  (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
+  p.peer_total = (int)pairs;
   dim3 grid(p.num_splits, a.Hkv * groups, a.B);
   note_launch("decode_simt");
   switch (a.q->dtype) {

@@ -98,6 +98,10 @@ struct KVCacheImpl {
   int64_t reserve_rows = 0;
   KVBuf k, v;
   cudaStream_t last_stream = nullptr;
+  // graph mode
+  int64_t graph_rows = 0;  // rows pinned by prepare_graph (0: not prepared)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
 };
 
 KVCacheImpl* kv_cache_create(int step, bool concat) {
@@ -112,6 +116,7 @@ void kv_cache_destroy(KVCacheImpl* c) {
   if (!c) return;
   if (c->k.p) cudaFreeAsync(c->k.p, c->last_stream);
   if (c->v.p) cudaFreeAsync(c->v.p, c->last_stream);
+  if (c->scratch) cudaFreeAsync(c->scratch, c->last_stream);
   delete c;
 }
 
@@ -153,6 +158,7 @@ void regrow(KVCacheImpl* c, KVBuf& b, int64_t keep, int64_t new_cap, bool zero_n
     if (b.p) OMX_CUDA(cudaFreeAsync(b.p, stream));
     b.p = np;
     b.phys = phys;
+    c->graph_rows = 0;  // the buffer moved: launches captured against the old address are stale
   }
   if (zero_new && new_cap > keep && row > 0 && heads > 0) {
     OMX_CUDA(cudaMemset2DAsync((char*)b.p + (size_t)keep * row, (size_t)b.phys * row, 0,
@@ -265,6 +271,81 @@ void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* val
   }
   fill_view(c, c->k, c->offset, keys_out);  // :190-193
   fill_view(c, c->v, c->offset, values_out);
+}
+
+void kv_cache_prepare_graph(KVCacheImpl* c, int max_rows, size_t scratch_bytes, cudaStream_t stream) {
+  OMX_CHECK(!c->concat, "[KVCache] graph mode is not defined for ConcatKeyValueCache");
+  OMX_CHECK(c->has, "[KVCache] prepare_graph needs a cache that has seen one update (shape and dtype come from it)");
+  OMX_CHECK(max_rows >= c->offset + 1, "[KVCache] prepare_graph: max_rows %d leaves no room after offset %d", max_rows,
+            c->offset);
+  c->last_stream = stream;
+  // the logical capacity can run up to one step past the last position (cache.rs:152-174): pin that too
+  const int64_t pin = ((int64_t)max_rows + c->step - 1) / c->step * c->step + c->step;
+  c->reserve_rows = std::max<int64_t>(c->reserve_rows, pin);
+  for (KVBuf* b : {&c->k, &c->v}) {
+    regrow(c, *b, c->cap, std::max<int64_t>(c->cap, pin), false, stream);  // may move the buffer
+    // physical rows past the logical capacity have never been exposed: zero them once so that a partial
+    // tile read beyond the position sees finite data (fresh allocations are not zeroed by the driver)
+    const size_t row = (size_t)b->D * dtype_size(b->dtype);
+    const size_t heads = (size_t)c->B * c->H;
+    const int64_t from = c->cap;
+    if (b->phys > from && row && heads)
+      OMX_CUDA(cudaMemset2DAsync((char*)b->p + (size_t)from * row, (size_t)b->phys * row, 0,
+                                 (size_t)(b->phys - from) * row, heads, stream));
+  }
+  if (scratch_bytes > c->scratch_bytes) {
+    if (c->scratch) OMX_CUDA(cudaFreeAsync(c->scratch, stream));
+    OMX_CUDA(cudaMallocAsync(&c->scratch, scratch_bytes, stream));
+    OMX_CUDA(cudaMemsetAsync(c->scratch, 0, scratch_bytes, stream));
+    c->scratch_bytes = scratch_bytes;
+  }
+  c->graph_rows = max_rows;
+}
+
+bool kv_cache_graph_view(const KVCacheImpl* c, omx_array* k, omx_array* v, void** scratch, size_t* scratch_bytes,
+                         int* max_rows) {
+  if (!c->has || c->graph_rows <= 0 || c->k.phys < c->graph_rows || c->v.phys < c->graph_rows) return false;
+  fill_view(c, c->k, c->graph_rows, k);
+  fill_view(c, c->v, c->graph_rows, v);
+  *scratch = c->scratch;
+  *scratch_bytes = c->scratch_bytes;
+  *max_rows = (int)c->graph_rows;
+  return true;
+}
+
+void kv_cache_advance(KVCacheImpl* c, int n, cudaStream_t stream) {
+  OMX_CHECK(!c->concat && c->has, "[KVCache] advance needs a non-empty step-allocated cache");
+  OMX_CHECK(n >= 0, "[KVCache] advance by a negative count");
+  OMX_CHECK(c->graph_rows > 0 && (int64_t)c->offset + n <= c->graph_rows,
+            "[KVCache] advance: offset %d + %d rows exceeds the %lld rows pinned by prepare_graph (the launches "
+            "past that point rewrote the last row)", c->offset, n, (long long)c->graph_rows);
+  const int prev = c->offset;
+  c->last_stream = stream;
+  if ((int64_t)prev + n > c->cap) {  // cache.rs:141-181, with the rows the kernels already wrote kept
+    const int n_steps = (c->step + n - 1) / c->step;
+    const int64_t keep = (prev % c->step != 0) ? prev : c->cap;
+    const int64_t new_cap = keep + (int64_t)n_steps * c->step;
+    // the reference zero-fills [keep, new_cap) and then writes the n rows; here the rows are already in
+    // place, so only the part after them is cleared (rows beyond the old capacity are zero since
+    // prepare_graph unless a trim exposed stale ones)
+    const int64_t from = std::max<int64_t>(keep, (int64_t)prev + n);
+    for (KVBuf* b : {&c->k, &c->v}) {
+      OMX_CHECK(new_cap <= b->phys, "[KVCache] advance: capacity %lld exceeds the pinned rows", (long long)new_cap);
+      const size_t row = (size_t)b->D * dtype_size(b->dtype);
+      const size_t heads = (size_t)c->B * c->H;
+      const int64_t to = std::min<int64_t>(new_cap, b->phys);
+      if (to > from && row && heads)
+        OMX_CUDA(cudaMemset2DAsync((char*)b->p + (size_t)from * row, (size_t)b->phys * row, 0,
+                                   (size_t)(to - from) * row, heads, stream));
+    }
+    c->cap = new_cap;
+  }
+  c->offset = prev + n;
+}
+
+void kv_cache_shape(const KVCacheImpl* c, int* B, int* H, int* Dk, int* Dv, int* dtype) {
+  OMX_CHECK(c->has, "[KVCache] cache is empty");
+  *B = c->B; *H = c->H; *Dk = c->k.D; *Dv = c->v.D; *dtype = c->k.dtype;
 }
 
 void kv_cache_state(const KVCacheImpl* c, omx_array* kbuf, omx_array* vbuf) {

@@ -530,6 +530,93 @@ int omx_attn_decode_fused_norm(const omx_array* out, const omx_array* q, const o
   });
 }
 
+static __global__ void omx_counter_add_kernel(int32_t* c, int delta) { *c += delta; }
+
+int omx_device_counter_add(int32_t* counter, int delta, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(counter, "[device_counter_add] null counter");
+    omx_counter_add_kernel<<<1, 1, 0, (cudaStream_t)s>>>(counter, delta);
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+  });
+}
+
+int omx_kv_cache_prepare_graph(omx_kv_cache c, int max_rows, int n_q_heads, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    auto* kc = (KVCacheImpl*)c.ctx;
+    OMX_CHECK(kc, "[KVCache] null handle");
+    int B, H, Dk, Dv, dt;
+    kv_cache_shape(kc, &B, &H, &Dk, &Dv, &dt);
+    OMX_CHECK(n_q_heads >= H && n_q_heads % H == 0, "[KVCache] prepare_graph: %d query heads over %d kv heads",
+              n_q_heads, H);
+    kv_cache_prepare_graph(kc, max_rows, decode_graph_scratch_bytes(B, H, n_q_heads, Dk, dt, max_rows),
+                           (cudaStream_t)s);
+  });
+}
+
+int omx_kv_cache_advance(omx_kv_cache c, int n, omx_stream s) {
+  return guarded([&] {
+    OMX_CHECK(c.ctx, "[KVCache] null handle");
+    kv_cache_advance((KVCacheImpl*)c.ctx, n, (cudaStream_t)s);
+  });
+}
+
+int omx_attn_decode_fused_dynamic(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                                  const omx_array* v_new, omx_kv_cache cache, const omx_array* q_norm_weight,
+                                  const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,
+                                  omx_optional_float base, float rope_scale, float sm_scale,
+                                  const int32_t* position, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    auto* c = (KVCacheImpl*)cache.ctx;
+    OMX_CHECK(c, "[attn_decode_fused_dynamic] null cache handle");
+    OMX_CHECK(position, "[attn_decode_fused_dynamic] null position pointer");
+    OMX_CHECK(q && k_new && v_new && out, "[attn_decode_fused_dynamic] null array");
+    OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4 && q->shape[2] == 1 &&
+                  k_new->shape[2] == 1 && v_new->shape[2] == 1,
+              "[attn_decode_fused_dynamic] q, k_new, v_new, out must be [B, H, 1, D]");
+    OMX_CHECK(k_new->dtype == q->dtype && v_new->dtype == q->dtype && out->dtype == q->dtype,
+              "[attn_decode_fused_dynamic] dtype mismatch");
+    const int D = (int)q->shape[3];
+    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
+    OMX_CHECK(rope_dims == 0 || base.has_value, "[attn_decode_fused_dynamic] rope needs a base (no freqs here)");
+    const bool qn = q_norm_weight && q_norm_weight->data, kn = k_norm_weight && k_norm_weight->data;
+    for (const omx_array* w : {qn ? q_norm_weight : nullptr, kn ? k_norm_weight : nullptr}) {
+      if (!w) continue;
+      OMX_CHECK(w->ndim == 1 && w->shape[0] == D && w->dtype == q->dtype && (w->strides[0] == 1 || D == 1),
+                "[attn_decode_fused_dynamic] norm weights must be contiguous [%d] vectors in the q dtype", D);
+    }
+    omx_array kview, vview;
+    DecodeFused f;
+    OMX_CHECK(kv_cache_graph_view(c, &kview, &vview, &f.scratch, &f.scratch_bytes, &f.max_rows),
+              "[attn_decode_fused_dynamic] call omx_kv_cache_prepare_graph first (or again: the cache grew past "
+              "the pinned rows)");
+    OMX_CHECK(k_new->shape[0] == kview.shape[0] && k_new->shape[1] == kview.shape[1] && k_new->shape[3] == kview.shape[3] &&
+                  v_new->shape[3] == vview.shape[3] && k_new->dtype == kview.dtype,
+              "[attn_decode_fused_dynamic] k_new / v_new do not match the cache shape or dtype");
+    SdpaArgs a = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    const char* why = nullptr;
+    const bool fast = decode_supported(a, &why) && k_new->strides[3] == 1 && v_new->strides[3] == 1;
+    OMX_CHECK(fast, "[attn_decode_fused_dynamic] layout not supported by the decode kernels: %s",
+              why ? why : "strided k_new/v_new");
+    f.enabled = true;
+    f.k_new = k_new;
+    f.v_new = v_new;
+    f.rope_dims = rope_dims;
+    f.traditional = traditional;
+    f.position = 0;  // table base; the kernel adds *position rows
+    f.pos_dev = position;
+    f.q_norm_w = qn ? q_norm_weight->data : nullptr;
+    f.k_norm_w = kn ? k_norm_weight->data : nullptr;
+    f.norm_eps = norm_eps;
+    if (rope_dims > 0) f.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, f.max_rows, stream);
+    decode_attention(a, f, stream);
+  });
+}
+
 int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
                            const omx_array* v_new, omx_kv_cache cache, const omx_array* q_norm_weight,
                            const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,

@@ -67,6 +67,15 @@ void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* val
                      omx_array* keys_out, omx_array* values_out, bool skip_copy,
                      cudaStream_t stream);
 void kv_cache_state(const KVCacheImpl* c, omx_array* kbuf, omx_array* vbuf);
+// Graph mode: pin the buffers at >= max_rows physical rows (never-written tail zeroed) and allocate the
+// cache-owned scratch; the addresses stay fixed until the cache grows past max_rows.
+void kv_cache_prepare_graph(KVCacheImpl* c, int max_rows, size_t scratch_bytes, cudaStream_t stream);
+// Views over all max_rows pinned rows + the scratch; false if prepare_graph has not been called.
+bool kv_cache_graph_view(const KVCacheImpl* c, omx_array* k, omx_array* v, void** scratch,
+                         size_t* scratch_bytes, int* max_rows);
+// Host bookkeeping for n rows appended by dynamic-position launches (reference growth rule, no copy).
+void kv_cache_advance(KVCacheImpl* c, int n, cudaStream_t stream);
+void kv_cache_shape(const KVCacheImpl* c, int* B, int* H, int* Dk, int* Dv, int* dtype);
 // Strided 4-D copy (dst, src same shape/dtype); used by caches and tests.
 void copy4d(const omx_array* dst, const omx_array* src, cudaStream_t stream);
 
@@ -111,7 +120,15 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   const void* q_norm_w = nullptr;
   const void* k_norm_w = nullptr;
   float norm_eps = 0.f;
+  // graph mode (omx_attn_decode_fused_dynamic): the position is read from device memory by the kernel;
+  // K/V views span max_rows rows, `position` above is 0, scratch is owned by the cache
+  const int* pos_dev = nullptr;
+  int max_rows = 0;
+  void* scratch = nullptr;  // split-K partials + arrival counters, zero-initialised, fixed address
+  size_t scratch_bytes = 0;
 };
+// Bytes of cache-owned scratch a dynamic-position launch of this shape can need.
+size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int max_rows);
 // q [B,Hq,1,D]; k/v views over Lk rows (Lk INCLUDES the new row when fused: the kernel reads
 // rows [0, Lk-1) from memory and takes row Lk-1 from k_new/v_new, writing it to k/v as well).
 bool decode_supported(const SdpaArgs& a, const char** why);

@@ -94,6 +94,10 @@ RopeTableRef get_rope_table(int dims, bool has_base, float base, float scale,
     if (freqs_host) t->freqs.assign(freqs_host, freqs_host + half);
   }
   if (need_positions > t->n_pos) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    OMX_CUDA(cudaStreamIsCapturing(stream, &cap));
+    OMX_CHECK(cap == cudaStreamCaptureStatusNone, "[rope] the position table for these parameters must be built "
+              "before stream capture: run the same call once eagerly first");
     int n = std::max(need_positions, std::max(2 * t->n_pos, 4096));
     n = (n + 1023) / 1024 * 1024;
     std::vector<float> c((size_t)n * half), s((size_t)n * half);

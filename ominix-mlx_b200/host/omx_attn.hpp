@@ -275,6 +275,10 @@ class KVCache : public KeyValueCache {
     check(omx_kv_cache_state(raw(), &ko, &vo));
     return {Array::from_desc(ko, h_), Array::from_desc(vo, h_)};
   }
+  /// CUDA-graph decode loop (include/omx_attn.h): pin buffers + split-K scratch for positions [0, max_rows).
+  void prepare_graph(int max_rows, int n_q_heads) { check(omx_kv_cache_prepare_graph(raw(), max_rows, n_q_heads, stream_.raw())); }
+  /// Host bookkeeping for n rows appended by dynamic-position launches / graph replays.
+  void advance(int n = 1) { check(omx_kv_cache_advance(raw(), n, stream_.raw())); }
   omx_kv_cache raw() const { return omx_kv_cache{h_.get()}; }
   std::shared_ptr<void> keepalive() const { return h_; }
 
@@ -373,6 +377,24 @@ inline Array attention_decode_fused(const Array& queries, const Array& keys, con
                                    fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
                                    rope ? rope->scale : 1.f, nullptr, scale, nullptr, nullptr, s.raw()));
   return out;
+}
+
+/// The fused decode step with the position read by the kernel from `position` (device int32): capturable
+/// with cudaStreamBeginCapture and replayable per token.  `out` is caller-owned (static under a graph).
+inline void attention_decode_fused_dynamic(Array& out, const Array& queries, const Array& keys, const Array& values,
+                                           KVCache& cache, const nn::Rope* rope, float scale, const int32_t* position,
+                                           const nn::RmsNorm* q_norm = nullptr, const nn::RmsNorm* k_norm = nullptr,
+                                           Stream s = {}) {
+  const float eps = q_norm ? q_norm->eps : (k_norm ? k_norm->eps : 0.f);
+  check(omx_attn_decode_fused_dynamic(out.desc(), queries.desc(), keys.desc(), values.desc(), cache.raw(),
+                                      q_norm ? q_norm->weight.desc() : nullptr,
+                                      k_norm ? k_norm->weight.desc() : nullptr, eps, rope ? rope->dimensions : 0,
+                                      rope ? rope->traditional : false,
+                                      fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
+                                      rope ? rope->scale : 1.f, scale, position, s.raw()));
+}
+inline void device_counter_add(int32_t* counter, int delta, Stream s = {}) {
+  check(omx_device_counter_add(counter, delta, s.raw()));
 }
 
 /// Attention::forward for L >= 1 new tokens with the minimum of memory passes (see omx_attn_prefill_fused).

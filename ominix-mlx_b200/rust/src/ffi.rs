@@ -103,6 +103,16 @@ extern "C" {
                                       base: omx_optional_float, rope_scale: f32, freqs: *const omx_array,
                                       sm_scale: f32, keys_out: *mut omx_array, values_out: *mut omx_array,
                                       s: omx_stream) -> c_int;
+    // CUDA-graph decode loop (position read on the device; see include/omx_attn.h)
+    pub fn omx_kv_cache_prepare_graph(c: omx_kv_cache, max_rows: c_int, n_q_heads: c_int, s: omx_stream) -> c_int;
+    pub fn omx_kv_cache_advance(c: omx_kv_cache, n: c_int, s: omx_stream) -> c_int;
+    pub fn omx_attn_decode_fused_dynamic(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                         v_new: *const omx_array, cache: omx_kv_cache,
+                                         q_norm_weight: *const omx_array, k_norm_weight: *const omx_array,
+                                         norm_eps: f32, rope_dims: c_int, traditional: bool,
+                                         base: omx_optional_float, rope_scale: f32, sm_scale: f32,
+                                         position: *const i32, s: omx_stream) -> c_int;
+    pub fn omx_device_counter_add(counter: *mut i32, delta: c_int, s: omx_stream) -> c_int;
     pub fn omx_attn_prefill_fused(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
                                   v_new: *const omx_array, cache: omx_kv_cache, q_norm_weight: *const omx_array,
                                   k_norm_weight: *const omx_array, norm_eps: f32, rope_dims: c_int,
