@@ -20,7 +20,12 @@
 //   row `position` (bit-identical to the unfused path) and folds that key in from registers,
 //   so the new row is never re-read from HBM.
 #include <algorithm>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <cstdlib>
+#include <vector>
 
 #include "omx_common.cuh"
 #include "omx_internal.h"
@@ -84,7 +89,21 @@ struct DecodeParams {
   // cos_row / sin_row the table base; the grid (num_splits) is fixed at capture.
   const int* pos_dev;
   int max_rows;
+  // 1: the splits of one (batch, kv-head) form a thread-block cluster and are combined through
+  // distributed shared memory (no partials in HBM/L2, no fence, no ticket)
+  int cluster;
+  // debugging aid (OMX_DECODE_TRACE=1): per-CTA phase timestamps, [cta][16] x %globaltimer ns; null otherwise
+  unsigned long long* trace;
 };
+
+__device__ __forceinline__ void trace_mark(const DecodeParams& p, int slot) {
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    p.trace[(size_t)cta * 16 + slot] = t;
+  }
+}
 
 // The launch's key count, split size and rope row: kernel arguments, or derived from *pos_dev.
 struct DecodeDyn {
@@ -146,77 +165,154 @@ __device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
   }
 }
 
-// roped / copied q heads -> shared memory (as T), used by both kernels
-// 1/rms of the staged q heads (rs[0..n_heads)) and of the new k row (rs[16]) when the fused
-// q_norm / k_norm prologue is on.  One thread per row: the left-to-right f32 sum is the contract.
-template <typename T>
-__device__ __forceinline__ void stage_norms(const DecodeParams& p, float* rs, int first_head, int n_heads,
-                                            int b, int hk, bool has_nt, int tid) {
-  if (p.q_norm_w && tid < n_heads) {
-    const T* qh = (const T*)p.q + b * p.qs[0] + (int64_t)(first_head + tid) * p.qs[1];
-    rs[tid] = rms_rsqrt_row<T>(qh, p.qs[3], p.D, p.norm_eps, p.norm_inv_n);
+// ---- prologue: everything the CTA needs besides K/V arrives in ONE parallel round trip ----
+// Single-sequence decode is a chain of dependent memory round trips (per-CTA timelines, OMX_DECODE_TRACE):
+// the earlier prologue spent 2-5 us in front of the first MMA on q -> row statistics -> weights / rope row,
+// each step waiting on global memory.  Now every thread first issues its share of ALL the loads (raw q
+// heads, rope row, norm weights and -- in the CTA that appends -- the new k / v rows), the CTA syncs once,
+// and the row statistics, normalisation and rotation run from shared memory only.
+// 1 / rms of a row held in shared memory: the reference's strict left-to-right f32 sum of squares.  The
+// row is pulled into registers with 128-bit loads first, so what remains serial is the FADD chain alone
+// (the scalar loop took 2.7 us for 128 bf16 elements: one exposed LDS per step).
+template <typename E>
+__device__ __forceinline__ float rms_rsqrt_smem(const E* row, int D, float eps, float inv_n) {
+  constexpr int V = 16 / (int)sizeof(E);
+  float acc = 0.f;
+  if ((D % (4 * V)) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    for (int c = 0; c < D; c += 4 * V) {
+      union { uint4 r[4]; E t[4 * V]; } u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) u.r[i] = *reinterpret_cast<const uint4*>(row + c + i * V);
+#pragma unroll
+      for (int i = 0; i < 4 * V; ++i) {
+        const float v = Num<E>::to_f(u.t[i]);
+        acc = __fadd_rn(acc, __fmul_rn(v, v));
+      }
+    }
+  } else {
+    for (int d = 0; d < D; ++d) {
+      const float v = Num<E>::to_f(row[d]);
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
   }
-  if (p.k_norm_w && has_nt && tid == 32) {
-    const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
-    rs[16] = rms_rsqrt_row<T>(kn, p.kns[3], p.D, p.norm_eps, p.norm_inv_n);
-  }
+  return __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fmul_rn(acc, inv_n), eps)));
 }
 
-template <typename T>
-__device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total,
-                                        int first_head, int n_heads, int b, int tid, int nthr,
-                                        const float* rs, const DecodeDyn& dy) {
-  const T* qg = (const T*)p.q + b * p.qs[0] + (int64_t)first_head * p.qs[1];
+struct PrologueSmem {       // static shared memory of both kernels
+  float cs[256];            // cos row | sin row, rounded to T (rope_dims <= 256)
+  float qw[256], kw[256];   // q_norm / k_norm weights as float (head_dim <= 256)
+  float rs[16];             // 1/rms of the staged q heads
+};
+
+// after_loads(): called once the prologue's own loads are issued and before anything waits on them (the
+// CUDA-core kernel requests its first K/V rows there).
+template <typename T, typename F>
+__device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total, int first_head,
+                                        int n_heads, int b, int hk, int tid, int nthr, PrologueSmem& ps,
+                                        float* nt_k, float* nt_v, bool has_nt, const DecodeDyn& dy,
+                                        F&& after_loads) {
   const int D = p.D;
-  const T* nw = (const T*)p.q_norm_w;
-  // element d of staged head g, after the optional RMSNorm (value already rounded to T)
-  auto qval = [&](const T* qh, int g, int d) -> float {
-    const float x = Num<T>::to_f(qh[d * p.qs[3]]);
-    return nw ? rms_apply<T>(x, rs[g], Num<T>::to_f(nw[d]), true) : x;
-  };
+  const bool rope = p.fused && p.rope_dims > 0;
+  const int half = p.rope_dims >> 1;
+  const T* qg = (const T*)p.q + b * p.qs[0] + (int64_t)first_head * p.qs[1];
+  // ---- loads (all independent)
+  constexpr int V = 16 / (int)sizeof(T);
+  const bool vec = p.qs[3] == 1 && (D % V) == 0 && (pitch % V) == 0 && p.qs[1] % V == 0 &&
+                   ((reinterpret_cast<uintptr_t>(qg) | reinterpret_cast<uintptr_t>(q_s)) & 15) == 0;
+  if (vec) {
+    const int per = D / V;
+    for (int idx = tid; idx < n_heads * per; idx += nthr) {
+      const int g = idx / per, c = idx % per;
+      *reinterpret_cast<uint4*>(q_s + g * pitch + c * V) = *reinterpret_cast<const uint4*>(qg + g * p.qs[1] + c * V);
+    }
+  } else {
+    for (int idx = tid; idx < n_heads * D; idx += nthr) {
+      const int g = idx / D, d = idx % D;
+      q_s[g * pitch + d] = qg[g * p.qs[1] + d * p.qs[3]];
+    }
+  }
   for (int idx = tid; idx < (rows_total - n_heads) * D; idx += nthr)
     q_s[(n_heads + idx / D) * pitch + idx % D] = Num<T>::from_f(0.f);
-  if (p.fused && p.rope_dims > 0) {
-    const int half = p.rope_dims >> 1;
+  const int rt = nthr - 1 - tid;  // the small tables start from the other end of the CTA
+  if (rope)
+    for (int u = rt; u < half; u += nthr) {
+      ps.cs[u] = rnd<T>(dy.cos_row[u]);
+      ps.cs[half + u] = rnd<T>(dy.sin_row[u]);
+    }
+  if (p.q_norm_w)
+    for (int d = rt; d < D; d += nthr) ps.qw[d] = Num<T>::to_f(((const T*)p.q_norm_w)[d]);
+  if (has_nt) {
+    const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
+    const T* vn = (const T*)p.v_new + b * p.vns[0] + hk * p.vns[1];
+    for (int d = rt; d < D; d += nthr) {
+      nt_k[d] = Num<T>::to_f(kn[d * p.kns[3]]);
+      nt_v[d] = Num<T>::to_f(vn[d * p.vns[3]]);
+    }
+    if (p.k_norm_w)
+      for (int d = rt; d < D; d += nthr) ps.kw[d] = Num<T>::to_f(((const T*)p.k_norm_w)[d]);
+  }
+  after_loads();
+  if (!rope && !p.q_norm_w) return;  // the caller's barrier publishes the copy
+  __syncthreads();
+  trace_mark(p, 12);
+  // ---- q_norm: the reference's left-to-right f32 sum, one thread per head, from shared memory
+  if (p.q_norm_w) {
+    // spread over the warps (one head per warp's lane 0) so the serial chains run on different schedulers
+    if ((tid & 31) == 0 && (tid >> 5) < n_heads)
+      ps.rs[tid >> 5] = rms_rsqrt_smem<T>(q_s + (tid >> 5) * pitch, D, p.norm_eps, p.norm_inv_n);
+    for (int g = (nthr >> 5) + tid; g < n_heads; g += nthr)  // more heads than warps (G = 16 on 4 warps)
+      ps.rs[g] = rms_rsqrt_smem<T>(q_s + g * pitch, D, p.norm_eps, p.norm_inv_n);
+    __syncthreads();
+    trace_mark(p, 13);
+  }
+  // ---- normalise + rotate in place (every element is owned by exactly one thread)
+  const bool nrm = p.q_norm_w != nullptr;
+  auto qval = [&](int g, int d) -> float {
+    const float x = Num<T>::to_f(q_s[g * pitch + d]);
+    return nrm ? rms_apply<T>(x, ps.rs[g], ps.qw[d], true) : x;
+  };
+  if (rope) {
     const int per = half + (D - p.rope_dims);
     for (int idx = tid; idx < n_heads * per; idx += nthr) {
       const int g = idx / per, u = idx % per;
-      const T* qh = qg + g * p.qs[1];
       if (u < half) {
         const int i1 = p.traditional ? 2 * u : u;
         const int i2 = p.traditional ? 2 * u + 1 : u + half;
         float o1, o2;
-        rope_pair<T>(qval(qh, g, i1), qval(qh, g, i2), rnd<T>(dy.cos_row[u]), rnd<T>(dy.sin_row[u]), o1, o2);
+        rope_pair<T>(qval(g, i1), qval(g, i2), ps.cs[u], ps.cs[half + u], o1, o2);
         q_s[g * pitch + i1] = Num<T>::from_f(o1);
         q_s[g * pitch + i2] = Num<T>::from_f(o2);
-      } else {
+      } else if (nrm) {
         const int d = p.rope_dims + (u - half);
-        q_s[g * pitch + d] = Num<T>::from_f(qval(qh, g, d));
+        q_s[g * pitch + d] = Num<T>::from_f(qval(g, d));
       }
     }
   } else {
     for (int idx = tid; idx < n_heads * D; idx += nthr) {
       const int g = idx / D, d = idx % D;
-      q_s[g * pitch + d] = Num<T>::from_f(qval(qg + g * p.qs[1], g, d));
+      q_s[g * pitch + d] = Num<T>::from_f(qval(g, d));
     }
   }
 }
 
-// One warp: rope k_new, append k'/v_new to the cache row, and score the new key against the
-// staged q heads.  nt_k/nt_v: float[D] scratch, nt_m[g] <- log2-domain score.
+// One warp: norm + rope the new k row (staged raw in nt_k by stage_q, v in nt_v), append k'/v_new to the
+// cache row, and score the new key against the staged q heads -- from shared memory only.
+// nt_k/nt_v: float[D], nt_m[g] <- log2-domain score.
 template <typename T>
 __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
                                           int b, int hk, int lane, float* nt_k, float* nt_v,
-                                          float* nt_m, const float* rs, const DecodeDyn& dy,
+                                          float* nt_m, const PrologueSmem& ps, const DecodeDyn& dy,
                                           bool write_cache = true) {
   const int D = p.D;
-  const T* kn = (const T*)p.k_new + b * p.kns[0] + hk * p.kns[1];
-  const T* nw = (const T*)p.k_norm_w;
-  auto kval = [&](int d) -> float {  // k_new element after the optional RMSNorm (rounded to T)
-    const float x = Num<T>::to_f(kn[d * p.kns[3]]);
-    return nw ? rms_apply<T>(x, rs[16], Num<T>::to_f(nw[d]), true) : x;
-  };
-  const T* vn = (const T*)p.v_new + b * p.vns[0] + hk * p.vns[1];
+  const bool nrm = p.k_norm_w != nullptr;
+  float kr = 0.f;
+  if (nrm) {  // left-to-right f32 sum over the raw row
+    if (lane == 0) kr = rms_rsqrt_smem<float>(nt_k, D, p.norm_eps, p.norm_inv_n);
+    kr = __shfl_sync(0xffffffffu, kr, 0);
+  }
+  // k_new element after the optional RMSNorm (rounded to T); nt_k[d] holds the raw value until the lane
+  // that owns it overwrites it below
+  auto kval = [&](int d) -> float { return nrm ? rms_apply<T>(nt_k[d], kr, ps.kw[d], true) : nt_k[d]; };
   T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(dy.Lk - 1) * p.kcs[2];
   T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(dy.Lk - 1) * p.vcs[2];
   const int half = p.rope_dims >> 1;
@@ -224,7 +320,7 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
     const int i1 = p.traditional ? 2 * u : u;
     const int i2 = p.traditional ? 2 * u + 1 : u + half;
     float o1, o2;
-    rope_pair<T>(kval(i1), kval(i2), rnd<T>(dy.cos_row[u]), rnd<T>(dy.sin_row[u]), o1, o2);
+    rope_pair<T>(kval(i1), kval(i2), ps.cs[u], ps.cs[half + u], o1, o2);
     if (write_cache) {
       kc[i1 * p.kcs[3]] = Num<T>::from_f(o1);
       kc[i2 * p.kcs[3]] = Num<T>::from_f(o2);
@@ -237,11 +333,8 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
     if (write_cache) kc[d * p.kcs[3]] = Num<T>::from_f(x);
     nt_k[d] = x;
   }
-  for (int d = lane; d < D; d += 32) {
-    const T x = vn[d * p.vns[3]];
-    if (write_cache) vc[d * p.vcs[3]] = x;
-    nt_v[d] = Num<T>::to_f(x);
-  }
+  if (write_cache)
+    for (int d = lane; d < D; d += 32) vc[d * p.vcs[3]] = Num<T>::from_f(nt_v[d]);  // exact round trip
   __syncwarp();
   for (int g = 0; g < n_heads; ++g) {
     float a = 0.f;
@@ -251,15 +344,45 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
   }
 }
 
+// ---- thread-block cluster primitives (split-K combine through distributed shared memory)
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+  return v;
+}
+constexpr int kMaxClusterSplits = 16;  // non-portable cluster size limit on sm_100
+// floats of cluster scratch behind the merge inputs: partial (m, l) | weights | sums, per row pitch
+__host__ __device__ constexpr int cluster_scratch_floats(int rows) { return (2 + 2 * kMaxClusterSplits) * rows; }
+
 // Merge per-warp states -> out (single split) or workspace + last-CTA combine.
 // mo: [n_ent][rows][D] floats, mml: [n_ent][rows][2]; rows = row pitch of the entries.
-template <typename T>
+template <typename T, int PF>
 __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const float* mo, const float* mml,
                                                 int n_ent, int rows, bool has_nt, const float* nt_m,
                                                 const float* nt_v, int first_head, int n_heads, int b,
-                                                int pair, int split, int tid, int nthr, int* s_ticket) {
+                                                int pair, int split, int tid, int nthr, int* s_ticket,
+                                                float* cl /* cluster scratch, cluster_scratch_floats(rows) */) {
   const int D = p.D;
   const int64_t ob = b * p.os[0];
+  const bool use_cluster = p.cluster && p.num_splits > 1;
+  float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
     const int g = idx / D, d = idx % D;
     float M = has_nt ? nt_m[g] : -INFINITY;
@@ -281,6 +404,12 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     if (p.num_splits == 1) {
       store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
       if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    } else if (use_cluster) {
+      part_o[g * D + d] = O;  // == mo[(0 * rows + g) * D + d], read above by this thread only
+      if (d == 0) {
+        cl[g * 2] = M;
+        cl[g * 2 + 1] = L;
+      }
     } else {
       const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
       p.ws_o[e * D + d] = O;
@@ -292,21 +421,103 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   }
   if (p.num_splits == 1) {
     peer_signal(p, tid);
+    trace_mark(p, 6);
+    return;
+  }
+  trace_mark(p, 3);
+  if (use_cluster) {
+    // ---- cluster combine.  Every CTA of the cluster publishes its partial in its own shared memory,
+    // one cluster barrier later each CTA pulls all (m, l) pairs (NS x heads x 8 B) and its slice of the
+    // output columns from its peers (~215-cycle DSMEM loads), and stores that slice.  Replaces partial
+    // write -> fence -> ticket -> L2 read-back (~5 us on the per-CTA timelines) by two cluster barriers.
+    const int NS = p.num_splits;
+    float* sm_w = cl + 2 * rows;                        // [NS][rows]
+    float* sm_l = sm_w + kMaxClusterSplits * rows;      // [NS][rows]
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    trace_mark(p, 4);
+    for (int idx = tid; idx < NS * n_heads; idx += nthr) {
+      const int sp = idx / n_heads, g = idx % n_heads;
+      const float2 ml = ld_dsmem_f2(dsmem_addr(cl + g * 2, sp));
+      sm_w[sp * rows + g] = ml.x;
+      sm_l[sp * rows + g] = ml.y;
+    }
+    __syncthreads();
+    for (int g = tid >> 5; g < n_heads; g += nthr >> 5) {  // one warp per head, lanes over the splits
+      const int ln = tid & 31;
+      const float m_a = ln < NS ? sm_w[ln * rows + g] : -INFINITY;
+      const float M = warp_max(m_a);
+      const float s_a = m_a > -INFINITY ? fast_exp2(m_a - M) : 0.f;
+      const float L = warp_sum(ln < NS ? sm_l[ln * rows + g] * s_a : 0.f);
+      if (ln < NS) sm_w[ln * rows + g] = s_a * (1.0f / L);
+      if (p.dead && ln == 0 && split == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    }
+    __syncthreads();
+    trace_mark(p, 5);
+    const int D4 = D >> 2;
+    const int C = n_heads * D4;
+    const int slice = (C + NS - 1) / NS;
+    const int c_begin = split * slice, c_end = min(C, c_begin + slice);  // split == rank within the cluster
+    for (int col = c_begin + tid; col < c_end; col += nthr) {
+      const int g = col / D4, d = (col % D4) * 4;
+      const float* src = part_o + g * D + d;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int sp = 0; sp < NS; ++sp) {
+        const float4 v = ld_dsmem_f4(dsmem_addr(src, sp));
+        const float w = sm_w[sp * rows + g];
+        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y);
+        acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+      }
+      const int64_t o = ob + (int64_t)(first_head + g) * p.os[1];
+      store_out<T>(p, o + (d + 0) * p.os[3], acc.x);
+      store_out<T>(p, o + (d + 1) * p.os[3], acc.y);
+      store_out<T>(p, o + (d + 2) * p.os[3], acc.z);
+      store_out<T>(p, o + (d + 3) * p.os[3], acc.w);
+    }
+    trace_mark(p, 11);
+    // nobody may leave while a peer can still read its shared memory
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    trace_mark(p, 6);
     return;
   }
   __threadfence();
   __syncthreads();
+  trace_mark(p, 4);
   if (tid == 0) *s_ticket = atomicAdd(&p.counters[pair], 1);
   __syncthreads();
+  trace_mark(p, 5);
   if (*s_ticket != p.num_splits - 1) return;
   __threadfence();
-  // ---- last CTA of this (batch, kv-head): combine the split partials.  Three short phases so that
-  // no thread walks the splits through dependent L2 round trips: (A) all (split, head) running
-  // max / sum pairs -> shared memory, coalesced; (B) one thread per head turns them into weights
-  // 2^(m_s - M) / L; (C) every (head, feature) accumulates its splits with independent loads.
+  trace_mark(p, 8);
+  // ---- last CTA of this (batch, kv-head): combine the split partials.  The combine sits at the very end
+  // of the launch's critical path, so it is organised as ONE round trip to L2: every thread owns a float4
+  // column (head, 4 features) for a subset of the splits and requests its first 8 partial vectors BEFORE
+  // the (m, l) pairs are turned into weights; (A) all (split, head) pairs -> shared memory, (B) one thread
+  // per head computes 2^(m_s - M) / L, (C) the prefetched vectors are folded in, the column groups are
+  // reduced through shared memory.  (Per-CTA timelines: the earlier three dependent phases took ~6 us
+  // for 16 splits x 4 heads.)
   float* sm_w = const_cast<float*>(mo);            // [num_splits][rows]  (the merge inputs are dead)
   float* sm_l = sm_w + kMaxSplits * rows;          // [num_splits][rows]
+  float4* red = reinterpret_cast<float4*>(sm_l + kMaxSplits * rows);  // [groups][C]
   const int64_t e0p = (int64_t)pair * p.num_splits * n_heads;
+  const int D4 = D >> 2;
+  const int C = n_heads * D4;  // float4 columns
+  // thread groups: as many as fit the CTA, the splits and the scratch left in `mo` (n_ent * rows * D floats)
+  int groups = max(1, min(min(nthr / C, p.num_splits), 4));
+  while (groups > 1 && 2 * kMaxSplits * rows + groups * C * 4 > n_ent * rows * D) --groups;
+  const int grp = tid / C, col0 = tid % C;
+  const bool first_pass = C <= nthr && grp < groups;
+  float4 pre[PF];  // PF x groups splits are in flight before the weights exist
+  if (first_pass) {
+    const float* po = p.ws_o + (e0p + col0 / D4) * D + (col0 % D4) * 4;
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int sp = grp + i * groups;
+      if (sp < p.num_splits) pre[i] = __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D));
+    }
+  }
   for (int idx = tid; idx < p.num_splits * n_heads; idx += nthr) {
     const int sp = idx / n_heads, g = idx % n_heads;
     const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + idx) * 2]));
@@ -314,32 +525,78 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     sm_l[sp * rows + g] = ml.y;
   }
   __syncthreads();
-  if (tid < n_heads) {
-    float M = -INFINITY;
-    for (int sp = 0; sp < p.num_splits; ++sp) M = fmaxf(M, sm_w[sp * rows + tid]);
-    float L = 0.f;
-    for (int sp = 0; sp < p.num_splits; ++sp) {
-      const float ms = sm_w[sp * rows + tid];
-      const float sc = ms > -INFINITY ? fast_exp2(ms - M) : 0.f;
-      L = fmaf(sm_l[sp * rows + tid], sc, L);
-      sm_w[sp * rows + tid] = sc;
-    }
+  trace_mark(p, 9);
+  // (B) one warp per head, lanes over the splits (kMaxSplits = 64 = 2 per lane), butterfly reductions
+  for (int g = tid >> 5; g < n_heads; g += nthr >> 5) {
+    const int ln = tid & 31;
+    const float m_a = ln < p.num_splits ? sm_w[ln * rows + g] : -INFINITY;
+    const float m_b = ln + 32 < p.num_splits ? sm_w[(ln + 32) * rows + g] : -INFINITY;
+    const float M = warp_max(fmaxf(m_a, m_b));
+    const float s_a = m_a > -INFINITY ? fast_exp2(m_a - M) : 0.f;
+    const float s_b = m_b > -INFINITY ? fast_exp2(m_b - M) : 0.f;
+    float L = ln < p.num_splits ? sm_l[ln * rows + g] * s_a : 0.f;
+    if (ln + 32 < p.num_splits) L = fmaf(sm_l[(ln + 32) * rows + g], s_b, L);
+    L = warp_sum(L);
     const float inv = 1.0f / L;
-    for (int sp = 0; sp < p.num_splits; ++sp) sm_w[sp * rows + tid] *= inv;
-    if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + tid] = L > 0.f ? 0 : 1;
+    if (ln < p.num_splits) sm_w[ln * rows + g] = s_a * inv;
+    if (ln + 32 < p.num_splits) sm_w[(ln + 32) * rows + g] = s_b * inv;
+    if (p.dead && ln == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
   }
   __syncthreads();
-  for (int idx = tid; idx < n_heads * D; idx += nthr) {
-    const int g = idx / D, d = idx % D;
-    const float* po = p.ws_o + (e0p + g) * D + d;
-    float O = 0.f;
+  trace_mark(p, 10);
+  auto fold = [](float4& a, const float4& v, float w) {
+    a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+  };
+  auto emit = [&](int col, const float4& a) {
+    const int g = col / D4, d = (col % D4) * 4;
+    const int64_t o = ob + (int64_t)(first_head + g) * p.os[1];
+    store_out<T>(p, o + (d + 0) * p.os[3], a.x);
+    store_out<T>(p, o + (d + 1) * p.os[3], a.y);
+    store_out<T>(p, o + (d + 2) * p.os[3], a.z);
+    store_out<T>(p, o + (d + 3) * p.os[3], a.w);
+  };
+  if (C <= nthr) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (first_pass) {
+      const int g = col0 / D4;
+      const float* po = p.ws_o + (e0p + g) * D + (col0 % D4) * 4;
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const int sp = grp + i * groups;
+        if (sp < p.num_splits) fold(acc, pre[i], sm_w[sp * rows + g]);
+      }
+#pragma unroll 4
+      for (int sp = grp + PF * groups; sp < p.num_splits; sp += groups)
+        fold(acc, __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D)), sm_w[sp * rows + g]);
+    }
+    if (groups > 1) {
+      if (first_pass) red[grp * C + col0] = acc;
+      __syncthreads();
+      if (tid < C) {
+        for (int gi = 1; gi < groups; ++gi) {
+          const float4 v = red[gi * C + tid];
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        emit(tid, acc);
+      }
+    } else if (tid < C) {
+      emit(tid, acc);
+    }
+  } else {  // more columns than threads (G = 16 at D = 128, D = 256): each thread walks its columns
+    for (int col = tid; col < C; col += nthr) {
+      const int g = col / D4;
+      const float* po = p.ws_o + (e0p + g) * D + (col % D4) * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
-    for (int sp = 0; sp < p.num_splits; ++sp)
-      O = fmaf(__ldcg(po + (int64_t)sp * n_heads * D), sm_w[sp * rows + g], O);
-    store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O);
+      for (int sp = 0; sp < p.num_splits; ++sp)
+        fold(acc, __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D)), sm_w[sp * rows + g]);
+      emit(col, acc);
+    }
   }
+  trace_mark(p, 11);
   if (tid == 0) p.counters[pair] = 0;  // self-reset for the next launch
   peer_signal(p, tid);
+  trace_mark(p, 6);
 }
 
 // ============================================================ 16-bit, D = 128: TMA + mma.sync
@@ -363,12 +620,13 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   float* nt_m = nt_v + D;
   __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE];
   __shared__ int s_ticket;
-  __shared__ float s_rs[17];
+  __shared__ PrologueSmem s_pro;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
+  trace_mark(p, 0);
   const DecodeDyn dy = load_dyn(p);
   const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
   const int tile_begin = split * dy.tps;
@@ -401,13 +659,15 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     tma_prefetch_desc(&tmV);
     pol = policy_evict_first();
     for (int t = 0; t < first; ++t) issue(t);
+    if (p.trace) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      p.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + 7] = tt;
+    }
   }
-  if (p.q_norm_w || p.k_norm_w) {
-    stage_norms<T>(p, s_rs, hk * G, G, b, hk, has_nt, tid);
-    __syncthreads();
-  }
-  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, tid, NTHR, s_rs, dy);
+  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [] {});
   __syncthreads();
+  trace_mark(p, 1);
 
   // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
   // that every warp reaches at the same program point)
@@ -419,7 +679,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   if (warp == NW) {
     // ------------------------------------------------ producer warp (first tiles already in flight)
-    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_rs, dy);
+    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy);
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
         mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
@@ -551,6 +811,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     }
   }
   __syncthreads();  // every stage consumed -> the ring is reused for the merge
+  trace_mark(p, 2);
   if (warp < NW) {
     float* mo = reinterpret_cast<float*>(stages);  // [NW][16][128]
     float* mml = mo + NW * 16 * D;                 // [NW][16][2]
@@ -575,8 +836,8 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   }
   __syncthreads();  // merge inputs visible
   const float* mo = reinterpret_cast<const float*>(stages);
-  merge_and_store<T>(p, mo, mo + NW * 16 * D, NW, 16, has_nt, nt_m, nt_v, hk * G, G, b, pair, split, tid,
-                     NTHR, &s_ticket);
+  merge_and_store<T, 16>(p, mo, mo + NW * 16 * D, NW, 16, has_nt, nt_m, nt_v, hk * G, G, b, pair, split, tid,
+                         NTHR, &s_ticket, const_cast<float*>(mo) + NW * 16 * (D + 2));
 }
 
 // ============================================================ generic: CUDA cores
@@ -610,12 +871,41 @@ __device__ __forceinline__ void load_row(const T* p, float (&f)[VE]) {
   }
 }
 
-constexpr int kSimtWarps = 8;
-constexpr int kSimtKeys = 4;  // keys in flight per warp iteration
+// VE elements of one K/V row as loaded (128-bit pieces where the size allows), converted on use
+template <typename T, int VE>
+struct RawRow {
+  static constexpr int BYTES = (int)sizeof(T) * VE;
+  union U {
+    uint4 q[BYTES >= 16 ? BYTES / 16 : 1];
+    uint2 d;
+    uint32_t w;
+    T t[VE];
+    __device__ U() {}
+  } u;
+  __device__ __forceinline__ void load(const T* p) {
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+      for (int i = 0; i < BYTES / 16; ++i) u.q[i] = reinterpret_cast<const uint4*>(p)[i];
+    } else if constexpr (BYTES == 8) {
+      u.d = *reinterpret_cast<const uint2*>(p);
+    } else if constexpr (BYTES == 4) {
+      u.w = *reinterpret_cast<const uint32_t*>(p);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VE; ++e) u.t[e] = p[e];
+    }
+  }
+  __device__ __forceinline__ float f(int e) const { return Num<T>::to_f(u.t[e]); }
+};
 
-template <typename T, int VE, int GT>
+constexpr int kSimtWarps = 8;
+// KPW = keys in flight per warp iteration: 4 when many CTAs share an SM (throughput regime), 16 for
+// one-wave grids (single-sequence decode), where a CTA's whole 128-key share is then requested up front
+// instead of through four dependent round trips to HBM.
+template <typename T, int VE, int GT, int KPW>
 __global__ void __launch_bounds__(kSimtWarps * 32)
 decode_simt_kernel(const DecodeParams p) {
+  constexpr int kSimtKeys = KPW;
   constexpr int D = 32 * VE;
   constexpr int NTHR = kSimtWarps * 32;
   extern __shared__ uint8_t smem_raw[];
@@ -626,7 +916,7 @@ decode_simt_kernel(const DecodeParams p) {
   float* nt_v = nt_k + D;
   float* nt_m = nt_v + D;                          // [GT]
   __shared__ int s_ticket;
-  __shared__ float s_rs[17];
+  __shared__ PrologueSmem s_pro;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x, b = blockIdx.z;
@@ -634,21 +924,34 @@ decode_simt_kernel(const DecodeParams p) {
   const int hk = blockIdx.y / groups, gsub = blockIdx.y % groups;
   const int first_head = hk * p.G + gsub * GT;
   const int pair = (b * p.Hkv + hk) * groups + gsub;
+  trace_mark(p, 0);
   const DecodeDyn dy = load_dyn(p);
   const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
   const int kend = min(dy.n_mem, kbeg + keys_per_split);
   const bool has_nt = p.fused && split == p.num_splits - 1;
 
-  if (p.q_norm_w || p.k_norm_w) {
-    stage_norms<T>(p, s_rs, first_head, GT, b, hk, has_nt, tid);
-    __syncthreads();
-  }
-  stage_q<T>(p, q_s, D, GT, first_head, GT, b, tid, NTHR, s_rs, dy);
+  // K/V do not depend on q: the first batch of rows is requested before the prologue's round trip
+  const T* kb = (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + lane * VE;
+  const T* vb = (const T*)p.v + b * p.vs[0] + hk * p.vs[1] + lane * VE;
+  // rows stay in their storage type until they are used, so that nothing waits on the loads early
+  RawRow<T, VE> kraw[kSimtKeys], vraw[kSimtKeys];
+  auto load_kv = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < kSimtKeys; ++u) kraw[u].load(kb + (int64_t)min(j0 + u, kend - 1) * p.ks[2]);
+#pragma unroll
+    for (int u = 0; u < kSimtKeys; ++u) vraw[u].load(vb + (int64_t)min(j0 + u, kend - 1) * p.vs[2]);
+  };
+  const int j_first = kbeg + warp * kSimtKeys;
+
+  stage_q<T>(p, q_s, D, GT, first_head, GT, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [&] {
+    if (j_first < kend) load_kv(j_first);
+  });
   __syncthreads();
+  trace_mark(p, 1);
   // the new row is appended once per kv head (gsub == 0 writes it); every group scores it
   if (has_nt && warp == kSimtWarps - 1)
-    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_rs, dy, /*write_cache=*/gsub == 0);
+    new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy, /*write_cache=*/gsub == 0);
 
   float qr[GT][VE], acc[GT][VE], m[GT], l[GT];
 #pragma unroll
@@ -659,21 +962,8 @@ decode_simt_kernel(const DecodeParams p) {
 #pragma unroll
     for (int e = 0; e < VE; ++e) acc[g][e] = 0.f;
   }
-  const T* kb = (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + lane * VE;
-  const T* vb = (const T*)p.v + b * p.vs[0] + hk * p.vs[1] + lane * VE;
-
-  for (int j0 = kbeg + warp * kSimtKeys; j0 < kend; j0 += kSimtWarps * kSimtKeys) {
-    float kf[kSimtKeys][VE], vf[kSimtKeys][VE];
-#pragma unroll
-    for (int u = 0; u < kSimtKeys; ++u) {
-      const int j = min(j0 + u, kend - 1);
-      load_row<T, VE>(kb + (int64_t)j * p.ks[2], kf[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < kSimtKeys; ++u) {
-      const int j = min(j0 + u, kend - 1);
-      load_row<T, VE>(vb + (int64_t)j * p.vs[2], vf[u]);
-    }
+  for (int j0 = j_first; j0 < kend; j0 += kSimtWarps * kSimtKeys) {
+    if (j0 != j_first) load_kv(j0);
 #pragma unroll
     for (int g = 0; g < GT; ++g) {
       float s[kSimtKeys];
@@ -681,7 +971,7 @@ decode_simt_kernel(const DecodeParams p) {
       for (int u = 0; u < kSimtKeys; ++u) {
         float a = 0.f;
 #pragma unroll
-        for (int e = 0; e < VE; ++e) a = fmaf(qr[g][e], kf[u][e], a);
+        for (int e = 0; e < VE; ++e) a = fmaf(qr[g][e], kraw[u].f(e), a);
         s[u] = a;
       }
 #pragma unroll
@@ -708,7 +998,7 @@ decode_simt_kernel(const DecodeParams p) {
       for (int e = 0; e < VE; ++e) {
         float a = acc[g][e] * c;
 #pragma unroll
-        for (int u = 0; u < kSimtKeys; ++u) a = fmaf(s[u], vf[u][e], a);
+        for (int u = 0; u < kSimtKeys; ++u) a = fmaf(s[u], vraw[u].f(e), a);
         acc[g][e] = a;
       }
     }
@@ -723,14 +1013,100 @@ decode_simt_kernel(const DecodeParams p) {
     }
   }
   __syncthreads();
-  merge_and_store<T>(p, mo, mml, kSimtWarps, GT, has_nt, nt_m, nt_v, first_head, GT, b, pair, split, tid,
-                     NTHR, &s_ticket);
+  trace_mark(p, 2);
+  merge_and_store<T, 4>(p, mo, mml, kSimtWarps, GT, has_nt, nt_m, nt_v, first_head, GT, b, pair, split, tid,
+                        NTHR, &s_ticket, nt_m + 4);
 }
 
 // ------------------------------------------------------------------ host side
 struct SplitPlan {
   int num_splits, tiles_per_split;
 };
+
+// OMX_DECODE_CLUSTER=0 turns the cluster / DSMEM combine off (A/B knob for the sweeps, not an API).
+bool cluster_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OMX_DECODE_CLUSTER");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
+
+// Can `cluster_x` CTAs of this kernel be co-scheduled as one cluster?  (> 8 needs the non-portable opt-in;
+// a CTA that fills an SM's shared memory needs `cluster_x` free SMs in one GPC -- B200 GPCs have 16-20.)
+template <typename K>
+int cluster_capacity(K kern, dim3 grid, int threads, size_t smem, int cluster_x) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+  int dev = 0;
+  OMX_CUDA(cudaGetDevice(&dev));
+  const auto key = std::make_tuple((const void*)kern, cluster_x, smem, dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  bool ok = true;
+  int n = 0;
+  if (cluster_x > 8)
+    ok = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+  if (ok) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_x;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ok = cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess;
+  }
+  (void)cudaGetLastError();
+  if (!ok) n = 0;
+  if (getenv("OMX_DECODE_TRACE"))
+    fprintf(stderr, "[omx decode] cluster size %d (%d threads, %zu B smem): %d co-resident clusters\n", cluster_x,
+            threads, smem, n);
+  cache[key] = n;
+  return n;
+}
+
+template <typename K, typename... Args>
+void launch_kernel(K kern, dim3 grid, int threads, size_t smem, cudaStream_t stream, int cluster_x, Args... args) {
+  if (cluster_x <= 1) {
+    kern<<<grid, threads, smem, stream>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster_x;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  OMX_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+}
+
+// The cluster combine takes at most kMaxClusterSplits splits (OMX_DECODE_CLUSTER_MAX lowers the cap for
+// sweeps): re-plan a wider split count down to it.
+int cluster_cap() {
+  static const int cap = [] {
+    const char* e = getenv("OMX_DECODE_CLUSTER_MAX");
+    const int v = e ? atoi(e) : kMaxClusterSplits;
+    return std::max(2, std::min(v, kMaxClusterSplits));
+  }();
+  return cap;
+}
+SplitPlan clamp_for_cluster(SplitPlan sp, int n_tiles, int cap) {
+  if (sp.num_splits <= cap) return sp;
+  const int tps = (n_tiles + cap - 1) / cap;
+  return {(n_tiles + tps - 1) / tps, tps};
+}
 
 // Split-K plan.  HBM bandwidth is a chip-wide resource, so what matters is (a) enough CTAs in flight
 // to cover it -- about one per SM, each with >= 96 KB of TMA loads outstanding -- and (b) as little
@@ -753,29 +1129,43 @@ SplitPlan plan_splits(int64_t pairs, int n_tiles, int sms, int min_tiles) {
 bool inner_contig(const omx_array* a) { return a->strides[3] == 1 || a->shape[3] == 1; }
 
 template <typename T, int VE>
-void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid) {
+void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
   auto go = [&](auto kern, int gt) {
-    const size_t smem = sizeof(float) * ((size_t)kSimtWarps * gt * (32 * VE + 2) + 2 * 32 * VE + gt) +
+    const size_t smem = sizeof(float) * ((size_t)kSimtWarps * gt * (32 * VE + 2) + 2 * 32 * VE + 4 +
+                                         cluster_scratch_floats(gt)) +
                         sizeof(T) * (size_t)gt * 32 * VE;
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kSimtWarps * 32, smem, stream>>>(p);
+    p.cluster = want_cluster && p.num_splits > 1 &&
+                        cluster_capacity(kern, grid, kSimtWarps * 32, smem, p.num_splits) >= (int)(grid.y * grid.z)
+                    ? 1 : 0;
+    launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, p);
   };
-  switch (Gt) {
-    case 1: go(decode_simt_kernel<T, VE, 1>, 1); break;
-    case 2: go(decode_simt_kernel<T, VE, 2>, 2); break;
-    default: go(decode_simt_kernel<T, VE, 4>, 4); break;
+  // the 16-key variant keeps 2 x 16 rows of VE floats per lane in registers: head_dim <= 128 only
+  constexpr int KBIG = VE <= 4 ? 16 : 4;
+  if (one_wave && KBIG != 4) {
+    switch (Gt) {
+      case 1: go(decode_simt_kernel<T, VE, 1, KBIG>, 1); break;
+      case 2: go(decode_simt_kernel<T, VE, 2, KBIG>, 2); break;
+      default: go(decode_simt_kernel<T, VE, 4, KBIG>, 4); break;
+    }
+  } else {
+    switch (Gt) {
+      case 1: go(decode_simt_kernel<T, VE, 1, 4>, 1); break;
+      case 2: go(decode_simt_kernel<T, VE, 2, 4>, 2); break;
+      default: go(decode_simt_kernel<T, VE, 4, 4>, 4); break;
+    }
   }
   count_launch();
   OMX_CUDA(cudaGetLastError());
 }
 
 template <typename T>
-void launch_simt_d(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid) {
+void launch_simt_d(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
   switch (p.D) {
-    case 32: launch_simt<T, 1>(p, stream, Gt, grid); break;
-    case 64: launch_simt<T, 2>(p, stream, Gt, grid); break;
-    case 128: launch_simt<T, 4>(p, stream, Gt, grid); break;
-    default: launch_simt<T, 8>(p, stream, Gt, grid); break;
+    case 32: launch_simt<T, 1>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    case 64: launch_simt<T, 2>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    case 128: launch_simt<T, 4>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    default: launch_simt<T, 8>(p, stream, Gt, grid, one_wave, want_cluster); break;
   }
 }
 
@@ -836,8 +1226,69 @@ bool decode_supported(const SdpaArgs& a, const char** why) {
   return true;
 }
 
+namespace {
+// OMX_DECODE_TRACE=1: every decode launch records per-CTA phase timestamps, is synchronised and dumped to
+// stderr (debugging aid for the latency-bound single-sequence shapes; never set in production).
+struct TraceDump {
+  unsigned long long* dev = nullptr;
+  size_t ctas = 0;
+  cudaStream_t stream = nullptr;
+  ~TraceDump() {
+    if (!dev) return;
+    cudaStreamSynchronize(stream);
+    constexpr int NS = 16;
+    std::vector<unsigned long long> h(ctas * NS);
+    cudaMemcpy(h.data(), dev, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (size_t c = 0; c < ctas; ++c)
+      if (h[c * NS]) t0 = std::min(t0, h[c * NS]);
+    double sum[NS] = {0}, mx[NS] = {0};
+    int cnt[NS] = {0};
+    for (size_t c = 0; c < ctas; ++c)
+      for (int s = 0; s < NS; ++s)
+        if (h[c * NS + s]) {
+          const double us = (double)(h[c * NS + s] - t0) * 1e-3;
+          sum[s] += us; mx[s] = std::max(mx[s], us); ++cnt[s];
+          t1 = std::max(t1, h[c * NS + s]);
+        }
+    fprintf(stderr, "[omx decode trace] ctas=%zu span=%.2fus | slot: n mean max (us since first CTA start):", ctas,
+            (double)(t1 - t0) * 1e-3);
+    static const char* nm[NS] = {"start", "q_staged", "loop_done", "merged", "fenced", "ticket", "end", "tma_issued",
+                                 "c_fence", "c_ml", "c_weights", "c_folded", "p_loaded", "p_rms", "", ""};
+    static const int order[NS] = {0, 7, 12, 13, 1, 2, 3, 4, 5, 8, 9, 10, 11, 6, 14, 15};
+    for (int i = 0; i < NS; ++i) {
+      const int s = order[i];
+      if (cnt[s]) fprintf(stderr, " %s: %d %.2f %.2f |", nm[s], cnt[s], sum[s] / cnt[s], mx[s]);
+    }
+    fprintf(stderr, "\n");
+    const char* e = getenv("OMX_DECODE_TRACE");
+    if (e && atoi(e) > 1)  // every CTA: index, then the slots in us since the first start (0 = not reached)
+      for (size_t c = 0; c < ctas; ++c) {
+        fprintf(stderr, "[omx decode trace cta %zu]", c);
+        for (int s = 0; s < NS; ++s)
+          fprintf(stderr, " %.2f", h[c * NS + s] ? (double)(h[c * NS + s] - t0) * 1e-3 : 0.0);
+        fprintf(stderr, "\n");
+      }
+  }
+};
+}  // namespace
+
 void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream) {
   DecodeParams p{};
+  static const bool trace_on = [] {
+    const char* e = getenv("OMX_DECODE_TRACE");
+    return e && atoi(e) > 0;
+  }();
+  TraceDump trace;  // destroyed after the launch below
+  auto arm_trace = [&](dim3 grid) {
+    if (!trace_on) return;
+    trace.ctas = (size_t)grid.x * grid.y * grid.z;
+    trace.stream = stream;
+    OMX_CUDA(cudaMalloc(&trace.dev, trace.ctas * 128));
+    OMX_CUDA(cudaMemset(trace.dev, 0, trace.ctas * 128));
+    p.trace = trace.dev;
+  };
   p.q = a.q->data;
   p.out = a.out->data;
   p.k = a.k->data;
@@ -947,17 +1398,23 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       return e ? atoi(e) : -1;
     }();
     const int64_t pairs = (int64_t)a.B * a.Hkv;
-    SplitPlan sp = plan_splits(pairs, n_tiles, sms, 4);
+    const SplitPlan natural = plan_splits(pairs, n_tiles, sms, 4);
+    const bool want_cluster = cluster_enabled() && !masked && !f.peers && natural.num_splits > 1;
+    // Cluster policy (measured, scripts/gpu_cluster_sweep.sh): the DSMEM combine saves ~2 us of tail, but a
+    // cluster must be co-resident in one GPC -- with one CTA per SM this B200 places 8 clusters of <= 10
+    // CTAs (7 of 16).  So: the natural plan if it fits; else a plan clamped to kClusterClamp splits when
+    // that costs at most 6 more 64-key tiles per CTA (Qwen3-8B ctx 8192: 17.6 -> 16.2 us; at ctx 32768
+    // the lost SMs cost more than the tail); else the HBM/L2 combine.
+    constexpr int kClusterClamp = 10;
+    const int cap = getenv("OMX_DECODE_CLUSTER_MAX") ? cluster_cap() : kClusterClamp;
+    const SplitPlan clamped = clamp_for_cluster(natural, n_tiles, cap);
+    const bool try_clamped = clamped.num_splits != natural.num_splits &&
+                             clamped.tiles_per_split - natural.tiles_per_split <= 6;
     // a grid that fits one CTA per SM runs the 6-stage / 1-CTA-per-SM variant (deeper TMA pipeline per
     // CTA: C5 31 us vs 34 us); larger grids the 3-stage / 2-CTA-per-SM one (C2 299 us vs 307 us)
-    const bool deep = cfg_env == 1 || (cfg_env < 0 && pairs * sp.num_splits <= sms);
+    const bool deep = cfg_env == 1 || (cfg_env < 0 && pairs * natural.num_splits <= sms);
     const int cfg = deep ? 1 : 0;
     const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
-    p.num_splits = sp.num_splits;
-    p.tiles_per_split = sp.tiles_per_split;
-    carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
-                    p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
-                    (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
     p.peer_total = (int)pairs;
     const bool bf = a.q->dtype == OMX_BFLOAT16;
     // graph mode: the map spans every reserved row (the tail beyond the position is masked in the kernel)
@@ -967,10 +1424,27 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
                                        a.v->strides[0], 64, 64, bf);
     const size_t smem = 1024 + (size_t)NSTAGE * kStageBytes + 16 * kQPitch * 2 + sizeof(float) * (128 + 128 + 16);
-    dim3 grid(p.num_splits, a.Hkv, a.B);
     auto go = [&](auto kern) {
       OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, (NSTAGE + 1) * 32, smem, stream>>>(tmK, tmV, p);
+      const int threads = (NSTAGE + 1) * 32;
+      auto fits = [&](const SplitPlan& c) {
+        return c.num_splits > 1 && c.num_splits <= kMaxClusterSplits &&
+               cluster_capacity(kern, dim3(c.num_splits, a.Hkv, a.B), threads, smem, c.num_splits) >= pairs;
+      };
+      SplitPlan sp = natural;
+      p.cluster = 0;
+      if (want_cluster) {
+        if (fits(natural)) p.cluster = 1;
+        else if (try_clamped && fits(clamped)) { sp = clamped; p.cluster = 1; }
+      }
+      p.num_splits = sp.num_splits;
+      p.tiles_per_split = sp.tiles_per_split;
+      carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
+                      p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
+                      (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
+      dim3 grid(p.num_splits, a.Hkv, a.B);
+      arm_trace(grid);
+      launch_kernel(kern, grid, threads, smem, stream, p.cluster ? p.num_splits : 1, tmK, tmV, p);
     };
     note_launch("decode_hmma_tma");
     if (bf) {
@@ -1001,6 +1475,10 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   const int groups = p.G / Gt;
   const int64_t pairs = (int64_t)a.B * a.Hkv * groups;
   SplitPlan sp = plan_splits(pairs, n_tiles, sms, 2);
+  // CUDA-core kernel: cluster combine only when the natural plan is co-resident as it is (a clamped plan
+  // lost more in the key loop than the combine saved: C1 12.9 -> 13.6 us)
+  const bool want_cluster = cluster_enabled() && !masked && !f.peers && sp.num_splits > 1 &&
+                            sp.num_splits <= kMaxClusterSplits;
   p.num_splits = sp.num_splits;
   p.tiles_per_split = sp.tiles_per_split;
   carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * p.D : 0,
@@ -1008,11 +1486,17 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
                   (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
   p.peer_total = (int)pairs;
   dim3 grid(p.num_splits, a.Hkv * groups, a.B);
+  arm_trace(grid);
   note_launch("decode_simt");
+  static const int kpw_env = [] {  // tuning knob for the sweeps, not an API: 0 = always 4 keys, 1 = always 16
+    const char* e = getenv("OMX_DECODE_KPW");
+    return e ? atoi(e) : -1;
+  }();
+  const bool one_wave = kpw_env >= 0 ? kpw_env == 1 : pairs * p.num_splits <= sms;
   switch (a.q->dtype) {
-    case OMX_FLOAT32: launch_simt_d<float>(p, stream, Gt, grid); break;
-    case OMX_BFLOAT16: launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid); break;
-    default: launch_simt_d<__half>(p, stream, Gt, grid); break;
+    case OMX_FLOAT32: launch_simt_d<float>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    case OMX_BFLOAT16: launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    default: launch_simt_d<__half>(p, stream, Gt, grid, one_wave, want_cluster); break;
   }
   if (masked) masked_rows_fixup(a, p.dead, stream);
 }

@@ -26,7 +26,7 @@ SHAPES = [
 ]
 
 
-def run(name, L, B, Hq, Hkv, S, dt, norm, steps, warmup):
+def run(name, L, B, Hq, Hkv, S, dt, norm, steps, warmup, modes=("eager", "graph")):
     D, dev = 128, "cuda"
     g = torch.Generator(device=dev).manual_seed(1)
 
@@ -50,7 +50,7 @@ def run(name, L, B, Hq, Hkv, S, dt, norm, steps, warmup):
             out.append(c)
         return out
     res = {}
-    for mode in ("eager", "graph"):
+    for mode in modes:
         cs = caches()
         outs = [torch.empty((B, Hq, 1, D), dtype=dt, device=dev) for _ in range(L)]
         if mode == "graph":
@@ -75,6 +75,9 @@ def run(name, L, B, Hq, Hkv, S, dt, norm, steps, warmup):
         del cs
     es = torch.finfo(dt).bits // 8
     kv_bytes = 2 * B * Hkv * S * D * es * L
+    if len(res) < 2:
+        print(json.dumps({"shape": name, **res}), flush=True)
+        return
     print(json.dumps({"shape": name, "layers": L, "batch": B, "ctx": S, "dtype": str(dt).split(".")[-1],
                       "kv_bytes_per_token_step": kv_bytes, "eager": res["eager"], "graph": res["graph"],
                       "graph_speedup": res["eager"]["ms_per_token_step"] / res["graph"]["ms_per_token_step"],
@@ -87,11 +90,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--modes", default="eager,graph")
     a = ap.parse_args()
     for s in SHAPES:
         if a.only and a.only not in s[0]:
             continue
-        run(*s, a.steps, a.warmup)
+        run(*s, a.steps, a.warmup, tuple(a.modes.split(",")))
 
 
 if __name__ == "__main__":
