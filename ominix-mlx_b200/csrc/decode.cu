@@ -670,12 +670,29 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   trace_mark(p, 1);
 
   // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
-  // that every warp reaches at the same program point)
-  const int g0 = lane >> 2, cq = (lane & 3) * 2;
-  float o[16][4];
+  // that every warp reaches at the same program point).
+  //
+  // Operand roles are SWAPPED relative to the textbook S = Q K^T: the keys (resp. features of V) take the
+  // 16-row M side of mma.m16n8k16 and the G <= 8 query heads the 8-wide N side,
+  //     S^T[key, head] = K[key, :] . Q[head, :]        O^T[feat, head] += V^T[feat, key] . P^T[key, head]
+  // so no MMA row is zero padding: 64 MMAs per 64-key tile instead of 128 (G = 4..8).  With one warp per
+  // tile the legacy-MMA issue rate, not HBM, bounded every grid below ~2 tiles in flight per scheduler
+  // (B = 8, ctx 4096: 4.3 TB/s).  P^T reaches its B-fragment layout through movmatrix (8x8 b16
+  // transpose).  G > 8 (HI): a second N block (heads 8..15) reuses the same A fragments.
+  constexpr int NG = HI ? 2 : 1;  // head groups of 8
+  const int kr = lane >> 2;       // C-fragment row (key resp. feature within 8)
+  const int hc = (lane & 3) * 2;  // C-fragment columns hc, hc + 1 (head within the group)
+  float ot[NG][8][4];             // O^T: [group][16-feature block][frag]
 #pragma unroll
-  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int n = 0; n < NG; ++n)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ot[n][i][0] = ot[n][i][1] = ot[n][i][2] = ot[n][i][3] = 0.f;
+  float mrun[NG][2], lrun[NG][2];  // running max / partial row sum of heads hc, hc + 1 of each group
+#pragma unroll
+  for (int n = 0; n < NG; ++n) {
+    mrun[n][0] = mrun[n][1] = -INFINITY;
+    lrun[n][0] = lrun[n][1] = 0.f;
+  }
 
   if (warp == NW) {
     // ------------------------------------------------ producer warp (first tiles already in flight)
@@ -690,14 +707,15 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   } else {
     // ------------------------------------------------ consumer warps
     using MMA = Mma16816<T>;
-    uint32_t qa[8][4];
+    // Q as the B operand: b0 = Q[head kr][16 ks + hc, +1], b1 = the same 8 features further
+    uint32_t qb[NG][8][2];
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(&q_s[g0 * kQPitch + ks * 16 + cq]);
-      qa[ks][2] = *reinterpret_cast<const uint32_t*>(&q_s[g0 * kQPitch + ks * 16 + cq + 8]);
-      qa[ks][1] = HI ? *reinterpret_cast<const uint32_t*>(&q_s[(g0 + 8) * kQPitch + ks * 16 + cq]) : 0u;
-      qa[ks][3] = HI ? *reinterpret_cast<const uint32_t*>(&q_s[(g0 + 8) * kQPitch + ks * 16 + cq + 8]) : 0u;
-    }
+    for (int n = 0; n < NG; ++n)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        qb[n][ks][0] = *reinterpret_cast<const uint32_t*>(&q_s[(n * 8 + kr) * kQPitch + ks * 16 + hc]);
+        qb[n][ks][1] = *reinterpret_cast<const uint32_t*>(&q_s[(n * 8 + kr) * kQPitch + ks * 16 + hc + 8]);
+      }
     const int r8 = lane & 7, mi = lane >> 3;
 
     for (int t = warp; t < my_tiles; t += NW) {
@@ -706,133 +724,133 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       const uint32_t sbK = smem_u32(stages + st * kStageBytes);
       const uint32_t sbV = sbK + 2 * kBoxBytes;
 
-      // S = Q K^T  (16 x 64)
-      float sa[8][4];
+      // S^T = K Q^T  (64 keys x 8 heads per group): A = K rows through ldmatrix (a0: keys 0-7 / feats 0-7,
+      // a1: keys 8-15, a2: feats 8-15, a3: both)
+      float sa[NG][4][4];
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        sa[nb][0] = sa[nb][1] = sa[nb][2] = sa[nb][3] = 0.f;
-        const uint32_t rowaddr = sbK + (uint32_t)(nb * 8 + r8) * 128u;
+      for (int n = 0; n < NG; ++n)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int c = kk * 4 + mi;  // 16-byte chunk of the 256-byte key row
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(b0, b1, b2, b3, rowaddr + (uint32_t)(c >> 3) * kBoxBytes + (uint32_t)(((c & 7) ^ r8) << 4));
-          MMA::run(sa[nb], qa[2 * kk], b0, b1);
-          MMA::run(sa[nb], qa[2 * kk + 1], b2, b3);
+        for (int kb = 0; kb < 4; ++kb) sa[n][kb][0] = sa[n][kb][1] = sa[n][kb][2] = sa[n][kb][3] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint32_t rowaddr = sbK + (uint32_t)(kb * 16 + (mi & 1) * 8 + r8) * 128u;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int c = ks * 2 + (mi >> 1);  // 16-byte chunk of the 256-byte key row
+          uint32_t af[4];
+          ldmatrix_x4(af[0], af[1], af[2], af[3],
+                      rowaddr + (uint32_t)(c >> 3) * kBoxBytes + (uint32_t)(((c & 7) ^ r8) << 4));
+#pragma unroll
+          for (int n = 0; n < NG; ++n) MMA::run(sa[n][kb], af, qb[n][ks][0], qb[n][ks][1]);
         }
       }
 
-      // online softmax (log2 domain)
+      // online softmax (log2 domain): this thread holds, for heads hc / hc + 1 of each group, the keys
+      // kb * 16 + kr (frag 0, 1) and + 8 (frag 2, 3)
       const int key_base = (tile_begin + t) * kTile;
       const bool partial = key_base + kTile > dy.n_mem;
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      uint32_t pb[NG][4][2];  // P^T as the B operand of O^T += V^T P^T
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
+      for (int n = 0; n < NG; ++n) {
+        float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int key = key_base + nb * 8 + cq + e;
-          const bool dead = partial && (key >= dy.n_mem);
-          sa[nb][e] = dead ? -INFINITY : sa[nb][e] * p.scale_log2;
-          if (HI) sa[nb][2 + e] = dead ? -INFINITY : sa[nb][2 + e] * p.scale_log2;
-          if (p.mask_kind && !dead) {  // launch-uniform
-            if (g0 < G) sa[nb][e] = mask_score<T>(p, sa[nb][e], b, hk * G + g0, key);
-            if (HI && g0 + 8 < G) sa[nb][2 + e] = mask_score<T>(p, sa[nb][2 + e], b, hk * G + g0 + 8, key);
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = key_base + kb * 16 + kr + (e >> 1) * 8;
+            const int head = n * 8 + hc + (e & 1);
+            const bool dead = partial && (key >= dy.n_mem);
+            float v = dead ? -INFINITY : sa[n][kb][e] * p.scale_log2;
+            if (p.mask_kind && !dead && head < G) v = mask_score<T>(p, v, b, hk * G + head, key);  // launch-uniform
+            sa[n][kb][e] = v;
+            mx[e & 1] = fmaxf(mx[e & 1], v);
           }
-          mx0 = fmaxf(mx0, sa[nb][e]);
-          if (HI) mx1 = fmaxf(mx1, sa[nb][2 + e]);
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      const float m0o = m0;
-      // (a masked row can have seen no key yet: subtract 0 instead of -inf so that 2^(-inf - m) = 0)
-      m0 = fmaxf(m0, mx0);
-      const float mn0 = m0 == -INFINITY ? 0.f : m0;
-      const float c0 = fast_exp2(m0o - mn0);
-      float mn1 = 0.f, c1 = 1.f;
-      if (HI) {
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float m1o = m1;
-        m1 = fmaxf(m1, mx1);
-        mn1 = m1 == -INFINITY ? 0.f : m1;
-        c1 = fast_exp2(m1o - mn1);
-      }
-      float rs0 = 0.f, rs1 = 0.f;
-      uint32_t pa[4][4];
+        float cf[2];
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
-        const float p0 = fast_exp2(sa[nb][0] - mn0), p1 = fast_exp2(sa[nb][1] - mn0);
-        rs0 += p0 + p1;
-        pa[nb >> 1][(nb & 1) * 2] = MMA::pack(p0, p1);
-        if (HI) {
-          const float p2 = fast_exp2(sa[nb][2] - mn1), p3 = fast_exp2(sa[nb][3] - mn1);
-          rs1 += p2 + p3;
-          pa[nb >> 1][(nb & 1) * 2 + 1] = MMA::pack(p2, p3);
-        } else {
-          pa[nb >> 1][(nb & 1) * 2 + 1] = 0u;
+        for (int h = 0; h < 2; ++h) {
+          float m = mx[h];
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+          const float mo_ = mrun[n][h];
+          mrun[n][h] = fmaxf(mo_, m);
+          // (a masked row can have seen no key yet: subtract 0 instead of -inf so that 2^(-inf - m) = 0)
+          mx[h] = mrun[n][h] == -INFINITY ? 0.f : mrun[n][h];
+          cf[h] = fast_exp2(mo_ - mx[h]);
         }
-      }
-      l0 = l0 * c0 + rs0;
-      if (HI) l1 = l1 * c1 + rs1;
+        float rs[2] = {0.f, 0.f};
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
-        o[nt][0] *= c0;
-        o[nt][1] *= c0;
-        if (HI) {
-          o[nt][2] *= c1;
-          o[nt][3] *= c1;
+        for (int kb = 0; kb < 4; ++kb) {
+          const float p0 = fast_exp2(sa[n][kb][0] - mx[0]), p1 = fast_exp2(sa[n][kb][1] - mx[1]);
+          const float p2 = fast_exp2(sa[n][kb][2] - mx[0]), p3 = fast_exp2(sa[n][kb][3] - mx[1]);
+          rs[0] += p0 + p2;
+          rs[1] += p1 + p3;
+          // [key kr][heads hc, hc+1] -> transpose -> [head kr][keys hc, hc+1] = the B fragment
+          pb[n][kb][0] = movmatrix_trans(MMA::pack(p0, p1));
+          pb[n][kb][1] = movmatrix_trans(MMA::pack(p2, p3));
+        }
+        lrun[n][0] = lrun[n][0] * cf[0] + rs[0];
+        lrun[n][1] = lrun[n][1] * cf[1] + rs[1];
+#pragma unroll
+        for (int fb = 0; fb < 8; ++fb) {
+          ot[n][fb][0] *= cf[0];
+          ot[n][fb][1] *= cf[1];
+          ot[n][fb][2] *= cf[0];
+          ot[n][fb][3] *= cf[1];
         }
       }
 
-      // O += P V  (16 x 128)
+      // O^T += V^T P^T  (128 features x 8 heads per group): A = V^T through ldmatrix.trans (a0: feats 0-7 /
+      // keys 0-7, a1: feats 8-15, a2: keys 8-15, a3: both)
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int key = kk * 16 + (mi & 1) * 8 + r8;
-        const uint32_t rowaddr = sbV + (uint32_t)key * 128u;
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint32_t rowaddr = sbV + (uint32_t)(kb * 16 + (mi >> 1) * 8 + r8) * 128u;
 #pragma unroll
-        for (int dp = 0; dp < 8; ++dp) {
-          const int c = dp * 2 + (mi >> 1);
-          uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(b0, b1, b2, b3,
+        for (int fb = 0; fb < 8; ++fb) {
+          const int c = fb * 2 + (mi & 1);
+          uint32_t af[4];
+          ldmatrix_x4_trans(af[0], af[1], af[2], af[3],
                             rowaddr + (uint32_t)(c >> 3) * kBoxBytes + (uint32_t)(((c & 7) ^ r8) << 4));
-          MMA::run(o[2 * dp], pa[kk], b0, b1);
-          MMA::run(o[2 * dp + 1], pa[kk], b2, b3);
+#pragma unroll
+          for (int n = 0; n < NG; ++n) MMA::run(ot[n][fb], af, pb[n][kb][0], pb[n][kb][1]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    if (HI) {
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    }
+#pragma unroll
+    for (int n = 0; n < NG; ++n)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float l = lrun[n][h];
+        l += __shfl_xor_sync(0xffffffffu, l, 4);
+        l += __shfl_xor_sync(0xffffffffu, l, 8);
+        l += __shfl_xor_sync(0xffffffffu, l, 16);
+        lrun[n][h] = l;
+      }
   }
   __syncthreads();  // every stage consumed -> the ring is reused for the merge
   trace_mark(p, 2);
   if (warp < NW) {
     float* mo = reinterpret_cast<float*>(stages);  // [NW][16][128]
     float* mml = mo + NW * 16 * D;                 // [NW][16][2]
-    if (g0 < G) {
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt)
-        *reinterpret_cast<float2*>(&mo[(warp * 16 + g0) * D + nt * 8 + cq]) = make_float2(o[nt][0], o[nt][1]);
-      if ((lane & 3) == 0) {
-        mml[(warp * 16 + g0) * 2] = m0;
-        mml[(warp * 16 + g0) * 2 + 1] = l0;
-      }
-    }
-    if (HI && g0 + 8 < G) {
+    for (int n = 0; n < NG; ++n)
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt)
-        *reinterpret_cast<float2*>(&mo[(warp * 16 + g0 + 8) * D + nt * 8 + cq]) = make_float2(o[nt][2], o[nt][3]);
-      if ((lane & 3) == 0) {
-        mml[(warp * 16 + g0 + 8) * 2] = m1;
-        mml[(warp * 16 + g0 + 8) * 2 + 1] = l1;
+      for (int h = 0; h < 2; ++h) {
+        const int head = n * 8 + hc + h;
+        if (head < G) {
+#pragma unroll
+          for (int fb = 0; fb < 8; ++fb) {
+            mo[(warp * 16 + head) * D + fb * 16 + kr] = ot[n][fb][h];
+            mo[(warp * 16 + head) * D + fb * 16 + kr + 8] = ot[n][fb][2 + h];
+          }
+          if (kr == 0) {
+            mml[(warp * 16 + head) * 2] = mrun[n][h];
+            mml[(warp * 16 + head) * 2 + 1] = lrun[n][h];
+          }
+        }
       }
-    }
   }
   __syncthreads();  // merge inputs visible
   const float* mo = reinterpret_cast<const float*>(stages);

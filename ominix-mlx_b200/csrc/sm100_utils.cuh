@@ -125,6 +125,13 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, ui
                : "r"(addr));
 }
 
+// 8x8 b16 transpose across the warp: in/out thread l holds row l/4, columns 2(l%4), 2(l%4)+1
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
 template <typename T>
 struct Mma16816;
 template <>
