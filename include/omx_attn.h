@@ -272,6 +272,31 @@ int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q,
                                   const omx_peer_group* peers, int head_offset, omx_stream s);
 int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s);
 
+/* ---- sequence-sharded single-sequence decode ---------------- */
+/*
+ * For contexts that should not (or do not) live on one GPU: rank r keeps the K/V rows of the token
+ * positions it owns (any assignment: attention is a sum over keys; the host mirror uses position % world)
+ * for ALL heads.  One step = one decode launch per rank + one exchange:
+ *   omx_attn_decode_seqshard: q' = rope(q, position); on the rank with append = true also
+ *     k' = rope(k_new, position) appended to the LOCAL cache row offset; attention of q' over the local rows;
+ *     the result -- the normalised output of the local keys and their (m, l) in the log2 domain, float32
+ *     [B,Hq,D+2] -- is stored into slot `rank` of EVERY rank's partial buffer [world,B,Hq,D+2] through the
+ *     peer mappings (peers->out[r] = rank r's buffer; null peers = single rank), arrival counters as in
+ *     omx_attn_decode_fused_sharded.  `position` is the GLOBAL position of the new token.
+ *   omx_seqshard_merge: waits (bounded) for all `world` arrivals of step `expected`, then
+ *     out[b,h,:] = sum_r w_r O_r / sum_r w_r,  w_r = l_r 2^(m_r - max_r m_r)      (one launch).
+ * The partial buffer must be double-buffered by step parity by the caller (a rank may run one step ahead).
+ */
+int omx_attn_decode_seqshard(const omx_array* partial /* float32 [world,B,Hq,D+2], this rank's buffer */,
+                             const omx_array* q, const omx_array* k_new /* null unless append */,
+                             const omx_array* v_new /* null unless append */, omx_kv_cache cache,
+                             int rope_dims, bool traditional, omx_optional_float base, float rope_scale,
+                             int position, bool append, float sm_scale,
+                             const omx_peer_group* peers /* may be null */, omx_stream s);
+int omx_seqshard_merge(const omx_array* out /* [B,Hq,1,D] */, const omx_array* partial,
+                       const omx_peer_group* peers /* may be null: no wait */, uint32_t expected,
+                       omx_stream s);
+
 /* ---- DiT joint attention ------------------------------------------------ */
 /* Table-driven interleaved rope: x [B,S,H,D], cos/sin [B,S,D/2] (x's dtype);
  * out0 = x0*c - x1*s, out1 = x1*c + x0*s per adjacent pair, rounding after every op. */

@@ -85,6 +85,10 @@ _SIGS = {
     "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                      OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                      ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),
+    "omx_attn_decode_seqshard": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
+                                                OmxOptionalFloat, ctypes.c_float, ctypes.c_int, ctypes.c_bool,
+                                                ctypes.c_float, ctypes.POINTER(OmxPeerGroup), ctypes.c_void_p]),
+    "omx_seqshard_merge": (ctypes.c_int, [_AP, _AP, ctypes.POINTER(OmxPeerGroup), ctypes.c_uint32, ctypes.c_void_p]),
     "omx_peer_wait": (ctypes.c_int, [ctypes.POINTER(OmxPeerGroup), ctypes.c_uint32, ctypes.c_void_p]),
     "omx_dit_rope": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_void_p]),
     "omx_dit_joint_attention": (ctypes.c_int, [_AP, _AP, _AP, _AP, ctypes.c_float, _AP, ctypes.c_void_p]),

@@ -24,6 +24,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <type_traits>
 #include <cstdlib>
 #include <vector>
 
@@ -92,6 +93,11 @@ struct DecodeParams {
   // 1: the splits of one (batch, kv-head) form a thread-block cluster and are combined through
   // distributed shared memory (no partials in HBM/L2, no fence, no ticket)
   int cluster;
+  // sequence-sharded decode (omx_attn_decode_seqshard): `out` / peer_out are FLOAT32 partial slots
+  // [B][Hq][D + 2] -- the normalised output of this rank's keys, then its (m, l) in the log2 domain -- and
+  // os[] holds that slot's strides; append = 0: this rank attends but does not own the new token
+  int partial;
+  int append;
   // debugging aid (OMX_DECODE_TRACE=1): per-CTA phase timestamps, [cta][16] x %globaltimer ns; null otherwise
   unsigned long long* trace;
 };
@@ -141,12 +147,31 @@ __device__ __forceinline__ float mask_score(const DecodeParams& p, float s, int 
 
 template <typename T>
 __device__ __forceinline__ void store_out(const DecodeParams& p, int64_t off, float v) {
+  if (p.partial) {  // f32 partial slot(s)
+    if (p.n_peers == 0) ((float*)p.out)[off] = v;
+    for (int r = 0; r < p.n_peers; ++r) ((float*)p.peer_out[r])[off] = v;
+    return;
+  }
   const T x = Num<T>::from_f(v);
   if (p.n_peers == 0) {
     ((T*)p.out)[off] = x;
     return;
   }
   for (int r = 0; r < p.n_peers; ++r) ((T*)p.peer_out[r])[off] = x;
+}
+
+// (m, l) of one (batch, head) behind its D partial-output floats (sequence-sharded mode only)
+__device__ __forceinline__ void store_ml(const DecodeParams& p, int b, int head, float M, float L) {
+  if (!p.partial) return;
+  const int64_t off = b * p.os[0] + (int64_t)head * p.os[1] + (int64_t)p.D * p.os[3];
+  if (p.n_peers == 0) {
+    ((float*)p.out)[off] = M;
+    ((float*)p.out)[off + 1] = L;
+  }
+  for (int r = 0; r < p.n_peers; ++r) {
+    ((float*)p.peer_out[r])[off] = M;
+    ((float*)p.peer_out[r])[off + 1] = L;
+  }
 }
 
 // After the final stores of one CTA (called by all its threads).  Writers fence their peer stores
@@ -403,6 +428,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     }
     if (p.num_splits == 1) {
       store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
+      if (d == 0) store_ml(p, b, first_head + g, M, L);
       if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
     } else if (use_cluster) {
       part_o[g * D + d] = O;  // == mo[(0 * rows + g) * D + d], read above by this thread only
@@ -450,6 +476,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
       const float s_a = m_a > -INFINITY ? fast_exp2(m_a - M) : 0.f;
       const float L = warp_sum(ln < NS ? sm_l[ln * rows + g] * s_a : 0.f);
       if (ln < NS) sm_w[ln * rows + g] = s_a * (1.0f / L);
+      if (ln == 0 && split == 0) store_ml(p, b, first_head + g, M, L);
       if (p.dead && ln == 0 && split == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
     }
     __syncthreads();
@@ -540,6 +567,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     const float inv = 1.0f / L;
     if (ln < p.num_splits) sm_w[ln * rows + g] = s_a * inv;
     if (ln + 32 < p.num_splits) sm_w[(ln + 32) * rows + g] = s_b * inv;
+    if (ln == 0) store_ml(p, b, first_head + g, M, L);
     if (p.dead && ln == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
   }
   __syncthreads();
@@ -631,7 +659,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
   const int tile_begin = split * dy.tps;
   const int my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
-  const bool has_nt = p.fused && split == p.num_splits - 1;
+  const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
 
   // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight BEFORE the
   // CTA stages q: the K/V stream does not depend on q, and with only a dozen tiles per CTA (single
@@ -947,7 +975,7 @@ decode_simt_kernel(const DecodeParams p) {
   const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
   const int kend = min(dy.n_mem, kbeg + keys_per_split);
-  const bool has_nt = p.fused && split == p.num_splits - 1;
+  const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
 
   // K/V do not depend on q: the first batch of rows is requested before the prologue's round trip
   const T* kb = (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + lane * VE;
@@ -1199,7 +1227,71 @@ __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expe
   __threadfence_system();
 }
 
+// One CTA per (batch, head): wait for every rank's arrival, then the log-sum-exp merge of the partial slots.
+template <typename T>
+__global__ void seqshard_merge_kernel(T* out, int64_t os0, int64_t os1, int64_t os3, const float* partial, int world,
+                                      int Hq, int D, const unsigned* flags, unsigned expected) {
+  __shared__ float s_w[kMaxPeers];
+  const int bh = blockIdx.x, b = bh / Hq, h = bh % Hq;
+  if (flags) {
+    if ((int)threadIdx.x < world) {
+      const volatile unsigned* f = flags + threadIdx.x;
+      unsigned spins = 0;
+      while ((int)(*f - expected) < 0) {  // counters only grow; the signed difference tolerates wrap-around
+        __nanosleep(64);
+        if (++spins > (1u << 25)) __trap();  // a lost peer becomes a launch failure, not a hung GPU
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
+  const int64_t slot = (int64_t)D + 2;
+  const float* base = partial + ((int64_t)b * Hq + h) * slot;
+  const int64_t rank_stride = (int64_t)gridDim.x * slot;
+  if (threadIdx.x == 0) {
+    float M = -INFINITY;
+    for (int r = 0; r < world; ++r) M = fmaxf(M, __ldcg(base + r * rank_stride + D));
+    float W = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const float m = __ldcg(base + r * rank_stride + D), l = __ldcg(base + r * rank_stride + D + 1);
+      const float w = (m > -INFINITY && l > 0.f) ? l * fast_exp2(m - M) : 0.f;
+      s_w[r] = w;
+      W += w;
+    }
+    const float inv = 1.0f / W;
+    for (int r = 0; r < world; ++r) s_w[r] *= inv;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const float w = s_w[r];
+      if (w > 0.f) acc = fmaf(__ldcg(base + r * rank_stride + d), w, acc);  // a rank without keys holds no number
+    }
+    out[b * os0 + h * os1 + d * os3] = Num<T>::from_f(acc);
+  }
+}
+
 }  // namespace
+
+void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
+                    const unsigned* flags, unsigned expected, cudaStream_t stream) {
+  if (B * Hq == 0) return;
+  const int threads = std::min(128, std::max(32, D));
+  auto go = [&](auto* o) {
+    using T = std::remove_pointer_t<decltype(o)>;
+    seqshard_merge_kernel<T><<<B * Hq, threads, 0, stream>>>(o, out->strides[0], out->strides[1], out->strides[3],
+                                                            partial, world, Hq, D, flags, expected);
+  };
+  note_launch("seqshard_merge");
+  switch (out->dtype) {
+    case OMX_FLOAT32: go((float*)out->data); break;
+    case OMX_BFLOAT16: go((__nv_bfloat16*)out->data); break;
+    default: go((__half*)out->data); break;
+  }
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+}
 
 void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream) {
   peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, expected);
@@ -1320,14 +1412,18 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   p.B = a.B; p.Hq = a.Hq; p.Hkv = a.Hkv; p.G = a.Hq / a.Hkv; p.D = a.D;
   p.Lk = a.Lk;
   p.fused = f.enabled ? 1 : 0;
-  p.n_mem = f.enabled ? a.Lk - 1 : a.Lk;
+  p.append = f.enabled && f.append ? 1 : 0;
+  p.partial = f.partial ? 1 : 0;
+  p.n_mem = p.append ? a.Lk - 1 : a.Lk;
   p.scale_log2 = a.scale * kLog2e;
   if (f.enabled) {
-    p.k_new = f.k_new->data;
-    p.v_new = f.v_new->data;
+    if (f.append) {
+      p.k_new = f.k_new->data;
+      p.v_new = f.v_new->data;
+    }
     for (int i = 0; i < 4; ++i) {
-      p.kns[i] = f.k_new->strides[i];
-      p.vns[i] = f.v_new->strides[i];
+      p.kns[i] = f.append ? f.k_new->strides[i] : 0;
+      p.vns[i] = f.append ? f.v_new->strides[i] : 0;
       p.kcs[i] = a.k->strides[i];
       p.vcs[i] = a.v->strides[i];
     }

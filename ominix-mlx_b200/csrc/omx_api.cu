@@ -739,6 +739,97 @@ int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q,
   });
 }
 
+int omx_attn_decode_seqshard(const omx_array* partial, const omx_array* q, const omx_array* k_new,
+                             const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                             omx_optional_float base, float rope_scale, int position, bool append, float sm_scale,
+                             const omx_peer_group* peers, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    auto* c = (KVCacheImpl*)cache.ctx;
+    OMX_CHECK(c, "[attn_decode_seqshard] null cache handle");
+    OMX_CHECK(q && partial, "[attn_decode_seqshard] null array");
+    OMX_CHECK(q->ndim == 4 && q->shape[2] == 1, "[attn_decode_seqshard] q must be [B, Hq, 1, D]");
+    const int64_t B = q->shape[0], Hq = q->shape[1], D = q->shape[3];
+    const int world = peers ? peers->world : 1, rank = peers ? peers->rank : 0;
+    OMX_CHECK(world >= 1 && world <= OMX_MAX_PEERS && rank >= 0 && rank < world, "[attn_decode_seqshard] bad peer group");
+    OMX_CHECK(partial->dtype == OMX_FLOAT32 && partial->ndim == 4 && partial->shape[0] == world &&
+                  partial->shape[1] == B && partial->shape[2] == Hq && partial->shape[3] == D + 2 &&
+                  partial->strides[3] == 1 && partial->strides[2] == D + 2 && partial->strides[1] == Hq * (D + 2) &&
+                  partial->strides[0] == B * Hq * (D + 2),
+              "[attn_decode_seqshard] partial must be a contiguous float32 [world, B, Hq, D + 2] buffer");
+    OMX_CHECK(position >= 0, "[attn_decode_seqshard] negative position");
+    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %lld", (long long)D);
+    OMX_CHECK(rope_dims == 0 || base.has_value, "[attn_decode_seqshard] rope needs a base (no freqs here)");
+    if (append) {
+      OMX_CHECK(k_new && v_new && k_new->ndim == 4 && v_new->ndim == 4 && k_new->shape[2] == 1 && v_new->shape[2] == 1 &&
+                    k_new->dtype == q->dtype && v_new->dtype == q->dtype,
+                "[attn_decode_seqshard] the appending rank needs k_new / v_new [B, Hkv, 1, D] in q's dtype");
+    }
+    if (peers) {
+      for (int r = 0; r < world; ++r)
+        OMX_CHECK(peers->out[r] && peers->flags[r], "[attn_decode_seqshard] peer %d is not mapped", r);
+      OMX_CHECK(peers->out[rank] == partial->data, "[attn_decode_seqshard] partial must be this rank's buffer of the peer group");
+    }
+    omx_array kview, vview;
+    if (append) {
+      kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
+    } else {
+      kv_cache_state(c, &kview, &vview);
+      kview.shape[2] = vview.shape[2] = kv_cache_offset(c);
+    }
+    OMX_CHECK(kview.shape[2] >= 1, "[attn_decode_seqshard] every rank must hold at least one key");
+    // this rank's slot of the (local) partial buffer, described as the kernel's [B, Hq, 1, D] output
+    const size_t slot_bytes = (size_t)B * Hq * (D + 2) * sizeof(float);
+    omx_array slot = *q;
+    slot.data = (char*)partial->data + (size_t)rank * slot_bytes;
+    slot.strides[0] = Hq * (D + 2);
+    slot.strides[1] = D + 2;
+    slot.strides[2] = D + 2;
+    slot.strides[3] = 1;
+    SdpaArgs a = make_sdpa_args(&slot, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    const char* why = nullptr;
+    const bool fast = decode_supported(a, &why) && (!append || (k_new->strides[3] == 1 && v_new->strides[3] == 1));
+    OMX_CHECK(fast, "[attn_decode_seqshard] layout not supported by the decode kernels: %s",
+              why ? why : "strided k_new/v_new");
+    DecodeFused f;
+    f.enabled = true;
+    f.append = append;
+    f.partial = true;
+    f.k_new = k_new;
+    f.v_new = v_new;
+    f.rope_dims = rope_dims;
+    f.traditional = traditional;
+    f.position = position;  // GLOBAL position of the new token: rope row; the cache row is the local offset
+    if (rope_dims > 0) f.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, position + 1, stream);
+    omx_peer_group shifted;
+    if (peers) {  // every rank's buffer receives this rank's slot
+      shifted = *peers;
+      for (int r = 0; r < world; ++r) shifted.out[r] = (char*)peers->out[r] + (size_t)rank * slot_bytes;
+      f.peers = &shifted;
+    }
+    decode_attention(a, f, stream);
+  });
+}
+
+int omx_seqshard_merge(const omx_array* out, const omx_array* partial, const omx_peer_group* peers, uint32_t expected,
+                       omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(out && partial && out->ndim == 4 && partial->ndim == 4 && out->shape[2] == 1, "[seqshard_merge] bad arrays");
+    const int64_t world = partial->shape[0], B = out->shape[0], Hq = out->shape[1], D = out->shape[3];
+    OMX_CHECK(partial->dtype == OMX_FLOAT32 && partial->shape[1] == B && partial->shape[2] == Hq &&
+                  partial->shape[3] == D + 2 && partial->strides[3] == 1 && partial->strides[2] == D + 2 &&
+                  partial->strides[1] == Hq * (D + 2) && partial->strides[0] == B * Hq * (D + 2),
+              "[seqshard_merge] partial must be a contiguous float32 [world, B, Hq, D + 2] buffer");
+    OMX_CHECK(is_float_dtype(out->dtype), "[seqshard_merge] out must be floating point");
+    OMX_CHECK(world >= 1 && world <= OMX_MAX_PEERS && (!peers || (peers->world == world && peers->rank >= 0 &&
+                  peers->rank < world && peers->flags[peers->rank])), "[seqshard_merge] bad peer group");
+    seqshard_merge(out, (const float*)partial->data, (int)world, (int)B, (int)Hq, (int)D,
+                   peers ? peers->flags[peers->rank] : nullptr, expected, (cudaStream_t)s);
+  });
+}
+
 int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s) {
   return guarded([&] {
     require_device();

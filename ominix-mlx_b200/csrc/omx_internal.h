@@ -120,6 +120,10 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   const void* q_norm_w = nullptr;
   const void* k_norm_w = nullptr;
   float norm_eps = 0.f;
+  // sequence-sharded decode: append = false on ranks that do not own the new token (k_new / v_new unused);
+  // partial = true: `out` is a float32 slot [B][Hq][D + 2] (normalised output of the local keys, m, l)
+  bool append = true;
+  bool partial = false;
   // graph mode (omx_attn_decode_fused_dynamic): the position is read from device memory by the kernel;
   // K/V views span max_rows rows, `position` above is 0, scratch is owned by the cache
   const int* pos_dev = nullptr;
@@ -135,6 +139,11 @@ bool decode_supported(const SdpaArgs& a, const char** why);
 void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream);
 // One thread per rank spins (bounded) until flags[r] has reached `expected` for every r.
 void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream);
+// Sequence-sharded decode, exchange step: waits (bounded) until flags[r] >= expected for every rank (flags may
+// be null: no wait), then out[b,h,:] = sum_r w_r O_r / sum_r w_r with w_r = l_r 2^(m_r - max m) over the `world`
+// float32 partial slots [world][B][Hq][D + 2].
+void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
+                    const unsigned* flags, unsigned expected, cudaStream_t stream);
 
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);

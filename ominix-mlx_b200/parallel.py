@@ -15,6 +15,11 @@ path needs and nothing more:
       into every rank's output buffer through NVLink peer mappings and bumps an arrival counter
       (omx_attn_decode_fused_sharded), then a one-warp wait kernel (omx_peer_wait).  Buffers come
       from torch's symmetric-memory allocator (plumbing only).
+* Sequence sharding for a single sequence whose KV should be spread over the GPUs with ALL
+  heads on every rank: rank r keeps the rows of the positions p with p % world == r; each step every rank
+  attends over its rows and the ranks exchange float32 partials (normalised output + (m, l)) -- pushed into
+  every peer's buffer by the decode kernel's final store (`gather="peer"`) or all-gathered (`"collective"`) --
+  followed by a log-sum-exp merge (`SeqShardedDecode`, omx_attn_decode_seqshard + omx_seqshard_merge).
 torch.distributed is used for rendezvous / the baseline collective only.
 """
 import ctypes
@@ -164,3 +169,116 @@ class HeadShardedDecode:
     def rewind(self, n=1):
         """Bench helper: drop the last n rows so that every step does identical work."""
         return self.cache.trim(n)
+
+
+# ---------------------------------------------------------------- sequence sharding (SURVEY 8f N4)
+
+def seq_shard_owner(position, world):
+    """Rank that stores the K/V row of global token position `position`."""
+    return int(position) % int(world)
+
+
+def seq_shard_rows(n_tokens, world, rank, start=0):
+    """Global positions in [start, start + n_tokens) owned by `rank`, as a slice-able index tensor."""
+    first = start + ((rank - start) % world)
+    end = start + n_tokens
+    return torch.arange(first, end, world) if first < end else torch.empty(0, dtype=torch.int64)
+
+
+def merge_partials(partial):
+    """Log-sum-exp merge of float32 partials [world, B, Hq, D + 2] (last two: m, l in the log2 domain) ->
+    [B, Hq, D].  Host-side restatement of omx_seqshard_merge (any device; used by the gloo tests and by the
+    collective spelling's checks)."""
+    o, m, l = partial[..., :-2], partial[..., -2], partial[..., -1]
+    M = m.max(dim=0, keepdim=True).values
+    w = torch.where((l > 0) & torch.isfinite(m), l * torch.exp2(m - M), torch.zeros_like(l))
+    w = w / w.sum(dim=0, keepdim=True)
+    return (torch.where(w.unsqueeze(-1) > 0, o, torch.zeros_like(o)) * w.unsqueeze(-1)).sum(dim=0)
+
+
+class SeqShardedDecode:
+    """One sequence, `world` GPUs, every rank holds all heads of the rows it owns (position % world == rank).
+
+    prefill(keys, values): the FULL [B,Hkv,n,D] roped keys / values of the prompt (replicated on every rank, as a
+    tensor-parallel prefill leaves them); each rank stores its rows.  step(q, k_new, v_new): the full-head
+    inputs of the step; returns the full attention output [B,Hq,1,D] on every rank."""
+
+    def __init__(self, n_heads, n_kv_heads, head_dim, dtype, rope, sm_scale, batch=1, group=None, gather="peer",
+                 device=None):
+        from .cache import KVCache
+        if gather not in ("collective", "peer"):
+            raise _lib.Exception_(f"unknown gather mode {gather!r}")
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_heads, self.n_kv_heads, self.head_dim, self.dtype = n_heads, n_kv_heads, head_dim, dtype
+        self.rope, self.sm_scale, self.gather = rope, sm_scale, gather
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.cache = KVCache()
+        self.position = 0  # global tokens seen
+        self.steps = 0
+        self._peer = None
+        shape = (2, self.world, batch, n_heads, head_dim + 2)  # double-buffered by step parity
+        if gather == "peer" and self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            grp = self.group if self.group is not None else dist.group.WORLD
+            self.partial = symm.empty(shape, dtype=torch.float32, device=self.device)
+            self._flags = symm.empty((_lib.OMX_MAX_PEERS,), dtype=torch.int32, device=self.device)
+            self._flags.zero_()
+            h_p, h_f = symm.rendezvous(self.partial, group=grp), symm.rendezvous(self._flags, group=grp)
+            self._handles = (h_p, h_f)
+            self._ptrs = [int(h_p.buffer_ptrs[r]) for r in range(self.world)]
+            self._fptrs = [int(h_f.buffer_ptrs[r]) for r in range(self.world)]
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=grp)
+            self._peer = True
+        else:
+            self.partial = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self.out = torch.empty((batch, n_heads, 1, head_dim), dtype=dtype, device=self.device)
+
+    def _group_for(self, parity):
+        if not self._peer:
+            return None
+        pg = _lib.OmxPeerGroup()
+        pg.world, pg.rank = self.world, self.rank
+        half = self.partial[0].numel() * 4
+        for r in range(self.world):
+            pg.out[r] = self._ptrs[r] + parity * half
+            pg.flags[r] = self._fptrs[r]
+        return pg
+
+    def prefill(self, keys, values):
+        n = keys.shape[2]
+        rows = seq_shard_rows(n, self.world, self.rank, self.position).to(keys.device) - self.position
+        self.position += n
+        if rows.numel() == 0:
+            return None
+        return self.cache.update_and_fetch(keys[:, :, rows], values[:, :, rows])
+
+    def step(self, q, k_new, v_new, stream=None):
+        parity = self.steps & 1
+        self.steps += 1
+        owner = seq_shard_owner(self.position, self.world) == self.rank
+        part = self.partial[parity]
+        pg = self._group_for(parity)
+        rope = self.rope
+        base = _lib.OmxOptionalFloat()
+        base.has_value = rope is not None
+        base.value = rope.base if rope is not None else 0.0
+        qd, pd, od = desc(q), desc(part), desc(self.out)
+        kd, vd = (desc(k_new), desc(v_new)) if owner else (None, None)
+        sp = stream_ptr(stream)
+        # without peer mappings the launch sees a one-rank buffer: this rank's slot of the local array
+        mine_d = pd if pg is not None else desc(part[self.rank:self.rank + 1])
+        _lib.check(_lib.lib().omx_attn_decode_seqshard(
+            ref(mine_d), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
+            bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0,
+            int(self.position), bool(owner), float(self.sm_scale), ctypes.byref(pg) if pg is not None else None, sp))
+        self.position += 1
+        if self.world > 1 and not self._peer:  # baseline exchange: all-gather the local slots
+            mine = part[self.rank].contiguous()
+            dist.all_gather_into_tensor(part.view(-1), mine.view(-1), group=self.group)
+        _lib.check(_lib.lib().omx_seqshard_merge(
+            ref(od), ref(pd), ctypes.byref(pg) if pg is not None else None,
+            ctypes.c_uint32(self.steps & 0xFFFFFFFF), sp))
+        return self.out

@@ -126,6 +126,13 @@ extern "C" {
                                          base: omx_optional_float, rope_scale: f32, freqs: *const omx_array,
                                          sm_scale: f32, peers: *const omx_peer_group, head_offset: c_int,
                                          s: omx_stream) -> c_int;
+    pub fn omx_attn_decode_seqshard(partial: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                    v_new: *const omx_array, cache: omx_kv_cache, rope_dims: c_int,
+                                    traditional: bool, base: omx_optional_float, rope_scale: f32,
+                                    position: c_int, append: bool, sm_scale: f32,
+                                    peers: *const omx_peer_group, s: omx_stream) -> c_int;
+    pub fn omx_seqshard_merge(out: *const omx_array, partial: *const omx_array, peers: *const omx_peer_group,
+                              expected: u32, s: omx_stream) -> c_int;
     pub fn omx_peer_wait(peers: *const omx_peer_group, expected: u32, s: omx_stream) -> c_int;
     pub fn omx_dit_rope(out: *const omx_array, x: *const omx_array, cos: *const omx_array,
                         sin: *const omx_array, s: omx_stream) -> c_int;

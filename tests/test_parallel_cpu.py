@@ -109,3 +109,68 @@ def test_head_sharded_gather_world2_gloo(dtype):
         p.join(120)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == [1, 1]
+
+
+# ---- sequence sharding: ownership + the log-sum-exp merge, world 2 over gloo ----
+
+def test_seq_shard_rows_partition_every_position_once():
+    for world in (1, 2, 3, 8):
+        for start, n in ((0, 0), (0, 1), (0, 17), (5, 9), (7, 64)):
+            seen = sorted(int(p) for r in range(world) for p in par.seq_shard_rows(n, world, r, start))
+            assert seen == list(range(start, start + n)), (world, start, n)
+            for r in range(world):
+                assert all(par.seq_shard_owner(int(p), world) == r for p in par.seq_shard_rows(n, world, r, start))
+
+
+def _partial(q, k, v, scale):
+    """What omx_attn_decode_seqshard leaves in a slot: normalised output of the local keys + (m, l), log2 domain."""
+    G = q.shape[1] // k.shape[1]
+    kk, vv = k.repeat_interleave(G, 1), v.repeat_interleave(G, 1)
+    s = torch.einsum("bhd,bhjd->bhj", q[:, :, 0].double(), kk.double()) * scale * 1.4426950408889634
+    m = s.max(-1).values
+    p = torch.exp2(s - m[..., None])
+    l = p.sum(-1)
+    o = torch.einsum("bhj,bhjd->bhd", p, vv.double()) / l[..., None]
+    return torch.cat([o, m[..., None], l[..., None]], -1).float()
+
+
+def _seq_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, Hq, Hkv, S, D = 2, 8, 2, 45, 32
+        g = torch.Generator().manual_seed(11)  # replicated inputs
+        q, k, v = (torch.randn(s, generator=g) for s in ((B, Hq, 1, D), (B, Hkv, S, D), (B, Hkv, S, D)))
+        scale = D ** -0.5
+        rows = par.seq_shard_rows(S, world, rank)
+        mine = _partial(q, k[:, :, rows], v[:, :, rows], scale)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        got = par.merge_partials(torch.stack(parts))
+        kk, vv = k.repeat_interleave(Hq // Hkv, 1), v.repeat_interleave(Hq // Hkv, 1)
+        want = torch.nn.functional.scaled_dot_product_attention(q.double(), kk.double(), vv.double(), scale=scale)[:, :, 0]
+        ok = torch.allclose(got.double(), want, rtol=1e-5, atol=1e-6)
+        # a rank without keys contributes (m, l) = (-inf, 0) and garbage output: it must not poison the merge
+        empty = torch.full_like(mine, float("nan"))
+        empty[..., -2], empty[..., -1] = float("-inf"), 0.0
+        got2 = par.merge_partials(torch.stack(parts + [empty]))
+        ok2 = torch.allclose(got2.double(), want, rtol=1e-5, atol=1e-6)
+        flags = torch.tensor([int(ok), int(ok2)])
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(flags.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_seq_sharded_merge_world2_gloo():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seq_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == [1, 1]

@@ -3,6 +3,7 @@ kernel on one device (world 1 through the raw C ABI), and, when the box has >= 2
 exchange spellings (NCCL all-gather baseline, fused peer stores) across 2 ranks against the
 oracle's unsharded answer."""
 import ctypes
+import importlib
 import os
 import socket
 
@@ -16,6 +17,7 @@ pytestmark = pytest.mark.gpu
 omx = load_pkg()
 orc = load_oracle()
 ROPE = (128, False, 1e6, 1.0)
+DEV = "cuda"
 
 
 def _oracle_full(k, v, q, kn, vn, dtype, S):
@@ -122,3 +124,125 @@ def test_head_sharded_decode_two_ranks(gather):
         assert err <= 2e-2, (rank, err)
         assert kv_ok, f"rank {rank}: KV shard not bit-exact"
         assert kern == "decode_hmma_tma"
+
+
+# ---- sequence-sharded decode ----
+
+def _seq_oracle(k, v, steps, dtype, S, Hq, Hkv, D, B):
+    """Unsharded chain: rope(q, pos), rope(k_new, pos), append, sdpa -- per step."""
+    oc = orc.KVCache()
+    oc.update_and_fetch(t2n(k, dtype), t2n(v, dtype))
+    outs = []
+    for t, (q, kn, vn) in enumerate(steps):
+        qo = orc.rope(t2n(q, dtype), D, False, 1e6, 1.0, S + t, dtype=dtype)
+        ko = orc.rope(t2n(kn, dtype), D, False, 1e6, 1.0, S + t, dtype=dtype)
+        K, V = oc.update_and_fetch(ko, t2n(vn, dtype))
+        outs.append(n2f(orc.sdpa(qo, np.ascontiguousarray(K), np.ascontiguousarray(V), D ** -0.5, None, dtype=dtype), dtype))
+    return outs, oc
+
+
+@pytest.mark.parametrize("dtype,world", [("bf16", 1), ("bf16", 2), ("f32", 3), ("bf16", 4)])
+def test_seq_sharded_virtual_ranks_one_gpu(dtype, world):
+    """All `world` ranks played by ONE GPU through the raw C ABI: rank r's partial buffer and counters are plain
+    device tensors, every peer pointer is a local address -- the kernels cannot tell.  Checks the partial / merge
+    math, the global-position rope, the ownership rule and the (bit-exact) distributed cache rows."""
+    import ctypes
+    L = importlib.import_module("ominix-mlx_b200._lib")
+    A = importlib.import_module("ominix-mlx_b200.array")
+    B, Hq, Hkv, D, S, T = 2, 8, 2, 128, 203, 5
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
+    steps = [(randn((B, Hq, 1, D), dtype, 10 + 3 * t), randn((B, Hkv, 1, D), dtype, 11 + 3 * t),
+              randn((B, Hkv, 1, D), dtype, 12 + 3 * t)) for t in range(T)]
+    want, oc = _seq_oracle(k, v, steps, dtype, S, Hq, Hkv, D, B)
+    caches = [omx.KVCache() for _ in range(world)]
+    kd, vd = k.to(DEV), v.to(DEV)
+    for r, c in enumerate(caches):
+        rows = omx.parallel.seq_shard_rows(S, world, r).to(DEV)
+        c.update_and_fetch(kd[:, :, rows], vd[:, :, rows])
+    parts = [torch.zeros((2, world, B, Hq, D + 2), dtype=torch.float32, device=DEV) for _ in range(world)]
+    flags = [torch.zeros(L.OMX_MAX_PEERS, dtype=torch.int32, device=DEV) for _ in range(world)]
+    outs = [torch.empty((B, Hq, 1, D), dtype=tdt, device=DEV) for _ in range(world)]
+    base = L.OmxOptionalFloat()
+    base.has_value, base.value = True, 1e6
+    sp = A.stream_ptr(None)
+    for t, (q, kn, vn) in enumerate(steps):
+        par_ = t & 1
+        pos = S + t
+        groups = []
+        for r in range(world):
+            pg = L.OmxPeerGroup()
+            pg.world, pg.rank = world, r
+            for j in range(world):
+                pg.out[j] = parts[j][par_].data_ptr()
+                pg.flags[j] = flags[j].data_ptr()
+            groups.append(pg)
+        qd, knd, vnd = q.to(DEV), kn.to(DEV), vn.to(DEV)
+        for r in range(world):
+            own = omx.parallel.seq_shard_owner(pos, world) == r
+            L.check(L.lib().omx_attn_decode_seqshard(
+                A.ref(A.desc(parts[r][par_])), A.ref(A.desc(qd)), A.ref(A.desc(knd)) if own else None,
+                A.ref(A.desc(vnd)) if own else None, caches[r].handle, D, False, base, 1.0, pos, own, D ** -0.5,
+                ctypes.byref(groups[r]), sp))
+        for r in range(world):
+            L.check(L.lib().omx_seqshard_merge(A.ref(A.desc(outs[r])), A.ref(A.desc(parts[r][par_])),
+                                               ctypes.byref(groups[r]), ctypes.c_uint32(t + 1), sp))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert_close(outs[r].float().cpu().numpy(), want[t], dtype, f"seq-sharded step {t} rank {r}")
+            assert torch.equal(outs[r], outs[0])
+        # the merge is what parallel.merge_partials says
+        ref_merge = omx.parallel.merge_partials(parts[0][par_])
+        np.testing.assert_allclose(outs[0][:, :, 0].float().cpu().numpy(), ref_merge.cpu().numpy(), rtol=1e-2, atol=1e-2)
+    # every rank holds exactly the rows it owns, bit-exact
+    for r, c in enumerate(caches):
+        rows = omx.parallel.seq_shard_rows(S + T, world, r).numpy()
+        assert c.offset() == len(rows)
+        sk, sv = c.state()
+        assert (t2n(sk[:, :, :len(rows)], dtype) == oc.keys[:, :, rows]).all()
+        assert (t2n(sv[:, :, :len(rows)], dtype) == oc.values[:, :, rows]).all()
+
+
+def _seq_rank_main(rank, world, port, gather, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        dtype, B, Hq, Hkv, D, S, T = "bf16", 1, 32, 8, 128, 4099, 4
+        k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
+        steps = [(randn((B, Hq, 1, D), dtype, 10 + 3 * t), randn((B, Hkv, 1, D), dtype, 11 + 3 * t),
+                  randn((B, Hkv, 1, D), dtype, 12 + 3 * t)) for t in range(T)]
+        want, oc = _seq_oracle(k, v, steps, dtype, S, Hq, Hkv, D, B)
+        eng = omx.parallel.SeqShardedDecode(Hq, Hkv, D, torch.bfloat16, omx.nn.Rope(*ROPE), D ** -0.5, batch=B,
+                                            gather=gather)
+        eng.prefill(k.cuda(), v.cuda())
+        errs = []
+        for t, (qq, kn, vn) in enumerate(steps):
+            out = eng.step(qq.cuda(), kn.cuda(), vn.cuda())
+            torch.cuda.synchronize()
+            errs.append(float(np.abs(out.float().cpu().numpy() - want[t]).max()))
+        rows = omx.parallel.seq_shard_rows(S + T, world, rank).numpy()
+        sk, _ = eng.cache.state()
+        kv_ok = bool((t2n(sk[:, :, :len(rows)], dtype) == oc.keys[:, :, rows]).all())
+        q.put((rank, max(errs), kv_ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("gather", ["collective", "peer"])
+def test_seq_sharded_decode_two_ranks(gather):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_seq_rank_main, args=(r, 2, port, gather, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0, f"rank process exited with {p.exitcode}"
+    for rank, err, kv_ok in sorted(q.get(timeout=5) for _ in range(2)):
+        assert err <= 2e-2, (rank, err)
+        assert kv_ok, f"rank {rank}: KV rows not bit-exact"
