@@ -196,6 +196,14 @@ __device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
 // each step waiting on global memory.  Now every thread first issues its share of ALL the loads (raw q
 // heads, rope row, norm weights and -- in the CTA that appends -- the new k / v rows), the CTA syncs once,
 // and the row statistics, normalisation and rotation run from shared memory only.
+// named barriers (id 1..15; id 0 is __syncthreads): `count` threads must arrive, sync blocks, arrive does not
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // 1 / rms of a row held in shared memory: the reference's strict left-to-right f32 sum of squares.  The
 // row is pulled into registers with 128-bit loads first, so what remains serial is the FADD chain alone
 // (the scalar loop took 2.7 us for 128 bf16 elements: one exposed LDS per step).
@@ -231,11 +239,12 @@ struct PrologueSmem {       // static shared memory of both kernels
 
 // after_loads(): called once the prologue's own loads are issued and before anything waits on them (the
 // CUDA-core kernel requests its first K/V rows there).
-template <typename T, typename F>
+// sync(): barrier over the `nthr` threads that run the prologue (the whole CTA, or the consumer warps only).
+template <typename T, typename F, typename S>
 __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch, int rows_total, int first_head,
                                         int n_heads, int b, int hk, int tid, int nthr, PrologueSmem& ps,
                                         float* nt_k, float* nt_v, bool has_nt, const DecodeDyn& dy,
-                                        F&& after_loads) {
+                                        F&& after_loads, S&& sync) {
   const int D = p.D;
   const bool rope = p.fused && p.rope_dims > 0;
   const int half = p.rope_dims >> 1;
@@ -278,7 +287,7 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
   }
   after_loads();
   if (!rope && !p.q_norm_w) return;  // the caller's barrier publishes the copy
-  __syncthreads();
+  sync();
   trace_mark(p, 12);
   // ---- q_norm: the reference's left-to-right f32 sum, one thread per head, from shared memory
   if (p.q_norm_w) {
@@ -287,7 +296,7 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
       ps.rs[tid >> 5] = rms_rsqrt_smem<T>(q_s + (tid >> 5) * pitch, D, p.norm_eps, p.norm_inv_n);
     for (int g = (nthr >> 5) + tid; g < n_heads; g += nthr)  // more heads than warps (G = 16 on 4 warps)
       ps.rs[g] = rms_rsqrt_smem<T>(q_s + g * pitch, D, p.norm_eps, p.norm_inv_n);
-    __syncthreads();
+    sync();
     trace_mark(p, 13);
   }
   // ---- normalise + rotate in place (every element is owned by exactly one thread)
@@ -408,6 +417,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   const int64_t ob = b * p.os[0];
   const bool use_cluster = p.cluster && p.num_splits > 1;
   float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
+  // (one element per thread: a float4-column variant halved the active threads and measured slower)
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
     const int g = idx / D, d = idx % D;
     float M = has_nt ? nt_m[g] : -INFINITY;
@@ -683,19 +693,44 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       mbar_init(&empty_bar[s], 1);
     }
     mbar_fence_init();
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    pol = policy_evict_first();
-    for (int t = 0; t < first; ++t) issue(t);
-    if (p.trace) {
-      unsigned long long tt;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
-      p.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + 7] = tt;
+  }
+  // One-wave grids (MINB == 1, single-sequence decode): the producer warp and the consumer warps run apart --
+  // the producer lane fetches the tensor maps and puts the first tiles in flight (~1 us of serial issue)
+  // WHILE the consumer warps stage q; barrier 2 = the consumer warps among themselves, barrier 1 = "q is
+  // staged" for the producer warp (consumers arrive without blocking).  A/B in one box: fused step -1..-2.6 %.
+  // Multi-wave grids (C2) keep the single-barrier flow, which measured 0.3 % faster there.
+  constexpr bool kDecouple = MINB == 1;
+  if constexpr (kDecouple) __syncthreads();  // barriers initialised before anyone waits on them
+  if (warp == NW || !kDecouple) {
+    if (tid == NW * 32) {
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      pol = policy_evict_first();
+      for (int t = 0; t < first; ++t) issue(t);
+      if (p.trace) {
+        unsigned long long tt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+        p.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + 7] = tt;
+      }
     }
   }
-  stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [] {});
-  __syncthreads();
-  trace_mark(p, 1);
+  if constexpr (kDecouple) {
+    if (warp == NW) {
+      __syncwarp();
+      named_bar_sync(1, NTHR);
+    } else {
+      stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, hk, tid, NW * 32, s_pro, nt_k, nt_v, has_nt, dy, [] {},
+                 [] { named_bar_sync(2, NW * 32); });
+      named_bar_sync(2, NW * 32);
+      named_bar_arrive(1, NTHR);
+      trace_mark(p, 1);
+    }
+  } else {
+    stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [] {},
+               [] { __syncthreads(); });
+    __syncthreads();
+    trace_mark(p, 1);
+  }
 
   // consumer state (declared at function scope so the merge below runs after CTA-wide barriers
   // that every warp reaches at the same program point).
@@ -992,7 +1027,7 @@ decode_simt_kernel(const DecodeParams p) {
 
   stage_q<T>(p, q_s, D, GT, first_head, GT, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [&] {
     if (j_first < kend) load_kv(j_first);
-  });
+  }, [] { __syncthreads(); });
   __syncthreads();
   trace_mark(p, 1);
   // the new row is appended once per kv head (gsub == 0 writes it); every group scores it

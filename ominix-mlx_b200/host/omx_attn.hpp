@@ -393,6 +393,22 @@ inline void attention_decode_fused_dynamic(Array& out, const Array& queries, con
                                       fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
                                       rope ? rope->scale : 1.f, scale, position, s.raw()));
 }
+/// Sequence-sharded decode step of one rank (see omx_attn_decode_seqshard): `partial` = this rank's float32
+/// [world,B,Hq,D+2] buffer, `position` = GLOBAL position of the new token, `append` on the owning rank only.
+inline void attention_decode_seqshard(Array& partial, const Array& queries, const Array* keys, const Array* values,
+                                      KVCache& cache, const nn::Rope* rope, int position, bool append, float scale,
+                                      const omx_peer_group* peers = nullptr, Stream s = {}) {
+  check(omx_attn_decode_seqshard(partial.desc(), queries.desc(), keys ? keys->desc() : nullptr,
+                                 values ? values->desc() : nullptr, cache.raw(), rope ? rope->dimensions : 0,
+                                 rope ? rope->traditional : false,
+                                 fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
+                                 rope ? rope->scale : 1.f, position, append, scale, peers, s.raw()));
+}
+/// Waits for the `expected`-th arrival of every rank (peers may be null: no wait), then merges the partials.
+inline void seqshard_merge(Array& out, const Array& partial, const omx_peer_group* peers, uint32_t expected,
+                           Stream s = {}) {
+  check(omx_seqshard_merge(out.desc(), partial.desc(), peers, expected, s.raw()));
+}
 inline void device_counter_add(int32_t* counter, int delta, Stream s = {}) {
   check(omx_device_counter_add(counter, delta, s.raw()));
 }
