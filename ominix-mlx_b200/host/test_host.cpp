@@ -303,6 +303,102 @@ static void test_attention_forward_prefill_then_decode() {
   EXPECT(oerr <= 2e-2f, "fused decode vs oracle max-abs %g", oerr);
 }
 
+// The decode loop as ONE CUDA graph from a compiled host: two layers, the position lives in
+// device memory, one capture, five replays; every replay must reproduce the eager fused step bit for bit.
+#define STAGE(msg) do { fprintf(stderr, "[graph loop test] %s\n", msg); fflush(stderr); } while (0)
+static void test_decode_loop_cuda_graph() {
+  const int B = 1, Hq = 16, Hkv = 8, D = 128, S0 = 250, LAYERS = 2, STEPS = 8;  // crosses the 256-row growth
+  const float scale = 1.0f / std::sqrt((float)D), eps = 1e-6f;
+  cudaStream_t st;
+  cudaStreamCreate(&st);
+  omx::Stream S{st};
+  omx::nn::Rope rope = omx::utils::initialize_rope(D, 1e6f, false);
+  auto qw = randn_bf16(D, 70), kw = randn_bf16(D, 71);
+  omx::nn::RmsNorm q_norm{Array::from_host(qw.data(), {D}, Dtype::Bfloat16, S), eps};
+  omx::nn::RmsNorm k_norm{Array::from_host(kw.data(), {D}, Dtype::Bfloat16, S), eps};
+  std::vector<omx::KVCache> eager, graphed;
+  std::vector<Array> q, k, v, out;
+  for (int l = 0; l < LAYERS; ++l) {
+    auto kh = randn_bf16((size_t)B * Hkv * S0 * D, 80 + l), vh = randn_bf16((size_t)B * Hkv * S0 * D, 90 + l);
+    Array k0 = Array::from_host(kh.data(), {B, Hkv, S0, D}, Dtype::Bfloat16, S);
+    Array v0 = Array::from_host(vh.data(), {B, Hkv, S0, D}, Dtype::Bfloat16, S);
+    eager.emplace_back(256, S);
+    graphed.emplace_back(256, S);
+    eager.back().update_and_fetch(k0, v0);
+    graphed.back().update_and_fetch(k0, v0);
+    graphed.back().prepare_graph(S0 + STEPS, Hq);
+    q.push_back(Array::empty({B, Hq, 1, D}, Dtype::Bfloat16));
+    k.push_back(Array::empty({B, Hkv, 1, D}, Dtype::Bfloat16));
+    v.push_back(Array::empty({B, Hkv, 1, D}, Dtype::Bfloat16));
+    out.push_back(Array::empty({B, Hq, 1, D}, Dtype::Bfloat16));
+  }
+  int32_t* pos = nullptr;
+  cudaMalloc(&pos, sizeof(int32_t));
+  const int32_t p0 = S0;
+  cudaMemcpyAsync(pos, &p0, sizeof(p0), cudaMemcpyHostToDevice, st);
+  auto step = [&] {
+    for (int l = 0; l < LAYERS; ++l)
+      omx::utils::attention_decode_fused_dynamic(out[l], q[l], k[l], v[l], graphed[l], &rope, scale, pos, &q_norm, &k_norm, S);
+    omx::utils::device_counter_add(pos, 1, S);
+  };
+  auto upload = [&](int t) {
+    for (int l = 0; l < LAYERS; ++l) {
+      auto a = randn_bf16((size_t)B * Hq * D, 1000 + 10 * t + l), b = randn_bf16((size_t)B * Hkv * D, 2000 + 10 * t + l),
+           c = randn_bf16((size_t)B * Hkv * D, 3000 + 10 * t + l);
+      cudaMemcpyAsync(q[l].data(), a.data(), a.size() * 2, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(k[l].data(), b.data(), b.size() * 2, cudaMemcpyHostToDevice, st);
+      cudaMemcpyAsync(v[l].data(), c.data(), c.size() * 2, cudaMemcpyHostToDevice, st);
+      cudaStreamSynchronize(st);  // the host vectors die at the end of the iteration
+    }
+  };
+  STAGE("setup done");
+  upload(0);
+  STAGE("uploaded");
+  step();                                  // eager warm-up: builds the rope table ...
+  omx::utils::device_counter_add(pos, -1, S);  // ... and is rolled back (row S0 is rewritten by the first replay)
+  STAGE("warm-up done");
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  EXPECT(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess, "begin capture");
+  step();
+  STAGE("captured");
+  EXPECT(cudaStreamEndCapture(st, &graph) == cudaSuccess, "end capture");
+  EXPECT(cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess, "instantiate");
+  STAGE("instantiated");
+  size_t n_nodes = 0;
+  cudaGraphGetNodes(graph, nullptr, &n_nodes);
+  EXPECT(n_nodes == (size_t)LAYERS + 1, "captured graph has %zu nodes, expected one launch per layer + the counter", n_nodes);
+  bool same = true;
+  for (int t = 0; t < STEPS; ++t) {
+    upload(t);
+    EXPECT(cudaGraphLaunch(exec, st) == cudaSuccess, "graph launch");
+    for (int l = 0; l < LAYERS; ++l) {
+      graphed[l].advance(1);
+      Array want = omx::utils::attention_decode_fused(q[l], k[l], v[l], eager[l], &rope, scale, &q_norm, &k_norm, S);
+      cudaStreamSynchronize(st);
+      same = same && download(want) == download(out[l]);
+    }
+  }
+  STAGE("replayed");
+  EXPECT(same, "graph replays must reproduce the eager fused step bit for bit");
+  int32_t pend = 0;
+  cudaMemcpy(&pend, pos, sizeof(pend), cudaMemcpyDeviceToHost);
+  EXPECT(pend == S0 + STEPS, "device position %d after %d replays", pend, STEPS);
+  for (int l = 0; l < LAYERS; ++l) {
+    EXPECT(graphed[l].offset() == S0 + STEPS && eager[l].offset() == S0 + STEPS, "offsets after the loop");
+    EXPECT(download(graphed[l].state().first) == download(eager[l].state().first), "KV keys after graph replays (layer %d)", l);
+    EXPECT(download(graphed[l].state().second) == download(eager[l].state().second), "KV values after graph replays (layer %d)", l);
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  cudaFree(pos);
+  // the caches free their buffers stream-ordered on the stream they were used on: drop them before it
+  eager.clear();
+  graphed.clear();
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+}
+
 int main() {
   int sm = 0;
   if (omx_device_check(&sm) != 0) {
@@ -315,6 +411,7 @@ int main() {
     test_kv_cache_appendix_a();
     test_sdpa_shapes_like_the_reference_test();
     test_attention_forward_prefill_then_decode();
+    test_decode_loop_cuda_graph();
   } catch (const std::exception& e) {
     printf("EXCEPTION: %s\n", e.what());
     return 1;
