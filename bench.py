@@ -218,6 +218,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "collective"],
                     help="c5 with --gpus > 1 (kv-head-sharded single sequence): exchange of the output heads "
                          "by peer stores fused into the decode kernel, or by an NCCL all-gather")
+    ap.add_argument("--layout", default="head", choices=["head", "seq"],
+                    help="c5 with --gpus > 1: shard the kv HEADS (BASELINE C5) or the SEQUENCE (rows of position p on "
+                         "rank p %% N, all heads everywhere, float32 partials + log-sum-exp merge)")
     ap.add_argument("--mask", default="string", choices=["string", "array"],
                     help="c3: pass the causal mask as the \"causal\" mode string or as the bool [T,T] array the LLM "
                          "crates build with create_causal_mask (classified per tile, same tiles skipped)")
@@ -271,12 +274,24 @@ def main():
         def rn0(*shape):
             return torch.randn(shape, generator=g0, device=dev, dtype=torch.float32).to(tdt)
         rope = omx.nn.Rope(D, False, 1e6, 1.0)
-        eng = omx.parallel.HeadShardedDecode(Hq, Hkv, D, tdt, rope, scale, batch=B, gather=args.gather)
+        if args.layout == "seq":
+            eng = omx.parallel.SeqShardedDecode(Hq, Hkv, D, tdt, rope, scale, batch=B, gather=args.gather)
+
+            def rewind(n=1):
+                eng.position -= 1
+                if omx.parallel.seq_shard_owner(eng.position, world) == rank:
+                    eng.cache.trim(1)
+            eng.rewind = rewind
+        else:
+            eng = omx.parallel.HeadShardedDecode(Hq, Hkv, D, tdt, rope, scale, batch=B, gather=args.gather)
+        # the exchange waits on "my own signal count" instead of a host-side step number, so that a captured
+        # step can be replayed (--graph): what a compiled host's decode loop would launch
+        eng.auto_wait = bool(args.graph)
         for s0 in range(0, S - 1, 4096):
             n = min(4096, S - 1 - s0)
             kk, vv = rn0(B, Hkv, n, D), rn0(B, Hkv, n, D)
             eng.prefill(kk, vv)
-        assert eng.cache.offset() == S - 1
+        assert args.layout == "seq" or eng.cache.offset() == S - 1
         q, kn, vn = rn0(B, Hq, 1, D), rn0(B, Hkv, 1, D), rn0(B, Hkv, 1, D)
 
         def step():
@@ -517,7 +532,9 @@ def main():
             "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
             "config": {"workload": cfg["label"], "per_gpu_batch": B, "global_batch": B if sharded else B * world,
                        "ctx" if kind == "decode" else "seq_len": S, "q_heads": Hq, "kv_heads": Hkv, "head_dim": D,
-                       "parallelism": (f"kv-head-sharded x{world}, output heads exchanged by "
+                       "parallelism": ((f"kv-head-sharded x{world}, output heads exchanged by " if args.layout == "head"
+                                        else f"sequence-sharded x{world} (rows of position p on rank p % N), float32 "
+                                             "partials exchanged by ")
                                        + ("peer stores fused into the decode kernel" if args.gather == "peer"
                                           else "NCCL all-gather")) if sharded
                        else f"batch-sharded x{world}, no data-path collective",

@@ -252,7 +252,10 @@ int omx_device_counter_add(int32_t* counter /* device */, int delta, omx_stream 
  * straight into EVERY rank's output buffer through NVLink peer mappings, and the last CTA of the
  * launch bumps one arrival counter per rank (system-scope fence, then atomic).  omx_peer_wait
  * enqueues a one-warp kernel that returns once all `world` counters of the local rank reached
- * `expected` (= number of sharded steps issued so far).
+ * `expected` (= number of sharded steps issued so far).  expected == 0 means "as many arrivals as this
+ * rank has itself signalled" (its own launch, earlier on the stream, bumped its own counter): no host-side
+ * step count, so launch + wait can be captured once into a CUDA graph and replayed; same for
+ * omx_seqshard_merge.
  */
 typedef struct omx_peer_group_ {
   int32_t world; /* <= OMX_MAX_PEERS */

@@ -1250,8 +1250,11 @@ void launch_simt_d(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool
   }
 }
 
-__global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expected) {
+__global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expected, int rank) {
   if ((int)threadIdx.x >= world) return;
+  // expected == 0: "as many arrivals as this rank has itself signalled" -- its own decode launch (earlier on the
+  // stream) bumped flags[rank], so the count needs no host argument and the wait can be replayed from a graph
+  if (expected == 0) expected = *(const volatile unsigned*)(flags + rank);
   const volatile unsigned* f = flags + threadIdx.x;
   unsigned spins = 0;
   // counters only grow; the signed difference tolerates wrap-around
@@ -1265,11 +1268,12 @@ __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expe
 // One CTA per (batch, head): wait for every rank's arrival, then the log-sum-exp merge of the partial slots.
 template <typename T>
 __global__ void seqshard_merge_kernel(T* out, int64_t os0, int64_t os1, int64_t os3, const float* partial, int world,
-                                      int Hq, int D, const unsigned* flags, unsigned expected) {
+                                      int Hq, int D, const unsigned* flags, unsigned expected, int rank) {
   __shared__ float s_w[kMaxPeers];
   const int bh = blockIdx.x, b = bh / Hq, h = bh % Hq;
   if (flags) {
     if ((int)threadIdx.x < world) {
+      if (expected == 0) expected = *(const volatile unsigned*)(flags + rank);  // see peer_wait_kernel
       const volatile unsigned* f = flags + threadIdx.x;
       unsigned spins = 0;
       while ((int)(*f - expected) < 0) {  // counters only grow; the signed difference tolerates wrap-around
@@ -1310,13 +1314,13 @@ __global__ void seqshard_merge_kernel(T* out, int64_t os0, int64_t os1, int64_t 
 }  // namespace
 
 void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
-                    const unsigned* flags, unsigned expected, cudaStream_t stream) {
+                    const unsigned* flags, unsigned expected, int rank, cudaStream_t stream) {
   if (B * Hq == 0) return;
   const int threads = std::min(128, std::max(32, D));
   auto go = [&](auto* o) {
     using T = std::remove_pointer_t<decltype(o)>;
     seqshard_merge_kernel<T><<<B * Hq, threads, 0, stream>>>(o, out->strides[0], out->strides[1], out->strides[3],
-                                                            partial, world, Hq, D, flags, expected);
+                                                            partial, world, Hq, D, flags, expected, rank);
   };
   note_launch("seqshard_merge");
   switch (out->dtype) {
@@ -1328,8 +1332,8 @@ void seqshard_merge(const omx_array* out, const float* partial, int world, int B
   OMX_CUDA(cudaGetLastError());
 }
 
-void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream) {
-  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, expected);
+void peer_wait(const unsigned* flags, int world, unsigned expected, int rank, cudaStream_t stream) {
+  peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, expected, rank);
   count_launch();
   OMX_CUDA(cudaGetLastError());
 }

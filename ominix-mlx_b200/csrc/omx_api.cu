@@ -826,7 +826,7 @@ int omx_seqshard_merge(const omx_array* out, const omx_array* partial, const omx
     OMX_CHECK(world >= 1 && world <= OMX_MAX_PEERS && (!peers || (peers->world == world && peers->rank >= 0 &&
                   peers->rank < world && peers->flags[peers->rank])), "[seqshard_merge] bad peer group");
     seqshard_merge(out, (const float*)partial->data, (int)world, (int)B, (int)Hq, (int)D,
-                   peers ? peers->flags[peers->rank] : nullptr, expected, (cudaStream_t)s);
+                   peers ? peers->flags[peers->rank] : nullptr, expected, peers ? peers->rank : 0, (cudaStream_t)s);
   });
 }
 
@@ -836,7 +836,7 @@ int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s) 
     OMX_CHECK(peers && peers->world >= 1 && peers->world <= OMX_MAX_PEERS && peers->rank >= 0 &&
                   peers->rank < peers->world && peers->flags[peers->rank],
               "[peer_wait] bad peer group");
-    peer_wait(peers->flags[peers->rank], peers->world, expected, (cudaStream_t)s);
+    peer_wait(peers->flags[peers->rank], peers->world, expected, peers->rank, (cudaStream_t)s);
   });
 }
 

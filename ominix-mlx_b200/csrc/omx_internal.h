@@ -138,12 +138,12 @@ size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int 
 bool decode_supported(const SdpaArgs& a, const char** why);
 void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stream);
 // One thread per rank spins (bounded) until flags[r] has reached `expected` for every r.
-void peer_wait(const unsigned* flags, int world, unsigned expected, cudaStream_t stream);
+void peer_wait(const unsigned* flags, int world, unsigned expected, int rank, cudaStream_t stream);
 // Sequence-sharded decode, exchange step: waits (bounded) until flags[r] >= expected for every rank (flags may
 // be null: no wait), then out[b,h,:] = sum_r w_r O_r / sum_r w_r with w_r = l_r 2^(m_r - max m) over the `world`
 // float32 partial slots [world][B][Hq][D + 2].
 void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
-                    const unsigned* flags, unsigned expected, cudaStream_t stream);
+                    const unsigned* flags, unsigned expected, int rank, cudaStream_t stream);
 
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);

@@ -108,6 +108,7 @@ class HeadShardedDecode:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.cache = KVCache()
         self.steps = 0
+        self.auto_wait = False  # True: expected = 0 ("my own signal count"), capturable into a CUDA graph
         self._peer = None
         if gather == "peer":
             self._init_peer(batch, dtype)
@@ -163,7 +164,8 @@ class HeadShardedDecode:
             ref(od), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
             bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0, None,
             float(self.sm_scale), ctypes.byref(self._peer), int(self.q0), sp))
-        _lib.check(_lib.lib().omx_peer_wait(ctypes.byref(self._peer), ctypes.c_uint32(self.steps & 0xFFFFFFFF), sp))
+        expected = 0 if self.auto_wait else self.steps & 0xFFFFFFFF
+        _lib.check(_lib.lib().omx_peer_wait(ctypes.byref(self._peer), ctypes.c_uint32(expected), sp))
         return self.out_full
 
     def rewind(self, n=1):
@@ -217,6 +219,7 @@ class SeqShardedDecode:
         self.cache = KVCache()
         self.position = 0  # global tokens seen
         self.steps = 0
+        self.auto_wait = False  # True: expected = 0 ("my own signal count"), capturable into a CUDA graph
         self._peer = None
         shape = (2, self.world, batch, n_heads, head_dim + 2)  # double-buffered by step parity
         if gather == "peer" and self.world > 1:
@@ -280,5 +283,5 @@ class SeqShardedDecode:
             dist.all_gather_into_tensor(part.view(-1), mine.view(-1), group=self.group)
         _lib.check(_lib.lib().omx_seqshard_merge(
             ref(od), ref(pd), ctypes.byref(pg) if pg is not None else None,
-            ctypes.c_uint32(self.steps & 0xFFFFFFFF), sp))
+            ctypes.c_uint32(0 if self.auto_wait else self.steps & 0xFFFFFFFF), sp))
         return self.out

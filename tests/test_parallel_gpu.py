@@ -246,3 +246,66 @@ def test_seq_sharded_decode_two_ranks(gather):
     for rank, err, kv_ok in sorted(q.get(timeout=5) for _ in range(2)):
         assert err <= 2e-2, (rank, err)
         assert kv_ok, f"rank {rank}: KV rows not bit-exact"
+
+
+def test_auto_expected_wait_is_replayable_one_gpu():
+    """expected == 0 ("as many arrivals as this rank has itself signalled") lets the sharded step -- decode launch +
+    wait / merge -- be captured ONCE and replayed: two virtual ranks on one GPU, sequence-sharded, the captured
+    pair of steps replayed three times against freshly computed eager results."""
+    import ctypes
+    L = importlib.import_module("ominix-mlx_b200._lib")
+    A = importlib.import_module("ominix-mlx_b200.array")
+    world, B, Hq, Hkv, D, S, dtype = 2, 1, 8, 2, 128, 301, "bf16"
+    k, v = randn((B, Hkv, S, D), dtype, 1).to(DEV), randn((B, Hkv, S, D), dtype, 2).to(DEV)
+    q, kn, vn = (randn(s, dtype, i).to(DEV) for i, s in ((3, (B, Hq, 1, D)), (4, (B, Hkv, 1, D)), (5, (B, Hkv, 1, D))))
+    caches = [omx.KVCache() for _ in range(world)]
+    for r, c in enumerate(caches):
+        rows = omx.parallel.seq_shard_rows(S, world, r).to(DEV)
+        c.update_and_fetch(k[:, :, rows], v[:, :, rows])
+        c.reserve(1024)
+    parts = [torch.zeros((world, B, Hq, D + 2), dtype=torch.float32, device=DEV) for _ in range(world)]
+    flags = [torch.zeros(L.OMX_MAX_PEERS, dtype=torch.int32, device=DEV) for _ in range(world)]
+    outs = [torch.empty((B, Hq, 1, D), dtype=torch.bfloat16, device=DEV) for _ in range(world)]
+    base = L.OmxOptionalFloat()
+    base.has_value, base.value = True, 1e6
+    groups = []
+    for r in range(world):
+        pg = L.OmxPeerGroup()
+        pg.world, pg.rank = world, r
+        for j in range(world):
+            pg.out[j], pg.flags[j] = parts[j].data_ptr(), flags[j].data_ptr()
+        groups.append(pg)
+    owner = omx.parallel.seq_shard_owner(S, world)
+
+    def step(expected):
+        sp = A.stream_ptr(None)
+        for r in range(world):
+            own = r == owner
+            L.check(L.lib().omx_attn_decode_seqshard(
+                A.ref(A.desc(parts[r])), A.ref(A.desc(q)), A.ref(A.desc(kn)) if own else None,
+                A.ref(A.desc(vn)) if own else None, caches[r].handle, D, False, base, 1.0, S, own, D ** -0.5,
+                ctypes.byref(groups[r]), sp))
+        for r in range(world):
+            L.check(L.lib().omx_seqshard_merge(A.ref(A.desc(outs[r])), A.ref(A.desc(parts[r])), ctypes.byref(groups[r]),
+                                               ctypes.c_uint32(expected), sp))
+        caches[owner].trim(1)  # identical work every step
+
+    step(1)  # eager, explicit step count
+    torch.cuda.synchronize()
+    want = outs[0].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(0)  # warm the capture stream
+    side.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step(0)
+        step(0)
+    for _ in range(3):
+        for o in outs:
+            o.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(o, want) for o in outs)
+    assert int(flags[0][0].item()) == 2 + 2 * 3  # every launch signalled: counters kept growing under replay
