@@ -2,23 +2,31 @@
 //
 // Collapses the decode step of the reference's Attention::forward
 // (qwen3-mlx/src/model.rs:186-212: rope(q, off), rope(k, off), cache.update_and_fetch, sdpa)
-// into ONE launch.  HBM-bandwidth bound: every K/V byte is read exactly once.
+// into ONE launch.  HBM-bandwidth bound at batch sizes that fill the chip (every K/V byte is read exactly
+// once); a chain of dependent round trips for a single sequence, which is what most of the structure below
+// is about (profiles/r01_small_decode.md).
 //
 //   grid  = (num_splits, Hkv, B); one CTA streams a contiguous chunk of the keys of ONE
 //           (batch, kv-head) and serves all G = Hq/Hkv query heads of that group from it.
-//   16-bit, D = 128 ("hmma_tma"): a producer warp feeds a 3-stage ring of 64-key K/V tiles with
-//           TMA (cp.async.bulk.tensor, 128 B swizzle, mbarrier completion, L2 evict-first);
-//           4 consumer warps each own whole tiles: S = Q K^T and O += P V on mma.sync m16n8k16
-//           (the G query heads padded to the 16-row M), online softmax with quad shuffles.
+//   16-bit, D = 128 ("hmma_tma"): a producer warp feeds a 3- or 6-stage ring of 64-key K/V tiles with
+//           TMA (cp.async.bulk.tensor, 128 B swizzle, mbarrier completion, L2 evict-first); each consumer
+//           warp owns whole tiles.  mma.sync m16n8k16 with SWAPPED roles -- keys / V features on the 16-row
+//           M side, the query heads on the 8-wide N side, P^T through movmatrix -- so no row is padding.
 //   float32 / other head dims ("simt"): 8 warps, 128-bit coalesced loads, FFMA dot products,
 //           warp-shuffle reductions.
-//   The per-warp (m, l, O) states are merged in shared memory; with num_splits > 1 partials go
-//   to a workspace and the LAST CTA of the (batch, kv-head) (atomic ticket) combines them, so
-//   there is no second launch.  Counters reset themselves.
-//   Fused mode: every CTA ropes its G query heads on the fly (table lookup, reference
+//   Prologue: all loads (q heads, rope row, norm weights, the new k / v rows) in ONE round trip, then
+//           row statistics / RMSNorm / rotation from shared memory (stage_q, new_token).
+//   The per-warp (m, l, O) states are merged in shared memory; with num_splits > 1 either the splits of a
+//   (batch, kv-head) form a thread-block CLUSTER and are combined through distributed shared memory, or
+//   partials go to a workspace and the LAST CTA of the pair (atomic ticket) combines them in one round trip
+//   to L2 -- no second launch either way.  Counters reset themselves.
+//   Fused mode: every CTA norms + ropes its G query heads on the fly (table lookup, reference
 //   rounding); the CTA owning the last chunk also ropes k_new, stores k'/v_new into the cache
-//   row `position` (bit-identical to the unfused path) and folds that key in from registers,
-//   so the new row is never re-read from HBM.
+//   row (bit-identical to the unfused path) and folds that key in from shared memory, so the new row is
+//   never re-read from HBM.
+//   Variants on the same kernels: position read from device memory (CUDA-graph decode loop), head-sharded
+//   output over NVLink peer stores, sequence-sharded float32 partials (+ seqshard_merge_kernel).
+//   OMX_DECODE_TRACE=1|2 dumps per-CTA phase timelines (debugging aid; p.trace is null otherwise).
 #include <algorithm>
 #include <cstdio>
 #include <map>
@@ -671,9 +679,10 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
   const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
 
-  // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight BEFORE the
-  // CTA stages q: the K/V stream does not depend on q, and with only a dozen tiles per CTA (single
-  // sequence, many splits) the q round trip would otherwise sit in front of the whole pipeline.
+  // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight before (or, on
+  // one-wave grids, while) the CTA stages q: the K/V stream does not depend on q, and with only a dozen
+  // tiles per CTA (single sequence, many splits) the q round trip would otherwise sit in front of the
+  // whole pipeline.
   uint64_t pol = 0;
   auto issue = [&](int t) {
     const int st = t % NSTAGE;
