@@ -1236,8 +1236,9 @@ void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool o
                     ? 1 : 0;
     launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, p);
   };
-  // the 16-key variant keeps 2 x 16 rows of VE floats per lane in registers: head_dim <= 128 only
-  constexpr int KBIG = VE <= 4 ? 16 : 4;
+  // the 16-key variant keeps 2 x 16 rows per lane in registers; instantiated where it is used and measured --
+  // float32 at head_dim 128 (C1; 16-bit head_dim 128 runs on the TMA kernel) -- to keep the build time down
+  constexpr int KBIG = (std::is_same<T, float>::value && VE == 4) ? 16 : 4;
   if (one_wave && KBIG != 4) {
     switch (Gt) {
       case 1: go(decode_simt_kernel<T, VE, 1, KBIG>, 1); break;
