@@ -1575,7 +1575,8 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     // that costs at most 6 more 64-key tiles per CTA (Qwen3-8B ctx 8192: 17.6 -> 16.2 us; at ctx 32768
     // the lost SMs cost more than the tail); else the HBM/L2 combine.
     constexpr int kClusterClamp = 10;
-    const int cap = getenv("OMX_DECODE_CLUSTER_MAX") ? cluster_cap() : kClusterClamp;
+    static const bool cap_from_env = getenv("OMX_DECODE_CLUSTER_MAX") != nullptr;  // sweep knob, read once
+    const int cap = cap_from_env ? cluster_cap() : kClusterClamp;
     const SplitPlan clamped = clamp_for_cluster(natural, n_tiles, cap);
     const bool try_clamped = clamped.num_splits != natural.num_splits &&
                              clamped.tiles_per_split - natural.tiles_per_split <= 6;
