@@ -617,9 +617,26 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
         const int sp = grp + i * groups;
         if (sp < p.num_splits) fold(acc, pre[i], sm_w[sp * rows + g]);
       }
+      // more splits than one batch of PF (a single (batch, kv-head) pair spread over 64 CTAs, e.g. one rank of
+      // the kv-head-sharded C5): further batches of PF loads in flight, not PF/4 -- 64 splits = 4 round trips
+      // to L2 instead of 13
+      if (p.num_splits <= (PF + 4) * groups) {  // a short tail (C5 on one GPU: 18 splits) keeps the plain loop
 #pragma unroll 4
-      for (int sp = grp + PF * groups; sp < p.num_splits; sp += groups)
-        fold(acc, __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D)), sm_w[sp * rows + g]);
+        for (int sp = grp + PF * groups; sp < p.num_splits; sp += groups)
+          fold(acc, __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D)), sm_w[sp * rows + g]);
+      } else
+      for (int base = grp + PF * groups; base < p.num_splits; base += PF * groups) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          const int sp = base + i * groups;
+          if (sp < p.num_splits) pre[i] = __ldcg(reinterpret_cast<const float4*>(po + (int64_t)sp * n_heads * D));
+        }
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+          const int sp = base + i * groups;
+          if (sp < p.num_splits) fold(acc, pre[i], sm_w[sp * rows + g]);
+        }
+      }
     }
     if (groups > 1) {
       if (first_pass) red[grp * C + col0] = acc;

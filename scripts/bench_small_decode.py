@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 omx = importlib.import_module("ominix-mlx_b200")
 dev = "cuda"
 SHAPES = [("c1 fp32 16/8 ctx2048", 1, 16, 8, 2048, torch.float32), ("0.6b bf16 16/8 ctx2048", 1, 16, 8, 2048, torch.bfloat16),
-          ("8b bf16 32/8 ctx8192", 1, 32, 8, 8192, torch.bfloat16), ("c5 bf16 32/8 ctx32768", 1, 32, 8, 32768, torch.bfloat16)]
+          ("8b bf16 32/8 ctx8192", 1, 32, 8, 8192, torch.bfloat16), ("c5 bf16 32/8 ctx32768", 1, 32, 8, 32768, torch.bfloat16),
+          ("c5 one rank of 8: bf16 4/1 ctx32768", 1, 4, 1, 32768, torch.bfloat16)]
 R, D = 16, 128
 for name, B, Hq, Hkv, S, dt in SHAPES:
     if len(sys.argv) > 1 and sys.argv[1] not in name:
