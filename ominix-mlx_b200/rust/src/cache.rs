@@ -74,6 +74,15 @@ impl KVCache {
     pub fn raw(&self) -> ffi::omx_kv_cache {
         self.h.0
     }
+    /// CUDA-graph decode loop (include/omx_attn.h): pin the buffers and the cache-owned split-K scratch for
+    /// positions [0, max_rows); addresses stay fixed until the cache outgrows them.
+    pub fn prepare_graph(&mut self, max_rows: i32, n_q_heads: i32) -> Result<()> {
+        check(unsafe { ffi::omx_kv_cache_prepare_graph(self.h.0, max_rows, n_q_heads, self.stream.0) })
+    }
+    /// Host bookkeeping for `n` rows appended by dynamic-position launches / graph replays.
+    pub fn advance(&mut self, n: i32) -> Result<()> {
+        check(unsafe { ffi::omx_kv_cache_advance(self.h.0, n, self.stream.0) })
+    }
     pub(crate) fn keepalive(&self) -> Arc<dyn std::any::Any + Send + Sync> {
         self.h.clone()
     }

@@ -77,3 +77,40 @@ pub fn attention_decode_fused(
     let _ = cache.keepalive();
     Ok(out)
 }
+
+/// `attention_decode_fused` with the position read by the KERNEL from `position` (device `int32`, shared by all
+/// layers): capturable with `cudaStreamBeginCapture` and replayable per token -- what `async_eval` pipelining gave
+/// the reference's decode loop (qwen3-mlx/src/model.rs:798-844).  `out` is caller-owned (static under a graph);
+/// the cache must have been pinned with `KVCache::prepare_graph`; the host offset is advanced separately with
+/// `KVCache::advance(n)` after the replays.  `q_norm` / `k_norm`: optional `[D]` RMSNorm weights + eps.
+#[allow(clippy::too_many_arguments)]
+pub fn attention_decode_fused_dynamic(
+    out: &Array,
+    queries: &Array,
+    keys: &Array,
+    values: &Array,
+    cache: &KVCache,
+    rope: Option<RopeParams>,
+    scale: f32,
+    position: *const i32,
+    q_norm: Option<(&Array, f32)>,
+    k_norm: Option<(&Array, f32)>,
+    stream: Stream,
+) -> Result<()> {
+    let (dims, trad, base, rscale) = match rope {
+        Some(r) => (r.dimensions, r.traditional, ffi::omx_optional_float { value: r.base, has_value: true }, r.scale),
+        None => (0, false, ffi::omx_optional_float::default(), 1.0),
+    };
+    let eps = q_norm.map(|n| n.1).or(k_norm.map(|n| n.1)).unwrap_or(0.0);
+    check(unsafe {
+        ffi::omx_attn_decode_fused_dynamic(out.as_ptr(), queries.as_ptr(), keys.as_ptr(), values.as_ptr(), cache.raw(),
+                                           q_norm.map_or(std::ptr::null(), |n| n.0.as_ptr()),
+                                           k_norm.map_or(std::ptr::null(), |n| n.0.as_ptr()), eps, dims, trad, base,
+                                           rscale, scale, position, stream.0)
+    })
+}
+
+/// `*counter += delta` on the stream: the per-token position bump of a graph-captured decode loop.
+pub fn device_counter_add(counter: *mut i32, delta: i32, stream: Stream) -> Result<()> {
+    check(unsafe { ffi::omx_device_counter_add(counter, delta, stream.0) })
+}
