@@ -40,16 +40,18 @@
 #include "omx_internal.h"
 #include "sm100_utils.cuh"
 
+// This file is compiled three times (csrc/Makefile) so that its ~50 kernels build in parallel:
+//   OMX_DECODE_PART 0 (default): host logic, the TMA / tensor-core kernels, the float32 CUDA-core kernels
+//   OMX_DECODE_PART 1 / 2: the bfloat16 / float16 instantiations of the CUDA-core kernel only
+#ifndef OMX_DECODE_PART
+#define OMX_DECODE_PART 0
+#endif
+
 namespace omx {
 
-namespace {
+namespace dd {  // shared by the three compilation parts of this file (same definition in each)
 
-constexpr int kTile = 64;              // keys per pipeline stage
-constexpr int kBoxBytes = 64 * 64 * 2;  // one TMA box: 64 keys x 64 features x 2 B
-constexpr int kStageBytes = 4 * kBoxBytes;  // K lo/hi + V lo/hi
-constexpr int kQPitch = 136;           // padded q row (elements) -> conflict-free fragment loads
 constexpr int kMaxPeers = OMX_MAX_PEERS;
-constexpr int kMaxSplits = 64;         // split-K upper bound (plan_splits), sizes the combine scratch
 
 struct DecodeParams {
   const void* q;
@@ -109,6 +111,24 @@ struct DecodeParams {
   // debugging aid (OMX_DECODE_TRACE=1): per-CTA phase timestamps, [cta][16] x %globaltimer ns; null otherwise
   unsigned long long* trace;
 };
+
+// 16-bit instantiations of the CUDA-core kernel (parts 1 / 2), called from decode_attention (part 0)
+void launch_simt_bf16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster);
+void launch_simt_f16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster);
+
+}  // namespace dd
+
+namespace {
+
+using dd::DecodeParams;
+using dd::kMaxPeers;
+
+constexpr int kTile = 64;              // keys per pipeline stage
+constexpr int kBoxBytes = 64 * 64 * 2;  // one TMA box: 64 keys x 64 features x 2 B
+constexpr int kStageBytes = 4 * kBoxBytes;  // K lo/hi + V lo/hi
+constexpr int kQPitch = 136;           // padded q row (elements) -> conflict-free fragment loads
+constexpr int kMaxSplits = 64;         // split-K upper bound (plan_splits), sizes the combine scratch
+
 
 __device__ __forceinline__ void trace_mark(const DecodeParams& p, int slot) {
   if (p.trace && threadIdx.x == 0) {
@@ -1346,6 +1366,18 @@ __global__ void seqshard_merge_kernel(T* out, int64_t os0, int64_t os1, int64_t 
 
 }  // namespace
 
+#if OMX_DECODE_PART == 1
+void dd::launch_simt_bf16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
+  launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid, one_wave, want_cluster);
+}
+#elif OMX_DECODE_PART == 2
+void dd::launch_simt_f16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
+  launch_simt_d<__half>(p, stream, Gt, grid, one_wave, want_cluster);
+}
+#endif
+
+#if OMX_DECODE_PART == 0
+
 void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
                     const unsigned* flags, unsigned expected, int rank, cudaStream_t stream) {
   if (B * Hq == 0) return;
@@ -1682,10 +1714,12 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   const bool one_wave = kpw_env >= 0 ? kpw_env == 1 : pairs * p.num_splits <= sms;
   switch (a.q->dtype) {
     case OMX_FLOAT32: launch_simt_d<float>(p, stream, Gt, grid, one_wave, want_cluster); break;
-    case OMX_BFLOAT16: launch_simt_d<__nv_bfloat16>(p, stream, Gt, grid, one_wave, want_cluster); break;
-    default: launch_simt_d<__half>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    case OMX_BFLOAT16: dd::launch_simt_bf16(p, stream, Gt, grid, one_wave, want_cluster); break;
+    default: dd::launch_simt_f16(p, stream, Gt, grid, one_wave, want_cluster); break;
   }
   if (masked) masked_rows_fixup(a, p.dead, stream);
 }
+
+#endif  // OMX_DECODE_PART == 0
 
 }  // namespace omx
