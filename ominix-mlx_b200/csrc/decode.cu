@@ -41,8 +41,8 @@
 #include "sm100_utils.cuh"
 
 // This file is compiled three times (csrc/Makefile) so that its ~50 kernels build in parallel:
-//   OMX_DECODE_PART 0 (default): host logic, the TMA / tensor-core kernels, the float32 CUDA-core kernels
-//   OMX_DECODE_PART 1 / 2: the bfloat16 / float16 instantiations of the CUDA-core kernel only
+//   OMX_DECODE_PART 0 (default): host logic and the TMA / tensor-core kernels
+//   OMX_DECODE_PART 1 / 2 / 3: the bfloat16 / float16 / float32 instantiations of the CUDA-core kernel only
 #ifndef OMX_DECODE_PART
 #define OMX_DECODE_PART 0
 #endif
@@ -115,6 +115,7 @@ struct DecodeParams {
 // 16-bit instantiations of the CUDA-core kernel (parts 1 / 2), called from decode_attention (part 0)
 void launch_simt_bf16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster);
 void launch_simt_f16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster);
+void launch_simt_f32(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster);
 
 }  // namespace dd
 
@@ -1374,6 +1375,10 @@ void dd::launch_simt_bf16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 gri
 void dd::launch_simt_f16(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
   launch_simt_d<__half>(p, stream, Gt, grid, one_wave, want_cluster);
 }
+#elif OMX_DECODE_PART == 3
+void dd::launch_simt_f32(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
+  launch_simt_d<float>(p, stream, Gt, grid, one_wave, want_cluster);
+}
 #endif
 
 #if OMX_DECODE_PART == 0
@@ -1713,7 +1718,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   }();
   const bool one_wave = kpw_env >= 0 ? kpw_env == 1 : pairs * p.num_splits <= sms;
   switch (a.q->dtype) {
-    case OMX_FLOAT32: launch_simt_d<float>(p, stream, Gt, grid, one_wave, want_cluster); break;
+    case OMX_FLOAT32: dd::launch_simt_f32(p, stream, Gt, grid, one_wave, want_cluster); break;
     case OMX_BFLOAT16: dd::launch_simt_bf16(p, stream, Gt, grid, one_wave, want_cluster); break;
     default: dd::launch_simt_f16(p, stream, Gt, grid, one_wave, want_cluster); break;
   }
