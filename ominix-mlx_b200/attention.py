@@ -132,9 +132,14 @@ def attn_prefill_fused(q, k_new, v_new, cache, rope, sm_scale, mask=None, stream
     """Attention::forward for L >= 1 new tokens (model.rs:172-212) with the minimum of memory passes:
     k' = rope(k_norm(k_new), off) lands directly in the cache rows, v_new is copied into its rows, then
     sdpa(rope(q_norm(q), off), K, V, sm_scale, mask).  `mask`: None, ScaledDotProductAttentionMask.Causal /
-    "causal", or a bool / additive tensor (what create_attention_mask returns)."""
+    "causal", or a bool / additive tensor (what create_attention_mask returns).  The callers' rule applies
+    (model.rs:203-207): `None` with L > 1 means Causal; pass mask=False for an unmasked multi-token call."""
     if out is None:
         out = torch.empty((q.shape[0], q.shape[1], q.shape[2], v_new.shape[3]), dtype=q.dtype, device=q.device)
+    if mask is None and q.shape[2] > 1:
+        mask = fast.ScaledDotProductAttentionMask.Causal
+    elif mask is False:
+        mask = None
     mode, m = fast._mode_and_mask(mask)
     base = _lib.OmxOptionalFloat()
     base.has_value = rope is not None

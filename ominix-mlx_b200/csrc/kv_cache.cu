@@ -343,6 +343,24 @@ void kv_cache_advance(KVCacheImpl* c, int n, cudaStream_t stream) {
   c->offset = prev + n;
 }
 
+KVCacheSnapshot kv_cache_snapshot(const KVCacheImpl* c) { return {c->offset, c->cap, c->has}; }
+
+void kv_cache_rollback(KVCacheImpl* c, const KVCacheSnapshot& s, cudaStream_t stream) {
+  if (!s.has && c->has) {
+    // the failed call was the cache's first update: forget the shape / dtype it latched and its buffers
+    for (KVBuf* b : {&c->k, &c->v}) {
+      if (b->p) cudaFreeAsync(b->p, stream);
+      *b = KVBuf();
+    }
+    c->has = false;
+    c->B = c->H = 0;
+    c->graph_rows = 0;
+  }
+  // rows [offset, cap) that a growth zero-filled stay zero; they are past the offset, i.e. never fetched
+  c->offset = s.offset;
+  c->cap = s.cap;
+}
+
 void kv_cache_shape(const KVCacheImpl* c, int* B, int* H, int* Dk, int* Dv, int* dtype) {
   OMX_CHECK(c->has, "[KVCache] cache is empty");
   *B = c->B; *H = c->H; *Dk = c->k.D; *Dv = c->v.D; *dtype = c->k.dtype;

@@ -415,9 +415,8 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   // cache bookkeeping (growth by the reference rule) without copying the new rows: the kernel
   // ropes k_new and writes row `position` itself.
   omx_array kview, vview;
+  KVCacheTxn txn(c, stream);  // a failure below restores offset / capacity
   kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
-  if (keys_out) *keys_out = kview;
-  if (values_out) *values_out = vview;
   SdpaArgs a = make_sdpa_args(&out_local, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
   const char* why = nullptr;
   const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
@@ -459,6 +458,9 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
       f.peers = &shifted;
     }
     decode_attention(a, f, stream);
+    txn.commit();
+    if (keys_out) *keys_out = kview;
+    if (values_out) *values_out = vview;
     return;
   }
   // Unfused composition for layouts the decode kernels do not take: (norm) -> rope -> row store -> sdpa.
@@ -506,6 +508,9 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     SdpaArgs a2 = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
     sdpa_generic(a2, stream);
   }
+  txn.commit();
+  if (keys_out) *keys_out = kview;
+  if (values_out) *values_out = vview;
 }
 }  // namespace
 
@@ -641,10 +646,16 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
     const int position = kv_cache_offset(c);
     // cache bookkeeping by the reference rule; the rows are written below, straight into the cache
     omx_array kview, vview;
+    OMX_CHECK(rope_dims == 0 || base.has_value != (freqs && freqs->data),
+              "[rope] Only one of base or freqs can have a value.");
+    KVCacheTxn txn(c, stream);  // a failure below restores offset / capacity
     kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
-    if (keys_out) *keys_out = kview;
-    if (values_out) *values_out = vview;
-    if ((int64_t)q->shape[0] * L == 0) return;
+    if ((int64_t)q->shape[0] * L == 0) {
+      txn.commit();
+      if (keys_out) *keys_out = kview;
+      if (values_out) *values_out = vview;
+      return;
+    }
     auto rows = [&](const omx_array& view) {  // rows [position, position + L) of a fetched view
       omx_array r = view;
       r.shape[2] = L;
@@ -700,7 +711,12 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
         dispatch_sdpa(a, stream);
       }
     }
-    if (fused_prologue) return;
+    if (fused_prologue) {
+      txn.commit();
+      if (keys_out) *keys_out = kview;
+      if (values_out) *values_out = vview;
+      return;
+    }
     // k: (norm) -> rope -> cache rows; v: copy -> cache rows; q: (norm) -> rope -> scratch
     if (kn && rope_dims > 0) {
       omx_array kt = dense(k_new, ws + qbytes);
@@ -725,6 +741,9 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
     }
     SdpaArgs a = make_sdpa_args(out, qa, &kview, &vview, sm_scale, mask_mode, mask_arr, nullptr);
     dispatch_sdpa(a, stream);
+    txn.commit();
+    if (keys_out) *keys_out = kview;
+    if (values_out) *values_out = vview;
   });
 }
 
@@ -772,6 +791,7 @@ int omx_attn_decode_seqshard(const omx_array* partial, const omx_array* q, const
       OMX_CHECK(peers->out[rank] == partial->data, "[attn_decode_seqshard] partial must be this rank's buffer of the peer group");
     }
     omx_array kview, vview;
+    KVCacheTxn txn(c, stream);  // a failure below restores offset / capacity
     if (append) {
       kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
     } else {
@@ -809,6 +829,7 @@ int omx_attn_decode_seqshard(const omx_array* partial, const omx_array* q, const
       f.peers = &shifted;
     }
     decode_attention(a, f, stream);
+    txn.commit();
   });
 }
 

@@ -67,6 +67,27 @@ void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* val
                      omx_array* keys_out, omx_array* values_out, bool skip_copy,
                      cudaStream_t stream);
 void kv_cache_state(const KVCacheImpl* c, omx_array* kbuf, omx_array* vbuf);
+// The composite entry points advance the cache (skip_copy) BEFORE the launch that writes the rows; if anything
+// between the two throws, the guard puts offset / capacity back so that a failed call leaves the cache as it
+// found it (no phantom row that a later step would attend).
+struct KVCacheSnapshot {
+  int offset;
+  int64_t cap;
+  bool has;
+};
+KVCacheSnapshot kv_cache_snapshot(const KVCacheImpl* c);
+void kv_cache_rollback(KVCacheImpl* c, const KVCacheSnapshot& s, cudaStream_t stream);
+struct KVCacheTxn {
+  KVCacheImpl* c;
+  KVCacheSnapshot snap;
+  cudaStream_t stream;
+  bool done = false;
+  KVCacheTxn(KVCacheImpl* c_, cudaStream_t s) : c(c_), snap(kv_cache_snapshot(c_)), stream(s) {}
+  void commit() { done = true; }
+  ~KVCacheTxn() {
+    if (!done) kv_cache_rollback(c, snap, stream);
+  }
+};
 // Graph mode: pin the buffers at >= max_rows physical rows (never-written tail zeroed) and allocate the
 // cache-owned scratch; the addresses stay fixed until the cache grows past max_rows.
 void kv_cache_prepare_graph(KVCacheImpl* c, int max_rows, size_t scratch_bytes, cudaStream_t stream);

@@ -176,3 +176,60 @@ def test_full_size_c2_against_oracle_and_properties():
     assert (o1.float() - out.float()).abs().max().item() <= 1e-2
     o3 = omx.fast.scaled_dot_product_attention(qr, K, (V.float() * 2).bfloat16(), D ** -0.5)
     assert (o3.float() - 2 * o1.float()).abs().max().item() <= 2e-2
+
+
+# ---- a composite call that fails leaves the cache exactly as it found it (offset, capacity, contents)
+def _cache_fingerprint(gc):
+    sk, sv = gc.state()
+    return gc.offset(), tuple(sk.shape), sk.clone(), sv.clone()
+
+
+def _same_cache(gc, fp):
+    off, shape, k0, v0 = fp
+    sk, sv = gc.state()
+    return gc.offset() == off and tuple(sk.shape) == shape and torch.equal(sk, k0) and torch.equal(sv, v0)
+
+
+@pytest.mark.parametrize("S", [255, 256])  # 256: the failing call would also have grown the cache
+def test_failed_fused_decode_leaves_cache_unchanged(S):
+    gc, oc = _prefill(2, 2, S, 128, "bf16", 31)
+    fp = _cache_fingerprint(gc)
+    q = randn((2, 8, 1, 128), "bf16", 1, DEV)
+    k = randn((2, 2, 1, 128), "bf16", 2, DEV)
+    v = randn((2, 2, 1, 128), "bf16", 3, DEV)
+    rope = omx.nn.Rope(128, False, 1e6, 1.0)
+    bad_out = torch.empty((2, 7, 1, 128), dtype=torch.bfloat16, device=DEV)  # wrong head count
+    with pytest.raises(omx.Exception):
+        omx.attn_decode_fused(q, k, v, gc, rope, 0.1, out=bad_out)
+    assert _same_cache(gc, fp), "a failed fused decode advanced / grew the cache"
+    q_bad = randn((2, 7, 1, 128), "bf16", 4, DEV)  # Hq % Hkv != 0
+    with pytest.raises(omx.Exception):
+        omx.attn_decode_fused(q_bad, k, v, gc, rope, 0.1)
+    assert _same_cache(gc, fp)
+    # ... and the next good step behaves as if nothing had happened
+    _step(gc, oc, 2, 8, 2, 128, "bf16", ROPE, 40)
+
+
+def test_failed_fused_prefill_leaves_cache_unchanged():
+    gc, oc = _prefill(1, 2, 100, 128, "bf16", 33)
+    fp = _cache_fingerprint(gc)
+    q = randn((1, 8, 200, 128), "bf16", 1, DEV)
+    k = randn((1, 2, 200, 128), "bf16", 2, DEV)
+    v = randn((1, 2, 200, 128), "bf16", 3, DEV)
+    rope = omx.nn.Rope(128, False, 1e6, 1.0)
+    bad_out = torch.empty((1, 8, 199, 128), dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(omx.Exception):
+        omx.attn_prefill_fused(q, k, v, gc, rope, 0.1, "causal", out=bad_out)
+    assert _same_cache(gc, fp), "a failed fused prefill advanced / grew the cache"
+
+
+def test_failed_first_update_forgets_the_latched_shape():
+    gc = omx.KVCache()
+    q = randn((1, 7, 1, 128), "bf16", 1, DEV)  # 7 q heads over 2 kv heads: rejected after the cache latched [1,2,*,128]
+    k = randn((1, 2, 1, 128), "bf16", 2, DEV)
+    with pytest.raises(omx.Exception):
+        omx.attn_decode_fused(q, k, k, gc, None, 0.1)
+    assert gc.offset() == 0
+    k4 = randn((1, 4, 3, 64), "bf16", 3, DEV)  # a different geometry is still acceptable: nothing was latched
+    gc.update_and_fetch(k4, k4)
+    assert gc.offset() == 3 and tuple(gc.state()[0].shape) == (1, 4, 256, 64)

@@ -38,6 +38,8 @@ def _call(gc, oc, B, Hq, Hkv, L, D, dtype, rope_t, mask_kind, seed, norms=None):
     elif mask_kind == "array":  # create_attention_mask(h, cache, Some(true)) (utils.rs:156-188)
         gm = omx.create_causal_mask(L, off, device=DEV)
         om = orc.create_causal_mask(L, off)
+    elif mask_kind == "none_multi":  # the callers' rule (model.rs:203-207): None && L > 1 -> Causal
+        gm, om = None, "causal"
     else:
         gm = om = None
     rope = None if rope_t is None else omx.nn.Rope(*rope_t)
@@ -102,3 +104,11 @@ def test_prefill_composite_merged_head_output_layout():
     m1 = torch.empty((B, 1, Hq * D), dtype=torch.bfloat16, device=DEV)
     omx.attn_decode_fused(q1, k1, v1, c2, rope, D ** -0.5, out=m1.view(B, 1, Hq, D).transpose(1, 2))
     assert torch.equal(m1, o_ref.transpose(1, 2).reshape(B, 1, Hq * D))
+
+
+def test_mask_none_with_several_new_tokens_is_causal():
+    # Attention::forward(x, mask=None, cache) with L > 1 runs Causal in every LLM crate (qwen3-mlx/src/model.rs:203-207)
+    B, Hq, Hkv, D, dtype = 1, 8, 2, 128, "bf16"
+    gc, oc = omx.KVCache(), orc.KVCache()
+    _call(gc, oc, B, Hq, Hkv, 40, D, dtype, (D, False, 1e6, 1.0), "causal", 5)
+    _call(gc, oc, B, Hq, Hkv, 130, D, dtype, (D, False, 1e6, 1.0), "none_multi", 6)
