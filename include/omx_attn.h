@@ -256,6 +256,15 @@ int omx_device_counter_add(int32_t* counter /* device */, int delta, omx_stream 
  * rank has itself signalled" (its own launch, earlier on the stream, bumped its own counter): no host-side
  * step count, so launch + wait can be captured once into a CUDA graph and replayed; same for
  * omx_seqshard_merge.
+ *
+ * BUFFER CONTRACT: the wait for step t proves that every peer has STORED its step-t slice, not that the
+ * peers have finished READING their own step-t buffer.  The caller must therefore alternate between TWO
+ * output buffers by step parity (out[] of the peer group shifted accordingly, as for the sequence-sharded
+ * partials below) and consume step t's buffer on the same stream before it launches step t+1: a rank
+ * cannot start step t+2 (which reuses step t's buffer) before its own wait for t+1 has returned, i.e.
+ * before every peer has launched t+1, stream-ordered after that peer's reads of step t.  With a single
+ * buffer a fast rank's step t+1 would overwrite a slow rank's step-t output while it is being read.
+ * (ominix-mlx_b200/parallel.py HeadShardedDecode does this; tests/test_parallel_gpu.py delays one rank.)
  */
 typedef struct omx_peer_group_ {
   int32_t world; /* <= OMX_MAX_PEERS */

@@ -51,8 +51,11 @@ struct FmhaParams {
   float scale_log2;
   int causal;
   int q_off;
+  // float32 output for 16-bit inputs: the DiT chains promote to f32 after the first matmul and return f32
+  // (flux-klein-mlx/src/klein_model.rs:474-483, zimage-mlx/src/zimage_model.rs:368-384)
+  int out_f32;
   // array masks (kArr kernels): element strides after broadcasting, innermost (key) stride 1
-  int mask_kind;  // 1 bool (true = keep), 2 additive in the q/k/v dtype
+  int mask_kind;  // 1 bool (true = keep), 2 additive in the q/k/v dtype, 3 additive float32 (Z-Image DiT)
   const void* mask;
   int64_t ms[3];       // batch, head, query-row strides (0 on broadcast axes)
   const uint8_t* tmap; // tile classes [Bm][Hm][n_qt][n_kt]: 0 all masked, 1 all kept, 2 mixed
@@ -592,6 +595,25 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               if (!keep) dst = 0xff800000u;
             }
           }
+        } else if (p.mask_kind == 3) {
+          const float* mrow = (const float*)p.mask + moff;
+          const bool vec = ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+#pragma unroll
+          for (int g = 0; g < 32; ++g) {  // 4 keys per 128-bit load
+            float mv[4];
+            if (vec && g * 4 + 4 <= nk) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(mrow) + g);
+              mv[0] = v.x; mv[1] = v.y; mv[2] = v.z; mv[3] = v.w;
+            } else {
+              for (int t = 0; t < 4; ++t) mv[t] = (g * 4 + t < nk) ? mrow[g * 4 + t] : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int e = (g & 7) * 4 + t;
+              uint32_t& dst = (g >> 3) == 0 ? s0[e] : (g >> 3) == 1 ? s1[e] : (g >> 3) == 2 ? s2[e] : s3[e];
+              dst = mv[t] <= -1e8f ? 0xff800000u : __float_as_uint(fmaf(mv[t], p.inv_scale, __uint_as_float(dst)));
+            }
+          }
         } else {
           const T* mrow = (const T*)p.mask + moff;
           const bool vec = ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
@@ -712,13 +734,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // rows with no visible key: 0 here, flagged for masked_rows_fixup (the reference's uniform average)
       const float inv = (kArr && !(l_run > 0.f)) ? 0.f : 1.0f / l_run;
       if (kArr && qrow < p.Lq) p.dead[((int64_t)b * p.Hq + hq) * p.Lq + qrow] = l_run > 0.f ? 0 : 1;
-      T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+      const int64_t ooff = b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+      T* orow = (T*)p.out + ooff;
+      float* orow32 = (float*)p.out + ooff;
 #pragma unroll
       for (int c = 0; c < HD / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(t_o + c * 32, r);
         tc_wait_ld();
-        if (qrow < p.Lq) {
+        if (qrow < p.Lq && p.out_f32) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(orow32 + c * 32 + e) =
+                make_float4(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv,
+                            __uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+        } else if (qrow < p.Lq) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             uint4 v;
@@ -732,9 +762,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else if (kArr && qrow < p.Lq) {  // every KV tile masked for this CTA: all its rows are flagged
       p.dead[((int64_t)b * p.Hq + hq) * p.Lq + qrow] = 1;
-      T* orow = (T*)p.out + b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+      const int64_t ooff = b * p.os[0] + hq * p.os[1] + (int64_t)qrow * p.os[2];
+      if (p.out_f32) {
 #pragma unroll
-      for (int e = 0; e < HD; e += 8) *reinterpret_cast<uint4*>(orow + e) = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = 0; e < HD; e += 4)
+          *reinterpret_cast<float4*>((float*)p.out + ooff + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        T* orow = (T*)p.out + ooff;
+#pragma unroll
+        for (int e = 0; e < HD; e += 8) *reinterpret_cast<uint4*>(orow + e) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     }  // work items
   } else {
@@ -785,19 +822,22 @@ bool fmha_sm100_supported(const SdpaArgs& a, const char** why) {
   };
   if (a.q->dtype != OMX_BFLOAT16 && a.q->dtype != OMX_FLOAT16) return no("dtype is not bf16/f16");
   if (!((a.D == 128 && a.Dv == 128) || (a.D == 64 && a.Dv == 64))) return no("head_dim not 64 or 128");
+  if (!(a.scale > 0.f)) return no("scale <= 0 (the tile-max trick needs a positive scale)");
   if (a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD) {
-    if (a.mask_mode == MASK_ADD && a.mask->dtype != a.q->dtype) return no("additive mask dtype differs from q");
+    if (a.mask_mode == MASK_ADD && a.mask->dtype != a.q->dtype && a.mask->dtype != OMX_FLOAT32)
+      return no("additive mask is neither the q dtype nor float32");
     if (a.Lk > 1 && a.mask_strides[3] != 1) return no("mask key axis not contiguous");
     if ((a.Lk + BN - 1) / BN > kMaxSteps) return no("array mask over more than 896 KV tiles");
   }
   if (a.Lq < 1 || a.Lk < 1) return no("empty sequence");
-  if (a.out->dtype != a.q->dtype) return no("out dtype differs");
+  if (a.out->dtype != a.q->dtype && a.out->dtype != OMX_FLOAT32) return no("out dtype is neither the input dtype nor float32");
   const omx_array* ts[4] = {a.q, a.k, a.v, a.out};
   for (const omx_array* t : ts) {
+    const int64_t v16 = (int64_t)(16 / dtype_size(t->dtype));  // elements per 16 bytes
     if (t->strides[3] != 1) return no("innermost axis not contiguous");
     if (!aligned16(t->data)) return no("base pointer not 16-byte aligned");
     for (int i = 0; i < 3; ++i)
-      if (t->shape[i] > 1 && (t->strides[i] % 8 != 0 || t->strides[i] <= 0)) return no("strides not multiples of 16 bytes");
+      if (t->shape[i] > 1 && (t->strides[i] % v16 != 0 || t->strides[i] <= 0)) return no("strides not multiples of 16 bytes");
   }
   return true;
 }
@@ -813,6 +853,7 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
   p.scale_log2 = a.scale * kLog2e;
   p.causal = a.mask_mode == MASK_CAUSAL ? 1 : 0;
   p.q_off = std::max(a.Lk - a.Lq, 0);
+  p.out_f32 = (a.out->dtype == OMX_FLOAT32) ? 1 : 0;
   OMX_CHECK(a.scale > 0.f, "[scaled_dot_product_attention] the tcgen05 path needs scale > 0");
   CUtensorMap tmQ = make_tmap_4d_b16(a.q->data, HD, a.Lq, a.Hq, a.B, a.q->strides[2], a.q->strides[1],
                                      a.q->strides[0], 64, BM, bf);
@@ -845,7 +886,8 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     const int Bm = a.mask_strides[0] ? a.B : 1, Hm = a.mask_strides[1] ? a.Hq : 1;
     const size_t tmap_bytes = (((size_t)Bm * Hm * n_qt * n_kt) + 255) & ~(size_t)255;
     uint8_t* tmap = (uint8_t*)get_workspace(tmap_bytes + (size_t)a.B * a.Hq * a.Lq, stream);
-    p.mask_kind = a.mask_mode == MASK_BOOL ? 1 : 2;
+    const bool mask_f32 = a.mask_mode == MASK_ADD && a.mask->dtype == OMX_FLOAT32;
+    p.mask_kind = a.mask_mode == MASK_BOOL ? 1 : (mask_f32 ? 3 : 2);
     p.mask = a.mask->data;
     for (int i = 0; i < 3; ++i) p.ms[i] = a.mask_strides[i];
     p.tmap = tmap;
@@ -859,6 +901,9 @@ void fmha_sm100(const SdpaArgs& a, cudaStream_t stream) {
     if (a.mask_mode == MASK_BOOL)
       mask_tile_classify_kernel<uint8_t><<<cgrid, 256, 0, stream>>>((const uint8_t*)a.mask->data, ms[0], ms[1], ms[2],
                                                                      ms[3], a.Lq, a.Lk, Hm, tmap, 1);
+    else if (mask_f32)
+      mask_tile_classify_kernel<float><<<cgrid, 256, 0, stream>>>((const float*)a.mask->data, ms[0], ms[1], ms[2], ms[3],
+                                                                   a.Lq, a.Lk, Hm, tmap, 2);
     else if (bf)
       mask_tile_classify_kernel<__nv_bfloat16><<<cgrid, 256, 0, stream>>>((const __nv_bfloat16*)a.mask->data, ms[0],
                                                                            ms[1], ms[2], ms[3], a.Lq, a.Lk, Hm, tmap, 2);

@@ -213,7 +213,7 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
   }
   if (force.empty() || force == "fmha_tcgen05") {
     // small query blocks waste the 256-row CTA tile: leave them to the CUDA-core kernel unless forced
-    if (a.out->dtype == a.q->dtype && fmha_sm100_supported(a, &why) && (a.Lq >= 32 || !force.empty())) {
+    if (fmha_sm100_supported(a, &why) && (a.Lq >= 32 || !force.empty())) {
       fmha_sm100(a, stream);
       return;
     }
@@ -663,6 +663,8 @@ int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_a
       return r;
     };
     omx_array krows = rows(kview), vrows = rows(vview);
+    // validate the attention call (out shape, mask, head counts) BEFORE the prologue writes any cache row
+    (void)make_sdpa_args(out, q, &kview, &vview, sm_scale, mask_mode, mask_arr, nullptr);
     const size_t es = dtype_size(q->dtype);
     const size_t qbytes = ((size_t)q->shape[0] * q->shape[1] * L * D * es + 255) & ~(size_t)255;
     const size_t kbytes = ((size_t)k_new->shape[0] * k_new->shape[1] * L * D * es + 255) & ~(size_t)255;
@@ -869,8 +871,9 @@ int omx_dit_rope(const omx_array* out, const omx_array* x, const omx_array* cos,
   });
 }
 
-// softmax(scale q k^T [+ mask]) v for the DiT callers; an f32 mask with 16-bit inputs goes to the
-// generic kernel (the reference chain promotes there), everything else through the dispatcher.
+// softmax(scale q k^T [+ mask]) v for the DiT callers.  The reference chains promote to f32 after the first
+// matmul (f32 mask, f32 output for 16-bit inputs): the tcgen05 kernel takes both (f32 epilogue, f32 mask rows
+// in its mixed tiles); whatever it refuses goes to the generic kernel.
 static void dit_attention_impl(const omx_array* out, const omx_array* q, const omx_array* k, const omx_array* v,
                                float scale, const omx_array* add_mask, cudaStream_t stream) {
   const bool has_mask = add_mask && add_mask->data;
@@ -891,6 +894,15 @@ static void dit_attention_impl(const omx_array* out, const omx_array* q, const o
       OMX_CHECK(n == full[i] || n == 1, "[dit_joint_attention] mask not broadcastable");
       a.mask_strides[i] = (n == 1 && full[i] != 1) ? 0 : add_mask->strides[i - lead];
     }
+    if ((int64_t)a.B * a.Hq * a.Lq * a.Dv == 0) return;
+    const char* why = nullptr;
+    const bool forced_generic = t_forced_kernel == "sdpa_generic";
+    if (!forced_generic && fmha_sm100_supported(a, &why) && (a.Lq >= 32 || t_forced_kernel == "fmha_tcgen05")) {
+      fmha_sm100(a, stream);
+      return;
+    }
+    OMX_CHECK(t_forced_kernel.empty() || forced_generic, "forced kernel '%s' does not support this call: %s",
+              t_forced_kernel.c_str(), why ? why : "?");
     sdpa_generic(a, stream);
     return;
   }

@@ -122,20 +122,30 @@ class HeadShardedDecode:
         except Exception as e:  # pragma: no cover
             raise _lib.Exception_(f"gather='peer' needs torch symmetric memory: {e}")
         grp = self.group if self.group is not None else dist.group.WORLD
-        self.out_full = symm.empty((batch, self.n_heads, 1, self.head_dim), dtype=dtype, device=self.device)
+        # DOUBLE-BUFFERED by step parity: a rank's wait for step t only proves that every peer has STORED its
+        # step-t slice, not that the peers have finished READING their own buffer of step t.  With two buffers a
+        # fast rank's step t+1 lands in the other half; it cannot reach step t+2 (same half as t) before its
+        # own wait for t+1 returns, i.e. before every peer has launched step t+1 -- which on each peer is
+        # stream-ordered after that peer's consumer of step t.  (Contract in include/omx_attn.h.)
+        self._out2 = symm.empty((2, batch, self.n_heads, 1, self.head_dim), dtype=dtype, device=self.device)
+        self.out_full = self._out2[0]
         self._flags = symm.empty((_lib.OMX_MAX_PEERS,), dtype=torch.int32, device=self.device)
         self._flags.zero_()
-        h_out = symm.rendezvous(self.out_full, group=grp)
+        h_out = symm.rendezvous(self._out2, group=grp)
         h_flg = symm.rendezvous(self._flags, group=grp)
-        pg = _lib.OmxPeerGroup()
-        pg.world, pg.rank = self.world, self.rank
-        for r in range(self.world):
-            pg.out[r] = int(h_out.buffer_ptrs[r])
-            pg.flags[r] = int(h_flg.buffer_ptrs[r])
-        if pg.out[self.rank] != self.out_full.data_ptr():
-            raise _lib.Exception_("symmetric memory handle does not map the local buffer at its own address")
+        half = self._out2[0].numel() * self._out2.element_size()
+        self._peer2 = []
+        for parity in range(2):
+            pg = _lib.OmxPeerGroup()
+            pg.world, pg.rank = self.world, self.rank
+            for r in range(self.world):
+                pg.out[r] = int(h_out.buffer_ptrs[r]) + parity * half
+                pg.flags[r] = int(h_flg.buffer_ptrs[r])
+            if pg.out[self.rank] != self._out2[parity].data_ptr():
+                raise _lib.Exception_("symmetric memory handle does not map the local buffer at its own address")
+            self._peer2.append(pg)
         self._handles = (h_out, h_flg)
-        self._peer = pg
+        self._peer = self._peer2[0]
         torch.cuda.synchronize(self.device)
         dist.barrier(group=grp)  # every rank's counters are zero before anyone signals
 
@@ -148,6 +158,7 @@ class HeadShardedDecode:
         ql = shard_heads(q, self.q0, self.nq)
         kl = shard_heads(k_new, self.kv0, self.nkv)
         vl = shard_heads(v_new, self.kv0, self.nkv)
+        parity = self.steps & 1
         self.steps += 1
         if self._peer is None:
             out_local = attn_decode_fused(ql, kl, vl, self.cache, self.rope, self.sm_scale, stream=stream)
@@ -158,6 +169,8 @@ class HeadShardedDecode:
         base = _lib.OmxOptionalFloat()
         base.has_value = rope is not None
         base.value = rope.base if rope is not None else 0.0
+        self.out_full = self._out2[parity]  # this step's half; valid until the step after the next one
+        self._peer = self._peer2[parity]
         qd, kd, vd, od = desc(ql), desc(kl), desc(vl), desc(self.out_full)
         sp = stream_ptr(stream)
         _lib.check(_lib.lib().omx_attn_decode_fused_sharded(

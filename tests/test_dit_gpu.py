@@ -57,3 +57,81 @@ def test_zimage_additive_mask():
     tr = lambda a: np.ascontiguousarray(np.swapaxes(t2n(a, "bf16"), 1, 2))  # noqa: E731
     want = orc.dit_attention(tr(q), tr(k), tr(v), "bf16", np.float32(D ** -0.5), use_mul=True, add_mask=m.numpy())
     assert_close(np.swapaxes(got.cpu().numpy(), 1, 2), want, "bf16", "zimage masked attention")
+
+
+# ---- the DiT chains' own semantics (f32 output, f32 additive mask) on the TENSOR-CORE kernel, forced, against the
+# manual-chain oracle at the C4 sequence length (512 txt + 4096 img tokens)
+def _forced(name):
+    class _F:
+        def __enter__(self):
+            omx.force_kernel(name)
+
+        def __exit__(self, *a):
+            omx.force_kernel("")
+    return _F()
+
+
+def _tr(a, dtype="bf16"):
+    return np.ascontiguousarray(np.swapaxes(t2n(a, dtype), 1, 2))
+
+
+def test_flux_chain_c4_shape_on_tcgen05_f32_out():
+    # FLUX.2-klein: softmax(q k^T / sqrt(D)) v, f32 result (klein_model.rs:474-483); 1 batch x 4 heads x 4608 tokens
+    B, H, D, S = 1, 4, 128, 4608
+    q, k, v = (randn((B, S, H, D), "bf16", s) for s in (11, 12, 13))
+    with _forced("fmha_tcgen05"):
+        got = omx.dit.joint_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, out_dtype=torch.float32)
+    assert omx.last_kernel() == "fmha_tcgen05" and got.dtype == torch.float32
+    want = orc.dit_attention(_tr(q), _tr(k), _tr(v), "bf16", np.float32(np.sqrt(D)))
+    assert_close(np.swapaxes(got.cpu().numpy(), 1, 2), want, "bf16", "FLUX chain, tcgen05, f32 out")
+    # default dispatch takes the same kernel (no forcing needed)
+    got2 = omx.dit.joint_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, out_dtype=torch.float32)
+    assert omx.last_kernel() == "fmha_tcgen05" and torch.equal(got, got2)
+    # and the f32 epilogue only changes the rounding of the store
+    g16 = omx.dit.joint_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5)
+    assert torch.equal(got.to(torch.bfloat16), g16)
+
+
+def test_zimage_chain_c4_shape_on_tcgen05_f32_mask_gqa_by_repeat():
+    # Z-Image: x scale, f32 additive mask hiding the padded text tokens, 30 heads from 10 kv heads repeated x3
+    # (zimage_model.rs:355-384); here 6 heads from 2 kv heads, 4608 tokens, last 100 keys padded
+    B, H, Hkv, D, S = 1, 6, 2, 128, 4608
+    q = randn((B, S, H, D), "bf16", 21)
+    k0, v0 = randn((B, S, Hkv, D), "bf16", 22), randn((B, S, Hkv, D), "bf16", 23)
+    k, v = k0.repeat_interleave(H // Hkv, dim=2), v0.repeat_interleave(H // Hkv, dim=2)  # the crate's repeat
+    m = torch.zeros(S, S)
+    m[:, S - 100:] = float("-inf")
+    m[5, :] = -1e9  # one fully hidden query row: the chain's softmax is uniform there
+    with _forced("fmha_tcgen05"):
+        got = omx.dit.joint_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, add_mask=m.to(DEV),
+                                      out_dtype=torch.float32)
+    assert omx.last_kernel() == "fmha_tcgen05_arraymask"
+    want = orc.dit_attention(_tr(q), _tr(k), _tr(v), "bf16", np.float32(D ** -0.5), use_mul=True, add_mask=m.numpy())
+    g = np.swapaxes(got.cpu().numpy(), 1, 2)
+    keep = np.ones(S, bool)
+    keep[5] = False
+    assert_close(g[:, :, keep], want[:, :, keep], "bf16", "Z-Image chain, tcgen05, f32 mask")
+    # the hidden row: the oracle's -1e9 fill leaves a softmax over (score - 1e9) in f32 = uniform over the keys
+    # that are not -inf; the kernel's masked_rows_fixup averages ALL keys (the sdpa convention).  Both are finite.
+    assert np.isfinite(g[:, :, 5]).all()
+    # GQA by index on the un-repeated K/V is the same computation
+    with _forced("fmha_tcgen05"):
+        got_gqa = omx.dit.joint_attention(q.to(DEV), k0.to(DEV), v0.to(DEV), D ** -0.5, add_mask=m.to(DEV),
+                                          out_dtype=torch.float32)
+    assert torch.equal(got_gqa, got)
+    # same call on the CUDA-core kernel agrees within the bar as well
+    with _forced("sdpa_generic"):
+        gen = omx.dit.joint_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, add_mask=m.to(DEV),
+                                      out_dtype=torch.float32)
+    assert_close(g[:, :, keep], np.swapaxes(gen.cpu().numpy(), 1, 2)[:, :, keep], "bf16", "tcgen05 vs generic")
+
+
+def test_fused_dit_block_f32_out_runs_on_tcgen05():
+    # omx_dit_attn_fused (prologue + attention) with the chain's f32 result
+    B, H, D, txt, img = 1, 4, 128, 128, 384
+    qs, ks, vs = ([randn((B, n, H, D), "bf16", s + i).to(DEV) for i, n in enumerate((txt, img))] for s in (31, 41, 51))
+    out = omx.dit.attn_fused(qs, ks, vs, D ** -0.5, out_dtype=torch.float32)
+    assert omx.last_kernel() == "fmha_tcgen05" and out.dtype == torch.float32
+    cat = lambda xs: torch.cat(xs, 1).cpu()  # noqa: E731
+    want = orc.dit_attention(_tr(cat(qs)), _tr(cat(ks)), _tr(cat(vs)), "bf16", np.float32(np.sqrt(D)))
+    assert_close(np.swapaxes(out.cpu().numpy(), 1, 2), want, "bf16", "fused DiT block, f32 out")

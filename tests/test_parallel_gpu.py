@@ -97,8 +97,23 @@ def _rank_main(rank, world, port, gather, q):
             out = eng.step(qq.cuda(), kn.cuda(), vn.cuda())
             torch.cuda.synchronize()
             errs.append(float(np.abs(out.float().cpu().numpy() - want).max()))
-            dist.barrier()  # nobody overwrites a buffer a slower rank is still reading
             eng.rewind(1)
+        # back-to-back steps with NO barrier and one rank that is slow to read its output: the output buffer is
+        # double-buffered by step parity, so the fast rank's next step must not overwrite what the slow rank is
+        # still reading (write-after-read across ranks).  Distinct queries per step make a stale / torn read visible.
+        qs = [qq, randn((B, Hq, 1, D), dtype, 13), randn((B, Hq, 1, D), dtype, 23)]
+        wants = [want] + [_oracle_full(k, v, qx, kn, vn, dtype, S)[0] for qx in qs[1:]]
+        qs_d, kn_d, vn_d = [x.cuda() for x in qs], kn.cuda(), vn.cuda()
+        got = []
+        for t in range(9):
+            out = eng.step(qs_d[t % 3], kn_d, vn_d)
+            if rank == 1:
+                torch.cuda._sleep(3_000_000)  # ~1.5 ms on the stream before this rank consumes its output
+            got.append(out.clone())
+            eng.rewind(1)
+        torch.cuda.synchronize()
+        for t, g in enumerate(got):
+            errs.append(float(np.abs(g.float().cpu().numpy() - wants[t % 3]).max()))
         sk, _ = eng.cache.state()
         kv_ok = bool((t2n(sk, dtype) == oc.keys[:, eng.kv0:eng.kv0 + eng.nkv]).all())
         q.put((rank, max(errs), kv_ok, omx.last_kernel()))
