@@ -243,6 +243,69 @@ int omx_attn_decode_fused_dynamic(const omx_array* out, const omx_array* q, cons
                                   const int32_t* position /* device */, omx_stream s);
 int omx_device_counter_add(int32_t* counter /* device */, int delta, omx_stream s);
 
+/* ---- paged KV cache (north_star: "fuses RoPE and the paged KV append") --------- */
+/*
+ * The reference's KVCache (mlx-rs-core/src/cache.rs:92-195) concatenates a fresh zero block every 256
+ * tokens -- an O(S) copy per growth -- and keeps one rectangular [B,Hkv,cap,D] buffer, so every sequence of
+ * a batch has the same length.  The paged cache keeps the trait contract (offset / update_and_fetch / reset,
+ * rows appended bit for bit) over a page pool:
+ *   pool K, pool V  [n_pages][Hkv][64][D], allocated ONCE; growth = a page id from the free list (zero copy)
+ *   block table     int32 [batch][max_pages_per_seq]: page of rows [64 t, 64 t + 64) of each sequence
+ *   lengths         per sequence: ragged batches, slots that are released and reused (continuous batching)
+ * One page = one 64-key pipeline stage of the decode kernel = one TMA box pair per tensor.
+ *   omx_paged_kv_cache_update_and_fetch  KeyValueCache::update_and_fetch for ALL sequences ([B,Hkv,n,D] appended
+ *        to each sequence at its own length).  keys_out / values_out may be null; when given, the reference's
+ *        [B,Hkv,offset,D] views (cache.rs:190-193) are MATERIALISED into a cache-owned contiguous buffer
+ *        (offset = the longest sequence; rows past a shorter sequence's end read +0.0) -- valid until the next
+ *        materialising call.
+ *   omx_paged_kv_cache_append_slot       the same for one sequence ([1,Hkv,n,D]): ragged prefill
+ *   omx_paged_kv_cache_fetch             materialise without appending
+ *   omx_paged_kv_cache_reset             KeyValueCache::reset for one sequence (slot) or all (slot < 0):
+ *        length 0, pages back to the free list
+ *   omx_paged_kv_cache_release           mark a slot inactive: omx_attn_decode_fused_paged skips it
+ *   omx_paged_kv_cache_reserve           pre-assign pages for `rows_ahead` more rows per active sequence: the next
+ *        rows_ahead fused steps need no host-side allocation (capturable into a CUDA graph, an even number
+ *        of steps per capture -- the device lengths are double-buffered by step parity)
+ *   omx_paged_kv_cache_sync_lengths      host mirror <- device lengths (synchronises the stream): after capturing /
+ *        replaying fused steps, which advance the device lengths without the host seeing it
+ *   omx_paged_kv_cache_trim              drop the last n rows of every active sequence (lengths only)
+ *   omx_attn_decode_fused_paged          omx_attn_decode_fused_norm over the pages, ONE launch: per sequence b,
+ *        off = len[b] (read by the kernel from device memory); q' = rope(norm(q[b]), off); k' = rope(norm(k_new[b]),
+ *        off) stored with v_new[b] into row off % 64 of page block_table[b][off / 64]; attention of q' over the
+ *        sequence's off + 1 keys, K/V tiles fetched page by page with TMA; len[b] += 1.  Appended rows and
+ *        outputs equal the contiguous cache's (same kernels, same arithmetic).
+ */
+typedef struct omx_paged_kv_cache_ {
+  void* ctx;
+} omx_paged_kv_cache;
+int omx_paged_kv_cache_new(omx_paged_kv_cache* res, int batch, int n_kv_heads, int head_dim_k, int head_dim_v,
+                           int dtype /* mlx_dtype value */, int64_t n_pages, int max_pages_per_seq);
+int omx_paged_kv_cache_free(omx_paged_kv_cache c);
+int omx_paged_kv_cache_offset(omx_paged_kv_cache c, int* offset /* longest sequence */);
+int omx_paged_kv_cache_lengths(omx_paged_kv_cache c, int32_t* lens /* host, [batch]; -1 = released slot */);
+int omx_paged_kv_cache_free_pages(omx_paged_kv_cache c, int64_t* n);
+int omx_paged_kv_cache_reset(omx_paged_kv_cache c, int slot, omx_stream s);
+int omx_paged_kv_cache_release(omx_paged_kv_cache c, int slot, omx_stream s);
+int omx_paged_kv_cache_reserve(omx_paged_kv_cache c, int rows_ahead, omx_stream s);
+int omx_paged_kv_cache_sync_lengths(omx_paged_kv_cache c, omx_stream s);
+int omx_paged_kv_cache_trim(omx_paged_kv_cache c, int n, omx_stream s);
+int omx_paged_kv_cache_update_and_fetch(omx_paged_kv_cache c, const omx_array* keys, const omx_array* values,
+                                        omx_array* keys_out /* may be null */, omx_array* values_out /* may be null */,
+                                        omx_stream s);
+int omx_paged_kv_cache_append_slot(omx_paged_kv_cache c, int slot, const omx_array* keys, const omx_array* values,
+                                   omx_stream s);
+int omx_paged_kv_cache_fetch(omx_paged_kv_cache c, omx_array* keys_out, omx_array* values_out, omx_stream s);
+/* Introspection (tests, debuggers): pool bases, the HOST mirror of the block table ([batch][max_pages_per_seq],
+ * valid until the next call on the cache) and its row length. */
+int omx_paged_kv_cache_pages(omx_paged_kv_cache c, void** k_pool, void** v_pool, const int32_t** block_table,
+                             int* max_pages_per_seq);
+int omx_attn_decode_fused_paged(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                                const omx_array* v_new, omx_paged_kv_cache cache,
+                                const omx_array* q_norm_weight /* may be null */,
+                                const omx_array* k_norm_weight /* may be null */, float norm_eps, int rope_dims,
+                                bool traditional, omx_optional_float base, float rope_scale, float sm_scale,
+                                omx_stream s);
+
 /* ---- head-sharded single-sequence decode (BASELINE C5) -------------------- */
 /*
  * The reference has no multi-device path (MLX is single-GPU); this is the exchange step the

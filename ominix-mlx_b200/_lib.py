@@ -29,6 +29,10 @@ class OmxKVCache(ctypes.Structure):
     _fields_ = [("ctx", ctypes.c_void_p)]
 
 
+class OmxPagedKVCache(ctypes.Structure):
+    _fields_ = [("ctx", ctypes.c_void_p)]
+
+
 OMX_MAX_PEERS = 8
 
 
@@ -82,6 +86,27 @@ _SIGS = {
                                                      ctypes.c_int, ctypes.c_bool, OmxOptionalFloat, ctypes.c_float,
                                                      ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]),
     "omx_device_counter_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "omx_paged_kv_cache_new": (ctypes.c_int, [ctypes.POINTER(OmxPagedKVCache), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int]),
+    "omx_paged_kv_cache_free": (ctypes.c_int, [OmxPagedKVCache]),
+    "omx_paged_kv_cache_offset": (ctypes.c_int, [OmxPagedKVCache, ctypes.POINTER(ctypes.c_int)]),
+    "omx_paged_kv_cache_lengths": (ctypes.c_int, [OmxPagedKVCache, ctypes.POINTER(ctypes.c_int32)]),
+    "omx_paged_kv_cache_free_pages": (ctypes.c_int, [OmxPagedKVCache, ctypes.POINTER(ctypes.c_int64)]),
+    "omx_paged_kv_cache_reset": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_int, ctypes.c_void_p]),
+    "omx_paged_kv_cache_release": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_int, ctypes.c_void_p]),
+    "omx_paged_kv_cache_reserve": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_int, ctypes.c_void_p]),
+    "omx_paged_kv_cache_sync_lengths": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_void_p]),
+    "omx_paged_kv_cache_trim": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_int, ctypes.c_void_p]),
+    "omx_paged_kv_cache_update_and_fetch": (ctypes.c_int, [OmxPagedKVCache, _AP, _AP, _AP, _AP, ctypes.c_void_p]),
+    "omx_paged_kv_cache_append_slot": (ctypes.c_int, [OmxPagedKVCache, ctypes.c_int, _AP, _AP, ctypes.c_void_p]),
+    "omx_paged_kv_cache_fetch": (ctypes.c_int, [OmxPagedKVCache, _AP, _AP, ctypes.c_void_p]),
+    "omx_paged_kv_cache_pages": (ctypes.c_int, [OmxPagedKVCache, ctypes.POINTER(ctypes.c_void_p),
+                                                ctypes.POINTER(ctypes.c_void_p),
+                                                ctypes.POINTER(ctypes.POINTER(ctypes.c_int32)),
+                                                ctypes.POINTER(ctypes.c_int)]),
+    "omx_attn_decode_fused_paged": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxPagedKVCache, _AP, _AP, ctypes.c_float,
+                                                   ctypes.c_int, ctypes.c_bool, OmxOptionalFloat, ctypes.c_float,
+                                                   ctypes.c_float, ctypes.c_void_p]),
     "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                      OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                      ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),

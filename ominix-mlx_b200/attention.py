@@ -68,6 +68,28 @@ def attn_decode_fused_dynamic(q, k_new, v_new, cache, rope, sm_scale, position, 
     return out
 
 
+def attn_decode_fused_paged(q, k_new, v_new, cache, rope, sm_scale, stream=None, out=None, q_norm=None, k_norm=None):
+    """attn_decode_fused over a PagedKVCache, ONE launch: per sequence b the position is its own length
+    (read by the kernel from device memory), k' / v_new land in row len % 64 of page block_table[b][len / 64],
+    K/V tiles are fetched page by page.  Released slots are skipped (their output rows are left untouched)."""
+    if out is None:
+        out = torch.empty((q.shape[0], q.shape[1], 1, v_new.shape[3]), dtype=q.dtype, device=q.device)
+    base = _lib.OmxOptionalFloat()
+    base.has_value = rope is not None
+    base.value = rope.base if rope is not None else 0.0
+    eps = (q_norm or k_norm).eps if (q_norm is not None or k_norm is not None) else 0.0
+    if q_norm is not None and k_norm is not None and q_norm.eps != k_norm.eps:
+        raise _lib.Exception_("q_norm and k_norm must share one eps in the fused step")
+    qd, kd, vd, od = desc(q), desc(k_new), desc(v_new), desc(out)
+    qw = desc(q_norm.weight) if q_norm is not None else None
+    kw = desc(k_norm.weight) if k_norm is not None else None
+    _lib.check(_lib.lib().omx_attn_decode_fused_paged(
+        ref(od), ref(qd), ref(kd), ref(vd), cache.handle, ref(qw), ref(kw), float(eps),
+        int(rope.dimensions if rope is not None else 0), bool(rope.traditional) if rope is not None else False,
+        base, float(rope.scale) if rope is not None else 1.0, float(sm_scale), stream_ptr(stream)))
+    return out
+
+
 def device_counter_add(counter, delta=1, stream=None):
     """counter (int32 CUDA tensor) += delta on the stream: the per-token position bump of a graph loop."""
     _lib.check(_lib.lib().omx_device_counter_add(counter.data_ptr(), int(delta), stream_ptr(stream)))

@@ -99,7 +99,17 @@ struct DecodeParams {
   // tiles_per_split above then hold the values of the LAST admissible position (max_rows - 1) and
   // cos_row / sin_row the table base; the grid (num_splits) is fixed at capture.
   const int* pos_dev;
+  int pos_stride;  // 0: one position shared by the batch; 1: pos_dev[b] (paged cache: per-sequence lengths)
   int max_rows;
+  // paged KV (omx_attn_decode_fused_paged): rows live in a page pool [n_pages][Hkv][64][D] (one page = one
+  // 64-key pipeline stage = one TMA box pair per tensor); tile t of sequence b is page
+  // block_table[b * bt_stride + t]; k / v / k_row0 / v_row0 are the pool bases, ks[0] / vs[0] the PAGE strides.
+  // Sequence b holds pos_dev[b] rows before the step (< 0: inactive slot, the CTA exits); the CTA that appends
+  // kv head 0 stores pos + 1 to lens_out[b] (a second buffer: other CTAs of the launch still read pos_dev[b]).
+  int paged;
+  const int* block_table;
+  int bt_stride;
+  int* lens_out;
   // 1: the splits of one (batch, kv-head) form a thread-block cluster and are combined through
   // distributed shared memory (no partials in HBM/L2, no fence, no ticket)
   int cluster;
@@ -146,12 +156,12 @@ struct DecodeDyn {
   const float *cos_row, *sin_row;
 };
 
-__device__ __forceinline__ DecodeDyn load_dyn(const DecodeParams& p) {
+__device__ __forceinline__ DecodeDyn load_dyn(const DecodeParams& p, int b) {
   DecodeDyn d{p.Lk, p.n_mem, p.tiles_per_split, p.cos_row, p.sin_row};
   if (p.pos_dev) {
     // clamped: a loop driven past the reserved rows rewrites the last row instead of leaving the buffer
     // (omx_kv_cache_advance reports the overflow to the host)
-    const int pos = min(max(__ldg(p.pos_dev), 0), p.max_rows - 1);
+    const int pos = min(max(__ldg(p.pos_dev + (size_t)b * p.pos_stride), 0), p.max_rows - 1);
     d.n_mem = pos;
     d.Lk = pos + 1;
     const int n_tiles = (pos + kTile - 1) / kTile;
@@ -382,8 +392,14 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
   // k_new element after the optional RMSNorm (rounded to T); nt_k[d] holds the raw value until the lane
   // that owns it overwrites it below
   auto kval = [&](int d) -> float { return nrm ? rms_apply<T>(nt_k[d], kr, ps.kw[d], true) : nt_k[d]; };
-  T* kc = (T*)p.k_row0 + b * p.kcs[0] + hk * p.kcs[1] + (int64_t)(dy.Lk - 1) * p.kcs[2];
-  T* vc = (T*)p.v_row0 + b * p.vcs[0] + hk * p.vcs[1] + (int64_t)(dy.Lk - 1) * p.vcs[2];
+  // cache row of the new token: row Lk - 1 of sequence b, or (paged) row (Lk - 1) % 64 of its last page
+  int64_t cb = b, crow = dy.Lk - 1;
+  if (p.paged) {
+    cb = __ldg(p.block_table + (size_t)b * p.bt_stride + (crow >> 6));
+    crow &= 63;
+  }
+  T* kc = (T*)p.k_row0 + cb * p.kcs[0] + hk * p.kcs[1] + crow * p.kcs[2];
+  T* vc = (T*)p.v_row0 + cb * p.vcs[0] + hk * p.vcs[1] + crow * p.vcs[2];
   const int half = p.rope_dims >> 1;
   for (int u = lane; u < half; u += 32) {
     const int i1 = p.traditional ? 2 * u : u;
@@ -717,11 +733,14 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
   trace_mark(p, 0);
-  const DecodeDyn dy = load_dyn(p);
+  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot (whole CTA, whole cluster: same b)
+  const DecodeDyn dy = load_dyn(p, b);
   const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
   const int tile_begin = split * dy.tps;
   const int my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
   const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
+  const int* bt_row = p.paged ? p.block_table + (size_t)b * p.bt_stride : nullptr;
+  if (p.paged && has_nt && hk == 0 && tid == 0) p.lens_out[b] = dy.Lk;  // the sequence's length after this step
 
   // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight before (or, on
   // one-wave grids, while) the CTA stages q: the K/V stream does not depend on q, and with only a dozen
@@ -731,12 +750,14 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   auto issue = [&](int t) {
     const int st = t % NSTAGE;
     uint8_t* sb = stages + st * kStageBytes;
-    const int key0 = (tile_begin + t) * kTile;
+    // contiguous cache: rows [key0, key0 + 64) of (b, hk); paged: the whole page block_table[b][tile]
+    const int key0 = p.paged ? 0 : (tile_begin + t) * kTile;
+    const int c3 = p.paged ? __ldg(bt_row + tile_begin + t) : b;
     mbar_expect_tx(&full_bar[st], kStageBytes);
-    tma_load_4d(sb, &tmK, &full_bar[st], 0, key0, hk, b, pol);
-    tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, b, pol);
-    tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, b, pol);
-    tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, b, pol);
+    tma_load_4d(sb, &tmK, &full_bar[st], 0, key0, hk, c3, pol);
+    tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, c3, pol);
+    tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, c3, pol);
+    tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, c3, pol);
   };
   const int first = min(my_tiles, NSTAGE);
   if (tid == NW * 32) {
@@ -1059,18 +1080,33 @@ decode_simt_kernel(const DecodeParams p) {
   const int first_head = hk * p.G + gsub * GT;
   const int pair = (b * p.Hkv + hk) * groups + gsub;
   trace_mark(p, 0);
-  const DecodeDyn dy = load_dyn(p);
+  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot
+  const DecodeDyn dy = load_dyn(p, b);
   const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
   const int kend = min(dy.n_mem, kbeg + keys_per_split);
   const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
+  if (p.paged && has_nt && hk == 0 && gsub == 0 && tid == 0) p.lens_out[b] = dy.Lk;
 
   // K/V do not depend on q: the first batch of rows is requested before the prologue's round trip
-  const T* kb = (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + lane * VE;
-  const T* vb = (const T*)p.v + b * p.vs[0] + hk * p.vs[1] + lane * VE;
+  const T* kb = (const T*)p.k + (p.paged ? 0 : b * p.ks[0]) + hk * p.ks[1] + lane * VE;
+  const T* vb = (const T*)p.v + (p.paged ? 0 : b * p.vs[0]) + hk * p.vs[1] + lane * VE;
+  const int* bt_row = p.paged ? p.block_table + (size_t)b * p.bt_stride : nullptr;
   // rows stay in their storage type until they are used, so that nothing waits on the loads early
   RawRow<T, VE> kraw[kSimtKeys], vraw[kSimtKeys];
   auto load_kv = [&](int j0) {
+    if (p.paged) {
+      // row j = row j % 64 of page block_table[b][j / 64]; j0 is a multiple of KPW and KPW divides 64, so the
+      // (clamped) rows of one batch share a page
+      const int64_t pg = __ldg(bt_row + (j0 >> 6));
+      const T* kp = kb + pg * p.ks[0];
+      const T* vp = vb + pg * p.vs[0];
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) kraw[u].load(kp + (int64_t)(min(j0 + u, kend - 1) & 63) * p.ks[2]);
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) vraw[u].load(vp + (int64_t)(min(j0 + u, kend - 1) & 63) * p.vs[2]);
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < kSimtKeys; ++u) kraw[u].load(kb + (int64_t)min(j0 + u, kend - 1) * p.ks[2]);
 #pragma unroll
@@ -1569,18 +1605,33 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     p.mks[1] = a.mask_strides[1];
     p.mks[2] = a.mask_strides[3];
   }
-  const bool dyn = f.enabled && f.pos_dev != nullptr;
+  const bool paged = f.enabled && f.paged != nullptr;
+  const bool dyn = f.enabled && f.pos_dev != nullptr && !paged;  // graph mode: cache-owned scratch, fixed addresses
   if (dyn) {
     OMX_CHECK(!f.peers && !masked, "the dynamic-position decode step takes no peer group and no array mask");
     OMX_CHECK(f.max_rows >= 1 && a.Lk == f.max_rows, "dynamic-position decode: K/V views must span max_rows");
     p.pos_dev = f.pos_dev;
+    p.pos_stride = 0;
     p.max_rows = f.max_rows;
+  }
+  if (paged) {
+    // a.k / a.v describe the POOL: data = base, strides[0] = page stride, [1] = head stride inside a page,
+    // [2] = row stride; a.Lk = longest sequence after the step (host mirror) -- it sizes the split plan only,
+    // every CTA derives its own key count from lens[b]
+    OMX_CHECK(!f.peers && !masked, "the paged decode step takes no peer group and no array mask");
+    p.paged = 1;
+    p.block_table = f.paged->block_table;
+    p.bt_stride = f.paged->bt_stride;
+    p.pos_dev = f.paged->lens_in;
+    p.pos_stride = 1;
+    p.lens_out = f.paged->lens_out;
+    p.max_rows = f.paged->bt_stride * kTile;
   }
   // one workspace request per call (a second one could move the first): split-K partials, then flags.
   // Graph mode carves the same layout (+ the counters) out of the cache-owned scratch instead, whose
   // address never changes under a captured launch.
   auto carve_workspace = [&](size_t no, size_t nml, size_t n_ctr) {
-    if (dyn) {
+    if (dyn || (paged && f.scratch)) {  // cache-owned scratch: its address is stable under a captured launch
       const size_t need = sizeof(float) * (no + nml) + sizeof(int) * n_ctr;
       OMX_CHECK(need <= f.scratch_bytes, "dynamic-position decode: scratch too small (%zu > %zu bytes); call "
                 "omx_kv_cache_prepare_graph with this launch's head count first", need, f.scratch_bytes);
@@ -1642,10 +1693,12 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     p.peer_total = (int)pairs;
     const bool bf = a.q->dtype == OMX_BFLOAT16;
     // graph mode: the map spans every reserved row (the tail beyond the position is masked in the kernel)
-    const uint64_t rows = (uint64_t)std::max(dyn ? p.max_rows : p.n_mem, 1);
-    CUtensorMap tmK = make_tmap_4d_b16(a.k->data, 128, rows, a.Hkv, a.B, a.k->strides[2], a.k->strides[1],
+    // paged: the map spans the pool, [n_pages][Hkv][64][128]; one box = half the features of a whole page
+    const uint64_t rows = paged ? (uint64_t)kTile : (uint64_t)std::max(dyn ? p.max_rows : p.n_mem, 1);
+    const uint64_t outer = paged ? (uint64_t)f.paged->n_pages : (uint64_t)a.B;
+    CUtensorMap tmK = make_tmap_4d_b16(a.k->data, 128, rows, a.Hkv, outer, a.k->strides[2], a.k->strides[1],
                                        a.k->strides[0], 64, 64, bf);
-    CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, a.B, a.v->strides[2], a.v->strides[1],
+    CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, outer, a.v->strides[2], a.v->strides[1],
                                        a.v->strides[0], 64, 64, bf);
     const size_t smem = 1024 + (size_t)NSTAGE * kStageBytes + 16 * kQPitch * 2 + sizeof(float) * (128 + 128 + 16);
     auto go = [&](auto kern) {

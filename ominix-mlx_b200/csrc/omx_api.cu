@@ -622,6 +622,184 @@ int omx_attn_decode_fused_dynamic(const omx_array* out, const omx_array* q, cons
   });
 }
 
+// ---- paged KV cache (paged_kv.cu) ----
+int omx_paged_kv_cache_new(omx_paged_kv_cache* res, int batch, int n_kv_heads, int head_dim_k, int head_dim_v, int dtype,
+                           int64_t n_pages, int max_pages_per_seq) {
+  return guarded([&] {
+    require_device();
+    OMX_CHECK(res != nullptr, "[PagedKVCache] null result handle");
+    res->ctx = paged_create(batch, n_kv_heads, head_dim_k, head_dim_v, dtype, n_pages, max_pages_per_seq);
+  });
+}
+int omx_paged_kv_cache_free(omx_paged_kv_cache c) {
+  return guarded([&] { paged_destroy((PagedKVImpl*)c.ctx); });
+}
+#define OMX_PAGED(c) \
+  auto* pc = (PagedKVImpl*)(c).ctx; \
+  OMX_CHECK(pc, "[PagedKVCache] null handle")
+int omx_paged_kv_cache_offset(omx_paged_kv_cache c, int* offset) {
+  return guarded([&] {
+    OMX_PAGED(c);
+    OMX_CHECK(offset, "[PagedKVCache] null result pointer");
+    *offset = std::max(paged_offset(pc), 0);
+  });
+}
+int omx_paged_kv_cache_lengths(omx_paged_kv_cache c, int32_t* lens) {
+  return guarded([&] {
+    OMX_PAGED(c);
+    OMX_CHECK(lens, "[PagedKVCache] null result pointer");
+    std::copy(paged_lengths(pc), paged_lengths(pc) + paged_batch(pc), lens);
+  });
+}
+int omx_paged_kv_cache_free_pages(omx_paged_kv_cache c, int64_t* n) {
+  return guarded([&] {
+    OMX_PAGED(c);
+    OMX_CHECK(n, "[PagedKVCache] null result pointer");
+    *n = paged_free_pages(pc);
+  });
+}
+int omx_paged_kv_cache_reset(omx_paged_kv_cache c, int slot, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    paged_reset(pc, slot, false, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_release(omx_paged_kv_cache c, int slot, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    OMX_CHECK(slot >= 0, "[PagedKVCache] release needs a slot index");
+    paged_reset(pc, slot, true, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_reserve(omx_paged_kv_cache c, int rows_ahead, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    paged_reserve(pc, rows_ahead, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_sync_lengths(omx_paged_kv_cache c, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    paged_sync_lengths(pc, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_trim(omx_paged_kv_cache c, int n, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    paged_trim(pc, n, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_update_and_fetch(omx_paged_kv_cache c, const omx_array* keys, const omx_array* values,
+                                        omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    OMX_CHECK(keys && keys->ndim == 4 && keys->shape[0] == paged_batch(pc),
+              "[PagedKVCache] update_and_fetch appends to every sequence: keys must be [%d, n_kv_heads, n, head_dim]",
+              paged_batch(pc));
+    paged_append(pc, 0, keys, values, (cudaStream_t)s);
+    if (keys_out || values_out) paged_materialize(pc, keys_out, values_out, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_append_slot(omx_paged_kv_cache c, int slot, const omx_array* keys, const omx_array* values,
+                                   omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    OMX_CHECK(keys && keys->ndim == 4 && keys->shape[0] == 1, "[PagedKVCache] append_slot takes [1, n_kv_heads, n, head_dim]");
+    paged_append(pc, slot, keys, values, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_fetch(omx_paged_kv_cache c, omx_array* keys_out, omx_array* values_out, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    OMX_PAGED(c);
+    paged_materialize(pc, keys_out, values_out, (cudaStream_t)s);
+  });
+}
+int omx_paged_kv_cache_pages(omx_paged_kv_cache c, void** k_pool, void** v_pool, const int32_t** block_table,
+                             int* max_pages_per_seq) {
+  return guarded([&] {
+    OMX_PAGED(c);
+    void *kp, *vp;
+    const int* bt;
+    paged_pool_ptrs(pc, &kp, &vp, &bt);
+    if (k_pool) *k_pool = kp;
+    if (v_pool) *v_pool = vp;
+    if (block_table) *block_table = bt;
+    int B, H, Dk, Dv, dt, mp;
+    int64_t np;
+    paged_shape(pc, &B, &H, &Dk, &Dv, &dt, &np, &mp);
+    if (max_pages_per_seq) *max_pages_per_seq = mp;
+  });
+}
+
+int omx_attn_decode_fused_paged(const omx_array* out, const omx_array* q, const omx_array* k_new,
+                                const omx_array* v_new, omx_paged_kv_cache cache, const omx_array* q_norm_weight,
+                                const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,
+                                omx_optional_float base, float rope_scale, float sm_scale, omx_stream s) {
+  return guarded([&] {
+    require_device();
+    cudaStream_t stream = (cudaStream_t)s;
+    OMX_PAGED(cache);
+    int B, H, Dk, Dv, dt, max_pages;
+    int64_t n_pages;
+    paged_shape(pc, &B, &H, &Dk, &Dv, &dt, &n_pages, &max_pages);
+    OMX_CHECK(q && k_new && v_new && out, "[attn_decode_fused_paged] null array");
+    OMX_CHECK(q->ndim == 4 && k_new->ndim == 4 && v_new->ndim == 4 && out->ndim == 4 && q->shape[2] == 1 &&
+                  k_new->shape[2] == 1 && v_new->shape[2] == 1,
+              "[attn_decode_fused_paged] q, k_new, v_new, out must be [B, H, 1, D]");
+    OMX_CHECK(q->dtype == dt && k_new->dtype == dt && v_new->dtype == dt && out->dtype == dt,
+              "[attn_decode_fused_paged] q, k_new, v_new, out must have the cache dtype");
+    OMX_CHECK(q->shape[0] == B && k_new->shape[0] == B && v_new->shape[0] == B && k_new->shape[1] == H &&
+                  v_new->shape[1] == H && k_new->shape[3] == Dk && v_new->shape[3] == Dv && q->shape[3] == Dk,
+              "[attn_decode_fused_paged] arrays do not match the cache geometry [%d, %d, *, %d]", B, H, Dk);
+    const int D = Dk;
+    OMX_CHECK(rope_dims >= 0 && rope_dims % 2 == 0 && rope_dims <= D, "[rope] dims must be even and <= %d", D);
+    OMX_CHECK(rope_dims == 0 || base.has_value, "[attn_decode_fused_paged] rope needs a base (no freqs here)");
+    const bool qn = q_norm_weight && q_norm_weight->data, kn = k_norm_weight && k_norm_weight->data;
+    for (const omx_array* w : {qn ? q_norm_weight : nullptr, kn ? k_norm_weight : nullptr}) {
+      if (!w) continue;
+      OMX_CHECK(w->ndim == 1 && w->shape[0] == D && w->dtype == q->dtype && (w->strides[0] == 1 || D == 1),
+                "[attn_decode_fused_paged] norm weights must be contiguous [%d] vectors in the q dtype", D);
+    }
+    OMX_CHECK(q->shape[1] % H == 0, "[scaled_dot_product_attention] n_heads must be a multiple of n_kv_heads, found "
+              "n_heads %lld for n_kv_heads %d", (long long)q->shape[1], H);
+    OMX_CHECK(out->shape[0] == B && out->shape[1] == q->shape[1] && out->shape[2] == 1 && out->shape[3] == Dv,
+              "[scaled_dot_product_attention] out must be [B, n_heads, L_q, D_v]");
+    PagedRef ref;
+    DecodeFused f;
+    omx_array kview, vview;
+    int max_len_after = 0, table_rows = 0;
+    paged_begin_step(pc, (int)q->shape[1], &kview, &vview, &ref, &f.scratch, &f.scratch_bytes, &max_len_after,
+                     &table_rows, stream);
+    if (max_len_after == 0) return;  // every slot released: nothing to do
+    SdpaArgs a = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+    const char* why = nullptr;
+    const bool fast = decode_supported(a, &why) && k_new->strides[3] == 1 && v_new->strides[3] == 1;
+    OMX_CHECK(fast, "[attn_decode_fused_paged] layout not supported by the decode kernels: %s",
+              why ? why : "strided k_new/v_new");
+    f.enabled = true;
+    f.k_new = k_new;
+    f.v_new = v_new;
+    f.rope_dims = rope_dims;
+    f.traditional = traditional;
+    f.position = 0;  // table base; the kernel adds len[b] rows
+    f.paged = &ref;
+    f.q_norm_w = qn ? q_norm_weight->data : nullptr;
+    f.k_norm_w = kn ? k_norm_weight->data : nullptr;
+    f.norm_eps = norm_eps;
+    if (rope_dims > 0) f.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, table_rows, stream);
+    decode_attention(a, f, stream);
+    paged_end_step(pc);
+  });
+}
+
 int omx_attn_prefill_fused(const omx_array* out, const omx_array* q, const omx_array* k_new,
                            const omx_array* v_new, omx_kv_cache cache, const omx_array* q_norm_weight,
                            const omx_array* k_norm_weight, float norm_eps, int rope_dims, bool traditional,

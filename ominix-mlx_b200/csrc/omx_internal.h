@@ -151,6 +151,15 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   int max_rows = 0;
   void* scratch = nullptr;  // split-K partials + arrival counters, zero-initialised, fixed address
   size_t scratch_bytes = 0;
+  // paged cache (paged_kv.cu): K/V views describe the page pool, per-sequence lengths live in device memory
+  const struct PagedRef* paged = nullptr;
+};
+struct PagedRef {
+  const int* block_table = nullptr;  // [B][bt_stride] page ids, device
+  int bt_stride = 0;                 // pages per sequence the table can hold
+  const int* lens_in = nullptr;      // [B] rows stored before the step (< 0: inactive slot), device
+  int* lens_out = nullptr;           // [B] receives lens_in + 1 for the sequences that appended
+  int64_t n_pages = 0;
 };
 // Bytes of cache-owned scratch a dynamic-position launch of this shape can need.
 size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int max_rows);
@@ -165,6 +174,26 @@ void peer_wait(const unsigned* flags, int world, unsigned expected, int rank, cu
 // float32 partial slots [world][B][Hq][D + 2].
 void seqshard_merge(const omx_array* out, const float* partial, int world, int B, int Hq, int D,
                     const unsigned* flags, unsigned expected, int rank, cudaStream_t stream);
+
+// ---- paged_kv.cu ----
+struct PagedKVImpl;
+PagedKVImpl* paged_create(int B, int H, int Dk, int Dv, int dtype, int64_t n_pages, int max_pages_per_seq);
+void paged_destroy(PagedKVImpl* c);
+int paged_offset(const PagedKVImpl* c);        // longest sequence
+const int* paged_lengths(const PagedKVImpl* c);  // host mirror, [B]; -1 = released slot
+int paged_batch(const PagedKVImpl* c);
+int64_t paged_free_pages(const PagedKVImpl* c);
+void paged_shape(const PagedKVImpl* c, int* B, int* H, int* Dk, int* Dv, int* dtype, int64_t* n_pages, int* max_pages);
+void paged_reset(PagedKVImpl* c, int slot, bool deactivate, cudaStream_t stream);
+void paged_reserve(PagedKVImpl* c, int rows_ahead, cudaStream_t stream);
+void paged_append(PagedKVImpl* c, int slot0, const omx_array* keys, const omx_array* values, cudaStream_t stream);
+void paged_materialize(PagedKVImpl* c, omx_array* keys_out, omx_array* values_out, cudaStream_t stream);
+void paged_begin_step(PagedKVImpl* c, int n_q_heads, omx_array* kpool_view, omx_array* vpool_view, PagedRef* ref,
+                      void** scratch, size_t* scratch_bytes, int* max_len_after, int* table_rows, cudaStream_t stream);
+void paged_sync_lengths(PagedKVImpl* c, cudaStream_t stream);
+void paged_end_step(PagedKVImpl* c);
+void paged_trim(PagedKVImpl* c, int n, cudaStream_t stream);
+void paged_pool_ptrs(const PagedKVImpl* c, void** kpool, void** vpool, const int** block_table);
 
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);

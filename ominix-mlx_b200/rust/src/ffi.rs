@@ -40,6 +40,13 @@ pub struct omx_kv_cache {
 
 pub const OMX_MAX_PEERS: usize = 8;
 
+/// Handle of the paged KV cache (include/omx_attn.h: omx_paged_kv_cache).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct omx_paged_kv_cache {
+    pub ctx: *mut c_void,
+}
+
 /// Peer mappings of the head-sharded decode step (include/omx_attn.h: omx_peer_group).
 #[repr(C)]
 #[derive(Clone, Copy, Debug)]
@@ -134,6 +141,33 @@ extern "C" {
     pub fn omx_seqshard_merge(out: *const omx_array, partial: *const omx_array, peers: *const omx_peer_group,
                               expected: u32, s: omx_stream) -> c_int;
     pub fn omx_peer_wait(peers: *const omx_peer_group, expected: u32, s: omx_stream) -> c_int;
+
+    pub fn omx_paged_kv_cache_new(res: *mut omx_paged_kv_cache, batch: c_int, n_kv_heads: c_int, head_dim_k: c_int,
+                                  head_dim_v: c_int, dtype: c_int, n_pages: i64, max_pages_per_seq: c_int) -> c_int;
+    pub fn omx_paged_kv_cache_free(c: omx_paged_kv_cache) -> c_int;
+    pub fn omx_paged_kv_cache_offset(c: omx_paged_kv_cache, offset: *mut c_int) -> c_int;
+    pub fn omx_paged_kv_cache_lengths(c: omx_paged_kv_cache, lens: *mut i32) -> c_int;
+    pub fn omx_paged_kv_cache_free_pages(c: omx_paged_kv_cache, n: *mut i64) -> c_int;
+    pub fn omx_paged_kv_cache_reset(c: omx_paged_kv_cache, slot: c_int, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_release(c: omx_paged_kv_cache, slot: c_int, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_reserve(c: omx_paged_kv_cache, rows_ahead: c_int, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_sync_lengths(c: omx_paged_kv_cache, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_trim(c: omx_paged_kv_cache, n: c_int, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_update_and_fetch(c: omx_paged_kv_cache, keys: *const omx_array,
+                                               values: *const omx_array, keys_out: *mut omx_array,
+                                               values_out: *mut omx_array, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_append_slot(c: omx_paged_kv_cache, slot: c_int, keys: *const omx_array,
+                                          values: *const omx_array, s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_fetch(c: omx_paged_kv_cache, keys_out: *mut omx_array, values_out: *mut omx_array,
+                                    s: omx_stream) -> c_int;
+    pub fn omx_paged_kv_cache_pages(c: omx_paged_kv_cache, k_pool: *mut *mut c_void, v_pool: *mut *mut c_void,
+                                    block_table: *mut *const i32, max_pages_per_seq: *mut c_int) -> c_int;
+    pub fn omx_attn_decode_fused_paged(out: *const omx_array, q: *const omx_array, k_new: *const omx_array,
+                                       v_new: *const omx_array, cache: omx_paged_kv_cache,
+                                       q_norm_weight: *const omx_array, k_norm_weight: *const omx_array,
+                                       norm_eps: f32, rope_dims: c_int, traditional: bool,
+                                       base: omx_optional_float, rope_scale: f32, sm_scale: f32,
+                                       s: omx_stream) -> c_int;
     pub fn omx_dit_rope(out: *const omx_array, x: *const omx_array, cos: *const omx_array,
                         sin: *const omx_array, s: omx_stream) -> c_int;
     pub fn omx_dit_joint_attention(out: *const omx_array, q: *const omx_array, k: *const omx_array,
