@@ -18,6 +18,7 @@ replayed from a CUDA graph the way a compiled host drives a decode loop.  The pe
   c5  Mixtral-shape single-sequence decode ctx 32768: one GPU at N = 1; kv-head-sharded over N GPUs at N > 1 with
       the output heads exchanged by peer stores fused into the decode kernel (`c5`) and by ncclAllGather
       (`c5_collective`)
+  c2_paged the headline shape through the PAGED cache (page pool + block table + per-sequence lengths)
   c2_weak (N > 1 only) the r01 spelling: batch 64 PER GPU.
 At N > 1 every sharded workload also runs one un-timed step whose result is compared on rank 0 with the
 unsharded computation of the same inputs (`parity_check`).
@@ -136,13 +137,15 @@ def physical_gpu_index(local):
 
 def workload_config(name, world):
     """The `config` object of a workload: a pure function of (name, N), printed identically by both arms."""
-    kind, cfg = WORKLOADS[name.replace("_weak", "").replace("_collective", "")]
+    kind, cfg = WORKLOADS[name.replace("_weak", "").replace("_collective", "").replace("_paged", "")]
     B, S = cfg["B"], cfg["S"]
     c = {"workload": cfg["label"], "q_heads": cfg["Hq"], "kv_heads": cfg["Hkv"], "head_dim": cfg["D"],
          "ctx" if kind == "decode" else "seq_len": S}
-    if name == "c2":
+    if name in ("c2", "c2_paged"):
         c.update(global_batch=B, per_gpu_batch=B // world,
                  parallelism=f"batch-sharded {B}/{world} rows per GPU, no data-path collective")
+        if name == "c2_paged":
+            c["kv_cache"] = "paged: 64-row pages, block table, per-sequence lengths"
     elif name == "c2_weak":
         c.update(global_batch=B * world, per_gpu_batch=B,
                  parallelism=f"batch {B} per GPU x{world} (weak), no data-path collective")
@@ -324,8 +327,8 @@ class Bench:
         torch = self.torch
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm the capture stream's scratch before capturing
-            for i in range(min(steps, 3)):
+        with torch.cuda.stream(side):  # warm the capture stream's scratch before capturing (one whole block)
+            for i in range(steps):
                 fn(i)
         side.synchronize()
         cg = torch.cuda.CUDAGraph()
@@ -386,13 +389,13 @@ class Bench:
                 "gpu_launches": per_block * len(blocks), "cuda_graph": bool(graph), "kernel": omx.last_kernel()}
 
     # ---- decode workloads (c1, c2, c2_weak, c5 at N = 1): rows [row0, row0 + Bl) of the global batch on this rank
-    def run_decode(self, name, cfg, rows, value_scale, steps, warmup, want_cpu):
+    def run_decode(self, name, cfg, rows, value_scale, steps, warmup, want_cpu, paged=False):
         torch, omx = self.torch, self.omx
         Hq, Hkv, D, S = cfg["Hq"], cfg["Hkv"], cfg["D"], cfg["S"]
         tdt = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
         es = 2 if cfg["dtype"] == "bf16" else 4
         Bl = len(rows)
-        tag = {"c1": 1, "c2": 2, "c2_weak": 2, "c5": 5}[name]
+        tag = {"c1": 1, "c2": 2, "c2_weak": 2, "c2_paged": 2, "c5": 5}[name]
         kv_bytes = 2 * Bl * Hkv * S * D * es
         # L2 policy: a working set below ~2x L2 is rotated through R distinct caches so every step reads HBM
         R = 1
@@ -402,8 +405,12 @@ class Bench:
             R = divs[0] if divs else steps
         caches = []
         for c in range(R):
-            cache = omx.KVCache()
-            cache.reserve(S + 256)
+            if paged:  # page pool sized for the batch's context + one spare page per sequence
+                n_seq_pages = (S + steps + 63) // 64 + 1
+                cache = omx.PagedKVCache(Bl, Hkv, D, tdt, n_pages=Bl * n_seq_pages, max_pages_per_seq=n_seq_pages)
+            else:
+                cache = omx.KVCache()
+                cache.reserve(S + 256)
             if c == 0:
                 for s0 in range(0, S - 1, 1024):  # fill in chunks to bound temporary memory
                     n = min(1024, S - 1 - s0)
@@ -411,11 +418,16 @@ class Bench:
                                                      (Hkv, n, D), tdt) for r in rows])
                     vv = torch.stack([self.row_randn(4321 + 1009 * tag + 7919 * r + 31 * (s0 // 1024 + 1),
                                                      (Hkv, n, D), tdt) for r in rows])
-                    cache.update_and_fetch(kk, vv)
+                    if paged:
+                        cache.update_and_fetch(kk, vv, fetch=False)
+                    else:
+                        cache.update_and_fetch(kk, vv)
             else:  # rotation copies: same values, distinct HBM addresses
                 k0, v0 = caches[0].state()
                 cache.update_and_fetch(k0[:, :, :S - 1], v0[:, :, :S - 1])
             assert cache.offset() == S - 1
+            if paged:
+                cache.reserve(steps + 2)  # no host-side page allocation inside the timed / captured region
             caches.append(cache)
         q = self.rows_randn(tag + 10, rows, (Hq, 1, D), tdt)
         kn = self.rows_randn(tag + 20, rows, (Hkv, 1, D), tdt)
@@ -424,12 +436,26 @@ class Bench:
         rope = omx.nn.Rope(D, False, 1e6, 1.0)
         scale = D ** -0.5
 
-        def step(i):
-            cache = caches[i % R]
-            omx.attn_decode_fused(q, kn, vn, cache, rope, scale, out=out)
-            cache.trim(1)  # host-side rewind: every step appends row S-1 and attends S keys
+        if paged:
+            steps += steps & 1  # the device lengths are double-buffered by step parity: even blocks
 
-        res = self.measure(step, steps, warmup, graph=True)
+        def fused(qq, kk, vv, oo, i, n):
+            cache = caches[i % R]
+            if paged:
+                # the rewind is a (tiny) kernel here, so it runs once per block: rows S-1 .. S-2+n are appended,
+                # then all n dropped (context 8192 .. 8191+n within a block: +0.1 % bytes, not counted)
+                omx.attn_decode_fused_paged(qq, kk, vv, cache, rope, scale, out=oo)
+                if i == n - 1:
+                    cache.trim(n)
+            else:
+                omx.attn_decode_fused(qq, kk, vv, cache, rope, scale, out=oo)
+                cache.trim(1)  # host-side rewind: every step appends row S-1 and attends S keys
+
+        def step(i):
+            fused(q, kn, vn, out, i % steps, steps)
+
+        # whole blocks only (the paged rewind closes a block)
+        res = self.measure(step, steps, steps * max(1, (warmup + steps - 1) // steps), graph=True)
         alg_bytes = 2 * Bl * Hkv * S * D * es + 2 * Bl * Hq * D * es + 2 * (2 * Bl * Hkv * D * es)
         alg_flops = 4.0 * Bl * Hq * S * D
 
@@ -463,9 +489,7 @@ class Bench:
                 cur.wait_event(d["ev_in"])
                 if i >= 2:
                     cur.wait_event(d["ev_out"])  # the previous download of this output buffer is done
-                cache = caches[i % R]
-                omx.attn_decode_fused(d["q"], d["k"], d["v"], cache, rope, scale, out=d["o"])
-                cache.trim(1)
+                fused(d["q"], d["k"], d["v"], d["o"], i, n)
                 d["ev_k"].record(cur)
                 s_out.wait_event(d["ev_k"])
                 with torch.cuda.stream(s_out):
@@ -477,8 +501,10 @@ class Bench:
         e2e = self.measure_e2e(e2e_block, steps)
         # the downloaded result is the kernel's output
         torch.cuda.synchronize()
-        e2e_ok = bool(torch.equal(dbuf[0]["pin"].view(torch.int16 if es == 2 else torch.int32),
-                                  out.cpu().view(torch.int16 if es == 2 else torch.int32)))
+        e2e_ok = None  # paged blocks append at advancing positions: the last resident / e2e steps are not the same step
+        if not paged:
+            e2e_ok = bool(torch.equal(dbuf[0]["pin"].view(torch.int16 if es == 2 else torch.int32),
+                                      out.cpu().view(torch.int16 if es == 2 else torch.int32)))
         units = Bl * value_scale  # tokens per step, whole job
         ms, e2e_ms = res["ms_per_step"], e2e["ms_per_step"]
         rec = {
@@ -502,13 +528,16 @@ class Bench:
                     "launches_per_step": res["launches_per_block"] / steps},
         }
         self.attach_traffic(rec, name)
+        if paged:
+            rec["run"]["cache"] = (f"PagedKVCache: pool [{caches[0].n_pages}][{Hkv}][64][{D}] per tensor, block table "
+                                   f"[{Bl}][{caches[0].max_pages_per_seq}]; rewind = one 1-block kernel per block")
         state = dict(caches=caches, q=q, kn=kn, vn=vn, out=out, rope=rope, scale=scale)
         return rec, state
 
     def measure_e2e(self, block_fn, steps):
         """block_fn(n) issues n pipelined e2e steps.  Captured into a graph when the capture succeeds."""
         torch = self.torch
-        block_fn(min(steps, 4))
+        block_fn(steps)
         torch.cuda.synchronize()
         run, graphed = (lambda: block_fn(steps)), False
         if not self.args.eager_e2e:
@@ -777,7 +806,7 @@ class Bench:
     def run(self, name, steps, warmup):
         torch = self.torch
         W, r = self.world, self.rank
-        kind, cfg = WORKLOADS[name.replace("_weak", "").replace("_collective", "")]
+        kind, cfg = WORKLOADS[name.replace("_weak", "").replace("_collective", "").replace("_paged", "")]
         cfg = dict(cfg)
         rec = None
         if name == "c2":
@@ -791,6 +820,13 @@ class Bench:
                 pc = self.parity_decode(name, cfg, rows, st)
                 if pc:
                     rec["parity_check"] = pc
+        elif name == "c2_paged":
+            start, cnt = self.omx.parallel.batch_shard(cfg["B"], W, r)
+            rows = list(range(start, start + cnt))
+            rec, st = self.run_decode(name, cfg, rows, 1, steps, warmup, False, paged=True)
+            rec["value"] = cfg["B"] / (rec["ms_per_step"] / 1e3)
+            rec["e2e"]["value"] = cfg["B"] / (rec["e2e"]["ms_per_step"] / 1e3)
+            rec["scaling"] = "strong"
         elif name == "c2_weak":
             rows = list(range(r * cfg["B"], (r + 1) * cfg["B"]))
             rec, st = self.run_decode(name, cfg, rows, W, steps, warmup, False)
@@ -841,7 +877,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=["all", "c2_paged"] + sorted(WORKLOADS))
     ap.add_argument("--impl", default="omx", choices=["omx", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--eager-e2e", action="store_true", help="run the e2e pipeline eagerly instead of from a graph")
@@ -862,7 +898,7 @@ def main():
     b = Bench(args)
     names = ["c2"] if args.workload in ("all", "c2") else [args.workload]
     if args.workload == "all":
-        names += ["c1", "c5"] + (["c5_collective"] if world > 1 and 8 % world == 0 else []) + ["c3", "c4"]
+        names += ["c2_paged", "c1", "c5"] + (["c5_collective"] if world > 1 and 8 % world == 0 else []) + ["c3", "c4"]
         if world > 1:
             names.append("c2_weak")
     recs = {}
