@@ -346,6 +346,17 @@ int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q,
                                   const omx_array* freqs /* may be null */, float sm_scale,
                                   const omx_peer_group* peers, int head_offset, omx_stream s);
 int omx_peer_wait(const omx_peer_group* peers, uint32_t expected, omx_stream s);
+/* The same step with the wait folded into the launch: the CTA that publishes this rank's arrival then spins
+ * (bounded) until every peer's arrival of the same step has reached the local counters, so the launch completes
+ * only when the full [B,Hq_total,1,D] output is in place -- ONE launch per step, no omx_peer_wait.  Every rank of
+ * the group must launch its step (a kernel only ever waits on its own SMs; no rank depends on another rank's
+ * launch having been scheduled first). */
+int omx_attn_decode_fused_sharded_sync(const omx_array* out_full, const omx_array* q,
+                                       const omx_array* k_new, const omx_array* v_new,
+                                       omx_kv_cache cache, int rope_dims, bool traditional,
+                                       omx_optional_float base, float rope_scale,
+                                       const omx_array* freqs /* may be null */, float sm_scale,
+                                       const omx_peer_group* peers, int head_offset, omx_stream s);
 
 /* ---- sequence-sharded single-sequence decode ---------------- */
 /*

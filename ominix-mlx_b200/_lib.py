@@ -110,6 +110,9 @@ _SIGS = {
     "omx_attn_decode_fused_sharded": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                      OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                      ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),
+    "omx_attn_decode_fused_sharded_sync": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
+                                                          OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
+                                                          ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),
     "omx_attn_decode_seqshard": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                 OmxOptionalFloat, ctypes.c_float, ctypes.c_int, ctypes.c_bool,
                                                 ctypes.c_float, ctypes.POINTER(OmxPeerGroup), ctypes.c_void_p]),

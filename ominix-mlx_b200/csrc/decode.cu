@@ -88,6 +88,7 @@ struct DecodeParams {
   void* peer_out[kMaxPeers];  // pre-offset to this rank's first global q head
   unsigned* peer_flag[kMaxPeers];  // rank r's counters live in rank r's memory: [world]
   int* peer_done;             // local, self-resetting
+  int peer_wait;              // 1: the signalling CTA also waits for every peer's arrival (no separate wait launch)
   // array mask over the keys (unfused calls only): bool (true = keep) or additive in the q dtype,
   // broadcast [B,Hq,1,Lk] with element strides (batch, head, key)
   const void* mask;
@@ -224,7 +225,25 @@ __device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
     if (t == p.peer_total - 1) {
       *p.peer_done = 0;  // self-reset for the next launch (stream-ordered)
       __threadfence_system();
-      for (int r = 0; r < p.n_peers; ++r) atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u);
+      unsigned mine = 0;
+      for (int r = 0; r < p.n_peers; ++r) {
+        if (r == p.peer_rank) mine = atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u) + 1u;
+        else atomicAdd_system(p.peer_flag[r] + p.peer_rank, 1u);
+      }
+      if (p.peer_wait) {
+        // The launch ends only when every rank's slice of THIS step has landed in the local buffer: the arrival
+        // counters only grow, "this step" = as many arrivals as this rank has itself signalled.  Replaces the
+        // separate one-warp wait launch (a kernel boundary + its launch latency per step).
+        const volatile unsigned* f = p.peer_flag[p.peer_rank];
+        for (int r = 0; r < p.n_peers; ++r) {
+          unsigned spins = 0;
+          while ((int)(f[r] - mine) < 0) {
+            __nanosleep(32);
+            if (++spins > (1u << 25)) __trap();  // a lost peer becomes a launch failure, not a hung GPU
+          }
+        }
+        __threadfence_system();
+      }
     }
   }
 }
@@ -1590,6 +1609,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   if (f.peers) {
     p.n_peers = f.peers->world;
     p.peer_rank = f.peers->rank;
+    p.peer_wait = f.peer_wait ? 1 : 0;
     for (int r = 0; r < p.n_peers; ++r) {  // already shifted to this rank's first head by the caller
       p.peer_out[r] = f.peers->out[r];
       p.peer_flag[r] = f.peers->flags[r];

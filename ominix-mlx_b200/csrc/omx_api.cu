@@ -212,8 +212,11 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
     OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
   }
   if (force.empty() || force == "fmha_tcgen05") {
-    // small query blocks waste the 256-row CTA tile: leave them to the CUDA-core kernel unless forced
-    if (fmha_sm100_supported(a, &why) && (a.Lq >= 32 || !force.empty())) {
+    // Small query blocks (speculative / chunked decode: 1 < Lq < 32 rows against a long cache) fill only part of
+    // the 256-row CTA tile, but the tile streams K/V with TMA and is still memory-bound: measured at B4, 32 / 8
+    // heads, 8192 keys, Lq = 2 .. 31: 97 us here vs 11 - 28 ms on the one-warp-per-row kernel
+    // (scripts/gpu_r02_small_lq.py), so every multi-row call the kernel supports takes it.
+    if (fmha_sm100_supported(a, &why) && (a.Lq >= 2 || !force.empty())) {
       fmha_sm100(a, stream);
       return;
     }
@@ -376,7 +379,7 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
                        omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
                        omx_array* keys_out, omx_array* values_out, const omx_peer_group* peers,
                        int head_offset, cudaStream_t stream, const omx_array* q_norm_w = nullptr,
-                       const omx_array* k_norm_w = nullptr, float norm_eps = 0.f) {
+                       const omx_array* k_norm_w = nullptr, float norm_eps = 0.f, bool peer_wait = false) {
   require_device();
   auto* c = (KVCacheImpl*)cache.ctx;
   OMX_CHECK(c, "[attn_decode_fused] null cache handle");
@@ -432,6 +435,7 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     f.traditional = traditional;
     f.position = position;
     f.peers = peers;
+    f.peer_wait = peer_wait;
     f.head_offset = 0;  // out_local already starts at this rank's first head
     f.q_norm_w = qn ? q_norm_w->data : nullptr;
     f.k_norm_w = kn ? k_norm_w->data : nullptr;
@@ -938,6 +942,18 @@ int omx_attn_decode_fused_sharded(const omx_array* out_full, const omx_array* q,
   });
 }
 
+int omx_attn_decode_fused_sharded_sync(const omx_array* out_full, const omx_array* q, const omx_array* k_new,
+                                       const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                                       omx_optional_float base, float rope_scale, const omx_array* freqs,
+                                       float sm_scale, const omx_peer_group* peers, int head_offset, omx_stream s) {
+  return guarded([&] {
+    OMX_CHECK(peers != nullptr, "[attn_decode_fused_sharded] null peer group");
+    decode_fused_impl(out_full, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs,
+                      sm_scale, nullptr, nullptr, peers, head_offset, (cudaStream_t)s, nullptr, nullptr, 0.f,
+                      /*peer_wait=*/true);
+  });
+}
+
 int omx_attn_decode_seqshard(const omx_array* partial, const omx_array* q, const omx_array* k_new,
                              const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
                              omx_optional_float base, float rope_scale, int position, bool append, float sm_scale,
@@ -1075,7 +1091,7 @@ static void dit_attention_impl(const omx_array* out, const omx_array* q, const o
     if ((int64_t)a.B * a.Hq * a.Lq * a.Dv == 0) return;
     const char* why = nullptr;
     const bool forced_generic = t_forced_kernel == "sdpa_generic";
-    if (!forced_generic && fmha_sm100_supported(a, &why) && (a.Lq >= 32 || t_forced_kernel == "fmha_tcgen05")) {
+    if (!forced_generic && fmha_sm100_supported(a, &why) && (a.Lq >= 2 || t_forced_kernel == "fmha_tcgen05")) {
       fmha_sm100(a, stream);
       return;
     }

@@ -136,6 +136,7 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   // head-sharded output: store this rank's heads into every rank's full [B,Hq_total,1,D] buffer
   const omx_peer_group* peers = nullptr;  // out pointers already shifted to this rank's first head
   int head_offset = 0;
+  bool peer_wait = false;  // the launch itself waits for every peer's arrival of this step
   // per-head RMSNorm of q / k_new before the rotation (Qwen3 q_norm / k_norm): [D] weights in the
   // q dtype, contiguous; null = no norm
   const void* q_norm_w = nullptr;

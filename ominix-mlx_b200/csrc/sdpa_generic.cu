@@ -140,7 +140,8 @@ void launch(const GenParams& p, cudaStream_t s) {
   if (need <= 1) sdpa_generic_kernel<T, 1><<<blocks, wpb * 32, 0, s>>>(p);
   else if (need <= 2) sdpa_generic_kernel<T, 2><<<blocks, wpb * 32, 0, s>>>(p);
   else if (need <= 4) sdpa_generic_kernel<T, 4><<<blocks, wpb * 32, 0, s>>>(p);
-  else sdpa_generic_kernel<T, 8><<<blocks, wpb * 32, 0, s>>>(p);
+  else if (need <= 8) sdpa_generic_kernel<T, 8><<<blocks, wpb * 32, 0, s>>>(p);
+  else sdpa_generic_kernel<T, 20><<<blocks, wpb * 32, 0, s>>>(p);  // absorbed MLA: Dk = 576, Dv = 512
   count_launch();
   OMX_CUDA(cudaGetLastError());
 }
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(128)
 masked_rows_fixup_kernel(const uint8_t* __restrict__ dead, const T* __restrict__ v, int64_t vs0, int64_t vs1,
                          int64_t vs2, int64_t vs3, void* out, int64_t os0, int64_t os1, int64_t os2, int64_t os3,
                          int Hq, int Hkv, int Lq, int Lk, int Dv, int out_is_f32) {
-  __shared__ float mean[256];
+  __shared__ float mean[640];
   __shared__ uint8_t fl[128];
   const int tid = threadIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row = blockIdx.x * 128 + tid;
@@ -186,7 +187,7 @@ masked_rows_fixup_kernel(const uint8_t* __restrict__ dead, const T* __restrict__
 
 void masked_rows_fixup(const SdpaArgs& a, const uint8_t* dead, cudaStream_t stream) {
   if ((int64_t)a.B * a.Hq * a.Lq == 0 || a.Lk == 0) return;
-  OMX_CHECK(a.Dv <= 256, "[scaled_dot_product_attention] head_dim > 256 is not supported");
+  OMX_CHECK(a.Dv <= 640, "[scaled_dot_product_attention] head_dim > 640 is not supported");
   dim3 grid((a.Lq + 127) / 128, a.Hq, a.B);
   const int64_t* vs = a.v->strides;
   const int64_t* os = a.out->strides;
@@ -206,7 +207,8 @@ void masked_rows_fixup(const SdpaArgs& a, const uint8_t* dead, cudaStream_t stre
 }
 
 void sdpa_generic(const SdpaArgs& a, cudaStream_t stream) {
-  OMX_CHECK(a.D <= 256 && a.Dv <= 256, "[scaled_dot_product_attention] head_dim > 256 is not supported");
+  // up to 640: the absorbed-MLA layout of GLM-4.7-Flash (keys 512 + 64, values 512; glm-4.7-flash-mlx/src/model.rs:263-299)
+  OMX_CHECK(a.D <= 640 && a.Dv <= 640, "[scaled_dot_product_attention] head_dim > 640 is not supported");
   GenParams p;
   p.q = a.q->data;
   p.k = a.k->data;

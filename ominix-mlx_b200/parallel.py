@@ -109,6 +109,9 @@ class HeadShardedDecode:
         self.cache = KVCache()
         self.steps = 0
         self.auto_wait = False  # True: expected = 0 ("my own signal count"), capturable into a CUDA graph
+        # gather = "peer": the wait for the peers' slices runs inside the decode launch itself (one launch per
+        # step); False = the r01 spelling, a separate one-warp wait kernel (omx_peer_wait)
+        self.wait_in_kernel = True
         self._peer = None
         if gather == "peer":
             self._init_peer(batch, dtype)
@@ -173,12 +176,14 @@ class HeadShardedDecode:
         self._peer = self._peer2[parity]
         qd, kd, vd, od = desc(ql), desc(kl), desc(vl), desc(self.out_full)
         sp = stream_ptr(stream)
-        _lib.check(_lib.lib().omx_attn_decode_fused_sharded(
-            ref(od), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
-            bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0, None,
-            float(self.sm_scale), ctypes.byref(self._peer), int(self.q0), sp))
-        expected = 0 if self.auto_wait else self.steps & 0xFFFFFFFF
-        _lib.check(_lib.lib().omx_peer_wait(ctypes.byref(self._peer), ctypes.c_uint32(expected), sp))
+        fn = (_lib.lib().omx_attn_decode_fused_sharded_sync if self.wait_in_kernel
+              else _lib.lib().omx_attn_decode_fused_sharded)
+        _lib.check(fn(ref(od), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
+                      bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0, None,
+                      float(self.sm_scale), ctypes.byref(self._peer), int(self.q0), sp))
+        if not self.wait_in_kernel:
+            expected = 0 if self.auto_wait else self.steps & 0xFFFFFFFF
+            _lib.check(_lib.lib().omx_peer_wait(ctypes.byref(self._peer), ctypes.c_uint32(expected), sp))
         return self.out_full
 
     def rewind(self, n=1):

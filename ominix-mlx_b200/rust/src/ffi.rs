@@ -141,6 +141,13 @@ extern "C" {
     pub fn omx_seqshard_merge(out: *const omx_array, partial: *const omx_array, peers: *const omx_peer_group,
                               expected: u32, s: omx_stream) -> c_int;
     pub fn omx_peer_wait(peers: *const omx_peer_group, expected: u32, s: omx_stream) -> c_int;
+    pub fn omx_attn_decode_fused_sharded_sync(out_full: *const omx_array, q: *const omx_array,
+                                              k_new: *const omx_array, v_new: *const omx_array,
+                                              cache: omx_kv_cache, rope_dims: c_int, traditional: bool,
+                                              base: omx_optional_float, rope_scale: f32,
+                                              freqs: *const omx_array, sm_scale: f32,
+                                              peers: *const omx_peer_group, head_offset: c_int,
+                                              s: omx_stream) -> c_int;
 
     pub fn omx_paged_kv_cache_new(res: *mut omx_paged_kv_cache, batch: c_int, n_kv_heads: c_int, head_dim_k: c_int,
                                   head_dim_v: c_int, dtype: c_int, n_pages: i64, max_pages_per_seq: c_int) -> c_int;

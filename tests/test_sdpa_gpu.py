@@ -260,3 +260,24 @@ def test_decode_mask_long_context_split_k():
     _decode_masked(1, 32, 8, Lk, 128, "bf16", m, "decode_hmma_tma")
     none = torch.zeros((1, Lk), dtype=torch.bool)
     _decode_masked(1, 32, 8, Lk, 128, "bf16", none, "decode_hmma_tma")
+
+
+@pytest.mark.parametrize("L", [1, 7])
+def test_absorbed_mla_glm47_flash_dk576_dv512(L):
+    # GLM-4.7-Flash absorbed MLA (glm-4.7-flash-mlx/src/model.rs:263-299): ONE shared kv head, keys
+    # [B,1,S,512+64], values [B,1,S,512] (a view of the keys' first 512 features in the crate), 20 query heads
+    B, H, S, Dk, Dv, dtype = 1, 20, 300, 576, 512, "bf16"
+    q = randn((B, H, L, Dk), dtype, 1)
+    k = randn((B, 1, S, Dk), dtype, 2)
+    v = k[..., :Dv]  # strided view, like the crate's `values = kv_latent`
+    mask = None if L == 1 else omx.fast.ScaledDotProductAttentionMask.Causal
+    got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), k.to(DEV)[..., :Dv], Dk ** -0.5, mask)
+    assert tuple(got.shape) == (B, H, L, Dv) and omx.last_kernel() == "sdpa_generic"
+    want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v.contiguous(), dtype), Dk ** -0.5,
+                    None if L == 1 else "causal", dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, "absorbed MLA attention")
+    # through the cache, Dk != Dv
+    c = omx.KVCache()
+    K, V = c.update_and_fetch(k.to(DEV), k.to(DEV)[..., :Dv].contiguous())
+    got2 = omx.fast.scaled_dot_product_attention(q.to(DEV), K, V, Dk ** -0.5, mask)
+    assert torch.equal(got, got2)
