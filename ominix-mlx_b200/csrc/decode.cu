@@ -114,6 +114,10 @@ struct DecodeParams {
   // 1: the splits of one (batch, kv-head) form a thread-block cluster and are combined through
   // distributed shared memory (no partials in HBM/L2, no fence, no ticket)
   int cluster;
+  // cluster combine, few splits (<= kPushSplits) and G <= 8: instead of publishing partials and PULLING column
+  // slices from every peer (two cluster barriers), ranks 1.. PUSH their (O, m, l) into receive slots in rank 0's
+  // shared memory and leave; rank 0 folds them after ONE cluster barrier.
+  int push_combine;
   // sequence-sharded decode (omx_attn_decode_seqshard): `out` / peer_out are FLOAT32 partial slots
   // [B][Hq][D + 2] -- the normalised output of this rank's keys, then its (m, l) in the log2 domain -- and
   // os[] holds that slot's strides; append = 0: this rank attends but does not own the new token
@@ -150,6 +154,17 @@ __device__ __forceinline__ void trace_mark(const DecodeParams& p, int slot) {
     p.trace[(size_t)cta * 16 + slot] = t;
   }
 }
+
+// Programmatic dependent launch (PDL).  Every decode launch carries the programmatic-stream-serialization
+// attribute: its CTAs may be dispatched while the previous kernel on the stream is still running its tail, and
+// wait here -- before their FIRST global-memory access -- until that kernel has completed and its writes are
+// visible (cache rows, split-K scratch, counters, q produced by the caller's projection ...).  The other half:
+// once a CTA has left its key loop it lets the next kernel's CTAs be dispatched (the next grid starts when every
+// CTA of this one has said so or exited), so the dispatch latency of launch N+1 and the drain of launch N overlap
+// instead of adding up (~1-2 us per launch in a back-to-back decode loop).  A predecessor that never triggers
+// releases its dependents on completion, i.e. behaves like a plain stream-ordered launch.
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release_next_grid() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // The launch's key count, split size and rope row: kernel arguments, or derived from *pos_dev.
 struct DecodeDyn {
@@ -466,6 +481,11 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t a) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_dsmem_f32(uint32_t a, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+constexpr int kPushSplits = 4;  // receive slots are sized (splits - 1) x G x (D + 2) floats per CTA
+__host__ __device__ constexpr int push_recv_floats(int splits, int heads, int D) { return (splits - 1) * heads * (D + 2); }
 __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t a) {
   float2 v;
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
@@ -482,10 +502,14 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
                                                 int n_ent, int rows, bool has_nt, const float* nt_m,
                                                 const float* nt_v, int first_head, int n_heads, int b,
                                                 int pair, int split, int tid, int nthr, int* s_ticket,
-                                                float* cl /* cluster scratch, cluster_scratch_floats(rows) */) {
+                                                float* cl /* cluster scratch, cluster_scratch_floats(rows) */,
+                                                float* recv = nullptr /* push-combine receive slots */) {
   const int D = p.D;
   const int64_t ob = b * p.os[0];
   const bool use_cluster = p.cluster && p.num_splits > 1;
+  const bool push = use_cluster && p.push_combine && recv != nullptr;
+  // receive slot of split s >= 1 inside RANK 0's shared memory: [s - 1][head][D | m | l]
+  auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
   float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
   // (one element per thread: a float4-column variant halved the active threads and measured slower)
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
@@ -510,6 +534,12 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
       store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
       if (d == 0) store_ml(p, b, first_head + g, M, L);
       if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    } else if (push && split != 0) {
+      st_dsmem_f32(dsmem_addr(recv_at(split, g, d), 0), O);
+      if (d == 0) {
+        st_dsmem_f32(dsmem_addr(recv_at(split, g, D), 0), M);
+        st_dsmem_f32(dsmem_addr(recv_at(split, g, D + 1), 0), L);
+      }
     } else if (use_cluster) {
       part_o[g * D + d] = O;  // == mo[(0 * rows + g) * D + d], read above by this thread only
       if (d == 0) {
@@ -531,6 +561,47 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     return;
   }
   trace_mark(p, 3);
+  if (push) {
+    // ---- push combine: ranks 1.. have stored into rank 0's receive slots; their arrive (release) publishes the
+    // stores and they leave -- nobody reads THEIR shared memory.  Rank 0 folds after the one barrier; every
+    // element is owned by the thread that produced rank 0's own partial, so no further CTA barrier is needed.
+    cluster_arrive_release();
+    if (split != 0) {
+      trace_mark(p, 6);
+      return;
+    }
+    cluster_wait_acquire();
+    __syncthreads();  // rank 0's own (m, l) in `cl` were written by the d == 0 owners only
+    trace_mark(p, 4);
+    const int NS = p.num_splits;
+    for (int idx = tid; idx < n_heads * D; idx += nthr) {
+      const int g = idx / D, d = idx % D;
+      float ms[kPushSplits], ls[kPushSplits];
+      ms[0] = cl[g * 2];
+      ls[0] = cl[g * 2 + 1];
+      float M = ms[0];
+#pragma unroll
+      for (int sp = 1; sp < kPushSplits; ++sp) {
+        ms[sp] = sp < NS ? *recv_at(sp, g, D) : -INFINITY;
+        ls[sp] = sp < NS ? *recv_at(sp, g, D + 1) : 0.f;
+        M = fmaxf(M, ms[sp]);
+      }
+      float L = 0.f, O = 0.f;
+#pragma unroll
+      for (int sp = 0; sp < kPushSplits; ++sp) {
+        if (sp < NS && ms[sp] > -INFINITY) {
+          const float w = fast_exp2(ms[sp] - M);
+          L = fmaf(ls[sp], w, L);
+          O = fmaf(sp == 0 ? part_o[g * D + d] : *recv_at(sp, g, d), w, O);
+        }
+      }
+      store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
+      if (d == 0) store_ml(p, b, first_head + g, M, L);
+      if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    }
+    trace_mark(p, 6);
+    return;
+  }
   if (use_cluster) {
     // ---- cluster combine.  Every CTA of the cluster publishes its partial in its own shared memory,
     // one cluster barrier later each CTA pulls all (m, l) pairs (NS x heads x 8 B) and its slice of the
@@ -751,6 +822,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
+  pdl_wait_prior_grid();
   trace_mark(p, 0);
   if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot (whole CTA, whole cluster: same b)
   const DecodeDyn dy = load_dyn(p, b);
@@ -809,8 +881,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   }
   if constexpr (kDecouple) {
     if (warp == NW) {
-      __syncwarp();
-      named_bar_sync(1, NTHR);
+      __syncwarp();  // (the producer warp meets barrier 1, "q is staged", after its issue loop)
     } else {
       stage_q<T>(p, q_s, kQPitch, 16, hk * G, G, b, hk, tid, NW * 32, s_pro, nt_k, nt_v, has_nt, dy, [] {},
                  [] { named_bar_sync(2, NW * 32); });
@@ -852,7 +923,10 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
 
   if (warp == NW) {
     // ------------------------------------------------ producer warp (first tiles already in flight)
-    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy);
+    // The K/V stream comes first: the new token (norm + rope of k_new, the cache row store, its score) is only
+    // needed by the merge, so it runs AFTER the last tile has been issued, under the consumers' last tiles.
+    // (Doing it first kept the appending CTAs' rings from refilling for ~1.5 us: those CTAs -- one per (batch,
+    // kv-head) -- finished ~2 us after the rest and set the launch's end; per-CTA timelines, B = 8 per GPU.)
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
         mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
@@ -860,6 +934,8 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       }
     }
     __syncwarp();
+    if constexpr (kDecouple) named_bar_sync(1, NTHR);  // q is staged (the consumers arrived long ago)
+    if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy);
   } else {
     // ------------------------------------------------ consumer warps
     using MMA = Mma16816<T>;
@@ -986,6 +1062,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       }
   }
   __syncthreads();  // every stage consumed -> the ring is reused for the merge
+  pdl_release_next_grid();
   trace_mark(p, 2);
   if (warp < NW) {
     float* mo = reinterpret_cast<float*>(stages);  // [NW][16][128]
@@ -1011,7 +1088,8 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   __syncthreads();  // merge inputs visible
   const float* mo = reinterpret_cast<const float*>(stages);
   merge_and_store<T, 16>(p, mo, mo + NW * 16 * D, NW, 16, has_nt, nt_m, nt_v, hk * G, G, b, pair, split, tid,
-                         NTHR, &s_ticket, const_cast<float*>(mo) + NW * 16 * (D + 2));
+                         NTHR, &s_ticket, const_cast<float*>(mo) + NW * 16 * (D + 2),
+                         p.push_combine ? nt_m + 16 : nullptr);
 }
 
 // ============================================================ generic: CUDA cores
@@ -1098,6 +1176,7 @@ decode_simt_kernel(const DecodeParams p) {
   const int hk = blockIdx.y / groups, gsub = blockIdx.y % groups;
   const int first_head = hk * p.G + gsub * GT;
   const int pair = (b * p.Hkv + hk) * groups + gsub;
+  pdl_wait_prior_grid();
   trace_mark(p, 0);
   if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot
   const DecodeDyn dy = load_dyn(p, b);
@@ -1202,6 +1281,7 @@ decode_simt_kernel(const DecodeParams p) {
     }
   }
   __syncthreads();
+  pdl_release_next_grid();
   trace_mark(p, 2);
   merge_and_store<T, 4>(p, mo, mml, kSimtWarps, GT, has_nt, nt_m, nt_v, first_head, GT, b, pair, split, tid,
                         NTHR, &s_ticket, nt_m + 4);
@@ -1260,24 +1340,43 @@ int cluster_capacity(K kern, dim3 grid, int threads, size_t smem, int cluster_x)
   return n;
 }
 
+// Which launches carry the programmatic-dependent-launch attribute.  Measured in one box, CUDA-graph replays
+// (scripts/gpu_r02_pdl_ab.sh): the CUDA-core kernel gains (C1 15.56 -> 14.64 us: its CTAs are small, the next
+// grid's CTAs become resident beside the running ones), the TMA kernel does not (one CTA fills an SM's shared
+// memory, early CTAs only spin on the idle SMs: C2 at 8 rows per GPU 45.2 -> 45.8 us, C5 30.5 -> 31.6 us), so
+// the default is CUDA-core launches only.  OMX_DECODE_PDL=0 / 1 forces it off / on everywhere (A/B knob).
+bool pdl_enabled(bool simt) {
+  static const int forced = [] {
+    const char* e = getenv("OMX_DECODE_PDL");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  return forced >= 0 ? forced == 1 : simt;
+}
+
 template <typename K, typename... Args>
-void launch_kernel(K kern, dim3 grid, int threads, size_t smem, cudaStream_t stream, int cluster_x, Args... args) {
-  if (cluster_x <= 1) {
-    kern<<<grid, threads, smem, stream>>>(args...);
-    return;
-  }
+void launch_kernel(K kern, dim3 grid, int threads, size_t smem, cudaStream_t stream, int cluster_x, bool pdl,
+                   Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cluster_x;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {  // see pdl_wait_prior_grid()
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = n;
   OMX_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
 }
 
@@ -1327,7 +1426,7 @@ void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool o
     p.cluster = want_cluster && p.num_splits > 1 &&
                         cluster_capacity(kern, grid, kSimtWarps * 32, smem, p.num_splits) >= (int)(grid.y * grid.z)
                     ? 1 : 0;
-    launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, p);
+    launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, pdl_enabled(true), p);
   };
   // the 16-key variant keeps 2 x 16 rows per lane in registers; instantiated where it is used and measured --
   // float32 at head_dim 128 (C1; 16-bit head_dim 128 runs on the TMA kernel) -- to keep the build time down
@@ -1720,7 +1819,14 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
                                        a.k->strides[0], 64, 64, bf);
     CUtensorMap tmV = make_tmap_4d_b16(a.v->data, 128, rows, a.Hkv, outer, a.v->strides[2], a.v->strides[1],
                                        a.v->strides[0], 64, 64, bf);
-    const size_t smem = 1024 + (size_t)NSTAGE * kStageBytes + 16 * kQPitch * 2 + sizeof(float) * (128 + 128 + 16);
+    const size_t smem_base = 1024 + (size_t)NSTAGE * kStageBytes + 16 * kQPitch * 2 + sizeof(float) * (128 + 128 + 16);
+    // few-way cluster splits fold through receive slots in rank 0 (push combine): a little more shared memory
+    static const bool push_env = [] {  // OMX_DECODE_PUSH=0: always the pull combine (A/B knob)
+      const char* e = getenv("OMX_DECODE_PUSH");
+      return !e || atoi(e) != 0;
+    }();
+    const bool push_ok = push_env && want_cluster && natural.num_splits <= kPushSplits && p.G <= 8 && !f.partial;
+    const size_t smem = smem_base + (push_ok ? sizeof(float) * push_recv_floats(natural.num_splits, p.G, 128) : 0);
     auto go = [&](auto kern) {
       OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int threads = (NSTAGE + 1) * 32;
@@ -1736,12 +1842,13 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       }
       p.num_splits = sp.num_splits;
       p.tiles_per_split = sp.tiles_per_split;
+      p.push_combine = (push_ok && p.cluster && p.num_splits <= kPushSplits) ? 1 : 0;
       carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
                       p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
                       (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
       dim3 grid(p.num_splits, a.Hkv, a.B);
       arm_trace(grid);
-      launch_kernel(kern, grid, threads, smem, stream, p.cluster ? p.num_splits : 1, tmK, tmV, p);
+      launch_kernel(kern, grid, threads, smem, stream, p.cluster ? p.num_splits : 1, pdl_enabled(false), tmK, tmV, p);
     };
     note_launch("decode_hmma_tma");
     if (bf) {
