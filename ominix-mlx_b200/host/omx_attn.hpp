@@ -422,6 +422,8 @@ inline Array attention_prefill_fused(const Array& queries, const Array& keys, co
   if (qs.size() != 4) throw Exception("attention_prefill_fused: queries must be [B, H, L, D]");
   Array out = Array::empty({qs[0], qs[1], qs[2], values.shape()[3]}, queries.dtype());
   const float eps = q_norm ? q_norm->eps : (k_norm ? k_norm->eps : 0.f);
+  // the callers' rule (qwen3-mlx/src/model.rs:203-207): no mask and L > 1 means Causal
+  if (mask.kind == SdpaMask::None && qs[2] > 1) mask = SdpaMask::causal();
   const auto m = mask.lower();
   check(omx_attn_prefill_fused(out.desc(), queries.desc(), keys.desc(), values.desc(), cache.raw(),
                                q_norm ? q_norm->weight.desc() : nullptr, k_norm ? k_norm->weight.desc() : nullptr, eps,
