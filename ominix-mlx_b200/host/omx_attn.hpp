@@ -10,6 +10,7 @@
 //   omx::KeyValueCache / KVCache / ConcatKeyValueCache           <- mlx-rs-core/src/cache.rs:7-195
 //   omx::utils::{initialize_rope, SdpaMask, scaled_dot_product_attention}   <- mlx-rs-core/src/utils.rs:52-209
 //   omx::utils::{attention_decode_fused, attention_prefill_fused}  <- Attention::forward, qwen3-mlx/src/model.rs:161-215
+//   omx::PagedKVCache, omx::utils::attention_decode_fused_paged    <- the same contract over a page pool (ragged batches)
 // Errors: every failing call throws omx::Exception{what} carrying the library message (the role
 // mlx_rs::error::Exception plays, mlx-rs/src/error.rs:236-288).
 // `Array` is a strided view of CUDA device memory (what mlx_rs::Array is on this path): owning when
@@ -313,6 +314,66 @@ class ConcatKeyValueCache : public KeyValueCache {
   Stream stream_;
 };
 
+/// The KeyValueCache contract over a page pool (include/omx_attn.h "paged KV cache"): pool [n_pages][Hkv][64][D]
+/// allocated once, block table, per-sequence lengths; growth = a page id from the free list.  update_and_fetch
+/// appends to EVERY sequence and returns MATERIALISED [B,Hkv,offset,D] arrays (valid until the next fetch).
+class PagedKVCache : public KeyValueCache {
+ public:
+  PagedKVCache(int batch, int n_kv_heads, int head_dim, Dtype dtype, int64_t n_pages, int max_pages_per_seq,
+               int head_dim_v = 0, Stream s = {})
+      : batch_(batch), stream_(s) {
+    omx_paged_kv_cache h{nullptr};
+    check(omx_paged_kv_cache_new(&h, batch, n_kv_heads, head_dim, head_dim_v ? head_dim_v : head_dim, (int)dtype,
+                                 n_pages, max_pages_per_seq));
+    h_ = std::shared_ptr<void>(h.ctx, [](void* c) { omx_paged_kv_cache_free(omx_paged_kv_cache{c}); });
+  }
+  int offset() const override {  // the longest sequence
+    int n = 0;
+    check(omx_paged_kv_cache_offset(raw(), &n));
+    return n;
+  }
+  std::optional<int> max_size() const override { return std::nullopt; }
+  void reset() override { check(omx_paged_kv_cache_reset(raw(), -1, stream_.raw())); }
+  void reset(int slot) { check(omx_paged_kv_cache_reset(raw(), slot, stream_.raw())); }
+  void release(int slot) { check(omx_paged_kv_cache_release(raw(), slot, stream_.raw())); }
+  void reserve(int rows_ahead) { check(omx_paged_kv_cache_reserve(raw(), rows_ahead, stream_.raw())); }
+  void trim(int n) { check(omx_paged_kv_cache_trim(raw(), n, stream_.raw())); }
+  void sync_lengths() { check(omx_paged_kv_cache_sync_lengths(raw(), stream_.raw())); }
+  std::vector<int32_t> lengths() const {
+    std::vector<int32_t> l(batch_);
+    check(omx_paged_kv_cache_lengths(raw(), l.data()));
+    return l;
+  }
+  int64_t free_pages() const {
+    int64_t n = 0;
+    check(omx_paged_kv_cache_free_pages(raw(), &n));
+    return n;
+  }
+  std::pair<Array, Array> update_and_fetch(const Array& keys, const Array& values) override {
+    omx_array ko, vo;
+    check(omx_paged_kv_cache_update_and_fetch(raw(), keys.desc(), values.desc(), &ko, &vo, stream_.raw()));
+    return {Array::from_desc(ko, h_), Array::from_desc(vo, h_)};
+  }
+  /// append without materialising the fetched views
+  void update(const Array& keys, const Array& values) {
+    check(omx_paged_kv_cache_update_and_fetch(raw(), keys.desc(), values.desc(), nullptr, nullptr, stream_.raw()));
+  }
+  void append_slot(int slot, const Array& keys, const Array& values) {
+    check(omx_paged_kv_cache_append_slot(raw(), slot, keys.desc(), values.desc(), stream_.raw()));
+  }
+  std::pair<Array, Array> fetch() {
+    omx_array ko, vo;
+    check(omx_paged_kv_cache_fetch(raw(), &ko, &vo, stream_.raw()));
+    return {Array::from_desc(ko, h_), Array::from_desc(vo, h_)};
+  }
+  omx_paged_kv_cache raw() const { return omx_paged_kv_cache{h_.get()}; }
+
+ private:
+  std::shared_ptr<void> h_;
+  int batch_;
+  Stream stream_;
+};
+
 // ------------------------------------------------------------------------------- utils
 namespace utils {
 
@@ -376,6 +437,23 @@ inline Array attention_decode_fused(const Array& queries, const Array& keys, con
                                    eps, rope ? rope->dimensions : 0, rope ? rope->traditional : false,
                                    fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
                                    rope ? rope->scale : 1.f, nullptr, scale, nullptr, nullptr, s.raw()));
+  return out;
+}
+
+/// The same step over a PagedKVCache: per sequence the position is its own length (device memory), ONE launch.
+inline Array attention_decode_fused_paged(const Array& queries, const Array& keys, const Array& values,
+                                          PagedKVCache& cache, const nn::Rope* rope, float scale,
+                                          const nn::RmsNorm* q_norm = nullptr, const nn::RmsNorm* k_norm = nullptr,
+                                          Stream s = {}) {
+  const auto qs = queries.shape();
+  if (qs.size() != 4 || qs[2] != 1) throw Exception("attention_decode_fused_paged: queries must be [B, H, 1, D]");
+  Array out = Array::empty({qs[0], qs[1], 1, values.shape()[3]}, queries.dtype());
+  const float eps = q_norm ? q_norm->eps : (k_norm ? k_norm->eps : 0.f);
+  check(omx_attn_decode_fused_paged(out.desc(), queries.desc(), keys.desc(), values.desc(), cache.raw(),
+                                    q_norm ? q_norm->weight.desc() : nullptr, k_norm ? k_norm->weight.desc() : nullptr,
+                                    eps, rope ? rope->dimensions : 0, rope ? rope->traditional : false,
+                                    fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
+                                    rope ? rope->scale : 1.f, scale, s.raw()));
   return out;
 }
 

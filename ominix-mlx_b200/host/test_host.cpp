@@ -399,6 +399,45 @@ static void test_decode_loop_cuda_graph() {
   cudaStreamDestroy(st);
 }
 
+static void test_paged_cache_equals_contiguous_cache() {
+  printf("test_paged_cache_equals_contiguous_cache\n");
+  // the decode loop of Attention::forward over a PagedKVCache and over the reference-shaped KVCache: same kernels,
+  // same arithmetic -> outputs and cache rows bit-identical, across a page boundary (120 -> 136 rows)
+  const int B = 2, Hq = 8, Hkv = 2, D = 128, S0 = 120, steps = 16;
+  const float scale = 1.0f / std::sqrt((float)D);
+  auto kh = randn_bf16((size_t)B * Hkv * S0 * D, 70), vh = randn_bf16((size_t)B * Hkv * S0 * D, 71);
+  Array k0 = Array::from_host(kh.data(), {B, Hkv, S0, D}, Dtype::Bfloat16);
+  Array v0 = Array::from_host(vh.data(), {B, Hkv, S0, D}, Dtype::Bfloat16);
+  omx::nn::Rope rope = omx::utils::initialize_rope(D, 1e6f, false);
+  omx::KVCache cc;
+  omx::PagedKVCache pc(B, Hkv, D, Dtype::Bfloat16, /*n_pages=*/8, /*max_pages_per_seq=*/4);
+  cc.update_and_fetch(k0, v0);
+  auto pf = pc.update_and_fetch(k0, v0);
+  EXPECT(download(pf.first) == kh && download(pf.second) == vh, "materialised prefill rows == the appended rows");
+  EXPECT(pc.offset() == S0 && pc.free_pages() == 8 - 2 * 2, "paged offsets / pages after prefill");
+  for (int t = 0; t < steps; ++t) {
+    auto qh = randn_bf16((size_t)B * Hq * D, 80 + t), k1h = randn_bf16((size_t)B * Hkv * D, 100 + t),
+         v1h = randn_bf16((size_t)B * Hkv * D, 120 + t);
+    Array q = Array::from_host(qh.data(), {B, Hq, 1, D}, Dtype::Bfloat16);
+    Array k1 = Array::from_host(k1h.data(), {B, Hkv, 1, D}, Dtype::Bfloat16);
+    Array v1 = Array::from_host(v1h.data(), {B, Hkv, 1, D}, Dtype::Bfloat16);
+    Array a = omx::utils::attention_decode_fused(q, k1, v1, cc, &rope, scale);
+    Array b = omx::utils::attention_decode_fused_paged(q, k1, v1, pc, &rope, scale);
+    EXPECT(download(a) == download(b), "step %d: paged and contiguous outputs must be bit-identical", t);
+  }
+  EXPECT(pc.offset() == S0 + steps && pc.free_pages() == 8 - 2 * 3, "a third page per sequence after the boundary");
+  auto kv = pc.fetch();
+  const auto ck = download(cc.state().first), pk = download(kv.first);
+  // contiguous state is [B,Hkv,cap,D] with cap >= offset; compare the first offset rows of every (b, h)
+  const int cap = (int)cc.state().first.shape()[2], n = S0 + steps;
+  bool same = true;
+  for (int bh = 0; bh < B * Hkv && same; ++bh)
+    same = std::equal(pk.begin() + (size_t)bh * n * D, pk.begin() + (size_t)(bh + 1) * n * D, ck.begin() + (size_t)bh * cap * D);
+  EXPECT(same, "paged rows == contiguous cache rows, bit for bit");
+  pc.release(1);
+  EXPECT(pc.lengths()[1] == -1 && pc.lengths()[0] == n && pc.free_pages() == 8 - 3, "release returns the pages");
+}
+
 int main() {
   int sm = 0;
   if (omx_device_check(&sm) != 0) {
@@ -412,6 +451,7 @@ int main() {
     test_sdpa_shapes_like_the_reference_test();
     test_attention_forward_prefill_then_decode();
     test_decode_loop_cuda_graph();
+    test_paged_cache_equals_contiguous_cache();
   } catch (const std::exception& e) {
     printf("EXCEPTION: %s\n", e.what());
     return 1;

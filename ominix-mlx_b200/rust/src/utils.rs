@@ -78,6 +78,40 @@ pub fn attention_decode_fused(
     Ok(out)
 }
 
+/// The same decode step over a `PagedKVCache`, ONE launch: per sequence the position is its own length (read by
+/// the kernel from device memory), k' / v land in row `len % 64` of page `block_table[b][len / 64]`; released slots
+/// are skipped.
+pub fn attention_decode_fused_paged(
+    queries: &Array,
+    keys: &Array,
+    values: &Array,
+    cache: &mut crate::cache::PagedKVCache,
+    rope: Option<RopeParams>,
+    scale: f32,
+    q_norm: Option<(&Array, f32)>,
+    k_norm: Option<(&Array, f32)>,
+    stream: Stream,
+) -> Result<Array> {
+    let qs = queries.shape();
+    if qs.len() != 4 || qs[2] != 1 {
+        return Err(Exception::custom("attention_decode_fused_paged: queries must be [B, H, 1, D]"));
+    }
+    let out = Array::empty(&[qs[0], qs[1], 1, values.shape()[3]], queries.dtype())?;
+    let (dims, trad, base, rscale) = match rope {
+        Some(r) => (r.dimensions, r.traditional, ffi::omx_optional_float { value: r.base, has_value: true }, r.scale),
+        None => (0, false, ffi::omx_optional_float::default(), 1.0),
+    };
+    let eps = q_norm.map(|n| n.1).or(k_norm.map(|n| n.1)).unwrap_or(0.0);
+    check(unsafe {
+        ffi::omx_attn_decode_fused_paged(out.as_ptr(), queries.as_ptr(), keys.as_ptr(), values.as_ptr(), cache.raw(),
+                                         q_norm.map_or(std::ptr::null(), |n| n.0.as_ptr()),
+                                         k_norm.map_or(std::ptr::null(), |n| n.0.as_ptr()), eps, dims, trad, base,
+                                         rscale, scale, stream.0)
+    })?;
+    let _ = cache.keepalive();
+    Ok(out)
+}
+
 /// `attention_decode_fused` with the position read by the KERNEL from `position` (device `int32`, shared by all
 /// layers): capturable with `cudaStreamBeginCapture` and replayable per token -- what `async_eval` pipelining gave
 /// the reference's decode loop (qwen3-mlx/src/model.rs:798-844).  `out` is caller-owned (static under a graph);
