@@ -337,11 +337,12 @@ class Bench:
                 fn(i)
         return cg
 
-    def timed_blocks(self, run_block, steps, min_s=MIN_TIMED_S, max_blocks=2000):
+    def timed_blocks(self, run_block, steps, min_s=None, max_blocks=2000):
         """Blocks of exactly `steps` steps, each bracketed by barrier + synchronize and timed with CUDA events on
         the launching stream (max over ranks); repeated until min_s of device time.  Returns the block times."""
         torch = self.torch
         out, total = [], 0.0
+        min_s = MIN_TIMED_S if min_s is None else min(min_s, MIN_TIMED_S)
         while (total < min_s * 1e3 or len(out) < 3) and len(out) < max_blocks:
             self.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -355,7 +356,7 @@ class Bench:
         self.barrier()
         return out
 
-    def measure(self, fn, steps, warmup, graph, min_s=MIN_TIMED_S):
+    def measure(self, fn, steps, warmup, graph, min_s=None):
         """fn(i): step i of a block.  Returns dict(ms_per_step = median block / steps, blocks, clocks, launches)."""
         omx = self.omx
         for i in range(warmup):
@@ -873,6 +874,7 @@ class Bench:
 
 
 def main():
+    global MIN_TIMED_S
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -882,7 +884,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--eager-e2e", action="store_true", help="run the e2e pipeline eagerly instead of from a graph")
     ap.add_argument("--batch", type=int, default=None, help="override C2's GLOBAL batch (sweeps / debugging)")
+    ap.add_argument("--min-seconds", type=float, default=MIN_TIMED_S,
+                    help="device time to accumulate per workload (default 0.5 s); profiler runs pass 0 (3 blocks)")
     args = ap.parse_args()
+    MIN_TIMED_S = max(0.0, args.min_seconds)
     args.warmup = max(args.warmup, 3)
     args.steps = max(args.steps, 2)
     rank = int(os.environ.get("RANK", "0"))

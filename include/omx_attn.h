@@ -144,7 +144,9 @@ int omx_kv_cache_reset(omx_kv_cache c); /* offset = 0; buffers untouched */
  * keys [B,Hkv,n,Dk], values [B,Hkv,n,Dv] (any strides).  Appends at rows [offset, offset+n),
  * growing by ceil(n/step)*step zero rows (old buffer trimmed to `offset` first when
  * offset % step != 0) exactly as cache.rs:141-181; then returns VIEWS [.., :offset, :] of
- * the cache-owned buffers in keys_out / values_out.  Views stay valid until the next growth.
+ * the cache-owned buffers in keys_out / values_out.  A growth step moves the rows into a new buffer; the buffer it
+ * replaces stays allocated (readable, with its old contents) until the NEXT growth or the cache's destruction, so a
+ * fetched view survives one growth step -- e.g. a consumer still running on another stream -- but not two.
  */
 int omx_kv_cache_update_and_fetch(omx_kv_cache c, const omx_array* keys, const omx_array* values,
                                   omx_array* keys_out, omx_array* values_out, omx_stream s);

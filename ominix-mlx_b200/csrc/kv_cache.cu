@@ -86,6 +86,10 @@ struct KVBuf {
   int D = 0;
   int dtype = 0;
   int64_t phys = 0;  // physical rows
+  // The buffer a growth step replaced.  The reference hands out refcounted arrays that outlive a growth; here
+  // fetched views are borrowed, so the previous buffer stays allocated (and readable, e.g. by a consumer still
+  // running on another stream) until the NEXT growth or the cache's destruction: views survive one growth step.
+  void* retired = nullptr;
 };
 
 struct KVCacheImpl {
@@ -114,8 +118,8 @@ KVCacheImpl* kv_cache_create(int step, bool concat) {
 
 void kv_cache_destroy(KVCacheImpl* c) {
   if (!c) return;
-  if (c->k.p) cudaFreeAsync(c->k.p, c->last_stream);
-  if (c->v.p) cudaFreeAsync(c->v.p, c->last_stream);
+  for (void* p : {c->k.p, c->v.p, c->k.retired, c->v.retired})
+    if (p) cudaFreeAsync(p, c->last_stream);
   if (c->scratch) cudaFreeAsync(c->scratch, c->last_stream);
   delete c;
 }
@@ -155,7 +159,8 @@ void regrow(KVCacheImpl* c, KVBuf& b, int64_t keep, int64_t new_cap, bool zero_n
       OMX_CUDA(cudaMemcpy2DAsync(np, (size_t)phys * row, b.p, (size_t)b.phys * row, (size_t)keep * row,
                                  heads, cudaMemcpyDeviceToDevice, stream));
     }
-    if (b.p) OMX_CUDA(cudaFreeAsync(b.p, stream));
+    if (b.retired) OMX_CUDA(cudaFreeAsync(b.retired, stream));
+    b.retired = b.p;
     b.p = np;
     b.phys = phys;
     c->graph_rows = 0;  // the buffer moved: launches captured against the old address are stale
@@ -350,6 +355,7 @@ void kv_cache_rollback(KVCacheImpl* c, const KVCacheSnapshot& s, cudaStream_t st
     // the failed call was the cache's first update: forget the shape / dtype it latched and its buffers
     for (KVBuf* b : {&c->k, &c->v}) {
       if (b->p) cudaFreeAsync(b->p, stream);
+      if (b->retired) cudaFreeAsync(b->retired, stream);
       *b = KVBuf();
     }
     c->has = false;

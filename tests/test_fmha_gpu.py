@@ -240,6 +240,50 @@ def test_full_size_properties_c3():
     assert_close(o[3:4, 8:12].float().cpu().numpy(), n2f(want, "bf16"), "bf16", "C3 slice")
 
 
+def _oracle_rows(q, k, v, triples, G, causal, q_off=0):
+    """Oracle output of sampled (batch, q head, query row) triples of a full-size launch: one Lq = 1 call each
+    against the keys that row sees (bottom-right aligned causal mask = a prefix of the keys)."""
+    D = q.shape[-1]
+    out = []
+    for b, h, r in triples:
+        n = (q_off + r + 1) if causal else k.shape[2]
+        want = orc.sdpa(t2n(q[b:b + 1, h:h + 1, r:r + 1], "bf16"), t2n(k[b:b + 1, h // G:h // G + 1, :n], "bf16"),
+                        t2n(v[b:b + 1, h // G:h // G + 1, :n], "bf16"), D ** -0.5, None, dtype="bf16")
+        out.append(n2f(want, "bf16")[0, 0, 0])
+    return np.stack(out)
+
+
+def test_full_size_c3_sampled_rows_against_the_oracle():
+    # the FULL C3 launch (B8, 32q/8kv, seq 8192, causal), 64 random (batch, head, row) triples against the oracle:
+    # every persistent CTA / work item / diagonal tile position is a candidate, not one fixed slice
+    B, Hq, Hkv, L, D = 8, 32, 8, 8192, 128
+    g = torch.Generator(device=DEV).manual_seed(4237)
+    q = torch.randn((B, Hq, L, D), generator=g, device=DEV).bfloat16()
+    k = torch.randn((B, Hkv, L, D), generator=g, device=DEV).bfloat16()
+    v = torch.randn((B, Hkv, L, D), generator=g, device=DEV).bfloat16()
+    o = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, Causal)
+    assert omx.last_kernel() == "fmha_tcgen05"
+    rng = np.random.default_rng(11)
+    triples = [(int(rng.integers(B)), int(rng.integers(Hq)), int(rng.integers(L))) for _ in range(56)]
+    triples += [(0, 0, 0), (7, 31, L - 1), (3, 5, 127), (3, 5, 128), (4, 17, 255), (4, 17, 256), (6, 30, 4095), (6, 30, 4096)]
+    got = np.stack([o[b, h, r].float().cpu().numpy() for b, h, r in triples])
+    assert_close(got, _oracle_rows(q, k, v, triples, Hq // Hkv, True), "bf16", "C3 full size, sampled rows")
+
+
+def test_full_size_c4_sampled_rows_against_the_oracle():
+    # the FULL C4 launch (B4, 24 heads, 512 txt + 4096 img), 64 random (batch, head, row) triples
+    B, H, S, D = 4, 24, 4608, 128
+    g = torch.Generator(device=DEV).manual_seed(4238)
+    q, k, v = (torch.randn((B, S, H, D), generator=g, device=DEV).bfloat16().transpose(1, 2) for _ in range(3))
+    o = omx.fast.scaled_dot_product_attention(q, k, v, D ** -0.5, None)
+    assert omx.last_kernel() == "fmha_tcgen05"
+    rng = np.random.default_rng(12)
+    triples = [(int(rng.integers(B)), int(rng.integers(H)), int(rng.integers(S))) for _ in range(60)]
+    triples += [(0, 0, 0), (3, 23, S - 1), (1, 7, 511), (1, 7, 512)]
+    got = np.stack([o[b, h, r].float().cpu().numpy() for b, h, r in triples])
+    assert_close(got, _oracle_rows(q, k, v, triples, 1, False), "bf16", "C4 full size, sampled rows")
+
+
 def test_full_size_properties_c4():
     # BASELINE C4 at full size (FLUX.2-klein joint attention: B4, 24 heads, 512 txt + 4096 img tokens, bf16)
     B, H, S, D = 4, 24, 4608, 128

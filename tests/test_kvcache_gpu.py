@@ -150,3 +150,21 @@ def test_c2_sized_cache_fill_bit_exact():
     gk, gv = c.update_and_fetch(k, v)
     assert c.offset() == S and c.state()[0].shape[2] == S
     assert torch.equal(gk, k) and torch.equal(gv, v)
+
+
+def test_view_survives_one_growth_step():
+    # the reference returns refcounted arrays; here fetched views are borrowed, and the buffer a growth step
+    # replaces stays allocated until the NEXT growth: a view taken before a growth still reads its rows after it
+    c = omx.KVCache()
+    k = randn((1, 2, 250, 64), "bf16", 5, DEV)
+    K0, V0 = c.update_and_fetch(k, k)
+    snap = K0.clone()
+    k2 = randn((1, 2, 20, 64), "bf16", 6, DEV)
+    K1, _ = c.update_and_fetch(k2, k2)  # 250 + 20 > 256: grows, rows move to a new buffer
+    assert K1.data_ptr() != K0.data_ptr()
+    filler = [torch.empty(1 << 20, device=DEV) for _ in range(8)]  # would reuse the block had it been freed
+    for f in filler:
+        f.fill_(1.0)
+    torch.cuda.synchronize()
+    assert torch.equal(K0, snap), "the pre-growth view was clobbered"
+    assert torch.equal(K1[:, :, :250], snap)
