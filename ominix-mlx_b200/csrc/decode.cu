@@ -123,6 +123,14 @@ struct DecodeParams {
   // os[] holds that slot's strides; append = 0: this rank attends but does not own the new token
   int partial;
   int append;
+  // Rows [0, stable_rows) of the K/V buffers were written by launches that precede the stream's previous kernel
+  // (the cache's bookkeeping: kv_cache_stable_rows): the TMA kernel may request tiles that lie wholly inside them
+  // BEFORE the dependency wait of its programmatic launch.  0: nothing is read before the wait.
+  int stable_rows;
+  // TMA kernel: every tile request to shared memory also asks L2 for the tile `l2_ahead` tiles further on
+  // (bytes in flight per SM beyond what the ring holds); l2_early = tiles past the ring requested into L2 before
+  // the dependency wait.  0 = off.
+  int l2_ahead, l2_early;
   // debugging aid (OMX_DECODE_TRACE=1): per-CTA phase timestamps, [cta][16] x %globaltimer ns; null otherwise
   unsigned long long* trace;
 };
@@ -155,14 +163,17 @@ __device__ __forceinline__ void trace_mark(const DecodeParams& p, int slot) {
   }
 }
 
-// Programmatic dependent launch (PDL).  Every decode launch carries the programmatic-stream-serialization
-// attribute: its CTAs may be dispatched while the previous kernel on the stream is still running its tail, and
-// wait here -- before their FIRST global-memory access -- until that kernel has completed and its writes are
-// visible (cache rows, split-K scratch, counters, q produced by the caller's projection ...).  The other half:
-// once a CTA has left its key loop it lets the next kernel's CTAs be dispatched (the next grid starts when every
-// CTA of this one has said so or exited), so the dispatch latency of launch N+1 and the drain of launch N overlap
-// instead of adding up (~1-2 us per launch in a back-to-back decode loop).  A predecessor that never triggers
-// releases its dependents on completion, i.e. behaves like a plain stream-ordered launch.
+// Programmatic dependent launch (PDL).  Decode launches carry the programmatic-stream-serialization attribute:
+// their CTAs may be dispatched while the previous kernel on the stream is still running, and wait -- before
+// their first access to memory that kernel may write (q / k_new / v_new produced by the caller's projection,
+// the cache row it appended, split-K scratch, counters) -- until it has completed and its writes are visible.
+// The TMA kernel releases the NEXT grid right after its own wait: a grid is released once every CTA of its
+// predecessor has said so or exited, so at most two consecutive launches overlap and everything written two
+// launches back is complete.  What the overlap buys: the next launch's CTAs take the SMs this launch leaves
+// idle (a 128-CTA grid on 148 SMs, CTAs that finish early) and fill their TMA rings with cache rows that are
+// older than the previous launch (DecodeParams::stable_rows) while this launch drains its slowest CTAs and
+// combines; launch latency, barrier init and the tensor-map fetch go under the same cover.  A predecessor that
+// never triggers releases its dependents on completion, i.e. behaves like a plain stream-ordered launch.
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release_next_grid() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -822,23 +833,22 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
-  pdl_wait_prior_grid();
-  trace_mark(p, 0);
-  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot (whole CTA, whole cluster: same b)
-  const DecodeDyn dy = load_dyn(p, b);
-  const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
-  const int tile_begin = split * dy.tps;
-  const int my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
-  const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
-  const int* bt_row = p.paged ? p.block_table + (size_t)b * p.bt_stride : nullptr;
-  if (p.paged && has_nt && hk == 0 && tid == 0) p.lens_out[b] = dy.Lk;  // the sequence's length after this step
-
-  // The producer lane initialises the barriers and puts the first NSTAGE tiles in flight before (or, on
-  // one-wave grids, while) the CTA stages q: the K/V stream does not depend on q, and with only a dozen
-  // tiles per CTA (single sequence, many splits) the q round trip would otherwise sit in front of the
-  // whole pipeline.
+  // ---- before the dependency wait: shared memory, and cache rows no running kernel can still be writing
+  int tile_begin = split * p.tiles_per_split, my_tiles = 0;
+  const int* bt_row = nullptr;
   uint64_t pol = 0;
-  auto issue = [&](int t) {
+  int pf_next = 0;  // (producer lane) next tile of this CTA to request into L2
+  auto l2_upto = [&](int from, int hi) {
+    for (pf_next = max(pf_next, from); pf_next < hi; ++pf_next) {
+      const int k0 = p.paged ? 0 : (tile_begin + pf_next) * kTile;
+      const int c = p.paged ? __ldg(bt_row + tile_begin + pf_next) : b;
+      tma_prefetch_l2_4d(&tmK, 0, k0, hk, c);
+      tma_prefetch_l2_4d(&tmK, 64, k0, hk, c);
+      tma_prefetch_l2_4d(&tmV, 0, k0, hk, c);
+      tma_prefetch_l2_4d(&tmV, 64, k0, hk, c);
+    }
+  };
+  auto issue = [&](int t, int lim) {
     const int st = t % NSTAGE;
     uint8_t* sb = stages + st * kStageBytes;
     // contiguous cache: rows [key0, key0 + 64) of (b, hk); paged: the whole page block_table[b][tile]
@@ -849,8 +859,9 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     tma_load_4d(sb + kBoxBytes, &tmK, &full_bar[st], 64, key0, hk, c3, pol);
     tma_load_4d(sb + 2 * kBoxBytes, &tmV, &full_bar[st], 0, key0, hk, c3, pol);
     tma_load_4d(sb + 3 * kBoxBytes, &tmV, &full_bar[st], 64, key0, hk, c3, pol);
+    if (p.l2_ahead > 0) l2_upto(t + 1, min(lim, t + 1 + p.l2_ahead));
   };
-  const int first = min(my_tiles, NSTAGE);
+  int n_early = 0;  // (producer lane) tiles requested before the wait
   if (tid == NW * 32) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
@@ -858,25 +869,46 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       mbar_init(&empty_bar[s], 1);
     }
     mbar_fence_init();
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    pol = policy_evict_first();
+    if (p.stable_rows > 0) {  // host: static position, contiguous cache
+      const int mine = max(0, min(p.tiles_per_split, (p.n_mem + kTile - 1) / kTile - tile_begin));
+      const int lim = max(0, min(mine, p.stable_rows / kTile - tile_begin));
+      n_early = min(lim, NSTAGE);
+      for (int t = 0; t < n_early; ++t) issue(t, lim);
+      l2_upto(n_early, min(lim, n_early + p.l2_early));
+    }
   }
+  pdl_wait_prior_grid();
+  pdl_release_next_grid();
+  trace_mark(p, 0);
+  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot (whole CTA, whole cluster: same b)
+  const DecodeDyn dy = load_dyn(p, b);
+  const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
+  tile_begin = split * dy.tps;
+  my_tiles = max(0, min(dy.tps, n_tiles - tile_begin));
+  const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
+  bt_row = p.paged ? p.block_table + (size_t)b * p.bt_stride : nullptr;
+  if (p.paged && has_nt && hk == 0 && tid == 0) p.lens_out[b] = dy.Lk;  // the sequence's length after this step
+
+  // The producer lane puts the first NSTAGE tiles in flight before (or, on one-wave grids, while) the CTA
+  // stages q: the K/V stream does not depend on q, and with only a dozen tiles per CTA (single sequence, many
+  // splits) the q round trip would otherwise sit in front of the whole pipeline.
+  const int first = min(my_tiles, NSTAGE);
   // One-wave grids (MINB == 1, single-sequence decode): the producer warp and the consumer warps run apart --
-  // the producer lane fetches the tensor maps and puts the first tiles in flight (~1 us of serial issue)
+  // the producer lane puts the first tiles in flight (~1 us of serial issue)
   // WHILE the consumer warps stage q; barrier 2 = the consumer warps among themselves, barrier 1 = "q is
   // staged" for the producer warp (consumers arrive without blocking).  A/B in one box: fused step -1..-2.6 %.
   // Multi-wave grids (C2) keep the single-barrier flow, which measured 0.3 % faster there.
   constexpr bool kDecouple = MINB == 1;
   if constexpr (kDecouple) __syncthreads();  // barriers initialised before anyone waits on them
-  if (warp == NW || !kDecouple) {
-    if (tid == NW * 32) {
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      pol = policy_evict_first();
-      for (int t = 0; t < first; ++t) issue(t);
-      if (p.trace) {
-        unsigned long long tt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
-        p.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + 7] = tt;
-      }
+  if (tid == NW * 32) {
+    for (int t = n_early; t < first; ++t) issue(t, my_tiles);
+    if (p.trace) {
+      unsigned long long tt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+      p.trace[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 16 + 7] = tt;
     }
   }
   if constexpr (kDecouple) {
@@ -930,7 +962,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     if (lane == 0) {
       for (int t = first; t < my_tiles; ++t) {
         mbar_wait(&empty_bar[t % NSTAGE], ((t / NSTAGE) - 1) & 1);
-        issue(t);
+        issue(t, my_tiles);
       }
     }
     __syncwarp();
@@ -1062,7 +1094,6 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
       }
   }
   __syncthreads();  // every stage consumed -> the ring is reused for the merge
-  pdl_release_next_grid();
   trace_mark(p, 2);
   if (warp < NW) {
     float* mo = reinterpret_cast<float*>(stages);  // [NW][16][128]
@@ -1340,17 +1371,25 @@ int cluster_capacity(K kern, dim3 grid, int threads, size_t smem, int cluster_x)
   return n;
 }
 
-// Which launches carry the programmatic-dependent-launch attribute.  Measured in one box, CUDA-graph replays
-// (scripts/gpu_r02_pdl_ab.sh): the CUDA-core kernel gains (C1 15.56 -> 14.64 us: its CTAs are small, the next
-// grid's CTAs become resident beside the running ones), the TMA kernel does not (one CTA fills an SM's shared
-// memory, early CTAs only spin on the idle SMs: C2 at 8 rows per GPU 45.2 -> 45.8 us, C5 30.5 -> 31.6 us), so
-// the default is CUDA-core launches only.  OMX_DECODE_PDL=0 / 1 forces it off / on everywhere (A/B knob).
+// Which launches carry the programmatic-dependent-launch attribute: all of them.  CUDA-graph replays in one box
+// (scripts/gpu_r02_pdl_ab.sh): the CUDA-core kernel gains from the overlapped dispatch alone (C1 15.56 -> 14.64 us);
+// the TMA kernel -- one CTA fills an SM's shared memory -- only once its next launch fills its rings under the
+// running launch's tail (stable_rows, see pdl_wait_prior_grid).  OMX_DECODE_PDL=0 / 1 forces the attribute off /
+// on everywhere, OMX_DECODE_EARLY=0 keeps every read behind the wait (A/B knobs).
 bool pdl_enabled(bool simt) {
   static const int forced = [] {
     const char* e = getenv("OMX_DECODE_PDL");
     return e ? (atoi(e) != 0 ? 1 : 0) : -1;
   }();
-  return forced >= 0 ? forced == 1 : simt;
+  (void)simt;
+  return forced != 0;
+}
+bool early_reads_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OMX_DECODE_EARLY");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
 }
 
 template <typename K, typename... Args>
@@ -1733,6 +1772,17 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     p.pos_stride = 0;
     p.max_rows = f.max_rows;
   }
+  if (f.enabled && !dyn && !paged && early_reads_enabled() && pdl_enabled(false))
+    p.stable_rows = std::max(0, std::min(f.stable_rows, p.n_mem));
+  {
+    // sweep knobs (scripts/gpu_r02_l2_ab*.sh).  In-loop L2 requests measured 10 % SLOWER at every batch (a tile
+    // asked into L2 and then loaded evict-first costs more than it hides), so l2_ahead stays 0; the pre-wait
+    // depth is set per grid type below (l2_early < 0 here = default).
+    static const int ahead = [] { const char* e = getenv("OMX_DECODE_L2AHEAD"); return e ? atoi(e) : 0; }();
+    static const int early = [] { const char* e = getenv("OMX_DECODE_L2EARLY"); return e ? atoi(e) : -1; }();
+    p.l2_ahead = std::max(0, ahead);
+    p.l2_early = early;
+  }
   if (paged) {
     // a.k / a.v describe the POOL: data = base, strides[0] = page stride, [1] = head stride inside a page,
     // [2] = row stride; a.Lk = longest sequence after the step (host mirror) -- it sizes the split plan only,
@@ -1809,6 +1859,10 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     const bool deep = cfg_env == 1 || (cfg_env < 0 && pairs * natural.num_splits <= sms);
     const int cfg = deep ? 1 : 0;
     const int NSTAGE = cfg == 1 ? 6 : 3;  // consumer warps == stages (see kernel comment)
+    // tiles past the ring asked into L2 before the dependency wait: ~5 us of the previous launch's tail x HBM
+    // rate = 8 tiles per CTA on one-wave grids (8 rows x 8 kv heads: 44.6 -> 42.9 us, 16 rows: 80.6 -> 79.0);
+    // multi-wave grids only overlap their last wave (32 rows: 160.2 -> 157.9, 64 rows: 305.7 -> 303.7)
+    if (p.l2_early < 0) p.l2_early = deep ? 8 : 4;
     p.peer_total = (int)pairs;
     const bool bf = a.q->dtype == OMX_BFLOAT16;
     // graph mode: the map spans every reserved row (the tail beyond the position is masked in the kernel)

@@ -102,6 +102,12 @@ struct KVCacheImpl {
   int64_t reserve_rows = 0;
   KVBuf k, v;
   cudaStream_t last_stream = nullptr;
+  // Rows [0, stable_now) were written by calls that precede the cache's most recent writing call, i.e. not by
+  // the kernel that may still be running when the next launch on the stream is dispatched early (programmatic
+  // dependent launch, decode.cu): the fused decode step may request them before its dependency wait.
+  // stable_next = rows in place before the most recent write (becomes stable_now at the next update);
+  // a call that grows / moves / zero-fills the buffer starts from 0.
+  int stable_next = 0, stable_now = 0;
   // graph mode
   int64_t graph_rows = 0;  // rows pinned by prepare_graph (0: not prepared)
   void* scratch = nullptr;
@@ -125,6 +131,7 @@ void kv_cache_destroy(KVCacheImpl* c) {
 }
 
 int kv_cache_offset(const KVCacheImpl* c) { return c->offset; }
+int kv_cache_stable_rows(const KVCacheImpl* c) { return c->stable_now; }
 bool kv_cache_is_concat(const KVCacheImpl* c) { return c->concat; }
 
 void kv_cache_reset(KVCacheImpl* c) {
@@ -135,6 +142,8 @@ int kv_cache_trim(KVCacheImpl* c, int n) {
   OMX_CHECK(!c->concat, "[KVCache] trim is not defined for ConcatKeyValueCache");
   const int t = std::max(0, std::min(n, c->offset));
   c->offset -= t;
+  c->stable_next = std::min(c->stable_next, c->offset);  // trimmed rows are rewritten by later steps
+  c->stable_now = std::min(c->stable_now, c->offset);
   return t;
 }
 
@@ -199,6 +208,10 @@ void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* val
     OMX_CHECK(keys->shape[i] == values->shape[i], "[KVCache] keys/values shape mismatch on axis %d", i);
   const int prev = c->offset;
   const int n = (int)keys->shape[2];
+  // rows the launch of THIS call may read ahead of its dependency wait (see KVCacheImpl::stable_now); a change
+  // of stream is ordered by the caller with events, which says nothing about the new stream's previous kernel
+  c->stable_now = (c->concat || stream != c->last_stream) ? 0 : std::min(c->stable_next, prev);
+  c->stable_next = prev;
   c->last_stream = stream;
 
   if (c->has) {
@@ -263,6 +276,7 @@ void kv_cache_update(KVCacheImpl* c, const omx_array* keys, const omx_array* val
     regrow(c, c->k, keep, new_cap, true, stream);
     regrow(c, c->v, keep, new_cap, true, stream);
     c->cap = new_cap;
+    c->stable_now = 0;  // copies / zero fills of this very call precede the launch
   }
   c->offset = prev + n;  // :183
   if (n > 0 && !skip_copy) {  // :187-188 slice update
@@ -284,6 +298,7 @@ void kv_cache_prepare_graph(KVCacheImpl* c, int max_rows, size_t scratch_bytes, 
   OMX_CHECK(max_rows >= c->offset + 1, "[KVCache] prepare_graph: max_rows %d leaves no room after offset %d", max_rows,
             c->offset);
   c->last_stream = stream;
+  c->stable_next = c->stable_now = 0;  // the buffers may move
   // the logical capacity can run up to one step past the last position (cache.rs:152-174): pin that too
   const int64_t pin = ((int64_t)max_rows + c->step - 1) / c->step * c->step + c->step;
   c->reserve_rows = std::max<int64_t>(c->reserve_rows, pin);
@@ -365,6 +380,8 @@ void kv_cache_rollback(KVCacheImpl* c, const KVCacheSnapshot& s, cudaStream_t st
   // rows [offset, cap) that a growth zero-filled stay zero; they are past the offset, i.e. never fetched
   c->offset = s.offset;
   c->cap = s.cap;
+  c->stable_next = std::min(c->stable_next, c->offset);
+  c->stable_now = 0;
 }
 
 void kv_cache_shape(const KVCacheImpl* c, int* B, int* H, int* Dk, int* Dv, int* dtype) {

@@ -434,6 +434,7 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     f.rope_dims = rope_dims;
     f.traditional = traditional;
     f.position = position;
+    f.stable_rows = kv_cache_stable_rows(c);
     f.peers = peers;
     f.peer_wait = peer_wait;
     f.head_offset = 0;  // out_local already starts at this rank's first head

@@ -57,6 +57,8 @@ struct KVCacheImpl;
 KVCacheImpl* kv_cache_create(int step, bool concat);
 void kv_cache_destroy(KVCacheImpl* c);
 int kv_cache_offset(const KVCacheImpl* c);
+// rows the launch of the call that just updated the cache may read before its dependency wait (decode.cu, PDL)
+int kv_cache_stable_rows(const KVCacheImpl* c);
 void kv_cache_reset(KVCacheImpl* c);
 void kv_cache_reserve(KVCacheImpl* c, int rows);
 int kv_cache_trim(KVCacheImpl* c, int n);
@@ -154,6 +156,9 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   size_t scratch_bytes = 0;
   // paged cache (paged_kv.cu): K/V views describe the page pool, per-sequence lengths live in device memory
   const struct PagedRef* paged = nullptr;
+  // rows [0, stable_rows) of k / v are older than the stream's previous kernel (kv_cache_stable_rows): the TMA
+  // kernel requests them before the dependency wait of its programmatic launch.  0 = unknown.
+  int stable_rows = 0;
 };
 struct PagedRef {
   const int* block_table = nullptr;  // [B][bt_stride] page ids, device

@@ -233,3 +233,31 @@ def test_failed_first_update_forgets_the_latched_shape():
     k4 = randn((1, 4, 3, 64), "bf16", 3, DEV)  # a different geometry is still acceptable: nothing was latched
     gc.update_and_fetch(k4, k4)
     assert gc.offset() == 3 and tuple(gc.state()[0].shape) == (1, 4, 256, 64)
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,start", [(1, 8, 2, 190), (2, 32, 8, 1000)])
+def test_back_to_back_steps_overlapped_launches(B, Hq, Hkv, start):
+    """Consecutive fused steps on ONE cache with no host synchronisation in between: launch t+1 is dispatched
+    while launch t still runs (programmatic dependent launch) and requests the cache rows older than launch t
+    before its dependency wait -- row `offset - 1`, written by launch t, must still be read after it.  Every
+    step's output and the final cache contents are compared with the oracle chain."""
+    D, dtype, steps = 128, "bf16", 40
+    gc, oc = _prefill(B, Hkv, start, D, dtype, 90)
+    rope = omx.nn.Rope(*ROPE)
+    scale = D ** -0.5
+    qs = randn((steps, B, Hq, 1, D), dtype, 91)
+    ks = randn((steps, B, Hkv, 1, D), dtype, 92)
+    vs = randn((steps, B, Hkv, 1, D), dtype, 93)
+    qd, kd, vd = qs.to(DEV), ks.to(DEV), vs.to(DEV)
+    outs = torch.empty((steps, B, Hq, 1, D), dtype=torch.bfloat16, device=DEV)
+    torch.cuda.synchronize()
+    for i in range(steps):
+        omx.attn_decode_fused(qd[i], kd[i], vd[i], gc, rope, scale, out=outs[i])
+    torch.cuda.synchronize()
+    assert omx.last_kernel() == "decode_hmma_tma"
+    for i in range(steps):
+        want = _oracle_step(oc, t2n(qs[i], dtype), t2n(ks[i], dtype), t2n(vs[i], dtype), dtype, ROPE, scale)
+        assert_close(outs[i].float().cpu().numpy(), n2f(want, dtype), dtype, f"back-to-back step {i}")
+    sk, sv = gc.state()
+    assert_bits_equal(sk, oc.keys, dtype, "KV cache keys after back-to-back steps")
+    assert_bits_equal(sv, oc.values, dtype, "KV cache values after back-to-back steps")
