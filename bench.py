@@ -840,7 +840,9 @@ class Bench:
                 rec, st = self.run_decode(name, cfg, [0], 1, steps, warmup, False)
                 rec["scaling"] = "single GPU"
             else:
-                rec = self.run_c5_sharded(cfg, "peer", steps, warmup)
+                # "peer" = data + flag words (omx_attn_decode_fused_sharded_ll); OMX_BENCH_C5_GATHER=peer_flags
+                # selects the r01 peer stores + arrival counters for A/B runs
+                rec = self.run_c5_sharded(cfg, os.environ.get("OMX_BENCH_C5_GATHER", "peer"), steps, warmup)
                 rec["scaling"] = "strong"
         elif name == "c5_collective":
             rec = self.run_c5_sharded(cfg, "collective", steps, warmup)

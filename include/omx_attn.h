@@ -360,6 +360,36 @@ int omx_attn_decode_fused_sharded_sync(const omx_array* out_full, const omx_arra
                                        const omx_array* freqs /* may be null */, float sm_scale,
                                        const omx_peer_group* peers, int head_offset, omx_stream s);
 
+/*
+ * The same step with a DATA + FLAG exchange (what NCCL calls the LL protocol): each rank owns a staging buffer of
+ * 8-byte words {payload (two 16-bit or one 32-bit element), sequence number of the step}; the thread that holds
+ * final output values stores them as such words into every peer's staging buffer (an aligned 8-byte store is one
+ * NVLink transaction, so a word whose flag equals the step's sequence number carries the step's payload) and
+ * then polls its own staging buffer for the same words of every peer, writing them into the local out_full.
+ * No system-scope fence, no arrival counters, no last-CTA ticket: the exchange costs one NVLink store latency.
+ * The launch completes when the full [B,Hq_total,1,D] output is in place in the LOCAL, private out_full (peers
+ * never write it, so it needs no double buffering).
+ *   staging[r]: rank r's buffer, uint64 [2][world][B * Hq_local * D * sizeof(T) / 4] (two halves alternate by
+ *               step parity: a rank can run at most one step ahead of a peer), zero-initialised, mapped into
+ *               this process; seq: LOCAL uint32 counter of completed steps (zero-initialised; every rank of the
+ *               group runs the same sequence of sharded launches, so the counters agree).
+ * Every rank of the group must launch its step.  Launch shapes that do not finish in the all-CTA combine run the
+ * plain local step followed by a one-CTA exchange kernel with the same protocol (two launches).
+ */
+typedef struct omx_ll_group_ {
+  int32_t world; /* <= OMX_MAX_PEERS */
+  int32_t rank;
+  void* staging[OMX_MAX_PEERS];
+  uint32_t* seq;
+} omx_ll_group;
+int omx_attn_decode_fused_sharded_ll(const omx_array* out_full, const omx_array* q, const omx_array* k_new,
+                                     const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                                     omx_optional_float base, float rope_scale,
+                                     const omx_array* freqs /* may be null */, float sm_scale,
+                                     const omx_ll_group* group, int head_offset, omx_stream s);
+/* bytes of one rank's staging buffer for a [B,Hq_local,1,D] slice of `dtype` */
+size_t omx_ll_staging_bytes(int world, int64_t B, int64_t Hq_local, int64_t D, int dtype);
+
 /* ---- sequence-sharded single-sequence decode ---------------- */
 /*
  * For contexts that should not (or do not) live on one GPU: rank r keeps the K/V rows of the token

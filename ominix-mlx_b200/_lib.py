@@ -41,6 +41,11 @@ class OmxPeerGroup(ctypes.Structure):
                 ("out", ctypes.c_void_p * OMX_MAX_PEERS), ("flags", ctypes.c_void_p * OMX_MAX_PEERS)]
 
 
+class OmxLLGroup(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("staging", ctypes.c_void_p * OMX_MAX_PEERS), ("seq", ctypes.c_void_p)]
+
+
 class Exception_(RuntimeError):
     """Counterpart of mlx_rs::error::Exception {what} (mlx-rs/src/error.rs)."""
 
@@ -113,6 +118,11 @@ _SIGS = {
     "omx_attn_decode_fused_sharded_sync": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                           OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
                                                           ctypes.POINTER(OmxPeerGroup), ctypes.c_int, ctypes.c_void_p]),
+    "omx_attn_decode_fused_sharded_ll": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
+                                                        OmxOptionalFloat, ctypes.c_float, _AP, ctypes.c_float,
+                                                        ctypes.POINTER(OmxLLGroup), ctypes.c_int, ctypes.c_void_p]),
+    "omx_ll_staging_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                               ctypes.c_int]),
     "omx_attn_decode_seqshard": (ctypes.c_int, [_AP, _AP, _AP, _AP, OmxKVCache, ctypes.c_int, ctypes.c_bool,
                                                 OmxOptionalFloat, ctypes.c_float, ctypes.c_int, ctypes.c_bool,
                                                 ctypes.c_float, ctypes.POINTER(OmxPeerGroup), ctypes.c_void_p]),

@@ -53,6 +53,89 @@ namespace dd {  // shared by the three compilation parts of this file (same defi
 
 constexpr int kMaxPeers = OMX_MAX_PEERS;
 
+// ---- data + flag ("LL") exchange over NVLink peer mappings
+// staging of rank r: uint64 [2 (step parity)][world (source rank)][words]; word = {payload, sequence number}
+struct LLDev {
+  int world, rank;            // world == 0: off
+  unsigned long long* buf[kMaxPeers];
+  unsigned* seq;              // local count of completed steps
+  int words;                  // words per source rank
+};
+__device__ __forceinline__ void st_ll(unsigned long long* a, uint32_t data, uint32_t flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(a), "r"(data), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const unsigned long long* a) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a) : "memory");
+  return v;
+}
+// One lane exchanges NW consecutive words starting at word w0 of its rank's slice: store to every peer, then
+// poll the local staging buffer until every peer's words of step `seq` have landed; sink(src, words) consumes them.
+template <int NW, typename Sink>
+__device__ __forceinline__ void ll_exchange(const LLDev& ll, unsigned seq, int64_t w0, const uint32_t (&w)[NW],
+                                            Sink&& sink) {
+  const int64_t half = (int64_t)(seq & 1u) * ll.world;
+#pragma unroll
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (r >= ll.world || r == ll.rank) continue;
+    unsigned long long* dst = ll.buf[r] + (half + ll.rank) * ll.words + w0;
+#pragma unroll
+    for (int j = 0; j < NW; ++j) st_ll(dst + j, w[j], seq);
+  }
+  unsigned pend = ((1u << ll.world) - 1u) & ~(1u << ll.rank);
+  const unsigned long long* mine = ll.buf[ll.rank] + half * ll.words + w0;
+  unsigned spins = 0;
+  while (pend) {
+    uint2 v[kMaxPeers][NW];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if ((pend >> r) & 1u) {
+#pragma unroll
+        for (int j = 0; j < NW; ++j) v[r][j] = ld_ll(mine + (int64_t)r * ll.words + j);
+      }
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; ++r)
+      if ((pend >> r) & 1u) {
+        bool ok = true;
+        uint32_t d[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+          ok = ok && v[r][j].y == seq;
+          d[j] = v[r][j].x;
+        }
+        if (ok) {
+          sink(r, d);
+          pend &= ~(1u << r);
+        }
+      }
+    if (++spins > (1u << 24)) __trap();  // a lost peer becomes a launch failure, not a hung GPU
+  }
+}
+template <typename T>
+struct LLPack;  // four consecutive elements <-> words
+template <>
+struct LLPack<float> {
+  static constexpr int NW = 4;
+  __device__ static void pack(const float4& v, uint32_t (&w)[4]) {
+    w[0] = __float_as_uint(v.x); w[1] = __float_as_uint(v.y); w[2] = __float_as_uint(v.z); w[3] = __float_as_uint(v.w);
+  }
+  __device__ static void store(float* dst, const uint32_t (&w)[4]) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <typename T>
+struct LLPack {  // 16-bit types
+  static constexpr int NW = 2;
+  __device__ static void pack(const float4& v, uint32_t (&w)[2]) {
+    union { T t[4]; uint32_t u[2]; } x;
+    x.t[0] = Num<T>::from_f(v.x); x.t[1] = Num<T>::from_f(v.y); x.t[2] = Num<T>::from_f(v.z); x.t[3] = Num<T>::from_f(v.w);
+    w[0] = x.u[0]; w[1] = x.u[1];
+  }
+  __device__ static void store(T* dst, const uint32_t (&w)[2]) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  }
+};
+
 struct DecodeParams {
   const void* q;
   void* out;
@@ -131,6 +214,18 @@ struct DecodeParams {
   // (bytes in flight per SM beyond what the ring holds); l2_early = tiles past the ring requested into L2 before
   // the dependency wait.  0 = off.
   int l2_ahead, l2_early;
+  // 1: split-K combine by ALL CTAs of the pair (one-wave grids only: every CTA is resident).  Each CTA publishes
+  // its partial, the CTAs of a (batch, kv-head) pair meet at a counter, and every CTA then folds ITS slice of the
+  // output columns over all partials in one round trip to L2 -- instead of the last CTA folding everything
+  // (a 64-way split: 6.7 us of dependent round trips in one CTA).  counters2[pair] counts the CTAs that have left.
+  int gsync;
+  int* counters2;
+  // data + flag exchange of the head-sharded step (omx_attn_decode_fused_sharded_ll; all-CTA combine only): the
+  // lane that holds four final output values stores them as {payload, sequence number} words into every peer's
+  // staging buffer, then polls its own staging buffer for the peers' words and unpacks them into ll_out (the
+  // local full-head output, strides os[]).  n_peers stays 0: `out` is the private local slice.
+  LLDev ll;
+  void* ll_out;
   // debugging aid (OMX_DECODE_TRACE=1): per-CTA phase timestamps, [cta][16] x %globaltimer ns; null otherwise
   unsigned long long* trace;
 };
@@ -474,6 +569,23 @@ __device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, i
   }
 }
 
+// all-CTA combine: NS splits are laid over groups of W lanes, K groups per output column
+struct GsyncShape {
+  int W, K;
+};
+__host__ __device__ inline GsyncShape gsync_shape(int ns) {
+  if (ns > 32) return {32, (ns + 31) / 32};
+  int w = 1;
+  while (w < ns) w <<= 1;
+  return {w, 1};
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- thread-block cluster primitives (split-K combine through distributed shared memory)
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -668,6 +780,165 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     // nobody may leave while a peer can still read its shared memory
     cluster_arrive_release();
     cluster_wait_acquire();
+    trace_mark(p, 6);
+    return;
+  }
+  if (p.gsync) {
+    // ---- all-CTA combine (one-wave grids).  publish -> meet -> every CTA folds its own column slice.
+    // Lanes run over the SPLITS: a group of W lanes holds one float4 column's contributions, so the per-head
+    // maximum / sum and the fold are warp shuffles; what is left of the tail is one round trip to L2 after the
+    // meeting point (partials + (m, l) requested together) and at most one CTA barrier behind it.
+    const int NS = p.num_splits;
+    __threadfence();
+    __syncthreads();
+    trace_mark(p, 4);
+    const int D4 = D >> 2;
+    const int C = n_heads * D4;                 // float4 columns of the pair's output
+    const int slice = (C + NS - 1) / NS;
+    const int c0 = split * slice, c1 = min(C, c0 + slice);
+    const int ncol = max(0, c1 - c0);
+    const GsyncShape gs = gsync_shape(NS);
+    const int W = gs.W, K = gs.K, cpw = 32 / W;
+    const int n_wi = W == 32 ? ncol * K : (ncol + cpw - 1) / cpw;  // warp-sized work items (host: <= 4 per warp)
+    const int nwarps = nthr >> 5, warp = tid >> 5, lane = tid & 31;
+    const int g0 = ncol ? c0 / D4 : 0, g1 = ncol ? (c1 - 1) / D4 : -1;  // heads the slice touches
+    const int nh = g1 - g0 + 1;
+    const int mlp = (NS * nh + 3) & ~3;
+    float* sm_m = const_cast<float*>(mo);       // [NS][nh]  (the merge inputs are dead: the own partial is in ws)
+    float* sm_l = sm_m + mlp;                   // [NS][nh]
+    float4* red = reinterpret_cast<float4*>(sm_l + mlp);  // [ncol][K]   (K > 1 only)
+    float* sm_inv = reinterpret_cast<float*>(red + ncol * K);  // [ncol]
+    const int64_t e0p = (int64_t)pair * NS * n_heads;
+    if (tid == 0) {
+      atomicAdd(&p.counters[pair], 1);
+      unsigned spins = 0;
+      while (ld_acquire_gpu(&p.counters[pair]) < NS)
+        if (++spins > (1u << 26)) __trap();  // a CTA that never became resident: a launch failure, not a hung GPU
+    }
+    __syncthreads();
+    trace_mark(p, 5);
+    // item i of this warp: column colL (local), split sp
+    auto item = [&](int i, int& colL, int& sp) {
+      const int wi = warp + i * nwarps;
+      if (W == 32) {
+        colL = wi / K;
+        sp = (wi % K) * 32 + lane;
+      } else {
+        colL = wi * cpw + lane / W;
+        sp = lane % W;
+      }
+      return wi < n_wi && colL < ncol && sp < NS;
+    };
+    float4 pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int colL, sp;
+      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item(i, colL, sp)) {
+        const int col = c0 + colL;
+        pre[i] = __ldcg(reinterpret_cast<const float4*>(p.ws_o + (e0p + (int64_t)sp * n_heads + col / D4) * D +
+                                                        (col % D4) * 4));
+      }
+    }
+    for (int idx = tid; idx < NS * nh; idx += nthr) {
+      const int sp = idx / nh, g = g0 + idx % nh;
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + (int64_t)sp * n_heads + g) * 2]));
+      sm_m[idx] = ml.x;
+      sm_l[idx] = ml.y;
+    }
+    __syncthreads();
+    trace_mark(p, 9);
+    // four consecutive features of local head g: plain stores, or the data + flag exchange
+    const unsigned ll_seq = p.ll.world ? __ldcg(p.ll.seq) + 1u : 0u;
+    auto emit4 = [&](int g, int d, const float4& v) {
+      const int64_t o = ob + (int64_t)(first_head + g) * p.os[1] + (int64_t)d * p.os[3];
+      if (p.ll.world == 0) {
+        store_out<T>(p, o, v.x);
+        store_out<T>(p, o + p.os[3], v.y);
+        store_out<T>(p, o + 2 * p.os[3], v.z);
+        store_out<T>(p, o + 3 * p.os[3], v.w);
+        return;
+      }
+      using LP = dd::LLPack<T>;
+      uint32_t w[LP::NW];
+      LP::pack(v, w);
+      LP::store((T*)p.out + o, w);  // the local slice (host: os[3] == 1, 16-byte aligned rows)
+      const int64_t e = ((int64_t)b * p.Hq + first_head + g) * D + d;  // element of this rank's [B,Hq,D] slice
+      dd::ll_exchange<LP::NW>(p.ll, ll_seq, e * (int64_t)sizeof(T) / 4, w, [&](int src, const uint32_t (&r)[LP::NW]) {
+        LP::store((T*)p.ll_out + b * p.os[0] + ((int64_t)src * p.Hq + first_head + g) * p.os[1] + d, r);
+      });
+    };
+    auto group_max = [&](float v) {
+      for (int o = W >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+      return v;
+    };
+    auto group_sum = [&](float v) {
+      for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      return v;
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (warp + i * nwarps >= n_wi) break;  // warp-uniform
+      int colL, sp;
+      const bool valid = item(i, colL, sp);
+      const int cc = min(colL, ncol - 1);     // lanes past the slice compute on its last column and store nothing
+      const int col = c0 + cc, g = col / D4, gi = g - g0;
+      float M = -INFINITY;
+      for (int s2 = lane % W; s2 < NS; s2 += W) M = fmaxf(M, sm_m[s2 * nh + gi]);
+      M = group_max(M);
+      float L = 0.f;
+      for (int s2 = lane % W; s2 < NS; s2 += W) {
+        const float ms = sm_m[s2 * nh + gi];
+        if (ms > -INFINITY) L = fmaf(sm_l[s2 * nh + gi], fast_exp2(ms - M), L);
+      }
+      L = group_sum(L);
+      const float mine = valid ? sm_m[sp * nh + gi] : -INFINITY;
+      const float e = mine > -INFINITY ? fast_exp2(mine - M) : 0.f;
+      float4 c = make_float4(group_sum(pre[i].x * e), group_sum(pre[i].y * e), group_sum(pre[i].z * e),
+                             group_sum(pre[i].w * e));
+      const bool lead = colL < ncol && (lane % W) == 0 && (W < 32 || (warp + i * nwarps) % K == 0);
+      if (lead && col % D4 == 0) {  // the CTA that owns the head's first column reports the row
+        store_ml(p, b, first_head + g, M, L);
+        if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+      }
+      if (K == 1) {
+        if (lead) {
+          const float inv = 1.0f / L;
+          emit4(g, (col % D4) * 4, make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv));
+        }
+      } else if (colL < ncol && lane == 0) {
+        red[colL * K + (warp + i * nwarps) % K] = c;
+        if (lead) sm_inv[colL] = 1.0f / L;
+      }
+    }
+    if (K > 1) {
+      __syncthreads();
+      trace_mark(p, 10);
+      for (int colL = tid; colL < ncol; colL += nthr) {
+        float4 a = red[colL * K];
+        for (int k = 1; k < K; ++k) {
+          const float4 r = red[colL * K + k];
+          a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        }
+        const float inv = sm_inv[colL];
+        const int col = c0 + colL;
+        emit4(col / D4, (col % D4) * 4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+      }
+    }
+    trace_mark(p, 11);
+    peer_signal(p, tid);  // (peer_total counts every CTA of the launch in this mode)
+    if (p.ll.world) __syncthreads();  // this CTA's exchange is complete
+    if (tid == 0) {
+      const int t = atomicAdd(&p.counters2[pair], 1);
+      if (t == NS - 1) {  // everybody has passed the meeting point: reset both counters for the next launch
+        p.counters[pair] = 0;
+        p.counters2[pair] = 0;
+      }
+      if (p.ll.world && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
+        *p.peer_done = 0;     // the launch's last CTA: every word of the step has been sent and received here
+        *p.ll.seq = ll_seq;
+      }
+    }
     trace_mark(p, 6);
     return;
   }
@@ -1435,20 +1706,41 @@ SplitPlan clamp_for_cluster(SplitPlan sp, int n_tiles, int cap) {
   return {(n_tiles + tps - 1) / tps, tps};
 }
 
+// All-CTA combine (DecodeParams::gsync): one-wave grids whose splits are not combined through a cluster.
+// OMX_DECODE_GSYNC=0 keeps the last-CTA combine (A/B knob).
+constexpr int kMaxSplitsGsync = 160;  // > the SM count: a one-wave grid never has more CTAs per pair
+bool gsync_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OMX_DECODE_GSYNC");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
+// does the slice bookkeeping of merge_and_store fit the merge scratch (n_ent x rows x D floats) and 4 items per warp?
+bool gsync_fits(int splits, int n_heads, int D, int nthr, int scratch_floats) {
+  const int D4 = D / 4, C = n_heads * D4;
+  const int slice = (C + splits - 1) / splits;
+  const GsyncShape gs = gsync_shape(splits);
+  const int n_wi = gs.W == 32 ? slice * gs.K : (slice + 32 / gs.W - 1) / (32 / gs.W);
+  const int nh = std::min(n_heads, (slice + D4 - 2) / D4 + 1);
+  const int ml = (splits * nh + 3) & ~3;
+  return n_wi <= 4 * (nthr / 32) && 2 * ml + 4 * slice * gs.K + slice <= scratch_floats;
+}
+
 // Split-K plan.  HBM bandwidth is a chip-wide resource, so what matters is (a) enough CTAs in flight
 // to cover it -- about one per SM, each with >= 96 KB of TMA loads outstanding -- and (b) as little
 // per-CTA overhead (q staging, partial write, combine) as possible.  Measured on B200
 // (gpurun_out/s19_sweep.log): C2 (512 (batch, kv-head) pairs) is fastest with NO split (299 us vs 315 us
 // with 4); C5 (8 pairs) is fastest with one CTA per SM (18 splits: 31 us; 37 splits: 40 us; 9: 33 us).
-SplitPlan plan_splits(int64_t pairs, int n_tiles, int sms, int min_tiles) {
+SplitPlan plan_splits(int64_t pairs, int n_tiles, int sms, int min_tiles, int cap = kMaxSplits) {
   if (n_tiles <= 0) return {1, 1};
   static const int forced = [] {  // debugging / tuning knob, not an API
     const char* e = getenv("OMX_DECODE_SPLITS");
     return e ? atoi(e) : 0;
   }();
   int want = forced > 0 ? forced : (pairs >= sms ? 1 : (int)(sms / pairs));
-  const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), kMaxSplits));
-  want = std::max(1, std::min(want, forced > 0 ? std::min(n_tiles, kMaxSplits) : max_s));
+  const int max_s = std::max(1, std::min(n_tiles / std::max(1, min_tiles), cap));
+  want = std::max(1, std::min(want, forced > 0 ? std::min(n_tiles, cap) : max_s));
   const int tps = (n_tiles + want - 1) / want;
   return {(n_tiles + tps - 1) / tps, tps};
 }
@@ -1465,6 +1757,11 @@ void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool o
     p.cluster = want_cluster && p.num_splits > 1 &&
                         cluster_capacity(kern, grid, kSimtWarps * 32, smem, p.num_splits) >= (int)(grid.y * grid.z)
                     ? 1 : 0;
+    const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+    p.gsync = (!p.cluster && p.num_splits > 1 && p.counters2 && gsync_enabled() && ctas <= sm_count() &&
+               gsync_fits(p.num_splits, gt, 32 * VE, kSimtWarps * 32, kSimtWarps * gt * 32 * VE))
+                  ? 1 : 0;
+    if (p.gsync) p.peer_total = (int)ctas;
     launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, pdl_enabled(true), p);
   };
   // the 16-key variant keeps 2 x 16 rows per lane in registers; instantiated where it is used and measured --
@@ -1510,6 +1807,28 @@ __global__ void peer_wait_kernel(const unsigned* flags, int world, unsigned expe
     if (++spins > (1u << 25)) __trap();  // a lost peer becomes a launch failure, not a hung GPU
   }
   __threadfence_system();
+}
+
+// The data + flag exchange as a kernel of its own (launch shapes whose final store is not the all-CTA combine):
+// one CTA sends this rank's [B,Hq,D] slice of out_full as staging words and unpacks every peer's slice.
+template <typename T>
+__global__ void ll_exchange_kernel(dd::LLDev ll, T* out_full, int64_t os0, int64_t os1, int B, int Hq, int D) {
+  using LP = dd::LLPack<T>;
+  const unsigned seq = *ll.seq + 1u;
+  const int quads = B * Hq * D / 4;
+  for (int qi = threadIdx.x; qi < quads; qi += blockDim.x) {
+    const int64_t e = (int64_t)qi * 4;
+    const int b = (int)(e / ((int64_t)Hq * D)), h = (int)((e / D) % Hq), d = (int)(e % D);
+    uint32_t w[LP::NW];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(out_full + b * os0 + ((int64_t)ll.rank * Hq + h) * os1 + d);
+#pragma unroll
+    for (int j = 0; j < LP::NW; ++j) w[j] = src[j];
+    dd::ll_exchange<LP::NW>(ll, seq, e * (int64_t)sizeof(T) / 4, w, [&](int r, const uint32_t (&x)[LP::NW]) {
+      LP::store(out_full + b * os0 + ((int64_t)r * Hq + h) * os1 + d, x);
+    });
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ll.seq = seq;
 }
 
 // One CTA per (batch, head): wait for every rank's arrival, then the log-sum-exp merge of the partial slots.
@@ -1611,9 +1930,10 @@ size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int 
     if (!simt && !(dtype != OMX_FLOAT32 && D == 128 && G <= 16)) continue;
     const int Gt = simt ? ((G % 4 == 0) ? 4 : (G % 2 == 0 ? 2 : 1)) : G;
     const int64_t pairs = (int64_t)B * Hkv * (simt ? G / Gt : 1);
-    const SplitPlan sp = plan_splits(pairs, n_tiles, sms, simt ? 2 : 4);
+    const SplitPlan sp = plan_splits(pairs, n_tiles, sms, simt ? 2 : 4,
+                                     (!simt && gsync_enabled()) ? kMaxSplitsGsync : kMaxSplits);
     const size_t part = sp.num_splits > 1 ? (size_t)pairs * sp.num_splits * Gt * (D + 2) : 0;
-    worst = std::max(worst, sizeof(float) * part + sizeof(int) * ((size_t)pairs + 1));
+    worst = std::max(worst, sizeof(float) * part + sizeof(int) * (2 * (size_t)pairs + 1));
   }
   return worst;
 }
@@ -1754,6 +2074,36 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     }
   }
 
+  if (f.ll) {  // data + flag exchange: armed below if the launch ends in the all-CTA combine, else a second kernel
+    OMX_CHECK(!f.peers, "[attn_decode_fused_sharded_ll] one exchange protocol per launch");
+    OMX_CHECK(a.out->strides[3] == 1 && a.out->strides[0] % 4 == 0 && a.out->strides[1] % 4 == 0 &&
+                  ((uintptr_t)f.ll_out_full & 15) == 0 && ((uintptr_t)a.out->data & 15) == 0 && a.D % 4 == 0,
+              "[attn_decode_fused_sharded_ll] out_full rows must be contiguous and 16-byte aligned");
+  }
+  auto ll_dev = [&]() {
+    dd::LLDev d{};
+    d.world = f.ll->world;
+    d.rank = f.ll->rank;
+    for (int r = 0; r < d.world; ++r) d.buf[r] = (unsigned long long*)f.ll->staging[r];
+    d.seq = f.ll->seq;
+    d.words = (int)((int64_t)a.B * a.Hq * a.D * (int64_t)dtype_size(a.q->dtype) / 4);
+    return d;
+  };
+  auto ll_second_kernel = [&]() {  // the launch stored the local slice plainly: exchange it now
+    const dd::LLDev d = ll_dev();
+    auto go = [&](auto* o) {
+      using T = std::remove_pointer_t<decltype(o)>;
+      ll_exchange_kernel<T><<<1, 256, 0, stream>>>(d, o, a.out->strides[0], a.out->strides[1], a.B, a.Hq, a.D);
+    };
+    switch (a.q->dtype) {
+      case OMX_FLOAT32: go((float*)f.ll_out_full); break;
+      case OMX_BFLOAT16: go((__nv_bfloat16*)f.ll_out_full); break;
+      default: go((__half*)f.ll_out_full); break;
+    }
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+  };
+
   const bool masked = a.mask_mode == MASK_BOOL || a.mask_mode == MASK_ADD;
   if (masked) {
     OMX_CHECK(!f.enabled, "the fused decode step takes no array mask");
@@ -1841,8 +2191,15 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       return e ? atoi(e) : -1;
     }();
     const int64_t pairs = (int64_t)a.B * a.Hkv;
-    const SplitPlan natural = plan_splits(pairs, n_tiles, sms, 4);
-    const bool want_cluster = cluster_enabled() && !masked && !f.peers && natural.num_splits > 1;
+    // all-CTA combine: a one-wave grid whose splits no cluster takes; it also lifts the 64-split cap (ONE pair --
+    // a rank of the kv-head-sharded C5 -- spreads over 128 CTAs of 4 tiles instead of 64 of 8)
+    auto gsync_for = [&](const SplitPlan& c) {
+      return gsync_enabled() && c.num_splits > 1 && pairs * c.num_splits <= sms &&
+             gsync_fits(c.num_splits, p.G, 128, 7 * 32, 6 * 16 * 128);
+    };
+    SplitPlan natural = plan_splits(pairs, n_tiles, sms, 4, gsync_enabled() ? kMaxSplitsGsync : kMaxSplits);
+    if (natural.num_splits > kMaxSplits && !gsync_for(natural)) natural = plan_splits(pairs, n_tiles, sms, 4);
+    const bool want_cluster = cluster_enabled() && !masked && !f.peers && !f.ll && natural.num_splits > 1;
     // Cluster policy (measured, scripts/gpu_cluster_sweep.sh): the DSMEM combine saves ~2 us of tail, but a
     // cluster must be co-resident in one GPC -- with one CTA per SM this B200 places 8 clusters of <= 10
     // CTAs (7 of 16).  So: the natural plan if it fits; else a plan clamped to kClusterClamp splits when
@@ -1894,12 +2251,27 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
         if (fits(natural)) p.cluster = 1;
         else if (try_clamped && fits(clamped)) { sp = clamped; p.cluster = 1; }
       }
+      static const bool gsync_first = [] {  // OMX_DECODE_GSYNC=2: all-CTA combine even where a clamped cluster fits
+        const char* e = getenv("OMX_DECODE_GSYNC");
+        return e && atoi(e) == 2;
+      }();
+      if (gsync_first && p.cluster && sp.num_splits != natural.num_splits && gsync_for(natural)) {
+        sp = natural;
+        p.cluster = 0;
+      }
       p.num_splits = sp.num_splits;
       p.tiles_per_split = sp.tiles_per_split;
       p.push_combine = (push_ok && p.cluster && p.num_splits <= kPushSplits) ? 1 : 0;
+      p.gsync = (!p.cluster && deep && gsync_for(sp)) ? 1 : 0;
+      if (p.gsync) p.peer_total = (int)pairs * p.num_splits;  // every CTA stores a slice
+      if (p.gsync && f.ll) {
+        p.ll = ll_dev();
+        p.ll_out = f.ll_out_full;
+      }
       carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
                       p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
-                      (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
+                      (p.num_splits > 1 || p.n_peers) ? (size_t)(p.gsync ? 2 : 1) * pairs + 1 : 0);
+      p.counters2 = p.gsync ? p.counters + pairs : nullptr;
       dim3 grid(p.num_splits, a.Hkv, a.B);
       arm_trace(grid);
       launch_kernel(kern, grid, threads, smem, stream, p.cluster ? p.num_splits : 1, pdl_enabled(false), tmK, tmV, p);
@@ -1925,6 +2297,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     count_launch();
     OMX_CUDA(cudaGetLastError());
     if (masked) masked_rows_fixup(a, p.dead, stream);
+    if (f.ll && !p.ll.world) ll_second_kernel();
     return;
   }
 
@@ -1935,13 +2308,15 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   SplitPlan sp = plan_splits(pairs, n_tiles, sms, 2);
   // CUDA-core kernel: cluster combine only when the natural plan is co-resident as it is (a clamped plan
   // lost more in the key loop than the combine saved: C1 12.9 -> 13.6 us)
-  const bool want_cluster = cluster_enabled() && !masked && !f.peers && sp.num_splits > 1 &&
+  const bool want_cluster = cluster_enabled() && !masked && !f.peers && !f.ll && sp.num_splits > 1 &&
                             sp.num_splits <= kMaxClusterSplits;
   p.num_splits = sp.num_splits;
   p.tiles_per_split = sp.tiles_per_split;
+  // (room for the all-CTA combine's second counter row; launch_simt decides once it knows about the cluster)
   carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * p.D : 0,
                   p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * 2 : 0,
-                  (p.num_splits > 1 || p.n_peers) ? (size_t)pairs + 1 : 0);
+                  (p.num_splits > 1 || p.n_peers) ? (size_t)2 * pairs + 1 : 0);
+  p.counters2 = p.counters ? p.counters + pairs : nullptr;
   p.peer_total = (int)pairs;
   dim3 grid(p.num_splits, a.Hkv * groups, a.B);
   arm_trace(grid);
@@ -1957,6 +2332,7 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
     default: dd::launch_simt_f16(p, stream, Gt, grid, one_wave, want_cluster); break;
   }
   if (masked) masked_rows_fixup(a, p.dead, stream);
+  if (f.ll) ll_second_kernel();  // (the CUDA-core kernel keeps the exchange as a kernel of its own)
 }
 
 #endif  // OMX_DECODE_PART == 0

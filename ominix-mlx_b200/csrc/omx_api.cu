@@ -379,7 +379,8 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
                        omx_optional_float base, float rope_scale, const omx_array* freqs, float sm_scale,
                        omx_array* keys_out, omx_array* values_out, const omx_peer_group* peers,
                        int head_offset, cudaStream_t stream, const omx_array* q_norm_w = nullptr,
-                       const omx_array* k_norm_w = nullptr, float norm_eps = 0.f, bool peer_wait = false) {
+                       const omx_array* k_norm_w = nullptr, float norm_eps = 0.f, bool peer_wait = false,
+                       const omx_ll_group* ll = nullptr) {
   require_device();
   auto* c = (KVCacheImpl*)cache.ctx;
   OMX_CHECK(c, "[attn_decode_fused] null cache handle");
@@ -414,6 +415,18 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     out_local.shape[1] = q->shape[1];
     out_local.data = (char*)out->data + (size_t)head_offset * out->strides[1] * dtype_size(out->dtype);
   }
+  if (ll) {
+    OMX_CHECK(ll->world >= 1 && ll->world <= OMX_MAX_PEERS && ll->rank >= 0 && ll->rank < ll->world && ll->seq,
+              "[attn_decode_fused_sharded_ll] bad group (world %d, rank %d)", ll->world, ll->rank);
+    for (int r = 0; r < ll->world; ++r)
+      OMX_CHECK(ll->staging[r], "[attn_decode_fused_sharded_ll] staging buffer of rank %d is not mapped", r);
+    OMX_CHECK(head_offset == ll->rank * q->shape[1] && (int64_t)ll->world * q->shape[1] == out->shape[1],
+              "[attn_decode_fused_sharded_ll] rank %d of %d with %lld local heads must write heads [%lld, ...) of %lld",
+              ll->rank, ll->world, (long long)q->shape[1], (long long)(ll->rank * q->shape[1]),
+              (long long)out->shape[1]);
+    out_local.shape[1] = q->shape[1];
+    out_local.data = (char*)out->data + (size_t)head_offset * out->strides[1] * dtype_size(out->dtype);
+  }
   const int position = kv_cache_offset(c);
   // cache bookkeeping (growth by the reference rule) without copying the new rows: the kernel
   // ropes k_new and writes row `position` itself.
@@ -424,7 +437,7 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   const char* why = nullptr;
   const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
                     v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
-  OMX_CHECK(fast || !peers, "[attn_decode_fused_sharded] layout not supported by the decode kernels: %s",
+  OMX_CHECK(fast || (!peers && !ll), "[attn_decode_fused_sharded] layout not supported by the decode kernels: %s",
             why ? why : "strided k_new/v_new");
   if (fast) {
     DecodeFused f;
@@ -437,6 +450,8 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     f.stable_rows = kv_cache_stable_rows(c);
     f.peers = peers;
     f.peer_wait = peer_wait;
+    f.ll = ll;
+    f.ll_out_full = out->data;
     f.head_offset = 0;  // out_local already starts at this rank's first head
     f.q_norm_w = qn ? q_norm_w->data : nullptr;
     f.k_norm_w = kn ? k_norm_w->data : nullptr;
@@ -953,6 +968,24 @@ int omx_attn_decode_fused_sharded_sync(const omx_array* out_full, const omx_arra
                       sm_scale, nullptr, nullptr, peers, head_offset, (cudaStream_t)s, nullptr, nullptr, 0.f,
                       /*peer_wait=*/true);
   });
+}
+
+int omx_attn_decode_fused_sharded_ll(const omx_array* out_full, const omx_array* q, const omx_array* k_new,
+                                     const omx_array* v_new, omx_kv_cache cache, int rope_dims, bool traditional,
+                                     omx_optional_float base, float rope_scale, const omx_array* freqs,
+                                     float sm_scale, const omx_ll_group* group, int head_offset, omx_stream s) {
+  return guarded([&] {
+    OMX_CHECK(group != nullptr, "[attn_decode_fused_sharded_ll] null group");
+    decode_fused_impl(out_full, q, k_new, v_new, cache, rope_dims, traditional, base, rope_scale, freqs,
+                      sm_scale, nullptr, nullptr, nullptr, head_offset, (cudaStream_t)s, nullptr, nullptr, 0.f,
+                      false, group);
+  });
+}
+
+size_t omx_ll_staging_bytes(int world, int64_t B, int64_t Hq_local, int64_t D, int dtype) {
+  if (world < 1 || B < 0 || Hq_local < 0 || D < 0) return 0;
+  const size_t es = (dtype == OMX_FLOAT32) ? 4 : 2;
+  return (size_t)2 * (size_t)world * ((size_t)B * Hq_local * D * es / 4) * 8;
 }
 
 int omx_attn_decode_seqshard(const omx_array* partial, const omx_array* q, const omx_array* k_new,

@@ -139,6 +139,10 @@ struct DecodeFused {  // optional fused rope + append of the new token (L == 1)
   const omx_peer_group* peers = nullptr;  // out pointers already shifted to this rank's first head
   int head_offset = 0;
   bool peer_wait = false;  // the launch itself waits for every peer's arrival of this step
+  // data + flag exchange (omx_attn_decode_fused_sharded_ll): staging words instead of peer stores + counters;
+  // out_full = base of the local full-head output the received words are unpacked into
+  const omx_ll_group* ll = nullptr;
+  void* ll_out_full = nullptr;
   // per-head RMSNorm of q / k_new before the rotation (Qwen3 q_norm / k_norm): [D] weights in the
   // q dtype, contiguous; null = no norm
   const void* q_norm_w = nullptr;

@@ -11,10 +11,13 @@ path needs and nothing more:
   all heads).  Two spellings:
     - `gather="collective"`: the local decode launch followed by dist.all_gather_into_tensor
       (NCCL over NVLink on the GPU box; gloo in the CPU tests) -- the baseline;
-    - `gather="peer"`: ONE launch -- the decode kernel's final store writes the rank's head slice
-      into every rank's output buffer through NVLink peer mappings and bumps an arrival counter
-      (omx_attn_decode_fused_sharded), then a one-warp wait kernel (omx_peer_wait).  Buffers come
-      from torch's symmetric-memory allocator (plumbing only).
+    - `gather="peer"`: ONE launch with a data + flag exchange -- the lanes that hold final output values store
+      them as {payload, step number} words into every rank's staging buffer over NVLink peer mappings and
+      poll their own staging buffer for the peers' words (omx_attn_decode_fused_sharded_ll): no system-scope
+      fence, no arrival counters; one NVLink store latency per step.
+    - `gather="peer_flags"`: the round-1 spelling -- the final store writes the rank's head slice into every
+      rank's output buffer and bumps an arrival counter (omx_attn_decode_fused_sharded[_sync]).
+      Staging / output buffers come from torch's symmetric-memory allocator (plumbing only).
 * Sequence sharding for a single sequence whose KV should be spread over the GPUs with ALL
   heads on every rank: rank r keeps the rows of the positions p with p % world == r; each step every rank
   attends over its rows and the ranks exchange float32 partials (normalised output + (m, l)) -- pushed into
@@ -97,7 +100,7 @@ class HeadShardedDecode:
     def __init__(self, n_heads, n_kv_heads, head_dim, dtype, rope, sm_scale, batch=1, group=None,
                  gather="collective", device=None):
         from .cache import KVCache
-        if gather not in ("collective", "peer"):
+        if gather not in ("collective", "peer", "peer_flags"):
             raise _lib.Exception_(f"unknown gather mode {gather!r}")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -113,7 +116,10 @@ class HeadShardedDecode:
         # step); False = the r01 spelling, a separate one-warp wait kernel (omx_peer_wait)
         self.wait_in_kernel = True
         self._peer = None
+        self._ll = None
         if gather == "peer":
+            self._init_ll(batch, dtype)
+        elif gather == "peer_flags":
             self._init_peer(batch, dtype)
         else:
             self.out_full = torch.empty((batch, n_heads, 1, head_dim), dtype=dtype, device=self.device)
@@ -152,6 +158,31 @@ class HeadShardedDecode:
         torch.cuda.synchronize(self.device)
         dist.barrier(group=grp)  # every rank's counters are zero before anyone signals
 
+    def _init_ll(self, batch, dtype):
+        try:
+            import torch.distributed._symmetric_memory as symm
+        except Exception as e:  # pragma: no cover
+            raise _lib.Exception_(f"gather='peer' needs torch symmetric memory: {e}")
+        grp = self.group if self.group is not None else dist.group.WORLD
+        dt = {torch.float32: _lib.OMX_FLOAT32, torch.bfloat16: _lib.OMX_BFLOAT16, torch.float16: _lib.OMX_FLOAT16}[dtype]
+        nbytes = int(_lib.lib().omx_ll_staging_bytes(self.world, batch, self.nq, self.head_dim, dt))
+        self._staging = symm.empty((nbytes // 8,), dtype=torch.int64, device=self.device)
+        self._staging.zero_()  # flag 0 never equals a step number (they start at 1)
+        self._seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+        h = symm.rendezvous(self._staging, group=grp)
+        ll = _lib.OmxLLGroup()
+        ll.world, ll.rank = self.world, self.rank
+        for r in range(self.world):
+            ll.staging[r] = int(h.buffer_ptrs[r])
+        if ll.staging[self.rank] != self._staging.data_ptr():
+            raise _lib.Exception_("symmetric memory handle does not map the local buffer at its own address")
+        ll.seq = self._seq.data_ptr()
+        self._ll, self._handles = ll, (h,)
+        # private: peers never write it, so one buffer is enough
+        self.out_full = torch.empty((batch, self.n_heads, 1, self.head_dim), dtype=dtype, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=grp)  # every rank's staging is zero before anyone stores into it
+
     def prefill(self, keys, values):
         """Append the local kv heads of full-head [B,Hkv,n,D] keys / values (already roped)."""
         return self.cache.update_and_fetch(shard_heads(keys, self.kv0, self.nkv),
@@ -163,6 +194,17 @@ class HeadShardedDecode:
         vl = shard_heads(v_new, self.kv0, self.nkv)
         parity = self.steps & 1
         self.steps += 1
+        if self._ll is not None:
+            rope = self.rope
+            base = _lib.OmxOptionalFloat()
+            base.has_value = rope is not None
+            base.value = rope.base if rope is not None else 0.0
+            qd, kd, vd, od = desc(ql), desc(kl), desc(vl), desc(self.out_full)
+            _lib.check(_lib.lib().omx_attn_decode_fused_sharded_ll(
+                ref(od), ref(qd), ref(kd), ref(vd), self.cache.handle, int(rope.dimensions if rope else 0),
+                bool(rope.traditional) if rope else False, base, float(rope.scale) if rope else 1.0, None,
+                float(self.sm_scale), ctypes.byref(self._ll), int(self.q0), stream_ptr(stream)))
+            return self.out_full
         if self._peer is None:
             out_local = attn_decode_fused(ql, kl, vl, self.cache, self.rope, self.sm_scale, stream=stream)
             if self.world == 1:
@@ -226,7 +268,7 @@ class SeqShardedDecode:
     def __init__(self, n_heads, n_kv_heads, head_dim, dtype, rope, sm_scale, batch=1, group=None, gather="peer",
                  device=None):
         from .cache import KVCache
-        if gather not in ("collective", "peer"):
+        if gather not in ("collective", "peer", "peer_flags"):
             raise _lib.Exception_(f"unknown gather mode {gather!r}")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1

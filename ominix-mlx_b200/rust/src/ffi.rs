@@ -57,6 +57,16 @@ pub struct omx_peer_group {
     pub flags: [*mut u32; OMX_MAX_PEERS],
 }
 
+/// Staging buffers of the data + flag exchange (include/omx_attn.h: omx_ll_group).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct omx_ll_group {
+    pub world: i32,
+    pub rank: i32,
+    pub staging: [*mut c_void; OMX_MAX_PEERS],
+    pub seq: *mut u32,
+}
+
 pub type omx_stream = *mut c_void; // cudaStream_t
 pub type omx_error_handler_func = Option<unsafe extern "C" fn(msg: *const c_char, data: *mut c_void)>;
 
@@ -148,6 +158,15 @@ extern "C" {
                                               freqs: *const omx_array, sm_scale: f32,
                                               peers: *const omx_peer_group, head_offset: c_int,
                                               s: omx_stream) -> c_int;
+
+    pub fn omx_attn_decode_fused_sharded_ll(out_full: *const omx_array, q: *const omx_array,
+                                            k_new: *const omx_array, v_new: *const omx_array,
+                                            cache: omx_kv_cache, rope_dims: c_int, traditional: bool,
+                                            base: omx_optional_float, rope_scale: f32,
+                                            freqs: *const omx_array, sm_scale: f32,
+                                            group: *const omx_ll_group, head_offset: c_int,
+                                            s: omx_stream) -> c_int;
+    pub fn omx_ll_staging_bytes(world: c_int, b: i64, hq_local: i64, d: i64, dtype: c_int) -> usize;
 
     pub fn omx_paged_kv_cache_new(res: *mut omx_paged_kv_cache, batch: c_int, n_kv_heads: c_int, head_dim_k: c_int,
                                   head_dim_v: c_int, dtype: c_int, n_pages: i64, max_pages_per_seq: c_int) -> c_int;

@@ -35,7 +35,10 @@ for name, B, Hq, Hkv, S, dt in SHAPES:
     def plain():
         for K, V in views:
             omx.fast.scaled_dot_product_attention(q, K, V, D ** -0.5, None, out=out)
+    only = os.environ.get("OMX_BENCH_LABELS")
     for label, fn in (("fused", fused(False)), ("fused_norm", fused(True)), ("sdpa_only", plain)):
+        if only and label not in only.split(","):
+            continue
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

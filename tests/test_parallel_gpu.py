@@ -73,6 +73,53 @@ def test_peer_store_path_world1_raw_abi(dtype, S):
     assert b"do not fit" in L.lib().omx_last_error()
 
 
+@pytest.mark.parametrize("dtype,B,Hq,Hkv,S", [("bf16", 1, 4, 1, 5000), ("bf16", 2, 8, 2, 777), ("f32", 1, 8, 2, 300),
+                                              ("bf16", 1, 4, 1, 40)])
+def test_ll_exchange_world1_raw_abi(dtype, B, Hq, Hkv, S):
+    """world = 1 of the data + flag exchange (omx_attn_decode_fused_sharded_ll): the all-CTA combine's word path
+    (long single sequence), the exchange as a second kernel (fp32 / short contexts), the step counter, and the
+    private out_full untouched outside this rank's heads."""
+    L = omx._lib
+    D = 128
+    k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
+    q, kn, vn = randn((B, Hq, 1, D), dtype, 3), randn((B, Hkv, 1, D), dtype, 4), randn((B, Hkv, 1, D), dtype, 5)
+    want, oc = _oracle_full(k, v, q, kn, vn, dtype, S)
+    cache = omx.KVCache()
+    cache.update_and_fetch(k.cuda(), v.cuda())
+    out_full = torch.full((B, Hq, 1, D), 7.0, dtype=q.dtype, device="cuda")
+    dt = L.OMX_FLOAT32 if dtype == "f32" else L.OMX_BFLOAT16
+    nbytes = int(L.lib().omx_ll_staging_bytes(1, B, Hq, D, dt))
+    assert nbytes == 2 * B * Hq * D * (4 if dtype == "f32" else 2) // 4 * 8
+    staging = torch.zeros(nbytes // 8, dtype=torch.int64, device="cuda")
+    seq = torch.zeros(1, dtype=torch.int32, device="cuda")
+    g = L.OmxLLGroup()
+    g.world, g.rank = 1, 0
+    g.staging[0], g.seq = staging.data_ptr(), seq.data_ptr()
+    base = L.OmxOptionalFloat()
+    base.has_value, base.value = True, ROPE[2]
+    A = omx.array
+    qg, kg, vg = q.cuda(), kn.cuda(), vn.cuda()
+    qd, kd, vd, od = A.desc(qg), A.desc(kg), A.desc(vg), A.desc(out_full)
+    sp = A.stream_ptr()
+    for step in (1, 2, 3):
+        L.check(L.lib().omx_attn_decode_fused_sharded_ll(A.ref(od), A.ref(qd), A.ref(kd), A.ref(vd), cache.handle,
+                                                         128, False, base, 1.0, None, 128 ** -0.5,
+                                                         ctypes.byref(g), 0, sp))
+        torch.cuda.synchronize()
+        assert int(seq[0]) == step
+        assert_close(out_full.float().cpu().numpy(), want, dtype, "ll exchange, world 1")
+        if step == 1:
+            sk, sv = cache.state()
+            assert_bits_equal(sk, oc.keys, dtype, "KV keys (ll step)")
+            assert_bits_equal(sv, oc.values, dtype, "KV values (ll step)")
+        cache.trim(1)
+        out_full.fill_(7.0)
+    # validation: the head slice must be rank * Hq_local
+    assert L.lib().omx_attn_decode_fused_sharded_ll(A.ref(od), A.ref(qd), A.ref(kd), A.ref(vd), cache.handle, 128,
+                                                    False, base, 1.0, None, 0.1, ctypes.byref(g), 4, sp) == 1
+    assert b"must write heads" in L.lib().omx_last_error()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -122,7 +169,7 @@ def _rank_main(rank, world, port, gather, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("gather", ["collective", "peer"])
+@pytest.mark.parametrize("gather", ["collective", "peer", "peer_flags"])
 def test_head_sharded_decode_two_ranks(gather):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
