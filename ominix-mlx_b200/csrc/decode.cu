@@ -47,6 +47,25 @@
 #define OMX_DECODE_PART 0
 #endif
 
+// A/B switches for `make variant` (scripts/gpu_r02_variants.sh): which cold paths are kept out of line.
+// One box, graph replay, us per fused step (all out of line / all inline / measured best = below):
+//   Qwen3-0.6B bf16 ctx 2048 10.37 / 8.81 / 8.54, Qwen3-8B B1 ctx 8192 15.65 / 14.81 / 13.87,
+//   C5 32 q / 8 kv ctx 32768 33.2 / 34.2 / 32.4, one rank of the sharded C5 14.60 / 15.15 / 14.55.
+// The split-K combines stay inline (their arguments would travel through local memory); the array-mask score,
+// the RMSNorm row sum and the new-token warp are calls.
+#ifndef OMX_NI_COMBINE
+#define OMX_NI_COMBINE __forceinline__
+#endif
+#ifndef OMX_NI_MASK
+#define OMX_NI_MASK __noinline__
+#endif
+#ifndef OMX_NI_RMS
+#define OMX_NI_RMS __noinline__
+#endif
+#ifndef OMX_NI_NT
+#define OMX_NI_NT __noinline__
+#endif
+
 namespace omx {
 
 namespace dd {  // shared by the three compilation parts of this file (same definition in each)
@@ -299,46 +318,61 @@ __device__ __forceinline__ DecodeDyn load_dyn(const DecodeParams& p, int b) {
 // score (log2 domain) of `key` for query head `h` after the array mask.  Additive entries <= -1e8
 // (the callers' -1e9 / -inf spelling of "hidden") hide the key outright, like the prefill kernel.
 template <typename T>
-__device__ __forceinline__ float mask_score(const DecodeParams& p, float s, int b, int h, int key) {
+__device__ OMX_NI_MASK float mask_score(const DecodeParams& p, float s, int b, int h, int key) {
   const int64_t mi = b * p.mks[0] + h * p.mks[1] + key * p.mks[2];
   if (p.mask_kind == 1) return ((const uint8_t*)p.mask)[mi] ? s : -INFINITY;
   const float mf = Num<T>::to_f(((const T*)p.mask)[mi]);
   return mf <= -1e8f ? -INFINITY : fmaf(mf, kLog2e, s);
 }
 
+// Code size matters here: a single-sequence launch runs every instruction of its tail once per CTA, on a cold
+// instruction cache (the kernels were 560 KB of SASS with the peer loops unrolled into each of the ~20 final
+// store sites).  The common case -- a local store in the output type -- stays inline; everything else is a call.
 template <typename T>
-__device__ __forceinline__ void store_out(const DecodeParams& p, int64_t off, float v) {
+__device__ __noinline__ void store_out_slow(const DecodeParams& p, int64_t off, float v) {
   if (p.partial) {  // f32 partial slot(s)
     if (p.n_peers == 0) ((float*)p.out)[off] = v;
+#pragma unroll 1
     for (int r = 0; r < p.n_peers; ++r) ((float*)p.peer_out[r])[off] = v;
     return;
   }
   const T x = Num<T>::from_f(v);
-  if (p.n_peers == 0) {
-    ((T*)p.out)[off] = x;
+#pragma unroll 1
+  for (int r = 0; r < p.n_peers; ++r) ((T*)p.peer_out[r])[off] = x;
+}
+template <typename T>
+__device__ __forceinline__ void store_out(const DecodeParams& p, int64_t off, float v) {
+  if (!p.partial && p.n_peers == 0) {
+    ((T*)p.out)[off] = Num<T>::from_f(v);
     return;
   }
-  for (int r = 0; r < p.n_peers; ++r) ((T*)p.peer_out[r])[off] = x;
+  store_out_slow<T>(p, off, v);
 }
 
 // (m, l) of one (batch, head) behind its D partial-output floats (sequence-sharded mode only)
-__device__ __forceinline__ void store_ml(const DecodeParams& p, int b, int head, float M, float L) {
-  if (!p.partial) return;
+__device__ __noinline__ void store_ml_slow(const DecodeParams& p, int b, int head, float M, float L) {
   const int64_t off = b * p.os[0] + (int64_t)head * p.os[1] + (int64_t)p.D * p.os[3];
   if (p.n_peers == 0) {
     ((float*)p.out)[off] = M;
     ((float*)p.out)[off + 1] = L;
   }
+#pragma unroll 1
   for (int r = 0; r < p.n_peers; ++r) {
     ((float*)p.peer_out[r])[off] = M;
     ((float*)p.peer_out[r])[off + 1] = L;
   }
 }
+__device__ __forceinline__ void store_ml(const DecodeParams& p, int b, int head, float M, float L) {
+  if (p.partial) store_ml_slow(p, b, head, M, L);
+}
 
 // After the final stores of one CTA (called by all its threads).  Writers fence their peer stores
 // at system scope, the CTA takes a ticket, and the launch's last ticket publishes the arrival.
+__device__ __noinline__ void peer_signal_slow(const DecodeParams& p, int tid);
 __device__ __forceinline__ void peer_signal(const DecodeParams& p, int tid) {
-  if (p.n_peers == 0) return;
+  if (p.n_peers) peer_signal_slow(p, tid);
+}
+__device__ __noinline__ void peer_signal_slow(const DecodeParams& p, int tid) {
   __threadfence_system();
   __syncthreads();
   if (tid == 0) {
@@ -387,7 +421,7 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
 // row is pulled into registers with 128-bit loads first, so what remains serial is the FADD chain alone
 // (the scalar loop took 2.7 us for 128 bf16 elements: one exposed LDS per step).
 template <typename E>
-__device__ __forceinline__ float rms_rsqrt_smem(const E* row, int D, float eps, float inv_n) {
+__device__ OMX_NI_RMS float rms_rsqrt_smem(const E* row, int D, float eps, float inv_n) {
   constexpr int V = 16 / (int)sizeof(E);
   float acc = 0.f;
   if ((D % (4 * V)) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
@@ -471,6 +505,7 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
       for (int d = rt; d < D; d += nthr) ps.kw[d] = Num<T>::to_f(((const T*)p.k_norm_w)[d]);
   }
   after_loads();
+  trace_mark(p, 14);
   if (!rope && !p.q_norm_w) return;  // the caller's barrier publishes the copy
   sync();
   trace_mark(p, 12);
@@ -518,7 +553,7 @@ __device__ __forceinline__ void stage_q(const DecodeParams& p, T* q_s, int pitch
 // cache row, and score the new key against the staged q heads -- from shared memory only.
 // nt_k/nt_v: float[D], nt_m[g] <- log2-domain score.
 template <typename T>
-__device__ __forceinline__ void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
+__device__ OMX_NI_NT void new_token(const DecodeParams& p, const T* q_s, int pitch, int n_heads,
                                           int b, int hk, int lane, float* nt_k, float* nt_v,
                                           float* nt_m, const PrologueSmem& ps, const DecodeDyn& dy,
                                           bool write_cache = true) {
@@ -618,73 +653,197 @@ constexpr int kMaxClusterSplits = 16;  // non-portable cluster size limit on sm_
 // floats of cluster scratch behind the merge inputs: partial (m, l) | weights | sums, per row pitch
 __host__ __device__ constexpr int cluster_scratch_floats(int rows) { return (2 + 2 * kMaxClusterSplits) * rows; }
 
-// Merge per-warp states -> out (single split) or workspace + last-CTA combine.
-// mo: [n_ent][rows][D] floats, mml: [n_ent][rows][2]; rows = row pitch of the entries.
-template <typename T, int PF>
-__device__ __forceinline__ void merge_and_store(const DecodeParams& p, const float* mo, const float* mml,
-                                                int n_ent, int rows, bool has_nt, const float* nt_m,
-                                                const float* nt_v, int first_head, int n_heads, int b,
-                                                int pair, int split, int tid, int nthr, int* s_ticket,
-                                                float* cl /* cluster scratch, cluster_scratch_floats(rows) */,
-                                                float* recv = nullptr /* push-combine receive slots */) {
+// ---- all-CTA split-K combine (DecodeParams::gsync; one-wave grids).  publish -> meet -> every CTA folds its own
+// slice of the output columns.  Lanes run over the SPLITS: a group of W lanes holds one float4 column's
+// contributions, so the per-head maximum / sum and the fold are warp shuffles; what is left of the tail is one
+// round trip to L2 behind the meeting point (partials and (m, l) requested together) and at most one CTA barrier.
+// Kept out of line and un-unrolled on purpose (see store_out_slow).
+template <typename T>
+__device__ __noinline__ void ll_quad(const DecodeParams& p, unsigned seq, int b, int head, int d, float4 v) {
+  using LP = dd::LLPack<T>;
+  uint32_t w[LP::NW];
+  LP::pack(v, w);
+  LP::store((T*)p.out + b * p.os[0] + (int64_t)head * p.os[1] + d, w);  // the local slice (host: os[3] == 1)
+  const int64_t e = ((int64_t)b * p.Hq + head) * p.D + d;              // element of this rank's [B,Hq,D] slice
+  dd::ll_exchange<LP::NW>(p.ll, seq, e * (int64_t)sizeof(T) / 4, w, [&](int src, const uint32_t (&r)[LP::NW]) {
+    LP::store((T*)p.ll_out + b * p.os[0] + ((int64_t)src * p.Hq + head) * p.os[1] + d, r);
+  });
+}
+
+template <typename T>
+__device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch, int first_head, int n_heads,
+                                           int b, int pair, int split, int tid, int nthr) {
+  const int NS = p.num_splits, D = p.D;
+  __threadfence();
+  __syncthreads();
+  trace_mark(p, 4);
+  const int D4 = D >> 2;
+  const int C = n_heads * D4;                 // float4 columns of the pair's output
+  const int slice = (C + NS - 1) / NS;
+  const int c0 = split * slice, c1 = min(C, c0 + slice);
+  const int ncol = max(0, c1 - c0);
+  const GsyncShape gs = gsync_shape(NS);
+  const int W = gs.W, K = gs.K;
+  const int wsh = 31 - __clz(W);              // W = 1 << wsh
+  const int n_wi = W == 32 ? ncol * K : (ncol + (32 >> wsh) - 1) >> (5 - wsh);  // warp-sized work items
+  const int nwarps = nthr >> 5, warp = tid >> 5, lane = tid & 31;
+  const int g0 = ncol ? c0 / D4 : 0, g1 = ncol ? (c1 - 1) / D4 : -1;  // heads the slice touches
+  const int nh = g1 - g0 + 1;
+  const int mlp = (NS * nh + 3) & ~3;
+  float* sm_m = scratch;                      // [NS][nh]  (the merge inputs are dead: the own partial is in ws)
+  float* sm_l = sm_m + mlp;                   // [NS][nh]
+  float4* red = reinterpret_cast<float4*>(sm_l + mlp);      // [ncol][K]   (K > 1 only)
+  float* sm_inv = reinterpret_cast<float*>(red + ncol * K);  // [ncol]
+  const int64_t e0p = (int64_t)pair * NS * n_heads;
+  const int64_t ob = b * p.os[0];
+  if (tid == 0) {
+    atomicAdd(&p.counters[pair], 1);
+    unsigned spins = 0;
+    while (ld_acquire_gpu(&p.counters[pair]) < NS)
+      if (++spins > (1u << 26)) __trap();  // a CTA that never became resident: a launch failure, not a hung GPU
+  }
+  __syncthreads();
+  trace_mark(p, 5);
+  const unsigned ll_seq = p.ll.world ? __ldcg(p.ll.seq) + 1u : 0u;
+  // work item wi of this warp: local column colL, split sp of this lane
+  auto item = [&](int wi, int& colL, int& sp) {
+    if (W == 32) {
+      colL = wi / K;
+      sp = (wi - colL * K) * 32 + lane;
+    } else {
+      colL = (wi << (5 - wsh)) + (lane >> wsh);
+      sp = lane & (W - 1);
+    }
+    return wi < n_wi && colL < ncol && sp < NS;
+  };
+  auto fetch = [&](int wi) {
+    int colL, sp;
+    if (!item(wi, colL, sp)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const int col = c0 + colL;
+    return __ldcg(reinterpret_cast<const float4*>(p.ws_o + (e0p + (int64_t)sp * n_heads + col / D4) * D + (col % D4) * 4));
+  };
+  float4 cur = fetch(warp);
+#pragma unroll 1
+  for (int idx = tid; idx < NS * nh; idx += nthr) {
+    const int sp = idx / nh, g = g0 + idx - sp * nh;
+    const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + (int64_t)sp * n_heads + g) * 2]));
+    sm_m[idx] = ml.x;
+    sm_l[idx] = ml.y;
+  }
+  __syncthreads();
+  trace_mark(p, 9);
+  auto emit4 = [&](int col, const float4& v) {
+    const int g = col / D4, d = (col - g * D4) * 4;
+    if (p.ll.world) {
+      ll_quad<T>(p, ll_seq, b, first_head + g, d, v);
+      return;
+    }
+    const int64_t o = ob + (int64_t)(first_head + g) * p.os[1] + (int64_t)d * p.os[3];
+    store_out<T>(p, o, v.x);
+    store_out<T>(p, o + p.os[3], v.y);
+    store_out<T>(p, o + 2 * p.os[3], v.z);
+    store_out<T>(p, o + 3 * p.os[3], v.w);
+  };
+#pragma unroll 1
+  for (int wi = warp; wi < n_wi; wi += nwarps) {  // (warp-uniform)
+    const float4 nxt = fetch(wi + nwarps);        // the next item's partial is in flight under this one's fold
+    int colL, sp;
+    const bool valid = item(wi, colL, sp);
+    const int cc = min(colL, ncol - 1);           // lanes past the slice compute on its last column and store nothing
+    const int col = c0 + cc, g = col / D4, gi = g - g0;
+    const int l0 = lane & (W - 1);
+    float M = -INFINITY;
+#pragma unroll 1
+    for (int s2 = l0; s2 < NS; s2 += W) M = fmaxf(M, sm_m[s2 * nh + gi]);
+#pragma unroll 1
+    for (int o = W >> 1; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    float L = 0.f;
+#pragma unroll 1
+    for (int s2 = l0; s2 < NS; s2 += W) {
+      const float ms = sm_m[s2 * nh + gi];
+      if (ms > -INFINITY) L = fmaf(sm_l[s2 * nh + gi], fast_exp2(ms - M), L);
+    }
+    const float mine = valid ? sm_m[sp * nh + gi] : -INFINITY;
+    const float e = mine > -INFINITY ? fast_exp2(mine - M) : 0.f;
+    float4 c = make_float4(cur.x * e, cur.y * e, cur.z * e, cur.w * e);
+#pragma unroll 1
+    for (int o = W >> 1; o > 0; o >>= 1) {
+      L += __shfl_xor_sync(0xffffffffu, L, o);
+      c.x += __shfl_xor_sync(0xffffffffu, c.x, o);
+      c.y += __shfl_xor_sync(0xffffffffu, c.y, o);
+      c.z += __shfl_xor_sync(0xffffffffu, c.z, o);
+      c.w += __shfl_xor_sync(0xffffffffu, c.w, o);
+    }
+    const int kk = W == 32 ? wi - (wi / K) * K : 0;  // which 32-split block of the column
+    const bool lead = colL < ncol && l0 == 0 && kk == 0;
+    if (lead && col % D4 == 0) {  // the CTA that owns the head's first column reports the row
+      store_ml(p, b, first_head + g, M, L);
+      if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    }
+    if (K == 1) {
+      if (lead) {
+        const float inv = 1.0f / L;
+        emit4(col, make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv));
+      }
+    } else if (colL < ncol && lane == 0) {
+      red[colL * K + kk] = c;
+      if (lead) sm_inv[colL] = 1.0f / L;
+    }
+    cur = nxt;
+  }
+  if (K > 1) {
+    __syncthreads();
+    trace_mark(p, 10);
+#pragma unroll 1
+    for (int colL = tid; colL < ncol; colL += nthr) {
+      float4 a = red[colL * K];
+#pragma unroll 1
+      for (int k = 1; k < K; ++k) {
+        const float4 r = red[colL * K + k];
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+      }
+      const float inv = sm_inv[colL];
+      emit4(c0 + colL, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
+    }
+  }
+  trace_mark(p, 11);
+  peer_signal(p, tid);  // (peer_total counts every CTA of the launch in this mode)
+  if (p.ll.world) __syncthreads();  // this CTA's exchange is complete
+  if (tid == 0) {
+    const int t = atomicAdd(&p.counters2[pair], 1);
+    if (t == NS - 1) {  // everybody has passed the meeting point: reset both counters for the next launch
+      p.counters[pair] = 0;
+      p.counters2[pair] = 0;
+    }
+    if (p.ll.world && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
+      *p.peer_done = 0;     // the launch's last CTA: every word of the step has been sent and received here
+      *p.ll.seq = ll_seq;
+    }
+  }
+  trace_mark(p, 6);
+}
+
+// The combines below run once per CTA at the very end of the launch; each is a function of its own so that a
+// launch only walks the code of the one it uses (see store_out_slow on code size).
+struct MergeArgs {
+  const float* mo;
+  int n_ent, rows, first_head, n_heads, b, pair, split, tid, nthr;
+  int* s_ticket;
+  float *cl, *recv;
+};
+
+template <typename T>
+__device__ OMX_NI_COMBINE void combine_push(const DecodeParams& p, const MergeArgs& a) {
+  const float* mo = a.mo;
+  const int n_ent = a.n_ent, rows = a.rows, first_head = a.first_head, n_heads = a.n_heads, b = a.b, pair = a.pair,
+            split = a.split, tid = a.tid, nthr = a.nthr;
+  int* s_ticket = a.s_ticket;
+  float *cl = a.cl, *recv = a.recv;
   const int D = p.D;
   const int64_t ob = b * p.os[0];
-  const bool use_cluster = p.cluster && p.num_splits > 1;
-  const bool push = use_cluster && p.push_combine && recv != nullptr;
-  // receive slot of split s >= 1 inside RANK 0's shared memory: [s - 1][head][D | m | l]
+  float* part_o = const_cast<float*>(mo);
   auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
-  float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
-  // (one element per thread: a float4-column variant halved the active threads and measured slower)
-  for (int idx = tid; idx < n_heads * D; idx += nthr) {
-    const int g = idx / D, d = idx % D;
-    float M = has_nt ? nt_m[g] : -INFINITY;
-    for (int w = 0; w < n_ent; ++w) M = fmaxf(M, mml[(w * rows + g) * 2]);
-    float L = 0.f, O = 0.f;
-    for (int w = 0; w < n_ent; ++w) {
-      const float mw = mml[(w * rows + g) * 2];
-      if (mw > -INFINITY) {
-        const float sc = fast_exp2(mw - M);
-        L = fmaf(mml[(w * rows + g) * 2 + 1], sc, L);
-        O = fmaf(mo[(w * rows + g) * D + d], sc, O);
-      }
-    }
-    if (has_nt) {
-      const float sc = fast_exp2(nt_m[g] - M);
-      L += sc;
-      O = fmaf(nt_v[d], sc, O);
-    }
-    if (p.num_splits == 1) {
-      store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
-      if (d == 0) store_ml(p, b, first_head + g, M, L);
-      if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
-    } else if (push && split != 0) {
-      st_dsmem_f32(dsmem_addr(recv_at(split, g, d), 0), O);
-      if (d == 0) {
-        st_dsmem_f32(dsmem_addr(recv_at(split, g, D), 0), M);
-        st_dsmem_f32(dsmem_addr(recv_at(split, g, D + 1), 0), L);
-      }
-    } else if (use_cluster) {
-      part_o[g * D + d] = O;  // == mo[(0 * rows + g) * D + d], read above by this thread only
-      if (d == 0) {
-        cl[g * 2] = M;
-        cl[g * 2 + 1] = L;
-      }
-    } else {
-      const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
-      p.ws_o[e * D + d] = O;
-      if (d == 0) {
-        p.ws_ml[e * 2] = M;
-        p.ws_ml[e * 2 + 1] = L;
-      }
-    }
-  }
-  if (p.num_splits == 1) {
-    peer_signal(p, tid);
-    trace_mark(p, 6);
-    return;
-  }
-  trace_mark(p, 3);
-  if (push) {
+  (void)n_ent; (void)rows; (void)pair; (void)split; (void)s_ticket; (void)cl; (void)recv; (void)ob; (void)part_o; (void)recv_at;
     // ---- push combine: ranks 1.. have stored into rank 0's receive slots; their arrive (release) publishes the
     // stores and they leave -- nobody reads THEIR shared memory.  Rank 0 folds after the one barrier; every
     // element is owned by the thread that produced rank 0's own partial, so no further CTA barrier is needed.
@@ -724,8 +883,20 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     }
     trace_mark(p, 6);
     return;
-  }
-  if (use_cluster) {
+}
+
+template <typename T>
+__device__ OMX_NI_COMBINE void combine_pull(const DecodeParams& p, const MergeArgs& a) {
+  const float* mo = a.mo;
+  const int n_ent = a.n_ent, rows = a.rows, first_head = a.first_head, n_heads = a.n_heads, b = a.b, pair = a.pair,
+            split = a.split, tid = a.tid, nthr = a.nthr;
+  int* s_ticket = a.s_ticket;
+  float *cl = a.cl, *recv = a.recv;
+  const int D = p.D;
+  const int64_t ob = b * p.os[0];
+  float* part_o = const_cast<float*>(mo);
+  auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
+  (void)n_ent; (void)rows; (void)pair; (void)split; (void)s_ticket; (void)cl; (void)recv; (void)ob; (void)part_o; (void)recv_at;
     // ---- cluster combine.  Every CTA of the cluster publishes its partial in its own shared memory,
     // one cluster barrier later each CTA pulls all (m, l) pairs (NS x heads x 8 B) and its slice of the
     // output columns from its peers (~215-cycle DSMEM loads), and stores that slice.  Replaces partial
@@ -782,166 +953,20 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
     cluster_wait_acquire();
     trace_mark(p, 6);
     return;
-  }
-  if (p.gsync) {
-    // ---- all-CTA combine (one-wave grids).  publish -> meet -> every CTA folds its own column slice.
-    // Lanes run over the SPLITS: a group of W lanes holds one float4 column's contributions, so the per-head
-    // maximum / sum and the fold are warp shuffles; what is left of the tail is one round trip to L2 after the
-    // meeting point (partials + (m, l) requested together) and at most one CTA barrier behind it.
-    const int NS = p.num_splits;
-    __threadfence();
-    __syncthreads();
-    trace_mark(p, 4);
-    const int D4 = D >> 2;
-    const int C = n_heads * D4;                 // float4 columns of the pair's output
-    const int slice = (C + NS - 1) / NS;
-    const int c0 = split * slice, c1 = min(C, c0 + slice);
-    const int ncol = max(0, c1 - c0);
-    const GsyncShape gs = gsync_shape(NS);
-    const int W = gs.W, K = gs.K, cpw = 32 / W;
-    const int n_wi = W == 32 ? ncol * K : (ncol + cpw - 1) / cpw;  // warp-sized work items (host: <= 4 per warp)
-    const int nwarps = nthr >> 5, warp = tid >> 5, lane = tid & 31;
-    const int g0 = ncol ? c0 / D4 : 0, g1 = ncol ? (c1 - 1) / D4 : -1;  // heads the slice touches
-    const int nh = g1 - g0 + 1;
-    const int mlp = (NS * nh + 3) & ~3;
-    float* sm_m = const_cast<float*>(mo);       // [NS][nh]  (the merge inputs are dead: the own partial is in ws)
-    float* sm_l = sm_m + mlp;                   // [NS][nh]
-    float4* red = reinterpret_cast<float4*>(sm_l + mlp);  // [ncol][K]   (K > 1 only)
-    float* sm_inv = reinterpret_cast<float*>(red + ncol * K);  // [ncol]
-    const int64_t e0p = (int64_t)pair * NS * n_heads;
-    if (tid == 0) {
-      atomicAdd(&p.counters[pair], 1);
-      unsigned spins = 0;
-      while (ld_acquire_gpu(&p.counters[pair]) < NS)
-        if (++spins > (1u << 26)) __trap();  // a CTA that never became resident: a launch failure, not a hung GPU
-    }
-    __syncthreads();
-    trace_mark(p, 5);
-    // item i of this warp: column colL (local), split sp
-    auto item = [&](int i, int& colL, int& sp) {
-      const int wi = warp + i * nwarps;
-      if (W == 32) {
-        colL = wi / K;
-        sp = (wi % K) * 32 + lane;
-      } else {
-        colL = wi * cpw + lane / W;
-        sp = lane % W;
-      }
-      return wi < n_wi && colL < ncol && sp < NS;
-    };
-    float4 pre[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int colL, sp;
-      pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (item(i, colL, sp)) {
-        const int col = c0 + colL;
-        pre[i] = __ldcg(reinterpret_cast<const float4*>(p.ws_o + (e0p + (int64_t)sp * n_heads + col / D4) * D +
-                                                        (col % D4) * 4));
-      }
-    }
-    for (int idx = tid; idx < NS * nh; idx += nthr) {
-      const int sp = idx / nh, g = g0 + idx % nh;
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + (int64_t)sp * n_heads + g) * 2]));
-      sm_m[idx] = ml.x;
-      sm_l[idx] = ml.y;
-    }
-    __syncthreads();
-    trace_mark(p, 9);
-    // four consecutive features of local head g: plain stores, or the data + flag exchange
-    const unsigned ll_seq = p.ll.world ? __ldcg(p.ll.seq) + 1u : 0u;
-    auto emit4 = [&](int g, int d, const float4& v) {
-      const int64_t o = ob + (int64_t)(first_head + g) * p.os[1] + (int64_t)d * p.os[3];
-      if (p.ll.world == 0) {
-        store_out<T>(p, o, v.x);
-        store_out<T>(p, o + p.os[3], v.y);
-        store_out<T>(p, o + 2 * p.os[3], v.z);
-        store_out<T>(p, o + 3 * p.os[3], v.w);
-        return;
-      }
-      using LP = dd::LLPack<T>;
-      uint32_t w[LP::NW];
-      LP::pack(v, w);
-      LP::store((T*)p.out + o, w);  // the local slice (host: os[3] == 1, 16-byte aligned rows)
-      const int64_t e = ((int64_t)b * p.Hq + first_head + g) * D + d;  // element of this rank's [B,Hq,D] slice
-      dd::ll_exchange<LP::NW>(p.ll, ll_seq, e * (int64_t)sizeof(T) / 4, w, [&](int src, const uint32_t (&r)[LP::NW]) {
-        LP::store((T*)p.ll_out + b * p.os[0] + ((int64_t)src * p.Hq + first_head + g) * p.os[1] + d, r);
-      });
-    };
-    auto group_max = [&](float v) {
-      for (int o = W >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-      return v;
-    };
-    auto group_sum = [&](float v) {
-      for (int o = W >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      return v;
-    };
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (warp + i * nwarps >= n_wi) break;  // warp-uniform
-      int colL, sp;
-      const bool valid = item(i, colL, sp);
-      const int cc = min(colL, ncol - 1);     // lanes past the slice compute on its last column and store nothing
-      const int col = c0 + cc, g = col / D4, gi = g - g0;
-      float M = -INFINITY;
-      for (int s2 = lane % W; s2 < NS; s2 += W) M = fmaxf(M, sm_m[s2 * nh + gi]);
-      M = group_max(M);
-      float L = 0.f;
-      for (int s2 = lane % W; s2 < NS; s2 += W) {
-        const float ms = sm_m[s2 * nh + gi];
-        if (ms > -INFINITY) L = fmaf(sm_l[s2 * nh + gi], fast_exp2(ms - M), L);
-      }
-      L = group_sum(L);
-      const float mine = valid ? sm_m[sp * nh + gi] : -INFINITY;
-      const float e = mine > -INFINITY ? fast_exp2(mine - M) : 0.f;
-      float4 c = make_float4(group_sum(pre[i].x * e), group_sum(pre[i].y * e), group_sum(pre[i].z * e),
-                             group_sum(pre[i].w * e));
-      const bool lead = colL < ncol && (lane % W) == 0 && (W < 32 || (warp + i * nwarps) % K == 0);
-      if (lead && col % D4 == 0) {  // the CTA that owns the head's first column reports the row
-        store_ml(p, b, first_head + g, M, L);
-        if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
-      }
-      if (K == 1) {
-        if (lead) {
-          const float inv = 1.0f / L;
-          emit4(g, (col % D4) * 4, make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv));
-        }
-      } else if (colL < ncol && lane == 0) {
-        red[colL * K + (warp + i * nwarps) % K] = c;
-        if (lead) sm_inv[colL] = 1.0f / L;
-      }
-    }
-    if (K > 1) {
-      __syncthreads();
-      trace_mark(p, 10);
-      for (int colL = tid; colL < ncol; colL += nthr) {
-        float4 a = red[colL * K];
-        for (int k = 1; k < K; ++k) {
-          const float4 r = red[colL * K + k];
-          a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-        }
-        const float inv = sm_inv[colL];
-        const int col = c0 + colL;
-        emit4(col / D4, (col % D4) * 4, make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv));
-      }
-    }
-    trace_mark(p, 11);
-    peer_signal(p, tid);  // (peer_total counts every CTA of the launch in this mode)
-    if (p.ll.world) __syncthreads();  // this CTA's exchange is complete
-    if (tid == 0) {
-      const int t = atomicAdd(&p.counters2[pair], 1);
-      if (t == NS - 1) {  // everybody has passed the meeting point: reset both counters for the next launch
-        p.counters[pair] = 0;
-        p.counters2[pair] = 0;
-      }
-      if (p.ll.world && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
-        *p.peer_done = 0;     // the launch's last CTA: every word of the step has been sent and received here
-        *p.ll.seq = ll_seq;
-      }
-    }
-    trace_mark(p, 6);
-    return;
-  }
+}
+
+template <typename T, int PF>
+__device__ OMX_NI_COMBINE void combine_ticket(const DecodeParams& p, const MergeArgs& a) {
+  const float* mo = a.mo;
+  const int n_ent = a.n_ent, rows = a.rows, first_head = a.first_head, n_heads = a.n_heads, b = a.b, pair = a.pair,
+            split = a.split, tid = a.tid, nthr = a.nthr;
+  int* s_ticket = a.s_ticket;
+  float *cl = a.cl, *recv = a.recv;
+  const int D = p.D;
+  const int64_t ob = b * p.os[0];
+  float* part_o = const_cast<float*>(mo);
+  auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
+  (void)n_ent; (void)rows; (void)pair; (void)split; (void)s_ticket; (void)cl; (void)recv; (void)ob; (void)part_o; (void)recv_at;
   __threadfence();
   __syncthreads();
   trace_mark(p, 4);
@@ -1077,6 +1102,84 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   trace_mark(p, 6);
 }
 
+// Merge per-warp states -> out (single split) or workspace + last-CTA combine.
+// mo: [n_ent][rows][D] floats, mml: [n_ent][rows][2]; rows = row pitch of the entries.
+template <typename T, int PF>
+__device__ __forceinline__ void merge_and_store(const DecodeParams& p, const float* mo, const float* mml,
+                                                int n_ent, int rows, bool has_nt, const float* nt_m,
+                                                const float* nt_v, int first_head, int n_heads, int b,
+                                                int pair, int split, int tid, int nthr, int* s_ticket,
+                                                float* cl /* cluster scratch, cluster_scratch_floats(rows) */,
+                                                float* recv = nullptr /* push-combine receive slots */) {
+  const int D = p.D;
+  const int64_t ob = b * p.os[0];
+  const bool use_cluster = p.cluster && p.num_splits > 1;
+  const bool push = use_cluster && p.push_combine && recv != nullptr;
+  // receive slot of split s >= 1 inside RANK 0's shared memory: [s - 1][head][D | m | l]
+  auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
+  float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
+  // (one element per thread: a float4-column variant halved the active threads and measured slower)
+  for (int idx = tid; idx < n_heads * D; idx += nthr) {
+    const int g = idx / D, d = idx % D;
+    float M = has_nt ? nt_m[g] : -INFINITY;
+    for (int w = 0; w < n_ent; ++w) M = fmaxf(M, mml[(w * rows + g) * 2]);
+    float L = 0.f, O = 0.f;
+    for (int w = 0; w < n_ent; ++w) {
+      const float mw = mml[(w * rows + g) * 2];
+      if (mw > -INFINITY) {
+        const float sc = fast_exp2(mw - M);
+        L = fmaf(mml[(w * rows + g) * 2 + 1], sc, L);
+        O = fmaf(mo[(w * rows + g) * D + d], sc, O);
+      }
+    }
+    if (has_nt) {
+      const float sc = fast_exp2(nt_m[g] - M);
+      L += sc;
+      O = fmaf(nt_v[d], sc, O);
+    }
+    if (p.num_splits == 1) {
+      store_out<T>(p, ob + (int64_t)(first_head + g) * p.os[1] + d * p.os[3], O / L);
+      if (d == 0) store_ml(p, b, first_head + g, M, L);
+      if (p.dead && d == 0) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
+    } else if (push && split != 0) {
+      st_dsmem_f32(dsmem_addr(recv_at(split, g, d), 0), O);
+      if (d == 0) {
+        st_dsmem_f32(dsmem_addr(recv_at(split, g, D), 0), M);
+        st_dsmem_f32(dsmem_addr(recv_at(split, g, D + 1), 0), L);
+      }
+    } else if (use_cluster) {
+      part_o[g * D + d] = O;  // == mo[(0 * rows + g) * D + d], read above by this thread only
+      if (d == 0) {
+        cl[g * 2] = M;
+        cl[g * 2 + 1] = L;
+      }
+    } else {
+      const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
+      p.ws_o[e * D + d] = O;
+      if (d == 0) {
+        p.ws_ml[e * 2] = M;
+        p.ws_ml[e * 2 + 1] = L;
+      }
+    }
+  }
+  if (p.num_splits == 1) {
+    peer_signal(p, tid);
+    trace_mark(p, 6);
+    return;
+  }
+  trace_mark(p, 3);
+  const MergeArgs ma{mo, n_ent, rows, first_head, n_heads, b, pair, split, tid, nthr, s_ticket, cl, recv};
+  if (push) {
+    combine_push<T>(p, ma);
+  } else if (use_cluster) {
+    combine_pull<T>(p, ma);
+  } else if (p.gsync) {
+    gsync_combine<T>(p, const_cast<float*>(mo), first_head, n_heads, b, pair, split, tid, nthr);
+  } else {
+    combine_ticket<T, PF>(p, ma);
+  }
+}
+
 // ============================================================ 16-bit, D = 128: TMA + mma.sync
 // NSTAGE consumer warps + 1 producer warp.  Consumer warp w owns stage w and its full/empty
 // mbarrier pair (tile t -> warp t % NSTAGE -> stage t % NSTAGE): every barrier then has exactly
@@ -1085,7 +1188,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
 template <typename T, int NSTAGE, bool HI, int MINB>
 __global__ void __launch_bounds__((NSTAGE + 1) * 32, MINB)
 decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const DecodeParams p) {
+                   const __grid_constant__ DecodeParams p) {
   constexpr int D = 128;
   constexpr int NW = NSTAGE;
   constexpr int NTHR = (NW + 1) * 32;
@@ -1110,6 +1213,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   uint64_t pol = 0;
   int pf_next = 0;  // (producer lane) next tile of this CTA to request into L2
   auto l2_upto = [&](int from, int hi) {
+#pragma unroll 1
     for (pf_next = max(pf_next, from); pf_next < hi; ++pf_next) {
       const int k0 = p.paged ? 0 : (tile_begin + pf_next) * kTile;
       const int c = p.paged ? __ldg(bt_row + tile_begin + pf_next) : b;
@@ -1458,7 +1562,7 @@ constexpr int kSimtWarps = 8;
 // instead of through four dependent round trips to HBM.
 template <typename T, int VE, int GT, int KPW>
 __global__ void __launch_bounds__(kSimtWarps * 32)
-decode_simt_kernel(const DecodeParams p) {
+decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   constexpr int kSimtKeys = KPW;
   constexpr int D = 32 * VE;
   constexpr int NTHR = kSimtWarps * 32;
@@ -1987,8 +2091,8 @@ struct TraceDump {
     fprintf(stderr, "[omx decode trace] ctas=%zu span=%.2fus | slot: n mean max (us since first CTA start):", ctas,
             (double)(t1 - t0) * 1e-3);
     static const char* nm[NS] = {"start", "q_staged", "loop_done", "merged", "fenced", "ticket", "end", "tma_issued",
-                                 "c_fence", "c_ml", "c_weights", "c_folded", "p_loaded", "p_rms", "", ""};
-    static const int order[NS] = {0, 7, 12, 13, 1, 2, 3, 4, 5, 8, 9, 10, 11, 6, 14, 15};
+                                 "c_fence", "c_ml", "c_weights", "c_folded", "p_loaded", "p_rms", "p_issued", ""};
+    static const int order[NS] = {0, 7, 14, 12, 13, 1, 2, 3, 4, 5, 8, 9, 10, 11, 6, 15};
     for (int i = 0; i < NS; ++i) {
       const int s = order[i];
       if (cnt[s]) fprintf(stderr, " %s: %d %.2f %.2f |", nm[s], cnt[s], sum[s] / cnt[s], mx[s]);
