@@ -881,7 +881,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="all", choices=["all", "c2_paged"] + sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=["all", "c2_paged", "c2_weak", "c5_collective"] + sorted(WORKLOADS))
     ap.add_argument("--impl", default="omx", choices=["omx", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--eager-e2e", action="store_true", help="run the e2e pipeline eagerly instead of from a graph")

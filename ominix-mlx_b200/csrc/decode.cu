@@ -239,6 +239,9 @@ struct DecodeParams {
   // (a 64-way split: 6.7 us of dependent round trips in one CTA).  counters2[pair] counts the CTAs that have left.
   int gsync;
   int* counters2;
+  // CUDA-core kernel, staged variant: byte offset (from the dynamic shared memory base) of the K stage, and the
+  // keys one stage holds (V follows K); 0 = rows are loaded straight into registers
+  int stage_off, stage_keys;
   // data + flag exchange of the head-sharded step (omx_attn_decode_fused_sharded_ll; all-CTA combine only): the
   // lane that holds four final output values stores them as {payload, sequence number} words into every peer's
   // staging buffer, then polls its own staging buffer for the peers' words and unpacks them into ll_out (the
@@ -1560,7 +1563,11 @@ constexpr int kSimtWarps = 8;
 // KPW = keys in flight per warp iteration: 4 when many CTAs share an SM (throughput regime), 16 for
 // one-wave grids (single-sequence decode), where a CTA's whole 128-key share is then requested up front
 // instead of through four dependent round trips to HBM.
-template <typename T, int VE, int GT, int KPW>
+// ST (staged; one-wave grids, contiguous rows): ONE thread asks for the CTA's whole key range with two bulk copies
+// into shared memory -- all of it in flight from the first microsecond, none of it in registers -- and the key
+// loop is the small 4-key body run from shared memory (the 16-key body is ~1000 straight-line instructions per
+// head pair: the per-CTA timelines show its first and only walk taking 5.4 us on a cold instruction cache).
+template <typename T, int VE, int GT, int KPW, bool ST = false>
 __global__ void __launch_bounds__(kSimtWarps * 32)
 decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   constexpr int kSimtKeys = KPW;
@@ -1582,6 +1589,27 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   const int hk = blockIdx.y / groups, gsub = blockIdx.y % groups;
   const int first_head = hk * p.G + gsub * GT;
   const int pair = (b * p.Hkv + hk) * groups + gsub;
+  __shared__ uint64_t st_bar;
+  T* ks_s = reinterpret_cast<T*>(smem_raw + p.stage_off);
+  T* vs_s = ks_s + (size_t)p.stage_keys * D;
+  bool st_issued = false;  // (thread 0)
+  auto stage_issue = [&](int k0, int k1) {  // rows [k0, k1) of (b, hk): contiguous in the cache (host check)
+    const uint32_t bytes = (uint32_t)(k1 - k0) * D * (uint32_t)sizeof(T);
+    mbar_expect_tx(&st_bar, 2 * bytes);
+    bulk_load_1d(ks_s, (const T*)p.k + b * p.ks[0] + hk * p.ks[1] + (int64_t)k0 * p.ks[2], bytes, &st_bar);
+    bulk_load_1d(vs_s, (const T*)p.v + b * p.vs[0] + hk * p.vs[1] + (int64_t)k0 * p.vs[2], bytes, &st_bar);
+    st_issued = true;
+  };
+  if constexpr (ST) {
+    if (tid == 0) {
+      mbar_init(&st_bar, 1);
+      mbar_fence_init();
+      if (p.stable_rows > 0) {  // rows older than the stream's previous kernel: requested before the dependency wait
+        const int k0 = split * p.tiles_per_split * kTile, k1 = min(p.n_mem, k0 + p.tiles_per_split * kTile);
+        if (k1 > k0 && k1 <= p.stable_rows) stage_issue(k0, k1);
+      }
+    }
+  }
   pdl_wait_prior_grid();
   trace_mark(p, 0);
   if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot
@@ -1589,6 +1617,9 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
   const int kend = min(dy.n_mem, kbeg + keys_per_split);
+  if constexpr (ST) {
+    if (tid == 0 && !st_issued && kend > kbeg) stage_issue(kbeg, kend);
+  }
   const bool has_nt = p.fused && p.append && split == p.num_splits - 1;
   if (p.paged && has_nt && hk == 0 && gsub == 0 && tid == 0) p.lens_out[b] = dy.Lk;
 
@@ -1599,6 +1630,13 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   // rows stay in their storage type until they are used, so that nothing waits on the loads early
   RawRow<T, VE> kraw[kSimtKeys], vraw[kSimtKeys];
   auto load_kv = [&](int j0) {
+    if constexpr (ST) {
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) kraw[u].load(ks_s + (size_t)(min(j0 + u, kend - 1) - kbeg) * D + lane * VE);
+#pragma unroll
+      for (int u = 0; u < kSimtKeys; ++u) vraw[u].load(vs_s + (size_t)(min(j0 + u, kend - 1) - kbeg) * D + lane * VE);
+      return;
+    }
     if (p.paged) {
       // row j = row j % 64 of page block_table[b][j / 64]; j0 is a multiple of KPW and KPW divides 64, so the
       // (clamped) rows of one batch share a page
@@ -1619,11 +1657,15 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   const int j_first = kbeg + warp * kSimtKeys;
 
   stage_q<T>(p, q_s, D, GT, first_head, GT, b, hk, tid, NTHR, s_pro, nt_k, nt_v, has_nt, dy, [&] {
-    if (j_first < kend) load_kv(j_first);
+    if constexpr (!ST) {
+      if (j_first < kend) load_kv(j_first);
+    }
   }, [] { __syncthreads(); });
   __syncthreads();
   trace_mark(p, 1);
-  // the new row is appended once per kv head (gsub == 0 writes it); every group scores it
+
+  // the new row is appended once per kv head (gsub == 0 writes it); every group scores it.  (Behind the key loop
+  // instead -- only the merge needs it -- measured slower: here it runs while the CTA's rows are still in flight.)
   if (has_nt && warp == kSimtWarps - 1)
     new_token<T>(p, q_s, D, GT, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy, /*write_cache=*/gsub == 0);
 
@@ -1636,8 +1678,12 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
 #pragma unroll
     for (int e = 0; e < VE; ++e) acc[g][e] = 0.f;
   }
+  if constexpr (ST) {
+    if (kend > kbeg) mbar_wait(&st_bar, 0);  // the staged rows have landed (the barrier was initialised before the
+  }                                          // CTA-wide syncs of stage_q)
+#pragma unroll 1
   for (int j0 = j_first; j0 < kend; j0 += kSimtWarps * kSimtKeys) {
-    if (j0 != j_first) load_kv(j0);
+    if (ST || j0 != j_first) load_kv(j0);
 #pragma unroll
     for (int g = 0; g < GT; ++g) {
       float s[kSimtKeys];
@@ -1853,10 +1899,28 @@ bool inner_contig(const omx_array* a) { return a->strides[3] == 1 || a->shape[3]
 
 template <typename T, int VE>
 void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool one_wave, bool want_cluster) {
+  // staged variant: the split's rows as two contiguous blocks behind the kernel's own shared memory
+  const size_t stage_bytes = 2 * (size_t)p.tiles_per_split * kTile * 32 * VE * sizeof(T);
+  auto base_smem = [&](int gt) {
+    return sizeof(float) * ((size_t)kSimtWarps * gt * (32 * VE + 2) + 2 * 32 * VE + 4 + cluster_scratch_floats(gt)) +
+           sizeof(T) * (size_t)gt * 32 * VE;
+  };
+  static const int staged_env = [] {  // OMX_DECODE_STAGED=0: never (A/B knob)
+    const char* e = getenv("OMX_DECODE_STAGED");
+    return e ? atoi(e) : 1;
+  }();
+  const bool rows_contig = p.ks[2] == 32 * VE && p.vs[2] == 32 * VE && p.ks[3] == 1 && p.vs[3] == 1;
+  constexpr bool kHasStaged = std::is_same<T, float>::value && VE == 4;  // instantiated where the 16-key body is
+  const bool staged = kHasStaged && staged_env != 0 && one_wave && !p.paged && rows_contig &&
+                      ((base_smem(4) + 127) & ~(size_t)127) + stage_bytes <= 200 * 1024;
   auto go = [&](auto kern, int gt) {
-    const size_t smem = sizeof(float) * ((size_t)kSimtWarps * gt * (32 * VE + 2) + 2 * 32 * VE + 4 +
-                                         cluster_scratch_floats(gt)) +
-                        sizeof(T) * (size_t)gt * 32 * VE;
+    size_t smem = base_smem(gt);
+    p.stage_off = p.stage_keys = 0;
+    if (staged) {
+      p.stage_off = (int)((smem + 127) & ~(size_t)127);
+      p.stage_keys = p.tiles_per_split * kTile;
+      smem = (size_t)p.stage_off + stage_bytes;
+    }
     OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.cluster = want_cluster && p.num_splits > 1 &&
                         cluster_capacity(kern, grid, kSimtWarps * 32, smem, p.num_splits) >= (int)(grid.y * grid.z)
@@ -1870,8 +1934,14 @@ void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool o
   };
   // the 16-key variant keeps 2 x 16 rows per lane in registers; instantiated where it is used and measured --
   // float32 at head_dim 128 (C1; 16-bit head_dim 128 runs on the TMA kernel) -- to keep the build time down
-  constexpr int KBIG = (std::is_same<T, float>::value && VE == 4) ? 16 : 4;
-  if (one_wave && KBIG != 4) {
+  constexpr int KBIG = kHasStaged ? 16 : 4;
+  if (staged && KBIG != 4) {
+    switch (Gt) {
+      case 1: go(decode_simt_kernel<T, VE, 1, 4, true>, 1); break;
+      case 2: go(decode_simt_kernel<T, VE, 2, 4, true>, 2); break;
+      default: go(decode_simt_kernel<T, VE, 4, 4, true>, 4); break;
+    }
+  } else if (one_wave && KBIG != 4) {
     switch (Gt) {
       case 1: go(decode_simt_kernel<T, VE, 1, KBIG>, 1); break;
       case 2: go(decode_simt_kernel<T, VE, 2, KBIG>, 2); break;
