@@ -471,6 +471,20 @@ inline void attention_decode_fused_dynamic(Array& out, const Array& queries, con
                                       fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
                                       rope ? rope->scale : 1.f, scale, position, s.raw()));
 }
+/// kv-head-sharded decode step of one rank with the data + flag exchange (see omx_attn_decode_fused_sharded_ll):
+/// queries / keys / values carry the LOCAL heads, `out_full` is this rank's private [B,Hq_total,1,D] output and is
+/// complete when the launch completes; `group` = every rank's staging buffer as mapped here + the local step counter.
+inline void attention_decode_fused_sharded(Array& out_full, const Array& queries, const Array& keys,
+                                           const Array& values, KVCache& cache, const nn::Rope* rope, float scale,
+                                           const omx_ll_group& group, Stream s = {}) {
+  const auto qs = queries.shape();
+  if (qs.size() != 4 || qs[2] != 1) throw Exception("attention_decode_fused_sharded: queries must be [B, H, 1, D]");
+  check(omx_attn_decode_fused_sharded_ll(out_full.desc(), queries.desc(), keys.desc(), values.desc(), cache.raw(),
+                                         rope ? rope->dimensions : 0, rope ? rope->traditional : false,
+                                         fast::opt(rope ? std::optional<float>(rope->base) : std::nullopt),
+                                         rope ? rope->scale : 1.f, nullptr, scale, &group,
+                                         (int)(group.rank * qs[1]), s.raw()));
+}
 /// Sequence-sharded decode step of one rank (see omx_attn_decode_seqshard): `partial` = this rank's float32
 /// [world,B,Hq,D+2] buffer, `position` = GLOBAL position of the new token, `append` on the owning rank only.
 inline void attention_decode_seqshard(Array& partial, const Array& queries, const Array* keys, const Array* values,

@@ -438,6 +438,51 @@ static void test_paged_cache_equals_contiguous_cache() {
   EXPECT(pc.lengths()[1] == -1 && pc.lengths()[0] == n && pc.free_pages() == 8 - 3, "release returns the pages");
 }
 
+// The head-sharded step with the data + flag exchange at world = 1 (the exchange degenerates to the local store
+// and the step counter): same bits as the plain fused step, counter = number of steps.
+static void test_head_sharded_ll_world1() {
+  printf("test_head_sharded_ll_world1\n");
+  const int B = 1, Hq = 4, Hkv = 1, D = 128, L = 3000;
+  const float scale = 1.0f / std::sqrt((float)D);
+  auto kh = randn_bf16((size_t)B * Hkv * L * D, 70), vh = randn_bf16((size_t)B * Hkv * L * D, 71);
+  Array k = Array::from_host(kh.data(), {B, Hkv, L, D}, Dtype::Bfloat16);
+  Array v = Array::from_host(vh.data(), {B, Hkv, L, D}, Dtype::Bfloat16);
+  omx::nn::Rope rope = omx::utils::initialize_rope(D, 1e6f, false);
+  omx::KVCache c1, c2;
+  c1.update_and_fetch(k, v);
+  c2.update_and_fetch(k, v);
+  const size_t sb = omx_ll_staging_bytes(1, B, Hq, D, OMX_BFLOAT16);
+  EXPECT(sb == (size_t)2 * B * Hq * D * 2 / 4 * 8, "staging bytes %zu", sb);
+  void* staging = nullptr;
+  uint32_t* seq = nullptr;
+  cudaMalloc(&staging, sb);
+  cudaMemset(staging, 0, sb);
+  cudaMalloc(&seq, 4);
+  cudaMemset(seq, 0, 4);
+  omx_ll_group g{};
+  g.world = 1;
+  g.rank = 0;
+  g.staging[0] = staging;
+  g.seq = seq;
+  Array out_full = Array::empty({B, Hq, 1, D}, Dtype::Bfloat16);
+  for (int step = 1; step <= 3; ++step) {
+    auto qh = randn_bf16((size_t)B * Hq * D, 72 + step), k1h = randn_bf16((size_t)B * Hkv * D, 80 + step),
+         v1h = randn_bf16((size_t)B * Hkv * D, 90 + step);
+    Array q1 = Array::from_host(qh.data(), {B, Hq, 1, D}, Dtype::Bfloat16);
+    Array k1 = Array::from_host(k1h.data(), {B, Hkv, 1, D}, Dtype::Bfloat16);
+    Array v1 = Array::from_host(v1h.data(), {B, Hkv, 1, D}, Dtype::Bfloat16);
+    Array ref = omx::utils::attention_decode_fused(q1, k1, v1, c1, &rope, scale);
+    omx::utils::attention_decode_fused_sharded(out_full, q1, k1, v1, c2, &rope, scale, g);
+    EXPECT(download(ref) == download(out_full), "step %d: sharded (world 1) output differs from the plain fused step", step);
+    uint32_t hs = 0;
+    cudaMemcpy(&hs, seq, 4, cudaMemcpyDeviceToHost);
+    EXPECT((int)hs == step, "step counter %u after %d steps", hs, step);
+  }
+  EXPECT(download(c1.state().first) == download(c2.state().first), "KV keys: sharded vs plain");
+  cudaFree(staging);
+  cudaFree(seq);
+}
+
 int main() {
   int sm = 0;
   if (omx_device_check(&sm) != 0) {
@@ -452,6 +497,7 @@ int main() {
     test_attention_forward_prefill_then_decode();
     test_decode_loop_cuda_graph();
     test_paged_cache_equals_contiguous_cache();
+    test_head_sharded_ll_world1();
   } catch (const std::exception& e) {
     printf("EXCEPTION: %s\n", e.what());
     return 1;
