@@ -631,6 +631,13 @@ __device__ __forceinline__ void cluster_arrive_release() {
 __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// "every CTA of the cluster has started": arrive at kernel entry, wait before the first store into a peer's shared
+// memory (the push combine stores before any other cluster barrier; compute-sanitizer flags a DSMEM write to a block
+// that "might not have entered yet" otherwise)
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_plain() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
@@ -1121,6 +1128,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   // receive slot of split s >= 1 inside RANK 0's shared memory: [s - 1][head][D | m | l]
   auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
   float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
+  if (push) cluster_wait_plain();  // pairs with the arrive at kernel entry: rank 0 is running, its slots exist
   // (one element per thread: a float4-column variant halved the active threads and measured slower)
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
     const int g = idx / D, d = idx % D;
@@ -1210,6 +1218,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const int split = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
   const int G = p.G;
   const int pair = b * p.Hkv + hk;
+  if (p.push_combine) cluster_arrive_relaxed();  // (see cluster_wait_plain in merge_and_store)
   // ---- before the dependency wait: shared memory, and cache rows no running kernel can still be writing
   int tile_begin = split * p.tiles_per_split, my_tiles = 0;
   const int* bt_row = nullptr;

@@ -222,6 +222,14 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
     }
     OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
   }
+  if (force.empty() || force == "sdpa_f32_tiled") {
+    // float32 with more than a handful of query rows: shared-memory tiles instead of one warp per row
+    if (sdpa_f32_tiled_supported(a, &why) && (a.Lq >= 16 || !force.empty())) {
+      sdpa_f32_tiled(a, stream);
+      return;
+    }
+    OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
+  }
   sdpa_generic(a, stream);
 }
 
@@ -262,7 +270,7 @@ int omx_force_kernel(const char* name) {
   return guarded([&] {
     const std::string n = name ? name : "";
     OMX_CHECK(n.empty() || n == "decode" || n == "decode_simt" || n == "decode_hmma_tma" ||
-                  n == "fmha_tcgen05" || n == "sdpa_generic",
+                  n == "fmha_tcgen05" || n == "sdpa_generic" || n == "sdpa_f32_tiled",
               "unknown kernel family '%s'", n.c_str());
     t_forced_kernel = n;
   });
@@ -1127,6 +1135,11 @@ static void dit_attention_impl(const omx_array* out, const omx_array* q, const o
     const bool forced_generic = t_forced_kernel == "sdpa_generic";
     if (!forced_generic && fmha_sm100_supported(a, &why) && (a.Lq >= 2 || t_forced_kernel == "fmha_tcgen05")) {
       fmha_sm100(a, stream);
+      return;
+    }
+    if (!forced_generic && t_forced_kernel != "fmha_tcgen05" && sdpa_f32_tiled_supported(a, &why) &&
+        (a.Lq >= 16 || t_forced_kernel == "sdpa_f32_tiled")) {
+      sdpa_f32_tiled(a, stream);  // the float32 DiT chains (the FLUX example runs in float32)
       return;
     }
     OMX_CHECK(t_forced_kernel.empty() || forced_generic, "forced kernel '%s' does not support this call: %s",

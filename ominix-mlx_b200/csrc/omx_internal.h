@@ -205,6 +205,10 @@ void paged_end_step(PagedKVImpl* c);
 void paged_trim(PagedKVImpl* c, int n, cudaStream_t stream);
 void paged_pool_ptrs(const PagedKVImpl* c, void** kpool, void** vpool, const int** block_table);
 
+// ---- sdpa_f32_tiled.cu ---- float32, Lq > 1, head_dim 64 / 128: 64 x 64 tiles on the FFMA pipe
+bool sdpa_f32_tiled_supported(const SdpaArgs& a, const char** why);
+void sdpa_f32_tiled(const SdpaArgs& a, cudaStream_t stream);
+
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);
 void fmha_sm100(const SdpaArgs& a, cudaStream_t stream);

@@ -281,3 +281,52 @@ def test_absorbed_mla_glm47_flash_dk576_dv512(L):
     K, V = c.update_and_fetch(k.to(DEV), k.to(DEV)[..., :Dv].contiguous())
     got2 = omx.fast.scaled_dot_product_attention(q.to(DEV), K, V, Dk ** -0.5, mask)
     assert torch.equal(got, got2)
+
+
+# ---- float32 with many query rows: the tiled FFMA kernel (sdpa_f32_tiled.cu) ----
+
+@pytest.mark.parametrize("mask", MASKS)
+@pytest.mark.parametrize("shape", [(2, 4, 2, 70, 70, 128), (1, 4, 4, 64, 200, 64), (1, 6, 2, 130, 257, 128)])
+def test_f32_tiled_all_masks(shape, mask):
+    """Forced kernel vs the oracle chain at the float32 bar (1e-4 relative): ragged row / key counts, GQA, the
+    bottom-right aligned causal mask with Lq < Lk, bool and additive arrays, both head dims."""
+    _run(shape, "f32", mask, force="sdpa_f32_tiled")
+
+
+def test_f32_tiled_is_the_default_for_float32_prefill_and_matches_generic():
+    shape = (1, 16, 8, 300, 300, 128)  # Qwen3-0.6B-shape prefill (C1's model), float32
+    got = _run(shape, "f32", "causal")
+    assert omx.last_kernel() == "sdpa_f32_tiled"
+    ref = _run(shape, "f32", "causal", force="sdpa_generic")
+    assert omx.last_kernel() == "sdpa_generic"
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6)
+    # a handful of rows stays on the row-per-warp kernel; 16-bit inputs never come here
+    _run((1, 4, 2, 8, 100, 128), "f32", "causal")
+    assert omx.last_kernel() == "sdpa_generic"
+    omx.force_kernel("sdpa_f32_tiled")
+    try:
+        with pytest.raises(omx.Exception, match="not float32"):
+            q = torch.zeros((1, 2, 32, 128), dtype=torch.bfloat16, device=DEV)
+            omx.fast.scaled_dot_product_attention(q, q, q, 1.0, None)
+    finally:
+        omx.force_kernel("")
+
+
+def test_f32_tiled_strided_views_and_fully_masked_rows():
+    # [B, L, H, D] projections viewed [B, H, L, D]; K / V as a slice of a longer cache buffer
+    _run((2, 4, 2, 90, 90, 128), "f32", "causal", force="sdpa_f32_tiled",
+         qview=lambda t: t.transpose(1, 2).contiguous().transpose(1, 2),
+         kvview=lambda t: torch.cat([t, torch.zeros_like(t)], 2)[:, :, :t.shape[2]])
+    # rows whose bool mask hides every key follow the finfo.min rule (uniform average), like the generic kernel
+    B, H, L, D = 1, 2, 80, 64
+    q, k, v = (randn((B, H, L, D), "f32", s) for s in (1, 2, 3))
+    m = torch.rand((L, L), generator=torch.Generator().manual_seed(5)) > 0.5
+    m[7, :] = False
+    m[70, :] = False
+    omx.force_kernel("sdpa_f32_tiled")
+    try:
+        got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, m.to(DEV))
+    finally:
+        omx.force_kernel("")
+    want = orc.sdpa(t2n(q, "f32"), t2n(k, "f32"), t2n(v, "f32"), D ** -0.5, m.numpy(), dtype="f32")
+    assert_close(got.cpu().numpy(), n2f(want, "f32"), "f32", "fully masked rows, tiled kernel")
