@@ -483,11 +483,79 @@ static void test_head_sharded_ll_world1() {
   cudaFree(seq);
 }
 
-int main() {
+// --bench: the fused decode step launched EAGERLY from compiled code (no Python, no graph): what a Rust / C++ host
+// pays per layer and token.  Caches are rotated so that every step reads HBM; the offset is rewound after each step.
+static void bench_eager_decode(const char* name, int B, int Hq, int Hkv, int S, Dtype dt, int R) {
+  const int D = 128;
+  const size_t es = dt == Dtype::Float32 ? 4 : 2;
+  const float scale = 1.0f / std::sqrt((float)D);
+  std::vector<uint16_t> h16;
+  std::vector<float> h32;
+  auto host = [&](size_t n, unsigned seed) -> const void* {
+    if (es == 2) {
+      h16 = randn_bf16(n, seed);
+      return h16.data();
+    }
+    std::mt19937 g(seed);
+    std::normal_distribution<float> d(0.f, 1.f);
+    h32.resize(n);
+    for (auto& x : h32) x = d(g);
+    return h32.data();
+  };
+  Array k = Array::from_host(host((size_t)B * Hkv * (S - 1) * D, 1), {B, Hkv, S - 1, D}, dt);
+  Array v = Array::from_host(host((size_t)B * Hkv * (S - 1) * D, 2), {B, Hkv, S - 1, D}, dt);
+  Array q1 = Array::from_host(host((size_t)B * Hq * D, 3), {B, Hq, 1, D}, dt);
+  Array k1 = Array::from_host(host((size_t)B * Hkv * D, 4), {B, Hkv, 1, D}, dt);
+  Array v1 = Array::from_host(host((size_t)B * Hkv * D, 5), {B, Hkv, 1, D}, dt);
+  Array out = Array::empty({B, Hq, 1, D}, dt);
+  std::vector<omx::KVCache> caches;
+  for (int r = 0; r < R; ++r) {
+    caches.emplace_back();
+    omx_kv_cache_reserve(caches.back().raw(), S + 256);
+    caches.back().update_and_fetch(k, v);
+  }
+  omx_optional_float base{1e6f, true};
+  auto step = [&](int i) {
+    omx::KVCache& c = caches[i % R];
+    omx::check(omx_attn_decode_fused(out.desc(), q1.desc(), k1.desc(), v1.desc(), c.raw(), D, false, base, 1.0f, nullptr,
+                                     scale, nullptr, nullptr, nullptr));
+    int t = 0;
+    omx_kv_cache_trim(c.raw(), 1, &t);
+  };
+  for (int i = 0; i < 3 * R; ++i) step(i);
+  cudaDeviceSynchronize();
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int N = 50 * R;
+  cudaEventRecord(e0);
+  for (int i = 0; i < N; ++i) step(i);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  printf("{\"host\": \"c++ eager\", \"shape\": \"%s\", \"us_per_step\": %.2f, \"kernel\": \"%s\", \"caches\": %d}\n", name,
+         ms * 1e3 / N, omx_last_kernel(), R);
+}
+
+int main(int argc, char** argv) {
   int sm = 0;
   if (omx_device_check(&sm) != 0) {
     printf("no sm_100a device: %s\n", omx_last_error());
     return 2;
+  }
+  if (argc > 1 && std::string(argv[1]) == "--bench") {
+    try {
+      bench_eager_decode("c1 fp32 16/8 ctx2048", 1, 16, 8, 2048, Dtype::Float32, 16);
+      bench_eager_decode("0.6b bf16 16/8 ctx2048", 1, 16, 8, 2048, Dtype::Bfloat16, 16);
+      bench_eager_decode("8b bf16 32/8 ctx8192", 1, 32, 8, 8192, Dtype::Bfloat16, 16);
+      bench_eager_decode("c5 bf16 32/8 ctx32768", 1, 32, 8, 32768, Dtype::Bfloat16, 4);
+      bench_eager_decode("c2 bf16 32/8 ctx8192 B8", 8, 32, 8, 8192, Dtype::Bfloat16, 1);
+    } catch (const std::exception& e) {
+      printf("EXCEPTION: %s\n", e.what());
+      return 1;
+    }
+    return 0;
   }
   try {
     test_rope_bit_exact();

@@ -8,3 +8,4 @@ for tool in memcheck racecheck; do
   echo "$tool rc=$? $(tail -1 gpurun_out/sanitizer2_${tool}_pytest.log) | $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer2_$tool.log)" | tee -a $out
 done
 python scripts/gpu_r02_f32_prefill.py 2>&1 | tee -a $out
+ominix-mlx_b200/host/test_host --bench 2>&1 | tee -a $out
