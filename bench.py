@@ -55,6 +55,10 @@ WORKLOADS = {
                            label="C3 Qwen3-8B causal prefill bf16 B8 seq8192")),
     "c4": ("prefill", dict(B=4, Hq=24, Hkv=24, D=128, S=4608, dtype="bf16", causal=False,
                            label="C4 FLUX.2-klein DiT joint attention bf16 B4 512txt+4096img")),
+    # not a BASELINE config: the PREFILL of config 1's model in its own dtype (float32 -> the tiled FFMA kernel,
+    # DESIGN 4.3), so that the float32 multi-row path has a driver-side number too (N = 1 only)
+    "c1_prefill": ("prefill", dict(B=1, Hq=16, Hkv=8, D=128, S=2048, dtype="f32", causal=True,
+                                   label="C1 model prefill: Qwen3-0.6B causal prefill fp32 B1 seq2048")),
 }
 L2_BYTES = 126e6
 MIN_TIMED_S = 0.5
@@ -66,7 +70,8 @@ def peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
-                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+                    tf_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
@@ -157,6 +162,8 @@ def workload_config(name, world):
         c.update(global_batch=B, per_gpu_batch=B,
                  parallelism="single GPU" if world == 1 else
                  f"kv-head-sharded {cfg['Hkv']}/{world} kv heads per GPU, output heads exchanged by {how}")
+    elif name == "c1_prefill":
+        c.update(global_batch=B, per_gpu_batch=B, mask="causal", parallelism="single GPU")
     elif name == "c3":
         c.update(global_batch=B, per_gpu_batch=B // world if world <= B else 1, mask="causal",
                  parallelism=f"batch-sharded {B}/{world} items per GPU, no data-path collective")
@@ -669,12 +676,13 @@ class Bench:
     def run_prefill(self, name, cfg, items, heads, value_scale, steps, warmup):
         torch, omx = self.torch, self.omx
         Hq, Hkv, D, S = cfg["Hq"], cfg["Hkv"], cfg["D"], cfg["S"]
-        tdt, es = torch.bfloat16, 2
+        f32 = cfg["dtype"] == "f32"
+        tdt, es = (torch.float32, 4) if f32 else (torch.bfloat16, 2)
         h0, Hl = heads
         G = Hq // Hkv
         Hkl = max(1, Hl // G)
         Bl = len(items)
-        tag = {"c3": 3, "c4": 4}[name]
+        tag = {"c3": 3, "c4": 4, "c1_prefill": 6}[name]
         q = self.rows_randn(tag + 10, items, (Hq, S, D), tdt)[:, h0:h0 + Hl].contiguous()
         k = self.rows_randn(tag + 20, items, (Hkv, S, D), tdt)[:, h0 // G:h0 // G + Hkl].contiguous()
         v = self.rows_randn(tag + 30, items, (Hkv, S, D), tdt)[:, h0 // G:h0 // G + Hkl].contiguous()
@@ -710,7 +718,7 @@ class Bench:
         tf = flops / (ms / 1e3) / 1e12
         rec = {
             "metric": "attn_prefill_tflops", "unit": "TFLOP/s", "value": tf * value_scale, "ms_per_step": ms,
-            "ms_per_step_min": res["ms_per_step_min"], "blocks": res["blocks"], "steps": steps, "dtype": "bf16",
+            "ms_per_step_min": res["ms_per_step_min"], "blocks": res["blocks"], "steps": steps, "dtype": cfg["dtype"],
             "tokens_per_s": Bl * S * value_scale / (ms / 1e3),
             "e2e": {"value": flops * value_scale / (e2e_ms / 1e3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "blocks": len(blocks), "cuda_graph": False,
@@ -731,6 +739,15 @@ class Bench:
                     "l2_policy": f"q+k+v+out {(2 * q.numel() + 2 * k.numel()) * es / 1e6:.0f} MB per GPU vs 126 MB L2",
                     "launches_per_step": res["launches_per_block"] / steps},
         }
+        if f32:  # the FFMA pipe bounds a float32 product that has to meet 1e-4: 2 FLOP x 128 lanes x SMs x clock
+            props = torch.cuda.get_device_properties(self.dev)
+            peak = 2.0 * 128 * props.multi_processor_count * self.pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+            rec["roofline"] = {"bound": "fp32_ffma", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                               "achieved_best_block": flops / (res["ms_per_step_min"] / 1e3) / 1e12,
+                               "peak_source": "2 x 128 FFMA lanes x SM count x max SM clock (no measured FFMA figure "
+                                              "in MEASURED_PEAKS.json)",
+                               "algorithmic_flops_per_launch": flops,
+                               "flops_convention": "4*B*Hq*Lq*Lk*D, causal counted as half"}
         self.attach_traffic(rec, name)
         return rec, dict(q=q, k=k, v=v, out=out, scale=scale, mask=mask)
 
@@ -847,6 +864,9 @@ class Bench:
         elif name == "c5_collective":
             rec = self.run_c5_sharded(cfg, "collective", steps, warmup)
             rec["scaling"] = "strong"
+        elif name == "c1_prefill":
+            rec, st = self.run_prefill(name, cfg, [0], (0, cfg["Hq"]), 1, steps, warmup)
+            rec["scaling"] = "single GPU"
         elif name in ("c3", "c4"):
             B, Hq = cfg["B"], cfg["Hq"]
             if W <= B:
@@ -906,6 +926,8 @@ def main():
     names = ["c2"] if args.workload in ("all", "c2") else [args.workload]
     if args.workload == "all":
         names += ["c2_paged", "c1", "c5"] + (["c5_collective"] if world > 1 and 8 % world == 0 else []) + ["c3", "c4"]
+        if world == 1:
+            names.append("c1_prefill")
         if world > 1:
             names.append("c2_weak")
     recs = {}

@@ -83,6 +83,11 @@ struct LLDev {
 __device__ __forceinline__ void st_ll(unsigned long long* a, uint32_t data, uint32_t flag) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(a), "r"(data), "r"(flag) : "memory");
 }
+__device__ __forceinline__ uint4 ld_ll2(const void* a) {  // two adjacent words (16-byte aligned)
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint2 ld_ll(const unsigned long long* a) {
   uint2 v;
   asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a) : "memory");
@@ -237,8 +242,14 @@ struct DecodeParams {
   // its partial, the CTAs of a (batch, kv-head) pair meet at a counter, and every CTA then folds ITS slice of the
   // output columns over all partials in one round trip to L2 -- instead of the last CTA folding everything
   // (a 64-way split: 6.7 us of dependent round trips in one CTA).  counters2[pair] counts the CTAs that have left.
-  int gsync;
+  int gsync;          // 1: meet at a counter; 2: no meeting point -- partials travel as {value, launch tag} words
   int* counters2;
+  // gsync == 2: every float of a partial (and its m, l) is an 8-byte word {value, tag}, tag = *gs_seq + 1 = this
+  // launch's number; readers poll the words they need, so the writer needs no fence and nobody takes a counter
+  // round trip.  ws_w: [pair][split][head][D + 2] words in a pool that only ever holds such words (zeroed when
+  // allocated; tags only grow), gs_seq: launches completed on that pool, bumped by the launch's last CTA.
+  uint2* ws_w;
+  unsigned* gs_seq;
   // CUDA-core kernel, staged variant: byte offset (from the dynamic shared memory base) of the K stage, and the
   // keys one stage holds (V follows K); 0 = rows are loaded straight into registers
   int stage_off, stage_keys;
@@ -663,6 +674,15 @@ constexpr int kMaxClusterSplits = 16;  // non-portable cluster size limit on sm_
 // floats of cluster scratch behind the merge inputs: partial (m, l) | weights | sums, per row pitch
 __host__ __device__ constexpr int cluster_scratch_floats(int rows) { return (2 + 2 * kMaxClusterSplits) * rows; }
 
+// gsync == 2: a CTA that leaves without taking part (inactive paged slot) still counts towards "the launch is over",
+// or the launch's tag would never be retired
+__device__ __forceinline__ void gs_leave_unused(const DecodeParams& p, unsigned gs_tag, int tid) {
+  if (p.gsync == 2 && tid == 0 && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
+    *p.peer_done = 0;
+    *p.gs_seq = gs_tag;
+  }
+}
+
 // ---- all-CTA split-K combine (DecodeParams::gsync; one-wave grids).  publish -> meet -> every CTA folds its own
 // slice of the output columns.  Lanes run over the SPLITS: a group of W lanes holds one float4 column's
 // contributions, so the per-head maximum / sum and the fold are warp shuffles; what is left of the tail is one
@@ -682,12 +702,18 @@ __device__ __noinline__ void ll_quad(const DecodeParams& p, unsigned seq, int b,
 
 template <typename T>
 __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch, int first_head, int n_heads,
-                                           int b, int pair, int split, int tid, int nthr) {
+                                           int b, int pair, int split, int tid, int nthr, unsigned gs_tag) {
   const int NS = p.num_splits, D = p.D;
-  __threadfence();
-  __syncthreads();
+  const bool tagged = p.gsync == 2;
+  // (A warm-up walk of this function by the idle producer warp while the tiles are in flight -- every load issued,
+  // no store / barrier / atomic -- was tried against the instruction-fetch cost of the tail and measured SLOWER:
+  // one rank of the sharded C5 14.0 -> 17.0 us, the walk outlasts a 4-tile key loop and the phases below did not
+  // get shorter; scripts/gpu_r02_warm_ab.sh.)
+  if (!tagged) __threadfence();
+  __syncthreads();  // (tagged: the merge inputs in `scratch` are dead from here on)
   trace_mark(p, 4);
   const int D4 = D >> 2;
+  const int d4sh = 31 - __clz(D4);            // head dims are powers of two (decode_supported): col / D4 = col >> d4sh
   const int C = n_heads * D4;                 // float4 columns of the pair's output
   const int slice = (C + NS - 1) / NS;
   const int c0 = split * slice, c1 = min(C, c0 + slice);
@@ -697,7 +723,7 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
   const int wsh = 31 - __clz(W);              // W = 1 << wsh
   const int n_wi = W == 32 ? ncol * K : (ncol + (32 >> wsh) - 1) >> (5 - wsh);  // warp-sized work items
   const int nwarps = nthr >> 5, warp = tid >> 5, lane = tid & 31;
-  const int g0 = ncol ? c0 / D4 : 0, g1 = ncol ? (c1 - 1) / D4 : -1;  // heads the slice touches
+  const int g0 = ncol ? c0 >> d4sh : 0, g1 = ncol ? (c1 - 1) >> d4sh : -1;  // heads the slice touches
   const int nh = g1 - g0 + 1;
   const int mlp = (NS * nh + 3) & ~3;
   float* sm_m = scratch;                      // [NS][nh]  (the merge inputs are dead: the own partial is in ws)
@@ -706,14 +732,27 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
   float* sm_inv = reinterpret_cast<float*>(red + ncol * K);  // [ncol]
   const int64_t e0p = (int64_t)pair * NS * n_heads;
   const int64_t ob = b * p.os[0];
-  if (tid == 0) {
-    atomicAdd(&p.counters[pair], 1);
-    unsigned spins = 0;
-    while (ld_acquire_gpu(&p.counters[pair]) < NS)
-      if (++spins > (1u << 26)) __trap();  // a CTA that never became resident: a launch failure, not a hung GPU
+  if (!tagged) {
+    if (tid == 0) {
+      atomicAdd(&p.counters[pair], 1);
+      unsigned spins = 0;
+      while (ld_acquire_gpu(&p.counters[pair]) < NS)
+        if (++spins > (1u << 26)) __trap();  // a CTA that never became resident: a launch failure, not a hung GPU
+    }
+    __syncthreads();
   }
-  __syncthreads();
   trace_mark(p, 5);
+  // tagged words: poll until both words of a 16-byte pair carry this launch's tag (bounded: see above)
+  auto poll2 = [&](const uint2* w) {
+    unsigned spins = 0;
+    uint4 v = dd::ld_ll2(w);
+    while (v.y != gs_tag || v.w != gs_tag) {
+      if (++spins > (1u << 24)) __trap();
+      __nanosleep(128);  // thousands of lanes poll: leave the L2 to the CTAs that are still streaming their keys
+      v = dd::ld_ll2(w);
+    }
+    return make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+  };
   const unsigned ll_seq = p.ll.world ? __ldcg(p.ll.seq) + 1u : 0u;
   // work item wi of this warp: local column colL, split sp of this lane
   auto item = [&](int wi, int& colL, int& sp) {
@@ -730,20 +769,26 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
     int colL, sp;
     if (!item(wi, colL, sp)) return make_float4(0.f, 0.f, 0.f, 0.f);
     const int col = c0 + colL;
-    return __ldcg(reinterpret_cast<const float4*>(p.ws_o + (e0p + (int64_t)sp * n_heads + col / D4) * D + (col % D4) * 4));
+    if (tagged) {
+      const uint2* w = p.ws_w + (e0p + (int64_t)sp * n_heads + (col >> d4sh)) * (D + 2) + (col & (D4 - 1)) * 4;
+      const float2 lo = poll2(w), hi = poll2(w + 2);
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    return __ldcg(reinterpret_cast<const float4*>(p.ws_o + (e0p + (int64_t)sp * n_heads + (col >> d4sh)) * D + (col & (D4 - 1)) * 4));
   };
   float4 cur = fetch(warp);
 #pragma unroll 1
   for (int idx = tid; idx < NS * nh; idx += nthr) {
-    const int sp = idx / nh, g = g0 + idx - sp * nh;
-    const float2 ml = __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + (int64_t)sp * n_heads + g) * 2]));
+    const int sp = nh == 1 ? idx : idx / nh, g = g0 + idx - sp * nh;
+    const float2 ml = tagged ? poll2(p.ws_w + (e0p + (int64_t)sp * n_heads + g) * (D + 2) + D)
+                             : __ldcg(reinterpret_cast<const float2*>(&p.ws_ml[(e0p + (int64_t)sp * n_heads + g) * 2]));
     sm_m[idx] = ml.x;
     sm_l[idx] = ml.y;
   }
   __syncthreads();
   trace_mark(p, 9);
   auto emit4 = [&](int col, const float4& v) {
-    const int g = col / D4, d = (col - g * D4) * 4;
+    const int g = col >> d4sh, d = (col & (D4 - 1)) * 4;
     if (p.ll.world) {
       ll_quad<T>(p, ll_seq, b, first_head + g, d, v);
       return;
@@ -760,7 +805,7 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
     int colL, sp;
     const bool valid = item(wi, colL, sp);
     const int cc = min(colL, ncol - 1);           // lanes past the slice compute on its last column and store nothing
-    const int col = c0 + cc, g = col / D4, gi = g - g0;
+    const int col = c0 + cc, g = col >> d4sh, gi = g - g0;
     const int l0 = lane & (W - 1);
     float M = -INFINITY;
 #pragma unroll 1
@@ -786,7 +831,7 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
     }
     const int kk = W == 32 ? wi - (wi / K) * K : 0;  // which 32-split block of the column
     const bool lead = colL < ncol && l0 == 0 && kk == 0;
-    if (lead && col % D4 == 0) {  // the CTA that owns the head's first column reports the row
+    if (lead && (col & (D4 - 1)) == 0) {  // the CTA that owns the head's first column reports the row
       store_ml(p, b, first_head + g, M, L);
       if (p.dead) p.dead[(int64_t)b * p.Hq + first_head + g] = L > 0.f ? 0 : 1;
     }
@@ -820,14 +865,17 @@ __device__ __noinline__ void gsync_combine(const DecodeParams& p, float* scratch
   peer_signal(p, tid);  // (peer_total counts every CTA of the launch in this mode)
   if (p.ll.world) __syncthreads();  // this CTA's exchange is complete
   if (tid == 0) {
-    const int t = atomicAdd(&p.counters2[pair], 1);
-    if (t == NS - 1) {  // everybody has passed the meeting point: reset both counters for the next launch
-      p.counters[pair] = 0;
-      p.counters2[pair] = 0;
+    if (!tagged) {
+      const int t = atomicAdd(&p.counters2[pair], 1);
+      if (t == NS - 1) {  // everybody has passed the meeting point: reset both counters for the next launch
+        p.counters[pair] = 0;
+        p.counters2[pair] = 0;
+      }
     }
-    if (p.ll.world && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
+    if ((tagged || p.ll.world) && atomicAdd(p.peer_done, 1) == p.peer_total - 1) {
       *p.peer_done = 0;     // the launch's last CTA: every word of the step has been sent and received here
-      *p.ll.seq = ll_seq;
+      if (p.ll.world) *p.ll.seq = ll_seq;
+      if (tagged) *p.gs_seq = gs_tag;
     }
   }
   trace_mark(p, 6);
@@ -1120,7 +1168,8 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
                                                 const float* nt_v, int first_head, int n_heads, int b,
                                                 int pair, int split, int tid, int nthr, int* s_ticket,
                                                 float* cl /* cluster scratch, cluster_scratch_floats(rows) */,
-                                                float* recv = nullptr /* push-combine receive slots */) {
+                                                float* recv = nullptr /* push-combine receive slots */,
+                                                unsigned gs_tag = 0 /* this launch's tag (gsync == 2) */) {
   const int D = p.D;
   const int64_t ob = b * p.os[0];
   const bool use_cluster = p.cluster && p.num_splits > 1;
@@ -1129,9 +1178,10 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   auto recv_at = [&](int sp, int g, int d) { return recv + ((sp - 1) * n_heads + g) * (D + 2) + d; };
   float* part_o = const_cast<float*>(mo);  // [n_heads][D]: written in place over warp 0's block (same owner)
   if (push) cluster_wait_plain();  // pairs with the arrive at kernel entry: rank 0 is running, its slots exist
+  const int dsh = 31 - __clz(D);  // head dims are powers of two (decode_supported)
   // (one element per thread: a float4-column variant halved the active threads and measured slower)
   for (int idx = tid; idx < n_heads * D; idx += nthr) {
-    const int g = idx / D, d = idx % D;
+    const int g = idx >> dsh, d = idx & (D - 1);
     float M = has_nt ? nt_m[g] : -INFINITY;
     for (int w = 0; w < n_ent; ++w) M = fmaxf(M, mml[(w * rows + g) * 2]);
     float L = 0.f, O = 0.f;
@@ -1164,6 +1214,13 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
         cl[g * 2] = M;
         cl[g * 2 + 1] = L;
       }
+    } else if (p.gsync == 2) {
+      uint2* w = p.ws_w + (((int64_t)pair * p.num_splits + split) * n_heads + g) * (D + 2);
+      dd::st_ll(reinterpret_cast<unsigned long long*>(w + d), __float_as_uint(O), gs_tag);
+      if (d == 0) {
+        dd::st_ll(reinterpret_cast<unsigned long long*>(w + D), __float_as_uint(M), gs_tag);
+        dd::st_ll(reinterpret_cast<unsigned long long*>(w + D + 1), __float_as_uint(L), gs_tag);
+      }
     } else {
       const int64_t e = ((int64_t)pair * p.num_splits + split) * n_heads + g;
       p.ws_o[e * D + d] = O;
@@ -1185,7 +1242,7 @@ __device__ __forceinline__ void merge_and_store(const DecodeParams& p, const flo
   } else if (use_cluster) {
     combine_pull<T>(p, ma);
   } else if (p.gsync) {
-    gsync_combine<T>(p, const_cast<float*>(mo), first_head, n_heads, b, pair, split, tid, nthr);
+    gsync_combine<T>(p, const_cast<float*>(mo), first_head, n_heads, b, pair, split, tid, nthr, gs_tag);
   } else {
     combine_ticket<T, PF>(p, ma);
   }
@@ -1270,7 +1327,11 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   pdl_wait_prior_grid();
   pdl_release_next_grid();
   trace_mark(p, 0);
-  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot (whole CTA, whole cluster: same b)
+  const unsigned gs_tag = p.gsync == 2 ? __ldcg(p.gs_seq) + 1u : 0u;  // (needed at the merge: in flight under the loop)
+  if (p.paged && __ldg(p.pos_dev + b) < 0) {  // inactive slot (whole CTA, whole cluster: same b)
+    gs_leave_unused(p, gs_tag, tid);
+    return;
+  }
   const DecodeDyn dy = load_dyn(p, b);
   const int n_tiles = (dy.n_mem + kTile - 1) / kTile;
   tile_begin = split * dy.tps;
@@ -1355,6 +1416,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
     __syncwarp();
     if constexpr (kDecouple) named_bar_sync(1, NTHR);  // q is staged (the consumers arrived long ago)
     if (has_nt) new_token<T>(p, q_s, kQPitch, G, b, hk, lane, nt_k, nt_v, nt_m, s_pro, dy);
+
   } else {
     // ------------------------------------------------ consumer warps
     using MMA = Mma16816<T>;
@@ -1507,7 +1569,7 @@ decode_hmma_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constan
   const float* mo = reinterpret_cast<const float*>(stages);
   merge_and_store<T, 16>(p, mo, mo + NW * 16 * D, NW, 16, has_nt, nt_m, nt_v, hk * G, G, b, pair, split, tid,
                          NTHR, &s_ticket, const_cast<float*>(mo) + NW * 16 * (D + 2),
-                         p.push_combine ? nt_m + 16 : nullptr);
+                         p.push_combine ? nt_m + 16 : nullptr, gs_tag);
 }
 
 // ============================================================ generic: CUDA cores
@@ -1621,7 +1683,11 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   }
   pdl_wait_prior_grid();
   trace_mark(p, 0);
-  if (p.paged && __ldg(p.pos_dev + b) < 0) return;  // inactive slot
+  const unsigned gs_tag = p.gsync == 2 ? __ldcg(p.gs_seq) + 1u : 0u;
+  if (p.paged && __ldg(p.pos_dev + b) < 0) {  // inactive slot
+    gs_leave_unused(p, gs_tag, tid);
+    return;
+  }
   const DecodeDyn dy = load_dyn(p, b);
   const int keys_per_split = dy.tps * kTile;
   const int kbeg = split * keys_per_split;
@@ -1745,7 +1811,7 @@ decode_simt_kernel(const __grid_constant__ DecodeParams p) {
   pdl_release_next_grid();
   trace_mark(p, 2);
   merge_and_store<T, 4>(p, mo, mml, kSimtWarps, GT, has_nt, nt_m, nt_v, first_head, GT, b, pair, split, tid,
-                        NTHR, &s_ticket, nt_m + 4);
+                        NTHR, &s_ticket, nt_m + 4, nullptr, gs_tag);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1875,6 +1941,14 @@ bool gsync_enabled() {
   }();
   return on;
 }
+// OMX_DECODE_GSLL=0: the all-CTA combine meets at a counter (gsync == 1) instead of polling tagged words (A/B knob)
+bool gsll_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("OMX_DECODE_GSLL");
+    return !e || atoi(e) != 0;
+  }();
+  return on;
+}
 // does the slice bookkeeping of merge_and_store fit the merge scratch (n_ent x rows x D floats) and 4 items per warp?
 bool gsync_fits(int splits, int n_heads, int D, int nthr, int scratch_floats) {
   const int D4 = D / 4, C = n_heads * D4;
@@ -1938,6 +2012,7 @@ void launch_simt(DecodeParams& p, cudaStream_t stream, int Gt, dim3 grid, bool o
     p.gsync = (!p.cluster && p.num_splits > 1 && p.counters2 && gsync_enabled() && ctas <= sm_count() &&
                gsync_fits(p.num_splits, gt, 32 * VE, kSimtWarps * 32, kSimtWarps * gt * 32 * VE))
                   ? 1 : 0;
+    if (p.gsync && p.ws_w) p.gsync = 2;
     if (p.gsync) p.peer_total = (int)ctas;
     launch_kernel(kern, grid, kSimtWarps * 32, smem, stream, p.cluster ? p.num_splits : 1, pdl_enabled(true), p);
   };
@@ -2116,7 +2191,7 @@ size_t decode_graph_scratch_bytes(int B, int Hkv, int Hq, int D, int dtype, int 
     const SplitPlan sp = plan_splits(pairs, n_tiles, sms, simt ? 2 : 4,
                                      (!simt && gsync_enabled()) ? kMaxSplitsGsync : kMaxSplits);
     const size_t part = sp.num_splits > 1 ? (size_t)pairs * sp.num_splits * Gt * (D + 2) : 0;
-    worst = std::max(worst, sizeof(float) * part + sizeof(int) * (2 * (size_t)pairs + 1));
+    worst = std::max(worst, (simt ? sizeof(float) : 8) * part + sizeof(int) * (2 * (size_t)pairs + 2));  // (8: tagged words)
   }
   return worst;
 }
@@ -2332,12 +2407,22 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
   // one workspace request per call (a second one could move the first): split-K partials, then flags.
   // Graph mode carves the same layout (+ the counters) out of the cache-owned scratch instead, whose
   // address never changes under a captured launch.
-  auto carve_workspace = [&](size_t no, size_t nml, size_t n_ctr) {
+  // n_words > 0: the tagged-word variant of the all-CTA combine (gsync == 2) -- its partials live in a pool of
+  // their own (only ever {value, tag} words, zeroed when allocated, tags only grow) next to the launch counter
+  auto carve_workspace = [&](size_t no, size_t nml, size_t n_ctr, size_t n_words = 0) {
     if (dyn || (paged && f.scratch)) {  // cache-owned scratch: its address is stable under a captured launch
-      const size_t need = sizeof(float) * (no + nml) + sizeof(int) * n_ctr;
+      const size_t need = n_words ? 8 * n_words + sizeof(int) * (n_ctr + 1)
+                                  : sizeof(float) * (no + nml) + sizeof(int) * n_ctr;
       OMX_CHECK(need <= f.scratch_bytes, "dynamic-position decode: scratch too small (%zu > %zu bytes); call "
                 "omx_kv_cache_prepare_graph with this launch's head count first", need, f.scratch_bytes);
       float* ws = (float*)f.scratch;
+      if (n_words) {  // (graph mode only: one plan per cache, so the layout -- and the counter's place -- never moves)
+        p.ws_w = reinterpret_cast<uint2*>(ws);
+        p.counters = reinterpret_cast<int*>(p.ws_w + n_words);
+        p.peer_done = p.counters + n_ctr - 1;
+        p.gs_seq = reinterpret_cast<unsigned*>(p.counters + n_ctr);
+        return;
+      }
       p.ws_o = ws;
       p.ws_ml = ws + no;
       if (n_ctr) {
@@ -2347,6 +2432,10 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       return;
     }
     const size_t fl = masked ? (size_t)a.B * a.Hq : 0;
+    if (n_words) {
+      p.ws_w = reinterpret_cast<uint2*>(get_tagged_workspace(8 * n_words, stream, &p.gs_seq));
+      no = nml = 0;
+    }
     if (no + nml + fl) {
       float* ws = (float*)get_workspace(sizeof(float) * (no + nml) + fl, stream);
       if (no) {
@@ -2446,6 +2535,12 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       p.tiles_per_split = sp.tiles_per_split;
       p.push_combine = (push_ok && p.cluster && p.num_splits <= kPushSplits) ? 1 : 0;
       p.gsync = (!p.cluster && deep && gsync_for(sp)) ? 1 : 0;
+      // tagged words instead of the meeting point: not with the r01 peer counters (they share the launch-wide
+      // counter) and not on the paged cache's scratch (its plan, hence its layout, changes as the sequences grow)
+      // ... and only for short key loops (<= 16 tiles per CTA): there the CTAs of a pair finish together and the
+      // polls hit at once (one rank of the sharded C5 14.3 -> 13.2 us, C1 13.9 -> 13.0); behind a long loop the
+      // early CTAs' polling competes with the late CTAs' streaming (C5 on one GPU, 29 tiles: 29.0 -> 29.5 us)
+      if (p.gsync && gsll_enabled() && !p.n_peers && !paged && sp.tiles_per_split <= 16) p.gsync = 2;
       if (p.gsync) p.peer_total = (int)pairs * p.num_splits;  // every CTA stores a slice
       if (p.gsync && f.ll) {
         p.ll = ll_dev();
@@ -2453,7 +2548,8 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
       }
       carve_workspace(p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * p.D : 0,
                       p.num_splits > 1 ? (size_t)pairs * p.num_splits * p.G * 2 : 0,
-                      (p.num_splits > 1 || p.n_peers) ? (size_t)(p.gsync ? 2 : 1) * pairs + 1 : 0);
+                      (p.num_splits > 1 || p.n_peers) ? (size_t)(p.gsync ? 2 : 1) * pairs + 1 : 0,
+                      p.gsync == 2 ? (size_t)pairs * p.num_splits * p.G * (p.D + 2) : 0);
       p.counters2 = p.gsync ? p.counters + pairs : nullptr;
       dim3 grid(p.num_splits, a.Hkv, a.B);
       arm_trace(grid);
@@ -2500,6 +2596,11 @@ void decode_attention(const SdpaArgs& a, const DecodeFused& f, cudaStream_t stre
                   p.num_splits > 1 ? (size_t)pairs * p.num_splits * Gt * 2 : 0,
                   (p.num_splits > 1 || p.n_peers) ? (size_t)2 * pairs + 1 : 0);
   p.counters2 = p.counters ? p.counters + pairs : nullptr;
+  // the tagged-word pool for the all-CTA combine, should launch_simt pick it (plain launches only: graph / paged
+  // launches of this kernel keep the meeting point)
+  if (p.num_splits > 1 && gsll_enabled() && !p.n_peers && !dyn && !paged && pairs * p.num_splits <= sms)
+    p.ws_w = reinterpret_cast<uint2*>(
+        get_tagged_workspace(8 * (size_t)pairs * p.num_splits * Gt * (p.D + 2), stream, &p.gs_seq));
   p.peer_total = (int)pairs;
   dim3 grid(p.num_splits, a.Hkv * groups, a.B);
   arm_trace(grid);

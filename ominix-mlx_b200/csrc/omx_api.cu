@@ -86,6 +86,26 @@ int* get_counters(size_t count, cudaStream_t stream) {
   return (int*)grow(g_ctr, count * sizeof(int), stream, 1 << 16);
 }
 
+void* get_tagged_workspace(size_t bytes, cudaStream_t stream, unsigned** seq) {
+  static std::map<std::pair<int, cudaStream_t>, Scratch> pool, seqs;
+  static std::map<std::pair<int, cudaStream_t>, uint64_t> launches;
+  unsigned* sq = (unsigned*)grow(seqs, 256, stream, 256);
+  void* ws = grow(pool, bytes, stream, 1 << 20);  // (a new, zeroed pool under an old counter: stale tags are all 0)
+  int dev = 0;
+  OMX_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    // the 32-bit tag wraps after 4 G launches: long before that, start over from a clean pool (stream-ordered)
+    if ((++launches[{dev, stream}] & ((1ull << 30) - 1)) == 0) {
+      const Scratch& sc = pool[{dev, stream}];
+      OMX_CUDA(cudaMemsetAsync(sc.p, 0, sc.bytes, stream));
+      OMX_CUDA(cudaMemsetAsync(sq, 0, 256, stream));
+    }
+  }
+  *seq = sq;
+  return ws;
+}
+
 int sm_count() {
   int dev = 0;
   OMX_CUDA(cudaGetDevice(&dev));

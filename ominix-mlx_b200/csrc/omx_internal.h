@@ -109,6 +109,9 @@ void* get_workspace(size_t bytes, cudaStream_t stream);
 void* get_outer_workspace(size_t bytes, cudaStream_t stream);
 // A second, separately zero-initialised region for self-resetting arrival counters.
 int* get_counters(size_t count, cudaStream_t stream);
+// Pool of {value, launch tag} words for the tagged all-CTA combine (decode.cu, gsync == 2): only ever holds such
+// words (zeroed when allocated), *seq = launches completed on it (device counter, never moves).
+void* get_tagged_workspace(size_t bytes, cudaStream_t stream, unsigned** seq);
 int sm_count();
 
 // ---- sdpa_generic.cu ----
