@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(128, 2) sdpa_f32_tiled_kernel(const __grid_con
   float* Ps = KVs + kBN * DP;       // [64][kPP]
 
   const int tid = threadIdx.x, ty = tid >> 3, tx = tid & 7;
-  const int m0 = blockIdx.x * kBM, h = blockIdx.y, b = blockIdx.z;
+  // causal: the row blocks near the end see the most keys -- launch them first (CTAs are dispatched in index order)
+  const int mb = p.mask_mode == MASK_CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int m0 = mb * kBM, h = blockIdx.y, b = blockIdx.z;
   const int hk = h / (p.Hq / p.Hkv);
   const float* qg = p.q + b * p.qs[0] + h * p.qs[1];
   const float* kg = p.k + b * p.ks[0] + hk * p.ks[1];
