@@ -242,6 +242,15 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
     }
     OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
   }
+  if (force.empty() || force == "sdpa_mma") {
+    // 16-bit calls the two kernels above refuse -- keys wider than values (absorbed MLA), head dims outside
+    // {64, 128}, layouts they do not take: mma.sync tiles with the kv head's whole query group packed into the rows
+    if (sdpa_mma_supported(a, &why)) {
+      sdpa_mma(a, stream);
+      return;
+    }
+    OMX_CHECK(force.empty(), "forced kernel '%s' does not support this call: %s", force.c_str(), why ? why : "?");
+  }
   if (force.empty() || force == "sdpa_f32_tiled") {
     // float32 with more than a handful of query rows: shared-memory tiles instead of one warp per row
     if (sdpa_f32_tiled_supported(a, &why) && (a.Lq >= 16 || !force.empty())) {
@@ -290,7 +299,7 @@ int omx_force_kernel(const char* name) {
   return guarded([&] {
     const std::string n = name ? name : "";
     OMX_CHECK(n.empty() || n == "decode" || n == "decode_simt" || n == "decode_hmma_tma" ||
-                  n == "fmha_tcgen05" || n == "sdpa_generic" || n == "sdpa_f32_tiled",
+                  n == "fmha_tcgen05" || n == "sdpa_generic" || n == "sdpa_f32_tiled" || n == "sdpa_mma",
               "unknown kernel family '%s'", n.c_str());
     t_forced_kernel = n;
   });
@@ -515,7 +524,7 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   const size_t es = dtype_size(q->dtype);
   const size_t qbytes = ((size_t)q->shape[0] * q->shape[1] * D * es + 255) & ~(size_t)255;
   const size_t kbytes = ((size_t)k_new->shape[0] * k_new->shape[1] * D * es + 255) & ~(size_t)255;
-  char* ws = (qn || kn || rope_dims > 0) ? (char*)get_workspace(2 * qbytes + kbytes, stream) : nullptr;
+  char* ws = (qn || kn || rope_dims > 0) ? (char*)get_outer_workspace(2 * qbytes + kbytes, stream) : nullptr;
   auto dense = [&](const omx_array* like, char* mem) {  // contiguous [B,H,1,D] scratch array
     omx_array t = *like;
     t.data = mem;
@@ -524,6 +533,11 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     t.strides[2] = D;
     t.strides[3] = 1;
     return t;
+  };
+  auto sdpa_rows = [&](const SdpaArgs& a2) {  // 16-bit rows on tensor cores where the layout allows, else one warp per row
+    const char* why2 = nullptr;
+    if (t_forced_kernel != "sdpa_generic" && sdpa_mma_supported(a2, &why2)) sdpa_mma(a2, stream);
+    else sdpa_generic(a2, stream);
   };
   omx_array qn_arr, kn_arr;
   if (qn) {
@@ -548,13 +562,13 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   }
   copy4d(&vrow, v_new, stream);
   if (rope_dims > 0) {
-    omx_array qr = dense(q, ws + qbytes);  // sdpa_generic itself uses no scratch
+    omx_array qr = dense(q, ws + qbytes);
     rope_forward(&qr, q, rope_dims, traditional, base, rope_scale, position, nullptr, 0, freqs, stream);
     SdpaArgs a2 = make_sdpa_args(out, &qr, &kview, &vview, sm_scale, "", nullptr, nullptr);
-    sdpa_generic(a2, stream);
+    sdpa_rows(a2);
   } else {
     SdpaArgs a2 = make_sdpa_args(out, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
-    sdpa_generic(a2, stream);
+    sdpa_rows(a2);
   }
   txn.commit();
   if (keys_out) *keys_out = kview;

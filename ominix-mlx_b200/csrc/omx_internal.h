@@ -212,6 +212,11 @@ void paged_pool_ptrs(const PagedKVImpl* c, void** kpool, void** vpool, const int
 bool sdpa_f32_tiled_supported(const SdpaArgs& a, const char** why);
 void sdpa_f32_tiled(const SdpaArgs& a, cudaStream_t stream);
 
+// ---- sdpa_mma.cu ---- bf16 / f16, keys up to 576 / values up to 512 features (multiples of 8): mma.sync tiles,
+// the kv head's query group packed into the rows (absorbed MLA, head dims outside {64, 128})
+bool sdpa_mma_supported(const SdpaArgs& a, const char** why);
+void sdpa_mma(const SdpaArgs& a, cudaStream_t stream);
+
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);
 void fmha_sm100(const SdpaArgs& a, cudaStream_t stream);

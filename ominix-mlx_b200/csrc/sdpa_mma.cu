@@ -1,0 +1,662 @@
+// sdpa_mma.cu -- 16-bit attention for the head shapes the tcgen05 / TMA kernels do not take, on tensor cores.
+//
+// Serves omx_fast_scaled_dot_product_attention (replaces mlx_fast_scaled_dot_product_attention,
+// mlx-c/mlx/c/fast.h:189-198) for bf16 / f16 calls with
+//   * keys wider than values -- the absorbed MLA of GLM-4.7-Flash: queries [B,20,L,576], keys [B,1,S,512+64],
+//     values [B,1,S,512], ONE shared kv head (glm-4.7-flash-mlx/src/model.rs:263-299), decode and prefill;
+//   * head dims outside {64, 128}: 72 / 80 (vision towers), 256 (qwen3.5), 16 / 32 (the reference's test shapes);
+//   * layouts / masks the specialised kernels refuse.
+// r01 / early r02 sent all of these to sdpa_generic (one warp per query row on CUDA cores).
+//
+// Shape of the kernel: `mma.sync.m16n8k16` (f32 accumulate) fed by `ldmatrix` from shared memory, `cp.async`
+// double-buffered K / V tiles.  A CTA owns 64 packed query rows of one (batch, kv head): the rows of ALL query
+// heads of the kv head's group are packed token-major (row = token * G + head-in-group), so a key tile is read
+// once for the whole group -- for the MLA layout that is all 20 heads.  Four row groups of 16 rows; value widths
+// above 256 put a second warp on each row group (each owns half of the output columns and repeats the small S =
+// QK^T product: no cross-warp softmax exchange).  Few CTAs (decode) -> the key range is split over CTAs and a
+// second launch merges the partials.  Mask semantics are sdpa_generic's (= the MLX fallback graph): masked bool
+// entries take finfo(T).min, additive masks are added to the scaled scores, causal is bottom-right aligned.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+#include "omx_common.cuh"
+#include "omx_internal.h"
+
+namespace omx {
+
+namespace {
+
+constexpr int kBM = 64;  // packed query rows per CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int n = valid ? 16 : 0;  // 0 source bytes: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct MmaParams {
+  const void *q, *k, *v, *mask;
+  void* out;
+  float* part;  // split partials: per (b, kv head, row tile, split): [64][DVP] O, [64] m, [64] l
+  int64_t qs[3], ks[3], vs[3], os[3], ms[4];
+  int B, Hq, Hkv, G, Lq, Lk, D, Dv, R, MT, nsplit;
+  float scale;
+  int mask_mode, mask_is_f32, out_is_f32;
+};
+
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int DKP, int DVP>
+struct MmaCfg {
+  static constexpr int NC = DVP > 256 ? 2 : 1;     // warps per row group (each owns DVP / NC output columns)
+  static constexpr int NT = 128 * NC;              // threads
+  static constexpr int BN = DKP >= 256 ? 32 : 64;  // keys per tile
+  static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
+  static constexpr int VP = DVP + 8;
+  static constexpr int WN = DVP / NC;
+  static constexpr size_t smem = sizeof(uint16_t) * ((size_t)kBM * KP + 2 * (size_t)BN * KP + 2 * (size_t)BN * VP);
+};
+
+// KS = 2 (launched when the packed rows fit 32: decode) turns two of the four row groups into a second key group:
+// each warp takes half of a tile's keys with its own running (m, l, O), merged once through shared memory at the end.
+template <typename T, int DKP, int DVP, int KS>
+__global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
+  using C = MmaCfg<DKP, DVP>;
+  constexpr int BN = C::BN, KP = C::KP, VP = C::VP, WN = C::WN, NT = C::NT;
+  constexpr int BNW = BN / KS;  // keys of a tile one warp scores
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Qs = reinterpret_cast<T*>(smem_raw);  // [64][KP]
+  T* Ks = Qs + kBM * KP;                   // [2][BN][KP]
+  T* Vs = Ks + 2 * BN * KP;                // [2][BN][VP]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = KS == 1 ? (warp & 3) : (warp & 1), wk = KS == 1 ? 0 : ((warp >> 1) & 1), wc = warp >> 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int mt = blockIdx.x, hk = blockIdx.y;
+  const int b = blockIdx.z / p.nsplit, split = blockIdx.z - b * p.nsplit;
+  const int m0 = mt * kBM;
+  const int q_off = max(p.Lk - p.Lq, 0);
+
+  // keys this CTA visits: causal launches stop at the diagonal of the tile's last token
+  int lk_eff = p.Lk;
+  if (p.mask_mode == MASK_CAUSAL) {
+    const int r_last = min(m0 + kBM, p.R) - 1;
+    lk_eff = min(p.Lk, q_off + r_last / p.G + 1);
+  }
+  const int nt_all = (lk_eff + BN - 1) / BN;
+  const int t0 = (int)((int64_t)nt_all * split / p.nsplit), t1 = (int)((int64_t)nt_all * (split + 1) / p.nsplit);
+
+  const T* qg = (const T*)p.q + b * p.qs[0];
+  const T* kg = (const T*)p.k + b * p.ks[0] + hk * p.ks[1];
+  const T* vg = (const T*)p.v + b * p.vs[0] + hk * p.vs[1];
+
+  // ---- Q tile (rows beyond R and features beyond D are zero-filled)
+  // (Measured alternative: one cp.async.bulk per row with mbarrier completion -- 20 % slower at 1152-byte rows, 70 %
+  // slower at 160-byte rows: the per-request cost of small bulk copies; a tensor-map box per tile would need
+  // swizzled, unpadded stages.)
+  constexpr int CH = DKP / 8;
+  for (int c = tid; c < kBM * CH; c += NT) {
+    const int row = c / CH, ch = c - row * CH;
+    const int r = m0 + row;
+    const bool ok = r < p.R && ch * 8 < p.D;
+    const int tok = ok ? r / p.G : 0, hg = ok ? r - tok * p.G : 0;
+    const T* src = ok ? qg + (int64_t)(hk * p.G + hg) * p.qs[1] + (int64_t)tok * p.qs[2] + ch * 8 : qg;
+    cp_async16(smem_u32(Qs + row * KP + ch * 8), src, ok);
+  }
+  cp_async_commit();
+  // `full`: every row and every chunk of the tile exists (all but a ragged last tile, widths == the configuration's)
+  // -- no predicates, no selects, immediate offsets from one running pointer per row.
+  auto load_rows = [&](T* dst, const T* src, int64_t row_stride, int j0, int nfeat, bool full, auto pitch_c,
+                       auto chunks_c) {
+    constexpr int PITCH = decltype(pitch_c)::value, CHK = decltype(chunks_c)::value;
+    if constexpr (CHK >= 32) {  // a warp per key row, lanes over the row's chunks
+      constexpr int NW = NT / 32;
+      const T* rp = src + (int64_t)(j0 + warp) * row_stride + lane * 8;
+      const uint32_t d0 = smem_u32(dst + warp * PITCH + lane * 8);
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < BN / NW; ++i, rp += NW * row_stride) {
+#pragma unroll
+          for (int cb = 0; cb < CHK; cb += 32)
+            if (cb + 32 <= CHK || lane < CHK - cb) cp_async16(d0 + (i * NW * PITCH + cb * 8) * 2, rp + cb * 8, true);
+        }
+      } else {
+        for (int i = 0; i < BN / NW; ++i, rp += NW * row_stride) {
+          const bool rok_ = j0 + warp + i * NW < p.Lk;
+#pragma unroll
+          for (int cb = 0; cb < CHK; cb += 32) {
+            const bool ok = rok_ && (cb + lane) * 8 < nfeat;
+            if (cb + lane < CHK) cp_async16(d0 + (i * NW * PITCH + cb * 8) * 2, ok ? rp + cb * 8 : src, ok);
+          }
+        }
+      }
+    } else {
+      if (full) {
+#pragma unroll
+        for (int c0 = 0; c0 < BN * CHK; c0 += NT) {
+          const int c = c0 + tid;
+          const int row = c / CHK, ch = c - row * CHK;
+          if (c0 + NT <= BN * CHK || c < BN * CHK)
+            cp_async16(smem_u32(dst + row * PITCH + ch * 8), src + (int64_t)(j0 + row) * row_stride + ch * 8, true);
+        }
+      } else {
+        for (int c = tid; c < BN * CHK; c += NT) {
+          const int row = c / CHK, ch = c - row * CHK;
+          const bool ok = j0 + row < p.Lk && ch * 8 < nfeat;
+          cp_async16(smem_u32(dst + row * PITCH + ch * 8), ok ? src + (int64_t)(j0 + row) * row_stride + ch * 8 : src, ok);
+        }
+      }
+    }
+  };
+  const bool own_width = p.D == DKP && p.Dv == DVP;
+  auto load_kv = [&](int tile, int stage) {
+    const bool full = own_width && (tile + 1) * BN <= p.Lk;
+    load_rows(Ks + stage * BN * KP, kg, p.ks[2], tile * BN, p.D, full, std::integral_constant<int, KP>{},
+              std::integral_constant<int, DKP / 8>{});
+    load_rows(Vs + stage * BN * VP, vg, p.vs[2], tile * BN, p.Dv, full, std::integral_constant<int, VP>{},
+              std::integral_constant<int, DVP / 8>{});
+  };
+  if (t0 < t1) load_kv(t0, 0);
+  cp_async_commit();
+  // The reference scales the queries first -- T(T(scale) * q) -- and multiplies those by the keys (mlx fast.cpp
+  // fallback graph; oracle/omx_oracle.c:257-275).  Every thread rescales the chunks it fetched itself.
+  cp_async_wait<1>();
+  {
+    const float sc = rnd<T>(p.scale);
+    for (int c = tid; c < kBM * CH; c += NT) {
+      const int row = c / CH, ch = c - row * CH;
+      if (m0 + row >= p.R || ch * 8 >= p.D) continue;
+      uint4* qp = reinterpret_cast<uint4*>(Qs + row * KP + ch * 8);
+      uint4 v = *qp;
+      T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = Num<T>::from_f(__fmul_rn(sc, Num<T>::to_f(e[i])));
+      *qp = v;
+    }
+  }
+
+  // ---- the two rows this thread holds in every accumulator fragment
+  int rtok[2], rjmax[2];
+  int64_t mrow[2];
+  bool rok[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int r = m0 + wr * 16 + g + 8 * e;
+    rok[e] = r < p.R;
+    const int tok = rok[e] ? r / p.G : 0, hg = rok[e] ? r - tok * p.G : 0;
+    rtok[e] = tok;
+    rjmax[e] = p.mask_mode == MASK_CAUSAL ? min(p.Lk, q_off + tok + 1) : p.Lk;
+    mrow[e] = b * p.ms[0] + (int64_t)(hk * p.G + hg) * p.ms[1] + (int64_t)tok * p.ms[2];
+  }
+  const float fill = Num<T>::lowest();
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[WN / 8][4];
+#pragma unroll
+  for (int n = 0; n < WN / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+
+  const bool warp_rows = m0 + wr * 16 < p.R;
+  const int nk = (p.D + 15) >> 4;  // k16 steps that hold real features
+  // per-lane ldmatrix offsets (elements)
+  const int a_off = (wr * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * KP + (lane >> 4) * 8;
+  const int bk_off = (wk * BNW + (lane & 7) + (lane >> 4) * 8) * KP + ((lane >> 3) & 1) * 8;
+  const int bv_off = (wk * BNW + (lane & 7) + ((lane >> 3) & 1) * 8) * VP + wc * WN + (lane >> 4) * 8;
+  const uint32_t q_base = smem_u32(Qs) + 2 * a_off;
+
+  for (int tile = t0; tile < t1; ++tile) {
+    const int stage = (tile - t0) & 1;
+    if (tile + 1 < t1) {
+      load_kv(tile + 1, stage ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (!warp_rows) {  // a row group past the last packed row (decode: 20 of 64 rows) only helps with the loads
+      __syncthreads();
+      continue;
+    }
+    const uint32_t k_base = smem_u32(Ks + stage * BN * KP) + 2 * bk_off;
+    const uint32_t v_base = smem_u32(Vs + stage * BN * VP) + 2 * bv_off;
+
+    // ---- S = Q K^T for this warp's 16 rows x BNW keys
+    float s[BNW / 8][4];
+#pragma unroll
+    for (int n = 0; n < BNW / 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+    {
+      // fragments of step kk + 1 are requested before the MMAs of step kk issue (the asm statements keep their order)
+      constexpr int NPQ = BNW / 16;
+      uint32_t a0[4], a1[4], b0[NPQ][4], b1[NPQ][4];
+      auto fetch = [&](int kk, uint32_t (&a)[4], uint32_t (&bb)[NPQ][4]) {
+        ldsm4(q_base + kk * 32, a);
+#pragma unroll
+        for (int np = 0; np < NPQ; ++np) ldsm4(k_base + (np * 16 * KP) * 2 + kk * 32, bb[np]);
+      };
+      auto mult = [&](const uint32_t (&a)[4], const uint32_t (&bb)[NPQ][4]) {
+#pragma unroll
+        for (int np = 0; np < NPQ; ++np) {
+          mma16816<T>(s[2 * np], a, bb[np][0], bb[np][1]);
+          mma16816<T>(s[2 * np + 1], a, bb[np][2], bb[np][3]);
+        }
+      };
+      if (nk == DKP / 16) {
+        // the configuration's own width (MLA: 36 steps): straight-line code, immediate offsets; with few key
+        // columns per warp the even / odd steps feed separate accumulators (chains half as long)
+        constexpr bool kTwo = BNW / 8 <= 2;
+        float s2[kTwo ? BNW / 8 : 1][4];
+#pragma unroll
+        for (int n = 0; n < (kTwo ? BNW / 8 : 1); ++n) s2[n][0] = s2[n][1] = s2[n][2] = s2[n][3] = 0.f;
+        fetch(0, a0, b0);
+#pragma unroll
+        for (int kk = 0; kk < DKP / 16; kk += 2) {
+          if (kk + 1 < DKP / 16) fetch(kk + 1, a1, b1);
+          mult(a0, b0);
+          if (kk + 1 < DKP / 16) {
+            if (kk + 2 < DKP / 16) fetch(kk + 2, a0, b0);
+            if constexpr (kTwo) {
+#pragma unroll
+              for (int np = 0; np < NPQ; ++np) {
+                mma16816<T>(s2[2 * np], a1, b1[np][0], b1[np][1]);
+                mma16816<T>(s2[2 * np + 1], a1, b1[np][2], b1[np][3]);
+              }
+            } else {
+              mult(a1, b1);
+            }
+          }
+        }
+        if constexpr (kTwo) {
+#pragma unroll
+          for (int n = 0; n < BNW / 8; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[n][c] += s2[n][c];
+        }
+      } else {
+        fetch(0, a0, b0);
+#pragma unroll 1
+        for (int kk = 0; kk < nk; kk += 2) {
+          if (kk + 1 < nk) fetch(kk + 1, a1, b1);
+          mult(a0, b0);
+          if (kk + 1 < nk) {
+            if (kk + 2 < nk) fetch(kk + 2, a0, b0);
+            mult(a1, b1);
+          }
+        }
+      }
+    }
+
+    // ---- scale, mask, online softmax (rows g and g + 8; a row's columns live in the 4 lanes of a quad)
+    // (the scores pass through the array dtype before and after the additive mask, as in the reference's op chain)
+    const int j0 = tile * BN + wk * BNW;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < BNW / 8; ++n) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = j0 + n * 8 + 2 * t + u;
+          float x = rnd<T>(s[n][2 * e + u]);
+          if (j >= rjmax[e]) {
+            x = -INFINITY;
+          } else if (p.mask_mode == MASK_BOOL) {
+            if (rok[e] && !((const uint8_t*)p.mask)[mrow[e] + j * p.ms[3]]) x = fill;
+          } else if (p.mask_mode == MASK_ADD) {
+            if (rok[e]) {
+              const int64_t mi = mrow[e] + j * p.ms[3];
+              x = rnd<T>(x + (p.mask_is_f32 ? ((const float*)p.mask)[mi] : Num<T>::to_f(((const T*)p.mask)[mi])));
+            }
+          }
+          s[n][2 * e + u] = x;
+          tmax = fmaxf(tmax, x);
+        }
+      }
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+      const float m_new = fmaxf(m_run[e], tmax);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = exp2f((m_run[e] - m_safe) * kLog2e);
+      float psum = 0.f;
+#pragma unroll
+      for (int n = 0; n < BNW / 8; ++n) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float pv = exp2f((s[n][2 * e + u] - m_safe) * kLog2e);
+          s[n][2 * e + u] = pv;
+          psum += pv;
+        }
+      }
+      l_run[e] = l_run[e] * corr + psum;
+      m_run[e] = m_new;
+      if (__any_sync(0xffffffffu, corr != 1.0f)) {  // (rarely after the first tiles)
+#pragma unroll
+        for (int n = 0; n < WN / 8; ++n) {
+          o[n][2 * e] *= corr;
+          o[n][2 * e + 1] *= corr;
+        }
+      }
+    }
+
+    // ---- O += P V over this warp's WN output columns (the next V fragment is requested ahead of the MMAs)
+    {
+      constexpr int NKS = BNW / 16, NPV = WN / 16, NSTEP = NKS * NPV;
+      uint32_t pa[NKS][4];
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
+        pa[ks][0] = pack2<T>(s[2 * ks][0], s[2 * ks][1]);
+        pa[ks][1] = pack2<T>(s[2 * ks][2], s[2 * ks][3]);
+        pa[ks][2] = pack2<T>(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+        pa[ks][3] = pack2<T>(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      }
+      uint32_t vb[2][4];
+      ldsm4_t(v_base, vb[0]);
+#pragma unroll
+      for (int i = 0; i < NSTEP; ++i) {
+        const int ks = i / NPV, np = i - ks * NPV;
+        if (i + 1 < NSTEP) {
+          const int ks1 = (i + 1) / NPV, np1 = (i + 1) - ks1 * NPV;
+          ldsm4_t(v_base + (ks1 * 16 * VP + np1 * 16) * 2, vb[(i + 1) & 1]);
+        }
+        mma16816<T>(o[2 * np], pa[ks], vb[i & 1][0], vb[i & 1][1]);
+        mma16816<T>(o[2 * np + 1], pa[ks], vb[i & 1][2], vb[i & 1][3]);
+      }
+    }
+    __syncthreads();  // the stage is free for the load issued two iterations from now
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    l_run[e] += __shfl_xor_sync(0xffffffffu, l_run[e], 1);
+    l_run[e] += __shfl_xor_sync(0xffffffffu, l_run[e], 2);
+  }
+  if constexpr (KS == 2) {
+    // the second key group hands its state over through the (now idle) K / V stages: word w of warp pair `pi` at
+    // [pi][w][lane], so both sides touch consecutive addresses
+    constexpr int NW = WN / 2 + 4;  // floats per lane: O fragment + m, l of both rows
+    float* xch = reinterpret_cast<float*>(Ks) + (size_t)(wc * 2 + wr) * NW * 32 + lane;
+    static_assert((size_t)C::NC * 2 * NW * 32 * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "exchange area");
+    __syncthreads();  // every warp is done with the stages
+    if (wk == 1) {
+#pragma unroll
+      for (int n = 0; n < WN / 8; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xch[(n * 4 + c) * 32] = o[n][c];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        xch[(WN / 2 + e) * 32] = m_run[e];
+        xch[(WN / 2 + 2 + e) * 32] = l_run[e];
+      }
+    }
+    __syncthreads();
+    if (wk == 1) return;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float m1 = xch[(WN / 2 + e) * 32], l1 = xch[(WN / 2 + 2 + e) * 32];
+      const float mm = fmaxf(m_run[e], m1);
+      const float ms = (mm == -INFINITY) ? 0.f : mm;
+      const float a0 = exp2f((m_run[e] - ms) * kLog2e), a1 = exp2f((m1 - ms) * kLog2e);
+      m_run[e] = mm;
+      l_run[e] = l_run[e] * a0 + l1 * a1;
+#pragma unroll
+      for (int n = 0; n < WN / 8; ++n) {
+        o[n][2 * e] = o[n][2 * e] * a0 + xch[(n * 4 + 2 * e) * 32] * a1;
+        o[n][2 * e + 1] = o[n][2 * e + 1] * a0 + xch[(n * 4 + 2 * e + 1) * 32] * a1;
+      }
+    }
+  }
+  if (p.nsplit == 1) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (!rok[e]) continue;
+      const int r = m0 + wr * 16 + g + 8 * e;
+      const int hg = r - rtok[e] * p.G;
+      const float inv = 1.0f / l_run[e];
+      const int64_t oo = b * p.os[0] + (int64_t)(hk * p.G + hg) * p.os[1] + (int64_t)rtok[e] * p.os[2];
+#pragma unroll
+      for (int n = 0; n < WN / 8; ++n) {
+        const int col = wc * WN + n * 8 + 2 * t;
+        if (col >= p.Dv) continue;
+        const float x0 = o[n][2 * e] * inv, x1 = o[n][2 * e + 1] * inv;
+        if (p.out_is_f32) *reinterpret_cast<float2*>((float*)p.out + oo + col) = make_float2(x0, x1);
+        else *reinterpret_cast<uint32_t*>((T*)p.out + oo + col) = pack2<T>(x0, x1);
+      }
+    }
+  } else {
+    float* part = p.part + ((((int64_t)b * p.Hkv + hk) * p.MT + mt) * p.nsplit + split) * (kBM * DVP + 2 * kBM);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (!rok[e]) continue;
+      const int row = wr * 16 + g + 8 * e;
+#pragma unroll
+      for (int n = 0; n < WN / 8; ++n) {
+        const int col = wc * WN + n * 8 + 2 * t;
+        if (col >= p.Dv) continue;
+        *reinterpret_cast<float2*>(part + row * DVP + col) = make_float2(o[n][2 * e], o[n][2 * e + 1]);
+      }
+      if (wc == 0 && t == 0) {
+        part[kBM * DVP + row] = m_run[e];
+        part[kBM * DVP + kBM + row] = l_run[e];
+      }
+    }
+  }
+}
+
+// Merge of the split partials: one CTA of 512 threads per packed query row.  The weights of the splits are settled
+// once in shared memory; the threads then cover (float4 column) x (split group) so that the loads of the fold are
+// independent and few per thread (a row's partials are nsplit x Dv floats spread over L2).
+constexpr int kCT = 512;
+template <typename T>
+__global__ void __launch_bounds__(kCT) sdpa_mma_combine_kernel(const __grid_constant__ MmaParams p, int DVP) {
+  __shared__ float ws[160];
+  __shared__ float red[2 * kCT / 32];
+  __shared__ float4 acc4[kCT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  const int mt = r / kBM, row = r - mt * kBM;
+  const int64_t pstride = (int64_t)kBM * DVP + 2 * kBM;
+  const float* part = p.part + (((int64_t)b * p.Hkv + hk) * p.MT + mt) * p.nsplit * pstride;
+  // nsplit <= 148 (launch_cfg): one split per thread
+  const float m0 = tid < p.nsplit ? part[tid * pstride + kBM * DVP + row] : -INFINITY;
+  const float l0 = tid < p.nsplit ? part[tid * pstride + kBM * DVP + kBM + row] : 0.f;
+  float M = warp_max(m0);
+  if (lane == 0) red[warp] = M;
+  __syncthreads();
+  M = red[0];
+#pragma unroll
+  for (int i = 1; i < 5; ++i) M = fmaxf(M, red[i]);  // warps 0 .. 4 hold the splits
+  const float m_safe = (M == -INFINITY) ? 0.f : M;
+  const float w0 = exp2f((m0 - m_safe) * kLog2e);
+  if (tid < p.nsplit) ws[tid] = w0;
+  const float lsum = warp_sum(w0 * l0);
+  if (lane == 0) red[kCT / 32 + warp] = lsum;
+  __syncthreads();
+  float L = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) L += red[kCT / 32 + i];
+  const float inv = 1.0f / L;
+
+  const int ncol4 = p.Dv >> 2;   // <= 128 (values up to 512 features, multiples of 8)
+  const int nsg = kCT / ncol4;   // split groups
+  const int sg = tid / ncol4, c4 = tid - sg * ncol4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sg < nsg) {
+    const float* src = part + row * DVP + 4 * c4;
+#pragma unroll 8
+    for (int s = sg; s < p.nsplit; s += nsg) {
+      const float w = ws[s];
+      const float4 v = *reinterpret_cast<const float4*>(src + s * pstride);
+      a.x = fmaf(w, v.x, a.x);
+      a.y = fmaf(w, v.y, a.y);
+      a.z = fmaf(w, v.z, a.z);
+      a.w = fmaf(w, v.w, a.w);
+    }
+  }
+  acc4[tid] = a;
+  __syncthreads();
+  if (sg != 0) return;
+  for (int g2 = 1; g2 < nsg; ++g2) {
+    const float4 v = acc4[g2 * ncol4 + c4];
+    a.x += v.x;
+    a.y += v.y;
+    a.z += v.z;
+    a.w += v.w;
+  }
+  const int tok = r / p.G, hg = r - tok * p.G;
+  const int64_t oo = b * p.os[0] + (int64_t)(hk * p.G + hg) * p.os[1] + (int64_t)tok * p.os[2] + 4 * c4;
+  if (p.out_is_f32) {
+    *reinterpret_cast<float2*>((float*)p.out + oo) = make_float2(a.x * inv, a.y * inv);
+    *reinterpret_cast<float2*>((float*)p.out + oo + 2) = make_float2(a.z * inv, a.w * inv);
+  } else {
+    *reinterpret_cast<uint32_t*>((T*)p.out + oo) = pack2<T>(a.x * inv, a.y * inv);
+    *reinterpret_cast<uint32_t*>((T*)p.out + oo + 2) = pack2<T>(a.z * inv, a.w * inv);
+  }
+}
+
+bool rows16h(const omx_array* a) {  // feature axis contiguous, rows 16-byte aligned (8 two-byte elements)
+  if (a->strides[3] != 1 && a->shape[3] != 1) return false;
+  if (reinterpret_cast<uintptr_t>(a->data) & 15) return false;
+  for (int i = 0; i < 3; ++i)
+    if (a->shape[i] > 1 && a->strides[i] % 8) return false;
+  return true;
+}
+
+template <typename T, int DKP, int DVP, int KS = 1>
+void launch_cfg(MmaParams& p, cudaStream_t stream) {
+  using C = MmaCfg<DKP, DVP>;
+  auto kern = sdpa_mma_kernel<T, DKP, DVP, KS>;
+  OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+  // split the key range when the row tiles alone leave SMs idle: at least 2 key tiles (both stages) per split
+  const int64_t base = (int64_t)p.MT * p.Hkv * p.B;
+  const int nt = (p.Lk + C::BN - 1) / C::BN;
+  static const int min_tiles = [] {
+    const char* e = getenv("OMX_MMA_MIN_TILES");
+    return e ? std::max(1, atoi(e)) : 2;
+  }();
+  int nsplit = 1;
+  if (base < sm_count())
+    nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(sm_count(), 148) / base, nt / min_tiles));
+  p.nsplit = nsplit;
+  if (nsplit > 1)
+    p.part = (float*)get_workspace(sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM), stream);
+  dim3 grid(p.MT, p.Hkv, p.B * nsplit);
+  kern<<<grid, C::NT, C::smem, stream>>>(p);
+  count_launch();
+  OMX_CUDA(cudaGetLastError());
+  if (nsplit > 1) {
+    dim3 cgrid(p.R, p.Hkv, p.B);
+    sdpa_mma_combine_kernel<T><<<cgrid, kCT, 0, stream>>>(p, DVP);
+    count_launch();
+    OMX_CUDA(cudaGetLastError());
+  }
+}
+
+template <typename T>
+void launch_t(MmaParams& p, cudaStream_t stream) {
+  const int d = p.D, dv = p.Dv;
+  if (d <= 32 && dv <= 32) launch_cfg<T, 32, 32>(p, stream);
+  else if (d <= 96 && dv <= 96) launch_cfg<T, 96, 96>(p, stream);
+  else if (d <= 128 && dv <= 128) launch_cfg<T, 128, 128>(p, stream);
+  else if (d <= 256 && dv <= 256) launch_cfg<T, 256, 256>(p, stream);
+  else if (p.R <= 32 && !getenv("OMX_MMA_NO_KS")) launch_cfg<T, 576, 512, 2>(p, stream);  // decode: 20 heads x 1 token
+  else launch_cfg<T, 576, 512>(p, stream);
+}
+
+}  // namespace
+
+bool sdpa_mma_supported(const SdpaArgs& a, const char** why) {
+  auto no = [&](const char* w) {
+    if (why) *why = w;
+    return false;
+  };
+  const int dt = a.q->dtype;
+  if (!(dt == OMX_BFLOAT16 || dt == OMX_FLOAT16) || a.k->dtype != dt || a.v->dtype != dt) return no("not bf16 / f16");
+  if (a.out->dtype != dt && a.out->dtype != OMX_FLOAT32) return no("output dtype");
+  if (a.D % 8 || a.Dv % 8 || a.D > 576 || a.Dv > 512 || a.D < 8 || a.Dv < 8)
+    return no("head dims must be multiples of 8, keys <= 576, values <= 512");
+  if (a.Lk < 1) return no("no keys");
+  if (a.Hkv < 1 || a.Hq % a.Hkv) return no("query heads not a multiple of kv heads");
+  if (a.Hkv > 65535 || (int64_t)a.B * 148 > 65535) return no("grid too large");
+  if (a.mask_mode == MASK_ADD && !(a.mask->dtype == dt || a.mask->dtype == OMX_FLOAT32)) return no("additive mask dtype");
+  if (!rows16h(a.q) || !rows16h(a.k) || !rows16h(a.v)) return no("rows not contiguous / 16-byte aligned");
+  // the output is stored as column pairs
+  if ((a.out->strides[3] != 1 && a.out->shape[3] != 1) ||
+      (reinterpret_cast<uintptr_t>(a.out->data) & 7))
+    return no("output rows not contiguous / aligned");
+  for (int i = 0; i < 3; ++i)
+    if (a.out->shape[i] > 1 && a.out->strides[i] % 2) return no("output rows not aligned");
+  return true;
+}
+
+void sdpa_mma(const SdpaArgs& a, cudaStream_t stream) {
+  MmaParams p{};
+  p.q = a.q->data;
+  p.k = a.k->data;
+  p.v = a.v->data;
+  p.out = a.out->data;
+  p.mask = a.mask ? a.mask->data : nullptr;
+  p.part = nullptr;
+  for (int i = 0; i < 3; ++i) {
+    p.qs[i] = a.q->strides[i];
+    p.ks[i] = a.k->strides[i];
+    p.vs[i] = a.v->strides[i];
+    p.os[i] = a.out->strides[i];
+  }
+  for (int i = 0; i < 4; ++i) p.ms[i] = a.mask_strides[i];
+  p.B = a.B; p.Hq = a.Hq; p.Hkv = a.Hkv; p.G = a.Hq / a.Hkv; p.Lq = a.Lq; p.Lk = a.Lk; p.D = a.D; p.Dv = a.Dv;
+  p.R = p.G * p.Lq;
+  p.MT = (p.R + kBM - 1) / kBM;
+  p.scale = a.scale;
+  p.mask_mode = a.mask_mode;
+  p.mask_is_f32 = (a.mask && a.mask->dtype == OMX_FLOAT32) ? 1 : 0;
+  p.out_is_f32 = a.out->dtype == OMX_FLOAT32 ? 1 : 0;
+  note_launch("sdpa_mma");
+  if (a.q->dtype == OMX_BFLOAT16) launch_t<__nv_bfloat16>(p, stream);
+  else launch_t<__half>(p, stream);
+}
+
+}  // namespace omx

@@ -175,7 +175,9 @@ def test_decode_kernel_families():
     _run((2, 8, 2, 1, 700, 128), "bf16", "bool2d")
     assert omx.last_kernel() == "decode_hmma_tma"   # array masks stay on the split-K decode kernels
     _run((2, 8, 2, 1, 700, 96), "bf16", "bool2d")
-    assert omx.last_kernel() == "sdpa_generic"      # head dims outside {32, 64, 128, 256}
+    assert omx.last_kernel() == "sdpa_mma"          # head dims outside {32, 64, 128, 256}: mma.sync tiles
+    _run((2, 8, 2, 1, 700, 100), "bf16", "bool2d")
+    assert omx.last_kernel() == "sdpa_generic"      # rows that are not 16-byte multiples: one warp per row
 
 
 def test_decode_on_cache_views():
@@ -272,7 +274,7 @@ def test_absorbed_mla_glm47_flash_dk576_dv512(L):
     v = k[..., :Dv]  # strided view, like the crate's `values = kv_latent`
     mask = None if L == 1 else omx.fast.ScaledDotProductAttentionMask.Causal
     got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), k.to(DEV)[..., :Dv], Dk ** -0.5, mask)
-    assert tuple(got.shape) == (B, H, L, Dv) and omx.last_kernel() == "sdpa_generic"
+    assert tuple(got.shape) == (B, H, L, Dv) and omx.last_kernel() == "sdpa_mma"
     want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v.contiguous(), dtype), Dk ** -0.5,
                     None if L == 1 else "causal", dtype=dtype)
     assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, "absorbed MLA attention")
@@ -281,6 +283,107 @@ def test_absorbed_mla_glm47_flash_dk576_dv512(L):
     K, V = c.update_and_fetch(k.to(DEV), k.to(DEV)[..., :Dv].contiguous())
     got2 = omx.fast.scaled_dot_product_attention(q.to(DEV), K, V, Dk ** -0.5, mask)
     assert torch.equal(got, got2)
+
+
+# ---- 16-bit shapes outside the tcgen05 / TMA kernels: mma.sync tiles with the query group packed (sdpa_mma.cu) ----
+
+def _run_wide(B, Hq, Hkv, Lq, Lk, Dk, Dv, dtype, mask_kind, seed=0, force="sdpa_mma", v_is_k_view=False):
+    q = randn((B, Hq, Lq, Dk), dtype, seed + 1)
+    k = randn((B, Hkv, Lk, Dk), dtype, seed + 2)
+    v = k[..., :Dv] if v_is_k_view else randn((B, Hkv, Lk, Dv), dtype, seed + 3)
+    gm, om = _mask(mask_kind, B, Hq, Lq, Lk, dtype, seed + 4)
+    kd = k.to(DEV)
+    vd = kd[..., :Dv] if v_is_k_view else v.to(DEV)
+    scale = Dk ** -0.5
+    omx.force_kernel(force)
+    try:
+        got = omx.fast.scaled_dot_product_attention(q.to(DEV), kd, vd, scale, gm)
+        assert omx.last_kernel() == force
+    finally:
+        omx.force_kernel("")
+    assert tuple(got.shape) == (B, Hq, Lq, Dv)
+    want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v.contiguous(), dtype), scale, om, dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype,
+                 f"sdpa_mma {(B, Hq, Hkv, Lq, Lk, Dk, Dv)} {dtype} {mask_kind}")
+    return got
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("mask", MASKS)
+def test_mma_all_masks(dtype, mask):
+    """Forced kernel vs the oracle chain: ragged rows / keys, GQA groups packed into the row tile (group size that
+    does not divide 64), Lq < Lk (bottom-right causal), every mask mode; head dims 80 (padded to 96) and 256."""
+    _run_wide(2, 6, 2, 37, 150, 80, 80, dtype, mask)
+    _run_wide(1, 4, 2, 70, 70, 256, 256, dtype, mask)
+
+
+@pytest.mark.parametrize("dims", [(16, 16), (24, 24), (72, 72), (96, 96), (128, 128), (192, 128), (256, 256),
+                                  (576, 512), (320, 264)])
+def test_mma_head_dims(dims):
+    Dk, Dv = dims
+    _run_wide(1, 6, 3, 33, 97, Dk, Dv, "bf16", "causal", seed=Dk)
+    _run_wide(2, 4, 1, 5, 200, Dk, Dv, "f16", "none", seed=Dk + 1)
+
+
+@pytest.mark.parametrize("L", [1, 3, 64, 130])
+def test_mma_absorbed_mla_decode_and_prefill(L):
+    """GLM-4.7-Flash absorbed MLA (glm-4.7-flash-mlx/src/model.rs:263-299): 20 heads over ONE latent kv head,
+    keys 512 + 64, values = the keys' first 512 features (a strided view); L = 1 splits the keys over CTAs and
+    merges in a second launch."""
+    S = 700 + L
+    _run_wide(2, 20, 1, L, S, 576, 512, "bf16", "none" if L == 1 else "causal", v_is_k_view=True)
+    got = _run_wide(1, 20, 1, L, S, 576, 512, "bf16", "bool2d")
+    ref = _run_wide(1, 20, 1, L, S, 576, 512, "bf16", "bool2d", force="sdpa_generic")
+    np.testing.assert_allclose(got.float().cpu().numpy(), ref.float().cpu().numpy(), atol=1.5e-2)
+
+
+@pytest.mark.parametrize("H,L,S", [(8, 1, 333), (16, 1, 64), (20, 1, 31), (32, 1, 1000), (16, 2, 500), (33, 1, 257)])
+def test_mma_mla_decode_key_groups(H, L, S):
+    """Packed rows <= 32 (decode) run the variant whose warps split each key tile into two key groups merged at the
+    end; 33 rows and up take the four-row-group layout.  Ragged key counts, bool mask, several batches."""
+    _run_wide(3, H, 1, L, S, 576, 512, "bf16", "none", seed=H + S)
+    _run_wide(2, H, 1, L, S, 576, 512, "f16", "bool4d", seed=H + S + 1)
+
+
+def test_mma_split_keys_long_context_and_masked_rows():
+    # one packed row tile, 9000 keys: split over the SMs; bool rows that hide every key follow the finfo.min rule
+    _run_wide(1, 20, 1, 1, 9000, 576, 512, "bf16", "none")
+    _run_wide(1, 8, 2, 1, 5000, 80, 80, "f16", "add")
+    B, H, Lq, Lk, D = 1, 4, 40, 300, 80
+    q, k, v = (randn((B, H, L, D), "bf16", s) for L, s in ((Lq, 1), (Lk, 2), (Lk, 3)))
+    m = torch.rand((Lq, Lk), generator=torch.Generator().manual_seed(5)) > 0.5
+    m[7, :] = False
+    omx.force_kernel("sdpa_mma")
+    try:
+        got = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), D ** -0.5, m.to(DEV))
+    finally:
+        omx.force_kernel("")
+    want = orc.sdpa(t2n(q, "bf16"), t2n(k, "bf16"), t2n(v, "bf16"), D ** -0.5, m.numpy(), dtype="bf16")
+    assert_close(got.float().cpu().numpy(), n2f(want, "bf16"), "bf16", "fully masked row")
+    np.testing.assert_allclose(got[0, :, 7].float().cpu().numpy(), v[0].float().mean(1).numpy(), atol=1e-2)
+
+
+def test_mma_strided_views_and_refusals():
+    # q stored [B, L, H, D]; k / v as slices of a longer cache buffer (the KVCache views, SURVEY F5)
+    B, Hq, Hkv, Lq, Lk, D, dtype = 2, 8, 2, 9, 77, 80, "bf16"
+    q = randn((B, Lq, Hq, D), dtype, 1)
+    kb, vb = randn((B, Hkv, 256, D), dtype, 2), randn((B, Hkv, 256, D), dtype, 3)
+    got = omx.fast.scaled_dot_product_attention(q.to(DEV).transpose(1, 2), kb.to(DEV)[:, :, :Lk], vb.to(DEV)[:, :, :Lk],
+                                                D ** -0.5, Causal)
+    assert omx.last_kernel() == "sdpa_mma"
+    want = orc.sdpa(t2n(q.transpose(1, 2), dtype), t2n(kb[:, :, :Lk], dtype), t2n(vb[:, :, :Lk], dtype), D ** -0.5,
+                    "causal", dtype=dtype)
+    assert_close(got.float().cpu().numpy(), n2f(want, dtype), dtype, "strided sdpa_mma")
+    omx.force_kernel("sdpa_mma")
+    try:
+        with pytest.raises(omx.Exception, match="not bf16 / f16"):
+            x = torch.zeros((1, 2, 32, 80), dtype=torch.float32, device=DEV)
+            omx.fast.scaled_dot_product_attention(x, x, x, 1.0, None)
+        with pytest.raises(omx.Exception, match="multiples of 8"):
+            x = torch.zeros((1, 2, 32, 100), dtype=torch.bfloat16, device=DEV)
+            omx.fast.scaled_dot_product_attention(x, x, x, 1.0, None)
+    finally:
+        omx.force_kernel("")
 
 
 # ---- float32 with many query rows: the tiled FFMA kernel (sdpa_f32_tiled.cu) ----
