@@ -446,7 +446,7 @@ int omx_dit_attn_fused(const omx_array* out, int n_streams, const omx_array* con
 
 /* ---- introspection (tests / bench) -------------------------------------- */
 /* Name of the kernel family the last successful attention call on this thread dispatched to
- * ("decode_hmma_tma", "decode_simt", "fmha_tcgen05", "sdpa_generic", ...). */
+ * ("decode_hmma_tma", "decode_simt", "fmha_tcgen05", "sdpa_mma", "sdpa_f32_tiled", "sdpa_generic", ...). */
 const char* omx_last_kernel(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 int64_t omx_launch_count(bool reset);
