@@ -59,6 +59,13 @@ WORKLOADS = {
     # DESIGN 4.3), so that the float32 multi-row path has a driver-side number too (N = 1 only)
     "c1_prefill": ("prefill", dict(B=1, Hq=16, Hkv=8, D=128, S=2048, dtype="f32", causal=True,
                                    label="C1 model prefill: Qwen3-0.6B causal prefill fp32 B1 seq2048")),
+    # not BASELINE configs either: GLM-4.7-Flash's absorbed MLA (glm-4.7-flash-mlx/src/model.rs:263-299; 20 query heads
+    # over ONE latent kv head, keys 512 + 64, values 512) through fast::sdpa on the mma.sync kernel, so
+    # that the Dk != Dv path has driver-side numbers (N = 1 only)
+    "mla_decode": ("mla", dict(B=64, Hq=20, Hkv=1, D=576, Dv=512, S=4096, L=1, dtype="bf16", causal=False,
+                               label="GLM-4.7-Flash absorbed-MLA decode bf16 B64 ctx4096 (keys 576 / values 512)")),
+    "mla_prefill": ("mla", dict(B=1, Hq=20, Hkv=1, D=576, Dv=512, S=4096, L=4096, dtype="bf16", causal=True,
+                                label="GLM-4.7-Flash absorbed-MLA causal prefill bf16 B1 seq4096 (keys 576 / values 512)")),
 }
 L2_BYTES = 126e6
 MIN_TIMED_S = 0.5
@@ -164,6 +171,9 @@ def workload_config(name, world):
                  f"kv-head-sharded {cfg['Hkv']}/{world} kv heads per GPU, output heads exchanged by {how}")
     elif name == "c1_prefill":
         c.update(global_batch=B, per_gpu_batch=B, mask="causal", parallelism="single GPU")
+    elif kind == "mla":
+        c.update(global_batch=B, per_gpu_batch=B, value_dim=cfg["Dv"], mask="causal" if cfg["causal"] else None,
+                 parallelism="single GPU")
     elif name == "c3":
         c.update(global_batch=B, per_gpu_batch=B // world if world <= B else 1, mask="causal",
                  parallelism=f"batch-sharded {B}/{world} items per GPU, no data-path collective")
@@ -751,6 +761,86 @@ class Bench:
         self.attach_traffic(rec, name)
         return rec, dict(q=q, k=k, v=v, out=out, scale=scale, mask=mask)
 
+    # ---- absorbed MLA through fast::scaled_dot_product_attention (keys wider than values, one latent kv head)
+    def run_mla(self, name, cfg, steps, warmup):
+        torch, omx = self.torch, self.omx
+        B, Hq, Hkv, D, Dv, S, L = (cfg[k] for k in ("B", "Hq", "Hkv", "D", "Dv", "S", "L"))
+        tdt, es = torch.bfloat16, 2
+        decode = L == 1
+        kv_bytes = B * Hkv * S * (D + Dv) * es
+        R = 1
+        if decode and kv_bytes < 2 * L2_BYTES:
+            need = int(math.ceil(2 * L2_BYTES / kv_bytes))
+            divs = [d for d in range(1, steps + 1) if steps % d == 0 and d >= need]
+            R = divs[0] if divs else steps
+        q = self.rows_randn(71, list(range(B)), (Hq, L, D), tdt)
+        ks = [self.rows_randn(72 + 10 * c, list(range(B)), (Hkv, S, D), tdt) for c in range(R)]
+        vs = [self.rows_randn(73 + 10 * c, list(range(B)), (Hkv, S, Dv), tdt) for c in range(R)]
+        out = torch.empty((B, Hq, L, Dv), dtype=tdt, device=self.dev)
+        scale = D ** -0.5
+        mask = omx.fast.ScaledDotProductAttentionMask.Causal if cfg["causal"] else None
+
+        def step(i):
+            omx.fast.scaled_dot_product_attention(q, ks[i % R], vs[i % R], scale, mask, out=out)
+
+        res = self.measure(step, steps, warmup, graph=decode)
+        ms = res["ms_per_step"]
+        flops = 2.0 * B * Hq * L * S * (D + Dv) * (0.5 if cfg["causal"] else 1.0)
+        alg_bytes = kv_bytes + B * Hq * L * (D + Dv) * es
+        pins = [torch.empty_like(t, device="cpu").pin_memory() for t in (q, ks[0], vs[0])]
+        for hp, t in zip(pins, (q, ks[0], vs[0])):
+            hp.copy_(t)
+        out_pin = torch.empty_like(out, device="cpu").pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in pins)
+        d2h = out.numel() * out.element_size()
+
+        def e2e_block(n):
+            for _ in range(n):
+                q.copy_(pins[0], non_blocking=True)
+                ks[0].copy_(pins[1], non_blocking=True)
+                vs[0].copy_(pins[2], non_blocking=True)
+                omx.fast.scaled_dot_product_attention(q, ks[0], vs[0], scale, mask, out=out)
+                out_pin.copy_(out, non_blocking=True)
+
+        n_e2e = max(2, min(steps, 5))
+        e2e_block(1)
+        blocks = self.timed_blocks(lambda: e2e_block(n_e2e), n_e2e, min_s=0.1, max_blocks=3)
+        e2e_ms = sorted(blocks)[len(blocks) // 2] / n_e2e
+        tf = flops / (ms / 1e3) / 1e12
+        gbs = alg_bytes / (ms / 1e3) / 1e9
+        per_s = (B if decode else B * S) / (ms / 1e3)
+        rec = {
+            "metric": "mla_decode_tokens_per_s" if decode else "mla_prefill_tflops",
+            "unit": "tokens/s" if decode else "TFLOP/s", "value": per_s if decode else tf,
+            "ms_per_step": ms, "ms_per_step_min": res["ms_per_step_min"], "blocks": res["blocks"], "steps": steps,
+            "dtype": cfg["dtype"], "tokens_per_s": per_s, "tflops": tf, "hbm_gbs": gbs,
+            "e2e": {"value": ((B if decode else flops / 1e12) / (e2e_ms / 1e3)), "unit": "tokens/s" if decode else "TFLOP/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "blocks": len(blocks),
+                    "cuda_graph": False,
+                    "how": "serial upload of q + the whole K / V -> kernel -> download on one stream: PCIe-bound ("
+                           f"{(h2d + d2h) / 1e6:.0f} MB per step over the host link; a serving loop keeps K / V resident)"},
+            "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
+            "run": {"kernel": res["kernel"], "cuda_graph": bool(decode),
+                    "l2_policy": (f"rotating {R} K/V sets of {kv_bytes / 1e6:.0f} MB" if R > 1 else
+                                  f"K/V {kv_bytes / 1e6:.0f} MB per step vs 126 MB L2"),
+                    "launches_per_step": res["launches_per_block"] / steps},
+        }
+        if decode:
+            rec["roofline"] = {"bound": "hbm", "achieved": gbs, "peak": self.pk["hbm"], "unit": "GB/s",
+                               "frac": gbs / self.pk["hbm"], "peak_source": self.pk["src"] + " copy bandwidth",
+                               "algorithmic_bytes_per_launch": alg_bytes,
+                               "bytes_convention": "K + V rows once (B*Hkv*S*(Dk+Dv)*2) + q + out"}
+        else:
+            # mma.sync path: its own measured ceiling on this chip is 552 TFLOP/s (scripts/microbench/hmma.cu,
+            # profiles/r02_mma.md); the fraction printed is against the same cuBLAS figure as C3 / C4
+            rec["roofline"] = {"bound": "tensor", "achieved": tf, "peak": self.pk["tf_sustained"], "unit": "TFLOP/s",
+                               "frac": tf / self.pk["tf_sustained"], "frac_of_legacy_mma_sync_peak_552": tf / 552.0,
+                               "achieved_best_block": flops / (res["ms_per_step_min"] / 1e3) / 1e12,
+                               "peak_source": self.pk["src"] + " cuBLAS bf16 sustained",
+                               "algorithmic_flops_per_launch": flops,
+                               "flops_convention": "2*B*Hq*Lq*Lk*(Dk+Dv), causal counted as half"}
+        return rec
+
     # ---- parity of the batch split (C2, C3, C4): gathered shard outputs vs the unsharded launch on rank 0
     def parity_decode(self, name, cfg, rows, st):
         torch, omx, dist = self.torch, self.omx, self.dist
@@ -867,6 +957,9 @@ class Bench:
         elif name == "c1_prefill":
             rec, st = self.run_prefill(name, cfg, [0], (0, cfg["Hq"]), 1, steps, warmup)
             rec["scaling"] = "single GPU"
+        elif kind == "mla":
+            rec = self.run_mla(name, cfg, steps, warmup)
+            rec["scaling"] = "single GPU"
         elif name in ("c3", "c4"):
             B, Hq = cfg["B"], cfg["Hq"]
             if W <= B:
@@ -927,7 +1020,7 @@ def main():
     if args.workload == "all":
         names += ["c2_paged", "c1", "c5"] + (["c5_collective"] if world > 1 and 8 % world == 0 else []) + ["c3", "c4"]
         if world == 1:
-            names.append("c1_prefill")
+            names += ["c1_prefill", "mla_decode", "mla_prefill"]
         if world > 1:
             names.append("c2_weak")
     recs = {}

@@ -90,28 +90,44 @@ __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int DKP, int DVP>
+template <int DKP, int DVP, int KS>
 struct MmaCfg {
-  static constexpr int NC = DVP > 256 ? 2 : 1;     // warps per row group (each owns DVP / NC output columns)
+  // warps per row group, each owning DVP / NC output columns: wide values need two (a 16 x 256 float32 fragment is
+  // 128 registers).  Measured alternative for the decode variant: four (16 warps of 128 registers, features split
+  // four ways) -- slower, B64 ctx 4096 198 us against 171 us: the shared-memory pipe (ldmatrix.x4 = 4 wavefronts)
+  // and the per-tile barriers, not per-warp latency, carry the cost.  OMX_MMA_DECODE_NC=4 at build time selects it.
+#ifndef OMX_MMA_DECODE_NC
+#define OMX_MMA_DECODE_NC 2
+#endif
+  static constexpr int NC = DVP > 256 ? (KS == 2 ? OMX_MMA_DECODE_NC : 2) : 1;
   static constexpr int NT = 128 * NC;              // threads
   static constexpr int BN = DKP >= 256 ? 32 : 64;  // keys per tile
   static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
-  static constexpr size_t smem = sizeof(uint16_t) * ((size_t)kBM * KP + 2 * (size_t)BN * KP + 2 * (size_t)BN * VP);
+  static constexpr int QR = KS == 2 ? 32 : kBM;    // query rows held in shared memory (decode: <= 32 packed rows)
+  static constexpr bool kSplitD = KS == 2 && NC > 1;
+  static constexpr size_t smem = sizeof(uint16_t) * ((size_t)QR * KP + 2 * (size_t)BN * KP + 2 * (size_t)BN * VP) +
+                                 (kSplitD ? 2 * (NT / 32) * 8 * 32 * sizeof(float) : 0);
 };
 
 // KS = 2 (launched when the packed rows fit 32: decode) turns two of the four row groups into a second key group:
 // each warp takes half of a tile's keys with its own running (m, l, O), merged once through shared memory at the end.
 template <typename T, int DKP, int DVP, int KS>
-__global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
-  using C = MmaCfg<DKP, DVP>;
+__global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
+  using C = MmaCfg<DKP, DVP, KS>;
   constexpr int BN = C::BN, KP = C::KP, VP = C::VP, WN = C::WN, NT = C::NT;
   constexpr int BNW = BN / KS;  // keys of a tile one warp scores
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Qs = reinterpret_cast<T*>(smem_raw);  // [64][KP]
-  T* Ks = Qs + kBM * KP;                   // [2][BN][KP]
+  constexpr int kQR = C::QR;
+  // several warps on a row group (wide values) in the decode variant: each multiplies its SHARE of the features and
+  // the partial score tiles are exchanged through shared memory, instead of all repeating the whole QK^T product
+  constexpr bool kSplitD = C::kSplitD;
+  constexpr int NC = C::NC;
+  T* Qs = reinterpret_cast<T*>(smem_raw);  // [kQR][KP]
+  T* Ks = Qs + kQR * KP;                   // [2][BN][KP]
   T* Vs = Ks + 2 * BN * KP;                // [2][BN][VP]
+  float* xbuf = reinterpret_cast<float*>(Vs + 2 * BN * VP);  // kSplitD: [2 parities][warps][8 words][32 lanes]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = KS == 1 ? (warp & 3) : (warp & 1), wk = KS == 1 ? 0 : ((warp >> 1) & 1), wc = warp >> 2;
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
   // slower at 160-byte rows: the per-request cost of small bulk copies; a tensor-map box per tile would need
   // swizzled, unpadded stages.)
   constexpr int CH = DKP / 8;
-  for (int c = tid; c < kBM * CH; c += NT) {
+  for (int c = tid; c < kQR * CH; c += NT) {
     const int row = c / CH, ch = c - row * CH;
     const int r = m0 + row;
     const bool ok = r < p.R && ch * 8 < p.D;
@@ -207,7 +223,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
   cp_async_wait<1>();
   {
     const float sc = rnd<T>(p.scale);
-    for (int c = tid; c < kBM * CH; c += NT) {
+    for (int c = tid; c < kQR * CH; c += NT) {
       const int row = c / CH, ch = c - row * CH;
       if (m0 + row >= p.R || ch * 8 >= p.D) continue;
       uint4* qp = reinterpret_cast<uint4*>(Qs + row * KP + ch * 8);
@@ -271,10 +287,20 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
       // fragments of step kk + 1 are requested before the MMAs of step kk issue (the asm statements keep their order)
       constexpr int NPQ = BNW / 16;
       uint32_t a0[4], a1[4], b0[NPQ][4], b1[NPQ][4];
+      // k16 steps [kb, kb + kc) are this warp's (all of them unless the features are split over the warp pair)
+      constexpr int CNT = DKP / 16 / (kSplitD ? NC : 1);
+      static_assert(DKP / 16 % (kSplitD ? NC : 1) == 0, "feature shares");
+      int kb = 0, kc = nk;
+      if constexpr (kSplitD) {
+        const int share = nk == DKP / 16 ? CNT : (nk + NC - 1) / NC;
+        kb = wc * share;
+        kc = max(0, min(nk, kb + share) - kb);
+      }
+      const uint32_t q_b = q_base + kb * 32, k_b = k_base + kb * 32;
       auto fetch = [&](int kk, uint32_t (&a)[4], uint32_t (&bb)[NPQ][4]) {
-        ldsm4(q_base + kk * 32, a);
+        ldsm4(q_b + kk * 32, a);
 #pragma unroll
-        for (int np = 0; np < NPQ; ++np) ldsm4(k_base + (np * 16 * KP) * 2 + kk * 32, bb[np]);
+        for (int np = 0; np < NPQ; ++np) ldsm4(k_b + (np * 16 * KP) * 2 + kk * 32, bb[np]);
       };
       auto mult = [&](const uint32_t (&a)[4], const uint32_t (&bb)[NPQ][4]) {
 #pragma unroll
@@ -286,17 +312,17 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
       if (nk == DKP / 16) {
         // the configuration's own width (MLA: 36 steps): straight-line code, immediate offsets; with few key
         // columns per warp the even / odd steps feed separate accumulators (chains half as long)
-        constexpr bool kTwo = BNW / 8 <= 2;
+        constexpr bool kTwo = BNW / 8 <= 2 && CNT >= 12;
         float s2[kTwo ? BNW / 8 : 1][4];
 #pragma unroll
         for (int n = 0; n < (kTwo ? BNW / 8 : 1); ++n) s2[n][0] = s2[n][1] = s2[n][2] = s2[n][3] = 0.f;
         fetch(0, a0, b0);
 #pragma unroll
-        for (int kk = 0; kk < DKP / 16; kk += 2) {
-          if (kk + 1 < DKP / 16) fetch(kk + 1, a1, b1);
+        for (int kk = 0; kk < CNT; kk += 2) {
+          if (kk + 1 < CNT) fetch(kk + 1, a1, b1);
           mult(a0, b0);
-          if (kk + 1 < DKP / 16) {
-            if (kk + 2 < DKP / 16) fetch(kk + 2, a0, b0);
+          if (kk + 1 < CNT) {
+            if (kk + 2 < CNT) fetch(kk + 2, a0, b0);
             if constexpr (kTwo) {
 #pragma unroll
               for (int np = 0; np < NPQ; ++np) {
@@ -315,16 +341,38 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
             for (int c = 0; c < 4; ++c) s[n][c] += s2[n][c];
         }
       } else {
-        fetch(0, a0, b0);
+        if (kc > 0) fetch(0, a0, b0);
 #pragma unroll 1
-        for (int kk = 0; kk < nk; kk += 2) {
-          if (kk + 1 < nk) fetch(kk + 1, a1, b1);
+        for (int kk = 0; kk < kc; kk += 2) {
+          if (kk + 1 < kc) fetch(kk + 1, a1, b1);
           mult(a0, b0);
-          if (kk + 1 < nk) {
-            if (kk + 2 < nk) fetch(kk + 2, a0, b0);
+          if (kk + 1 < kc) {
+            if (kk + 2 < kc) fetch(kk + 2, a0, b0);
             mult(a1, b1);
           }
         }
+      }
+      if constexpr (kSplitD) {
+        // partial scores of the other shares of the features: slot [tile parity][warp], word w at [w][lane]; the NC
+        // warps of a row / key group (same warp & 3) meet at their own named barrier and every one of them adds the
+        // NC partials in the same order (identical scores in all of them).  A slot is rewritten two tiles later, after
+        // the barrier of the tile in between, which the partners reach only after they have read.
+        static_assert(BNW == 16, "exchange slots hold 8 words per lane");
+        float* slot = xbuf + ((tile - t0) & 1) * (NT / 32) * 256 + (warp & 3) * 256 + lane;
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) slot[wc * 4 * 256 + (n * 4 + c) * 32] = s[n][c];
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "n"(32 * NC) : "memory");
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float a = slot[(n * 4 + c) * 32];
+#pragma unroll
+            for (int w = 1; w < NC; ++w) a += slot[w * 4 * 256 + (n * 4 + c) * 32];
+            s[n][c] = a;
+          }
       }
     }
 
@@ -419,7 +467,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP>::NT, 1) sdpa_mma_kernel(const
     // [pi][w][lane], so both sides touch consecutive addresses
     constexpr int NW = WN / 2 + 4;  // floats per lane: O fragment + m, l of both rows
     float* xch = reinterpret_cast<float*>(Ks) + (size_t)(wc * 2 + wr) * NW * 32 + lane;
-    static_assert((size_t)C::NC * 2 * NW * 32 * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "exchange area");
+    static_assert((size_t)NC * 2 * NW * 32 * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "hand-over area");
     __syncthreads();  // every warp is done with the stages
     if (wk == 1) {
 #pragma unroll
@@ -567,9 +615,10 @@ bool rows16h(const omx_array* a) {  // feature axis contiguous, rows 16-byte ali
 
 template <typename T, int DKP, int DVP, int KS = 1>
 void launch_cfg(MmaParams& p, cudaStream_t stream) {
-  using C = MmaCfg<DKP, DVP>;
+  using C = MmaCfg<DKP, DVP, KS>;
   auto kern = sdpa_mma_kernel<T, DKP, DVP, KS>;
-  OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+  constexpr size_t smem = C::smem;
+  OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // split the key range when the row tiles alone leave SMs idle: at least 2 key tiles (both stages) per split
   const int64_t base = (int64_t)p.MT * p.Hkv * p.B;
   const int nt = (p.Lk + C::BN - 1) / C::BN;
@@ -584,7 +633,7 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
   if (nsplit > 1)
     p.part = (float*)get_workspace(sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM), stream);
   dim3 grid(p.MT, p.Hkv, p.B * nsplit);
-  kern<<<grid, C::NT, C::smem, stream>>>(p);
+  kern<<<grid, C::NT, smem, stream>>>(p);
   count_launch();
   OMX_CUDA(cudaGetLastError());
   if (nsplit > 1) {
