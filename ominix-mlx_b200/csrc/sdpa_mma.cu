@@ -272,10 +272,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(c
       cp_async_wait<0>();
     }
     __syncthreads();
-    if (!warp_rows) {  // a row group past the last packed row (decode: 20 of 64 rows) only helps with the loads
-      __syncthreads();
-      continue;
-    }
+    if (warp_rows) {  // (a row group past the last packed row only helps with the loads)
     const uint32_t k_base = smem_u32(Ks + stage * BN * KP) + 2 * bk_off;
     const uint32_t v_base = smem_u32(Vs + stage * BN * VP) + 2 * bv_off;
 
@@ -452,6 +449,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(c
         mma16816<T>(o[2 * np + 1], pa[ks], vb[i & 1][2], vb[i & 1][3]);
       }
     }
+    }  // warp_rows
     __syncthreads();  // the stage is free for the load issued two iterations from now
   }
   cp_async_wait<0>();
