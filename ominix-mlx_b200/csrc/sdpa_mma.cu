@@ -106,9 +106,12 @@ struct MmaCfg {
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
   static constexpr int QR = KS == 2 ? 32 : kBM;    // query rows held in shared memory (decode: <= 32 packed rows)
-  static constexpr bool kSplitD = KS == 2 && NC > 1;
+  // several warps on a row group split the FEATURES of QK^T and exchange partial score tiles (one slot per warp:
+  // BN / KS / 2 words per lane).  576 / 512 prefill: 216,064 + 16,384 = 232,448 bytes, the whole opt-in maximum.
+  static constexpr bool kSplitD = NC > 1;
   static constexpr size_t smem = sizeof(uint16_t) * ((size_t)QR * KP + 2 * (size_t)BN * KP + 2 * (size_t)BN * VP) +
-                                 (kSplitD ? 2 * (NT / 32) * 8 * 32 * sizeof(float) : 0);
+                                 (kSplitD ? (NT / 32) * (BN / KS / 2) * 32 * sizeof(float) : 0);
+  static_assert(smem <= 232448, "shared memory per CTA");
 };
 
 // KS = 2 (launched when the packed rows fit 32: decode) turns two of the four row groups into a second key group:
@@ -120,14 +123,14 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(c
   constexpr int BNW = BN / KS;  // keys of a tile one warp scores
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kQR = C::QR;
-  // several warps on a row group (wide values) in the decode variant: each multiplies its SHARE of the features and
-  // the partial score tiles are exchanged through shared memory, instead of all repeating the whole QK^T product
+  // several warps on a row group (wide values): each multiplies its SHARE of the features and the partial score
+  // tiles are exchanged through shared memory, instead of all repeating the whole QK^T product
   constexpr bool kSplitD = C::kSplitD;
   constexpr int NC = C::NC;
   T* Qs = reinterpret_cast<T*>(smem_raw);  // [kQR][KP]
   T* Ks = Qs + kQR * KP;                   // [2][BN][KP]
   T* Vs = Ks + 2 * BN * KP;                // [2][BN][VP]
-  float* xbuf = reinterpret_cast<float*>(Vs + 2 * BN * VP);  // kSplitD: [2 parities][warps][8 words][32 lanes]
+  float* xbuf = reinterpret_cast<float*>(Vs + 2 * BN * VP);  // kSplitD: [warps][BNW / 2 words][32 lanes]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = KS == 1 ? (warp & 3) : (warp & 1), wk = KS == 1 ? 0 : ((warp >> 1) & 1), wc = warp >> 2;
@@ -350,24 +353,24 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(c
         }
       }
       if constexpr (kSplitD) {
-        // partial scores of the other shares of the features: slot [tile parity][warp], word w at [w][lane]; the NC
-        // warps of a row / key group (same warp & 3) meet at their own named barrier and every one of them adds the
-        // NC partials in the same order (identical scores in all of them).  A slot is rewritten two tiles later, after
-        // the barrier of the tile in between, which the partners reach only after they have read.
-        static_assert(BNW == 16, "exchange slots hold 8 words per lane");
-        float* slot = xbuf + ((tile - t0) & 1) * (NT / 32) * 256 + (warp & 3) * 256 + lane;
+        // partial scores of the other shares of the features: slot [column group][row / key group], word w at
+        // [w][lane]; the NC warps of a row / key group (same warp & 3) meet at their own named barrier and every one of
+        // them adds the NC partials in the same order (identical scores in all of them).  The barrier that closes
+        // the tile step stands between these reads and the next step's writes.
+        constexpr int XW = BNW / 2;  // words per lane
+        float* slot = xbuf + (warp & 3) * (XW * 32) + lane;
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+        for (int n = 0; n < BNW / 8; ++n)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) slot[wc * 4 * 256 + (n * 4 + c) * 32] = s[n][c];
+          for (int c = 0; c < 4; ++c) slot[wc * 4 * (XW * 32) + (n * 4 + c) * 32] = s[n][c];
         asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "n"(32 * NC) : "memory");
 #pragma unroll
-        for (int n = 0; n < 2; ++n)
+        for (int n = 0; n < BNW / 8; ++n)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float a = slot[(n * 4 + c) * 32];
 #pragma unroll
-            for (int w = 1; w < NC; ++w) a += slot[w * 4 * 256 + (n * 4 + c) * 32];
+            for (int w = 1; w < NC; ++w) a += slot[w * 4 * (XW * 32) + (n * 4 + c) * 32];
             s[n][c] = a;
           }
       }
