@@ -101,6 +101,7 @@ struct MmaCfg {
 #endif
   static constexpr int NC = DVP > 256 ? (KS == 2 ? OMX_MMA_DECODE_NC : 2) : 1;
   static constexpr int NT = 128 * NC;              // threads
+  static constexpr int MINB = DKP <= 96 ? 3 : 1;  // resident CTAs per SM the register budget aims at
   static constexpr int BN = DKP >= 256 ? 32 : 64;  // keys per tile
   static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
   static constexpr int VP = DVP + 8;
@@ -117,7 +118,7 @@ struct MmaCfg {
 // KS = 2 (launched when the packed rows fit 32: decode) turns two of the four row groups into a second key group:
 // each warp takes half of a tile's keys with its own running (m, l, O), merged once through shared memory at the end.
 template <typename T, int DKP, int DVP, int KS>
-__global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, 1) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
+__global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>::MINB) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
   using C = MmaCfg<DKP, DVP, KS>;
   constexpr int BN = C::BN, KP = C::KP, VP = C::VP, WN = C::WN, NT = C::NT;
   constexpr int BNW = BN / KS;  // keys of a tile one warp scores

@@ -24,7 +24,7 @@ for name, B, Hq, Hkv, Lq, Lk, Dk, Dv, causal, greps in SHAPES:
     out = torch.empty((B, Hq, Lq, Dv), device="cuda", dtype=torch.bfloat16)
     flops = 2.0 * B * Hq * Lq * Lk * (Dk + Dv) * (0.5 if causal else 1.0)
     res, outs = {}, {}
-    variants = [("sdpa_mma", 20 * nrot), ("sdpa_generic", greps * nrot)]
+    variants = [("sdpa_mma", 20 * nrot), ("sdpa_generic", (greps if not os.environ.get("OMX_ATTN_LIB") else 0) * nrot)]
     if Lq == 1 and Dk == 576:
         variants.insert(1, ("sdpa_mma/no_key_groups", 20 * nrot))
     for kern, reps in variants:
