@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wr = KS == 1 ? (warp & 3) : (warp & 1), wk = KS == 1 ? 0 : ((warp >> 1) & 1), wc = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
-  const int mt = blockIdx.x, hk = blockIdx.y;
-  const int b = blockIdx.z / p.nsplit, split = blockIdx.z - b * p.nsplit;
+  const int mt = blockIdx.x / p.nsplit, split = blockIdx.x - mt * p.nsplit, hk = blockIdx.y, b = blockIdx.z;
   const int m0 = mt * kBM;
   const int q_off = max(p.Lk - p.Lq, 0);
 
@@ -634,7 +633,7 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
   p.nsplit = nsplit;
   if (nsplit > 1)
     p.part = (float*)get_workspace(sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM), stream);
-  dim3 grid(p.MT, p.Hkv, p.B * nsplit);
+  dim3 grid(p.MT * nsplit, p.Hkv, p.B);
   kern<<<grid, C::NT, smem, stream>>>(p);
   count_launch();
   OMX_CUDA(cudaGetLastError());
@@ -671,7 +670,7 @@ bool sdpa_mma_supported(const SdpaArgs& a, const char** why) {
     return no("head dims must be multiples of 8, keys <= 576, values <= 512");
   if (a.Lk < 1) return no("no keys");
   if (a.Hkv < 1 || a.Hq % a.Hkv) return no("query heads not a multiple of kv heads");
-  if (a.Hkv > 65535 || (int64_t)a.B * 148 > 65535) return no("grid too large");
+  if (a.Hkv > 65535 || a.B > 65535) return no("grid too large");
   if (a.mask_mode == MASK_ADD && !(a.mask->dtype == dt || a.mask->dtype == OMX_FLOAT32)) return no("additive mask dtype");
   if (!rows16h(a.q) || !rows16h(a.k) || !rows16h(a.v)) return no("rows not contiguous / 16-byte aligned");
   // the output is stored as column pairs

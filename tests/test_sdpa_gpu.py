@@ -345,6 +345,12 @@ def test_mma_mla_decode_key_groups(H, L, S):
     _run_wide(2, H, 1, L, S, 576, 512, "f16", "bool4d", seed=H + S + 1)
 
 
+def test_mma_large_batch_grid():
+    # the batch index rides grid.z, (row tile, key split) grid.x: batches beyond a few hundred stay on this kernel
+    _run_wide(700, 2, 1, 1, 40, 80, 80, "bf16", "none")
+    _run_wide(300, 4, 2, 3, 70, 576, 512, "f16", "causal")
+
+
 def test_mma_split_keys_long_context_and_masked_rows():
     # one packed row tile, 9000 keys: split over the SMs; bool rows that hide every key follow the finfo.min rule
     _run_wide(1, 20, 1, 1, 9000, 576, 512, "bf16", "none")
