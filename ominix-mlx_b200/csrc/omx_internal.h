@@ -15,6 +15,9 @@ struct RopeTableRef {
   const float* sin = nullptr;
   int half = 0;
   int n_pos = 0;
+  // the same rows rounded once to bf16 ([0]) / f16 ([1]), [n_pos, half]
+  const void* cos16[2] = {nullptr, nullptr};
+  const void* sin16[2] = {nullptr, nullptr};
 };
 RopeTableRef get_rope_table(int dims, bool has_base, float base, float scale,
                             const float* freqs_host, int need_positions, cudaStream_t stream);

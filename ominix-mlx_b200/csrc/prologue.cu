@@ -52,6 +52,7 @@ struct PrologueParams {
   int traditional;  // mode 1 only (mode 2 is always adjacent pairs)
   int mode;         // 1: float32 tables [n_pos, half] by position (fast::rope); 2: T tables [B, S, half] (DiT)
   const float *cos, *sin;
+  const void *cos16, *sin16;  // mode 1, 16-bit rows: the table rounded to the row dtype (null: round on the fly)
   int n_pos;
   const void *tcos, *tsin;
   int64_t cs[3], ss[3];
@@ -95,6 +96,39 @@ __device__ __forceinline__ void transform_row16(const PrologueParams& p, const S
   using T2 = typename Q::T2;
   constexpr int NP = D / 2;  // packed registers
   T2* h2 = reinterpret_cast<T2*>(rv);
+  constexpr int HALF = DIMS > 0 ? DIMS / 2 : 2;
+  constexpr int HP = HALF / 2;  // packed cos / sin registers
+  T2 c2[HP], s2[HP];
+  const bool roped = DIMS > 0 && s.rope;
+  bool early = false;
+  if constexpr (DIMS > 0) {
+    // the table row in the row dtype (fast::rope tables rounded once on the host, or the DiT callers' own tables),
+    // requested AHEAD of the norm arithmetic: in the profile of the float32-table version 22 % of the kernel's stall
+    // samples sat on the first use of these loads (32 LDG.128 per thread issued after the norm; now 16, before it)
+    const T *tc = nullptr, *ts = nullptr;
+    if (roped && p.mode == 1 && p.cos16 != nullptr) {
+      const int pos = min(s.tok0 + l, p.n_pos - 1);
+      tc = (const T*)p.cos16 + (size_t)pos * HALF;
+      ts = (const T*)p.sin16 + (size_t)pos * HALF;
+    } else if (roped && p.mode != 1 && p.tvec) {
+      tc = (const T*)p.tcos + b * p.cs[0] + (int64_t)(s.tok0 + l) * p.cs[1];
+      ts = (const T*)p.tsin + b * p.ss[0] + (int64_t)(s.tok0 + l) * p.ss[1];
+    }
+    early = tc != nullptr;
+    if (early) {
+      const uint4* cq = reinterpret_cast<const uint4*>(tc);
+      const uint4* sq = reinterpret_cast<const uint4*>(ts);
+#pragma unroll
+      for (int i = 0; i < HALF / 8; ++i) {
+        const uint4 cv = cq[i], sv = sq[i];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          c2[i * 4 + e] = reinterpret_cast<const T2*>(&cv)[e];
+          s2[i * 4 + e] = reinterpret_cast<const T2*>(&sv)[e];
+        }
+      }
+    }
+  }
   if (s.w) {
     float acc = 0.f;
 #pragma unroll
@@ -117,11 +151,10 @@ __device__ __forceinline__ void transform_row16(const PrologueParams& p, const S
     }
   }
   if constexpr (DIMS > 0) {
-    if (!s.rope) return;
-    constexpr int HALF = DIMS / 2;
-    constexpr int HP = HALF / 2;  // packed cos / sin registers
-    T2 c2[HP], s2[HP];
-    if (p.mode == 1) {
+    if (!roped) return;
+    if (early) {
+      // c2 / s2 hold the row already
+    } else if (p.mode == 1) {
       const int pos = min(s.tok0 + l, p.n_pos - 1);
       const float4* c4 = reinterpret_cast<const float4*>(p.cos + (size_t)pos * HALF);
       const float4* s4 = reinterpret_cast<const float4*>(p.sin + (size_t)pos * HALF);
@@ -136,23 +169,11 @@ __device__ __forceinline__ void transform_row16(const PrologueParams& p, const S
     } else {
       const T* tc = (const T*)p.tcos + b * p.cs[0] + (int64_t)(s.tok0 + l) * p.cs[1];
       const T* ts = (const T*)p.tsin + b * p.ss[0] + (int64_t)(s.tok0 + l) * p.ss[1];
-      if (p.tvec) {
+      // (contiguous, aligned tables took the early path above)
 #pragma unroll
-        for (int i = 0; i < HALF / 8; ++i) {
-          const uint4 cq = reinterpret_cast<const uint4*>(tc)[i];
-          const uint4 sq = reinterpret_cast<const uint4*>(ts)[i];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            c2[i * 4 + e] = reinterpret_cast<const T2*>(&cq)[e];
-            s2[i * 4 + e] = reinterpret_cast<const T2*>(&sq)[e];
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < HP; ++j) {
-          c2[j] = Q::make(tc[(2 * j) * p.cs[2]], tc[(2 * j + 1) * p.cs[2]]);
-          s2[j] = Q::make(ts[(2 * j) * p.ss[2]], ts[(2 * j + 1) * p.ss[2]]);
-        }
+      for (int j = 0; j < HP; ++j) {
+        c2[j] = Q::make(tc[(2 * j) * p.cs[2]], tc[(2 * j + 1) * p.cs[2]]);
+        s2[j] = Q::make(ts[(2 * j) * p.ss[2]], ts[(2 * j + 1) * p.ss[2]]);
       }
     }
     if (p.mode == 1 && !p.traditional) {
@@ -397,6 +418,11 @@ bool qkv_prologue(const PrologueCall& c, cudaStream_t stream) {
     p.cos = c.table.cos;
     p.sin = c.table.sin;
     p.n_pos = c.table.n_pos;
+    if (dt == OMX_BFLOAT16 || dt == OMX_FLOAT16) {
+      p.cos16 = c.table.cos16[dt == OMX_BFLOAT16 ? 0 : 1];
+      p.sin16 = c.table.sin16[dt == OMX_BFLOAT16 ? 0 : 1];
+      if (!p.cos16 || !p.sin16) p.cos16 = p.sin16 = nullptr;
+    }
   } else if (any_rope) {
     if (!c.tcos || !c.tsin || c.tcos->dtype != dt || c.tsin->dtype != dt) return false;
     p.tcos = c.tcos->data;

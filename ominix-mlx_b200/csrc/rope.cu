@@ -34,6 +34,9 @@ struct RopeTable {
   int n_pos = 0;
   float* d_cos = nullptr;  // [n_pos, half]
   float* d_sin = nullptr;
+  // the same rows rounded once to bf16 ([0]) / f16 ([1]): what the 16-bit kernels multiply with (prologue.cu)
+  void* d_cos16[2] = {nullptr, nullptr};
+  void* d_sin16[2] = {nullptr, nullptr};
 };
 
 std::mutex g_tbl_mu;
@@ -107,8 +110,32 @@ RopeTableRef get_rope_table(int dims, bool has_base, float base, float scale,
     OMX_CUDA(cudaMalloc(&ds, sizeof(float) * s.size()));
     OMX_CUDA(cudaMemcpyAsync(dc, c.data(), sizeof(float) * c.size(), cudaMemcpyHostToDevice, stream));
     OMX_CUDA(cudaMemcpyAsync(ds, s.data(), sizeof(float) * s.size(), cudaMemcpyHostToDevice, stream));
+    // 16-bit copies, rounded on the host with the same round-to-nearest-even the kernels' conversions use
+    std::vector<uint16_t> h16(c.size());
+    void* d16[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    for (int ty = 0; ty < 2; ++ty) {
+      for (int cs = 0; cs < 2; ++cs) {
+        const std::vector<float>& src = cs ? s : c;
+        for (size_t i = 0; i < src.size(); ++i) {
+          if (ty == 0) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(src[i]);
+            memcpy(&h16[i], &v, 2);
+          } else {
+            const __half v = __float2half_rn(src[i]);
+            memcpy(&h16[i], &v, 2);
+          }
+        }
+        OMX_CUDA(cudaMalloc(&d16[ty][cs], sizeof(uint16_t) * h16.size()));
+        // (pageable source: the call returns once the staging copy is done, so h16 can be reused)
+        OMX_CUDA(cudaMemcpyAsync(d16[ty][cs], h16.data(), sizeof(uint16_t) * h16.size(), cudaMemcpyHostToDevice, stream));
+      }
+    }
     // Rare (creation / doubling): make the table visible to every stream before first use.
     OMX_CUDA(cudaStreamSynchronize(stream));
+    for (int ty = 0; ty < 2; ++ty) {
+      t->d_cos16[ty] = d16[ty][0];
+      t->d_sin16[ty] = d16[ty][1];
+    }
     // Old buffers may still be read by kernels in flight on other streams: retire, never free.
     t->d_cos = dc;
     t->d_sin = ds;
@@ -119,6 +146,10 @@ RopeTableRef get_rope_table(int dims, bool has_base, float base, float scale,
   r.sin = t->d_sin;
   r.half = half;
   r.n_pos = t->n_pos;
+  for (int ty = 0; ty < 2; ++ty) {
+    r.cos16[ty] = t->d_cos16[ty];
+    r.sin16[ty] = t->d_sin16[ty];
+  }
   return r;
 }
 
