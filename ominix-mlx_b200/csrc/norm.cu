@@ -50,6 +50,53 @@ __global__ void rms_norm_rows_kernel(const NormParams p) {
   }
 }
 
+// contiguous, 16-byte aligned rows of any length that is a multiple of 16 bytes: 128-bit loads, several in flight
+// (the element-wise kernel above waits out one memory round trip per element: 256-wide rows -- Qwen3.5's q_norm /
+// k_norm -- took ~130 us per call on a handful of rows).  Two passes: sum, then reload (L1 / L2) and scale.
+template <typename T>
+__global__ void rms_norm_chunk_kernel(const NormParams p, int w_vec) {
+  constexpr int VE = 16 / sizeof(T);
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.rows) return;
+  int64_t rem = r, xo = 0, oo = 0;
+  for (int i = p.nlead - 1; i >= 0; --i) {
+    const int64_t c = rem % p.n[i];
+    rem /= p.n[i];
+    xo += c * p.xs[i];
+    oo += c * p.os[i];
+  }
+  const uint4* xv = reinterpret_cast<const uint4*>((const T*)p.x + xo);
+  uint4* ov = reinterpret_cast<uint4*>((T*)p.out + oo);
+  const int nv = p.D / VE;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < nv; ++i) {
+    const uint4 c = xv[i];
+    const T* e = reinterpret_cast<const T*>(&c);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) {
+      const float v = Num<T>::to_f(e[j]);
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
+  }
+  const float rs = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fmul_rn(acc, p.inv_n), p.eps)));
+  const T* w = (const T*)p.w;
+#pragma unroll 4
+  for (int i = 0; i < nv; ++i) {
+    uint4 c = xv[i];
+    T* e = reinterpret_cast<T*>(&c);
+    uint4 wc = make_uint4(0, 0, 0, 0);
+    if (w && w_vec) wc = reinterpret_cast<const uint4*>(w)[i];
+    const T* we = reinterpret_cast<const T*>(&wc);
+#pragma unroll
+    for (int j = 0; j < VE; ++j) {
+      const float wj = !w ? 0.f : (w_vec ? Num<T>::to_f(we[j]) : Num<T>::to_f(w[(i * VE + j) * p.w_inner]));
+      e[j] = Num<T>::from_f(rms_apply<T>(Num<T>::to_f(e[j]), rs, wj, w != nullptr));
+    }
+    ov[i] = c;
+  }
+}
+
 // contiguous 16-bit / 32-bit rows of a compile-time length: whole row in registers, 128-bit I/O
 template <typename T, int D>
 __global__ void rms_norm_vec_kernel(const NormParams p) {
@@ -95,6 +142,10 @@ void launch(const NormParams& p, bool vec_ok, cudaStream_t s) {
     rms_norm_vec_kernel<T, 128><<<blocks, threads, 0, s>>>(p);
   } else if (vec_ok && p.D == 64) {
     rms_norm_vec_kernel<T, 64><<<blocks, threads, 0, s>>>(p);
+  } else if (vec_ok && p.D % (16 / (int)sizeof(T)) == 0) {
+    const int w_vec = p.w && p.w_inner == 1 && aligned16(p.w) ? 1 : 0;
+    const int th = 32;  // few rows per call in practice (decode): spread them over SMs
+    rms_norm_chunk_kernel<T><<<(unsigned)((p.rows + th - 1) / th), th, 0, s>>>(p, w_vec);
   } else {
     rms_norm_rows_kernel<T><<<blocks, threads, 0, s>>>(p);
   }

@@ -223,6 +223,10 @@ void dispatch_sdpa(const SdpaArgs& a, cudaStream_t stream) {
   if ((int64_t)a.B * a.Hq * a.Lq * a.Dv == 0) return;
   const std::string& force = t_forced_kernel;
   const char* why = nullptr;
+  if (force.empty() && sdpa_mma_preferred_for_decode(a)) {
+    sdpa_mma(a, stream);  // grouped-query single-token calls outside head dim 128: key-group mma.sync tiles
+    return;
+  }
   if (force.empty() || force == "decode" || force == "decode_simt" || force == "decode_hmma_tma") {
     if (a.out->dtype == a.q->dtype && decode_supported(a, &why)) {
       DecodeFused none;
@@ -472,8 +476,11 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
   SdpaArgs a = make_sdpa_args(&out_local, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
   const char* why = nullptr;
+  // (grouped-query heads outside head dim 128: the unfused composition with the mma.sync attention beats the one
+  // CUDA-core launch 2 - 3x at batch sizes that matter and is level at one sequence; sharded steps stay fused)
+  const bool mma_better = t_forced_kernel.empty() && !peers && !ll && sdpa_mma_preferred_for_decode(a);
   const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
-                    v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
+                    v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic" && !mma_better;
   OMX_CHECK(fast || (!peers && !ll), "[attn_decode_fused_sharded] layout not supported by the decode kernels: %s",
             why ? why : "strided k_new/v_new");
   if (fast) {
@@ -539,6 +546,49 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
     if (t_forced_kernel != "sdpa_generic" && sdpa_mma_supported(a2, &why2)) sdpa_mma(a2, stream);
     else sdpa_generic(a2, stream);
   };
+  {
+    // One launch for norm + rope + the row stores when the layout allows (prologue.cu), like the prefill composite:
+    // k' -> cache row, v -> cache row, q' -> scratch; then the attention.  Otherwise the standalone ops below.
+    omx_array krow0 = kview, vrow0 = vview;
+    krow0.shape[2] = 1;
+    vrow0.shape[2] = 1;
+    krow0.data = (char*)kview.data + (size_t)position * kview.strides[2] * dtype_size(kview.dtype);
+    vrow0.data = (char*)vview.data + (size_t)position * vview.strides[2] * dtype_size(vview.dtype);
+    const bool has_freqs = freqs && freqs->data;
+    if (!has_freqs && (rope_dims == 0 || base.has_value) && t_forced_kernel != "sdpa_generic") {
+      PrologueCall pc;
+      pc.dims = rope_dims;
+      pc.traditional = traditional;
+      pc.mode = 1;
+      pc.eps = norm_eps;
+      if (rope_dims > 0)
+        pc.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, position + 1, stream);
+      int n = 0;
+      omx_array qt0{};
+      if (qn || rope_dims > 0) {
+        qt0 = dense(q, ws + qbytes);
+        pc.seg[n].x = q; pc.seg[n].out = qt0; pc.seg[n].w = qn ? q_norm_w : nullptr;
+        pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+      }
+      pc.seg[n].x = k_new; pc.seg[n].out = krow0; pc.seg[n].w = kn ? k_norm_w : nullptr;
+      pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+      const bool v_in = v_new->shape[3] == D;
+      if (v_in) {
+        pc.seg[n].x = v_new; pc.seg[n].out = vrow0; pc.seg[n].w = nullptr; pc.seg[n].rope = false; ++n;
+      }
+      pc.nseg = n;
+      note_launch("qkv_prologue");
+      if (qkv_prologue(pc, stream)) {
+        if (!v_in) copy4d(&vrow0, v_new, stream);
+        SdpaArgs a2 = make_sdpa_args(out, (qn || rope_dims > 0) ? &qt0 : q, &kview, &vview, sm_scale, "", nullptr, nullptr);
+        sdpa_rows(a2);
+        txn.commit();
+        if (keys_out) *keys_out = kview;
+        if (values_out) *values_out = vview;
+        return;
+      }
+    }
+  }
   omx_array qn_arr, kn_arr;
   if (qn) {
     qn_arr = dense(q, ws);

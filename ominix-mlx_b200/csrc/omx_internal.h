@@ -219,6 +219,8 @@ void sdpa_f32_tiled(const SdpaArgs& a, cudaStream_t stream);
 // the kv head's query group packed into the rows (absorbed MLA, head dims outside {64, 128})
 bool sdpa_mma_supported(const SdpaArgs& a, const char** why);
 void sdpa_mma(const SdpaArgs& a, cudaStream_t stream);
+// single-token 16-bit calls outside head dim 128 with >= 2 query heads per kv head: faster here than on decode_simt
+bool sdpa_mma_preferred_for_decode(const SdpaArgs& a);
 
 // ---- fmha_sm100.cu ----
 bool fmha_sm100_supported(const SdpaArgs& a, const char** why);

@@ -342,8 +342,9 @@ bool launch_t(const PrologueParams& p, int D, int dims, int64_t rows, cudaStream
   const int64_t n_tiles = (rows + 31) / 32;
   const size_t smem = 2 * (size_t)kThreads * ((size_t)D * sizeof(T) / 16 + 1) * 16;
   // persistent warps: as many blocks as stay resident, never more than the work
+  const int resident = smem > 112 * 1024 ? 1 : kBlocksPerSM<T>();  // (512-byte rows: one block's tiles fill the SM)
   const unsigned blocks = (unsigned)std::min<int64_t>((n_tiles + kThreads / 32 - 1) / (kThreads / 32),
-                                                      (int64_t)sm_count() * kBlocksPerSM<T>());
+                                                      (int64_t)sm_count() * resident);
 #define OMX_PRO(DD, RR)                                                                                  \
   if (D == DD && dims == RR) {                                                                           \
     auto kern = qkv_prologue_kernel<T, DD, RR>;                                                          \
@@ -357,6 +358,10 @@ bool launch_t(const PrologueParams& p, int D, int dims, int64_t rows, cudaStream
   OMX_PRO(128, 0)
   OMX_PRO(64, 64)
   OMX_PRO(64, 0)
+  if constexpr (sizeof(T) == 2) {  // 512-byte rows (Qwen3.5: head dim 256, rope on the first 64 features)
+    OMX_PRO(256, 64)
+    OMX_PRO(256, 0)
+  }
 #undef OMX_PRO
   return false;
 }
@@ -367,11 +372,11 @@ bool qkv_prologue(const PrologueCall& c, cudaStream_t stream) {
   if (c.nseg < 1 || c.nseg > kMaxSeg) return false;
   const int dt = c.seg[0].x->dtype;
   const int D = (int)c.seg[0].x->shape[3];
-  if (!(D == 128 || D == 64)) return false;
+  if (!(D == 128 || D == 64 || (D == 256 && dtype_size(dt) == 2))) return false;
   bool any_rope = false;
   for (int i = 0; i < c.nseg; ++i) any_rope = any_rope || c.seg[i].rope;
   const int dims = any_rope ? c.dims : 0;
-  if (!(dims == 0 || dims == D || (D == 128 && dims == 64))) return false;
+  if (D == 256 ? !(dims == 0 || dims == 64) : !(dims == 0 || dims == D || (D == 128 && dims == 64))) return false;
   if (c.mode == 2 && any_rope && dims != D) return false;
   const int64_t ve = (int64_t)(16 / dtype_size(dt));
   PrologueParams p{};

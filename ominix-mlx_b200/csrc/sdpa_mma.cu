@@ -92,21 +92,24 @@ __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) {
 
 template <int DKP, int DVP, int KS>
 struct MmaCfg {
+  // KS key groups: with few packed rows (decode) the four warps of a column group are not four row groups of 16 rows
+  // but RG = 4 / KS row groups x KS key groups -- each warp scores BN / KS keys of a tile with its own running (m, l, O),
+  // merged once at the end (KS = 2: <= 32 rows, KS = 4: <= 16 rows; not for the 576 / 512 widths, whose 32-key tiles
+  // leave 8 keys per warp).
+  static constexpr int RG = 4 / KS;
   // warps per row group, each owning DVP / NC output columns: wide values need two (a 16 x 256 float32 fragment is
-  // 128 registers).  Measured alternative for the decode variant: four (16 warps of 128 registers, features split
-  // four ways) -- slower, B64 ctx 4096 198 us against 171 us: the shared-memory pipe (ldmatrix.x4 = 4 wavefronts)
-  // and the per-tile barriers, not per-warp latency, carry the cost.  OMX_MMA_DECODE_NC=4 at build time selects it.
-#ifndef OMX_MMA_DECODE_NC
-#define OMX_MMA_DECODE_NC 2
-#endif
-  static constexpr int NC = DVP > 256 ? (KS == 2 ? OMX_MMA_DECODE_NC : 2) : 1;
+  // 128 registers); KS = 4 at 256 columns takes two as well (8 warps per CTA: its stages leave room for one CTA per
+  // SM only).  Measured alternative for the 576 / 512 decode variant: four column groups (16 warps of 128 registers,
+  // features split four ways) -- slower, B64 ctx 4096 198 us against 171 us (profiles/r02_mma.md).
+  static constexpr int NC = DVP > 256 ? 2 : (KS == 4 && DVP == 256 ? 2 : 1);
   static constexpr int NT = 128 * NC;              // threads
-  static constexpr int MINB = DKP <= 96 ? 3 : 1;  // resident CTAs per SM the register budget aims at
-  static constexpr int BN = DKP >= 256 ? 32 : 64;  // keys per tile
+  static constexpr int MINB = DKP <= 96 ? 3 : (DKP <= 128 ? 2 : 1);  // resident CTAs per SM the register budget aims at
+  static constexpr int BN = DKP >= 256 ? (KS == 4 ? 64 : 32) : 64;  // keys per tile (>= 16 per key group)
   static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
-  static constexpr int QR = KS == 2 ? 32 : kBM;    // query rows held in shared memory (decode: <= 32 packed rows)
+  static constexpr int QR = 16 * RG;               // query rows held in shared memory
+  static_assert(BN / KS >= 16 && (KS == 1 || KS == 2 || KS == 4), "key groups");
   // several warps on a row group split the FEATURES of QK^T and exchange partial score tiles (one slot per warp:
   // BN / KS / 2 words per lane).  576 / 512 prefill: 216,064 + 16,384 = 232,448 bytes, the whole opt-in maximum.
   static constexpr bool kSplitD = NC > 1;
@@ -115,8 +118,6 @@ struct MmaCfg {
   static_assert(smem <= 232448, "shared memory per CTA");
 };
 
-// KS = 2 (launched when the packed rows fit 32: decode) turns two of the four row groups into a second key group:
-// each warp takes half of a tile's keys with its own running (m, l, O), merged once through shared memory at the end.
 template <typename T, int DKP, int DVP, int KS>
 __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>::MINB) sdpa_mma_kernel(const __grid_constant__ MmaParams p) {
   using C = MmaCfg<DKP, DVP, KS>;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   float* xbuf = reinterpret_cast<float*>(Vs + 2 * BN * VP);  // kSplitD: [warps][BNW / 2 words][32 lanes]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = KS == 1 ? (warp & 3) : (warp & 1), wk = KS == 1 ? 0 : ((warp >> 1) & 1), wc = warp >> 2;
+  constexpr int RG = C::RG;
+  const int wr = warp & (RG - 1), wk = (warp & 3) / RG, wc = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
   const int mt = blockIdx.x / p.nsplit, split = blockIdx.x - mt * p.nsplit, hk = blockIdx.y, b = blockIdx.z;
   const int m0 = mt * kBM;
@@ -463,38 +465,44 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
     l_run[e] += __shfl_xor_sync(0xffffffffu, l_run[e], 1);
     l_run[e] += __shfl_xor_sync(0xffffffffu, l_run[e], 2);
   }
-  if constexpr (KS == 2) {
-    // the second key group hands its state over through the (now idle) K / V stages: word w of warp pair `pi` at
-    // [pi][w][lane], so both sides touch consecutive addresses
+  if constexpr (KS > 1) {
+    // key groups 1 .. KS - 1 hand their states over through the (now idle) K / V stages: word w of warp slot `si` at
+    // [si][w][lane], so both sides touch consecutive addresses; key group 0 folds them in
     constexpr int NW = WN / 2 + 4;  // floats per lane: O fragment + m, l of both rows
-    float* xch = reinterpret_cast<float*>(Ks) + (size_t)(wc * 2 + wr) * NW * 32 + lane;
-    static_assert((size_t)NC * 2 * NW * 32 * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "hand-over area");
+    float* xch = reinterpret_cast<float*>(Ks) + (size_t)(wc * RG + wr) * NW * 32 + lane;
+    constexpr size_t kSlot = (size_t)NC * RG * NW * 32;  // floats per key group
+    static_assert((KS - 1) * kSlot * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "hand-over area");
     __syncthreads();  // every warp is done with the stages
-    if (wk == 1) {
+    if (wk > 0) {
+      float* mine = xch + (size_t)(wk - 1) * kSlot;
 #pragma unroll
       for (int n = 0; n < WN / 8; ++n)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xch[(n * 4 + c) * 32] = o[n][c];
+        for (int c = 0; c < 4; ++c) mine[(n * 4 + c) * 32] = o[n][c];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        xch[(WN / 2 + e) * 32] = m_run[e];
-        xch[(WN / 2 + 2 + e) * 32] = l_run[e];
+        mine[(WN / 2 + e) * 32] = m_run[e];
+        mine[(WN / 2 + 2 + e) * 32] = l_run[e];
       }
     }
     __syncthreads();
-    if (wk == 1) return;
+    if (wk > 0) return;
+#pragma unroll 1
+    for (int j = 1; j < KS; ++j) {
+      const float* theirs = xch + (size_t)(j - 1) * kSlot;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const float m1 = xch[(WN / 2 + e) * 32], l1 = xch[(WN / 2 + 2 + e) * 32];
-      const float mm = fmaxf(m_run[e], m1);
-      const float ms = (mm == -INFINITY) ? 0.f : mm;
-      const float a0 = exp2f((m_run[e] - ms) * kLog2e), a1 = exp2f((m1 - ms) * kLog2e);
-      m_run[e] = mm;
-      l_run[e] = l_run[e] * a0 + l1 * a1;
+      for (int e = 0; e < 2; ++e) {
+        const float m1 = theirs[(WN / 2 + e) * 32], l1 = theirs[(WN / 2 + 2 + e) * 32];
+        const float mm = fmaxf(m_run[e], m1);
+        const float ms = (mm == -INFINITY) ? 0.f : mm;
+        const float a0 = exp2f((m_run[e] - ms) * kLog2e), a1 = exp2f((m1 - ms) * kLog2e);
+        m_run[e] = mm;
+        l_run[e] = l_run[e] * a0 + l1 * a1;
 #pragma unroll
-      for (int n = 0; n < WN / 8; ++n) {
-        o[n][2 * e] = o[n][2 * e] * a0 + xch[(n * 4 + 2 * e) * 32] * a1;
-        o[n][2 * e + 1] = o[n][2 * e + 1] * a0 + xch[(n * 4 + 2 * e + 1) * 32] * a1;
+        for (int n = 0; n < WN / 8; ++n) {
+          o[n][2 * e] = o[n][2 * e] * a0 + theirs[(n * 4 + 2 * e) * 32] * a1;
+          o[n][2 * e + 1] = o[n][2 * e + 1] * a0 + theirs[(n * 4 + 2 * e + 1) * 32] * a1;
+        }
       }
     }
   }
@@ -627,9 +635,11 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
     const char* e = getenv("OMX_MMA_MIN_TILES");
     return e ? std::max(1, atoi(e)) : 2;
   }();
+  // as many CTAs as stay resident (the combine kernel handles up to 148 splits)
+  const int64_t slots = (int64_t)sm_count() * C::MINB;
   int nsplit = 1;
-  if (base < sm_count())
-    nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(sm_count(), 148) / base, nt / min_tiles));
+  if (base < slots)
+    nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slots / base, 148), nt / min_tiles));
   p.nsplit = nsplit;
   if (nsplit > 1)
     p.part = (float*)get_workspace(sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM), stream);
@@ -645,15 +655,26 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
   }
 }
 
+template <typename T, int DKP, int DVP>
+void launch_ks(MmaParams& p, cudaStream_t stream) {
+  // decode-sized row counts: key groups instead of idle row groups (OMX_MMA_NO_KS=1: A/B runs)
+  const bool ks_ok = !getenv("OMX_MMA_NO_KS");
+  if constexpr (DKP <= 256) {
+    if (ks_ok && p.R <= 16) return launch_cfg<T, DKP, DVP, 4>(p, stream);
+  }
+  if (ks_ok && p.R <= 32) return launch_cfg<T, DKP, DVP, 2>(p, stream);
+  launch_cfg<T, DKP, DVP, 1>(p, stream);
+}
+
 template <typename T>
 void launch_t(MmaParams& p, cudaStream_t stream) {
   const int d = p.D, dv = p.Dv;
-  if (d <= 32 && dv <= 32) launch_cfg<T, 32, 32>(p, stream);
-  else if (d <= 96 && dv <= 96) launch_cfg<T, 96, 96>(p, stream);
-  else if (d <= 128 && dv <= 128) launch_cfg<T, 128, 128>(p, stream);
-  else if (d <= 256 && dv <= 256) launch_cfg<T, 256, 256>(p, stream);
-  else if (p.R <= 32 && !getenv("OMX_MMA_NO_KS")) launch_cfg<T, 576, 512, 2>(p, stream);  // decode: 20 heads x 1 token
-  else launch_cfg<T, 576, 512>(p, stream);
+  if (d <= 32 && dv <= 32) launch_ks<T, 32, 32>(p, stream);
+  else if (d <= 64 && dv <= 64) launch_ks<T, 64, 64>(p, stream);
+  else if (d <= 96 && dv <= 96) launch_ks<T, 96, 96>(p, stream);
+  else if (d <= 128 && dv <= 128) launch_ks<T, 128, 128>(p, stream);
+  else if (d <= 256 && dv <= 256) launch_ks<T, 256, 256>(p, stream);
+  else launch_ks<T, 576, 512>(p, stream);
 }
 
 }  // namespace
@@ -680,6 +701,18 @@ bool sdpa_mma_supported(const SdpaArgs& a, const char** why) {
   for (int i = 0; i < 3; ++i)
     if (a.out->shape[i] > 1 && a.out->strides[i] % 2) return no("output rows not aligned");
   return true;
+}
+
+// Single-token calls the TMA decode kernel does not take (16-bit, head dim != 128) used to run on the CUDA-core
+// split-K kernel.  With two or more query heads per kv head the key-group variants here are 2 - 7x faster (B32,
+// ctx 4096, bf16: head dim 256, 16 / 2 heads 260 -> 72 us; 64, 16 / 4 heads 210 -> 62 us; 32: 202 -> 29 us --
+// scripts/gpu_r02_simt_vs_mma.py); one query head per kv head stays there (182 vs 258 us at head dim 256).
+bool sdpa_mma_preferred_for_decode(const SdpaArgs& a) {
+  const int dt = a.q->dtype;
+  if (!(dt == OMX_BFLOAT16 || dt == OMX_FLOAT16) || a.Lq != 1) return false;
+  if (a.D == 128 && a.Dv == 128) return false;  // decode_hmma_tma's shape
+  if (a.Hkv < 1 || a.Hq / a.Hkv < 2) return false;
+  return sdpa_mma_supported(a, nullptr);
 }
 
 void sdpa_mma(const SdpaArgs& a, cudaStream_t stream) {

@@ -171,6 +171,10 @@ def test_decode_kernel_families():
     _run((2, 8, 2, 1, 700, 128), "f32", "none")
     assert omx.last_kernel() == "decode_simt"
     _run((2, 8, 2, 1, 700, 64), "bf16", "none")
+    assert omx.last_kernel() == "sdpa_mma"          # grouped heads outside head dim 128: key-group mma.sync tiles
+    _run((2, 4, 4, 1, 700, 64), "bf16", "none")
+    assert omx.last_kernel() == "decode_simt"       # one query head per kv head stays on the CUDA-core split-K kernel
+    _run((2, 8, 2, 1, 700, 64), "bf16", "none", force="decode_simt")
     assert omx.last_kernel() == "decode_simt"
     _run((2, 8, 2, 1, 700, 128), "bf16", "bool2d")
     assert omx.last_kernel() == "decode_hmma_tma"   # array masks stay on the split-K decode kernels
@@ -218,7 +222,7 @@ def _decode_masked(B, Hq, Hkv, Lk, D, dtype, mask_t, expect):
 
 
 @pytest.mark.parametrize("dtype,D,expect", [("bf16", 128, "decode_hmma_tma"), ("f16", 128, "decode_hmma_tma"),
-                                            ("f32", 128, "decode_simt"), ("bf16", 64, "decode_simt"),
+                                            ("f32", 128, "decode_simt"), ("bf16", 64, "sdpa_mma"),
                                             ("f32", 64, "decode_simt")])
 def test_decode_sliding_window_bool_mask(dtype, D, expect):
     Lk = 1500
@@ -343,6 +347,16 @@ def test_mma_mla_decode_key_groups(H, L, S):
     end; 33 rows and up take the four-row-group layout.  Ragged key counts, bool mask, several batches."""
     _run_wide(3, H, 1, L, S, 576, 512, "bf16", "none", seed=H + S)
     _run_wide(2, H, 1, L, S, 576, 512, "f16", "bool4d", seed=H + S + 1)
+
+
+@pytest.mark.parametrize("D", [32, 64, 80, 128, 256])
+@pytest.mark.parametrize("Hq,Hkv,L", [(4, 4, 1), (8, 2, 1), (16, 2, 1), (32, 2, 1), (8, 2, 2), (8, 1, 5)])
+def test_mma_decode_key_groups_every_width(D, Hq, Hkv, L):
+    """Few packed rows (G x L <= 16: four key groups per tile, <= 32: two) on every width configuration: ragged
+    key counts incl. fewer keys than one tile, key range split over CTAs at the longer context, causal for L > 1."""
+    mask = "none" if L == 1 else "causal"
+    _run_wide(2, Hq, Hkv, L, 45, D, D, "bf16", mask, seed=D + Hq)
+    _run_wide(3, Hq, Hkv, L, 1500 + 7 * L, D, D, "f16", "bool4d" if L == 1 else mask, seed=D + Hq + 1)
 
 
 def test_mma_large_batch_grid():
