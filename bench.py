@@ -62,6 +62,10 @@ WORKLOADS = {
     # not BASELINE configs either: GLM-4.7-Flash's absorbed MLA (glm-4.7-flash-mlx/src/model.rs:263-299; 20 query heads
     # over ONE latent kv head, keys 512 + 64, values 512) through fast::sdpa on the mma.sync kernel, so
     # that the Dk != Dv path has driver-side numbers (N = 1 only)
+    # Qwen3.5-35B-A3B full-attention layers (qwen3.5-35B-mlx/src/attention.rs: 16 q / 2 kv heads, head_dim 256, rope on
+    # the first 64 features): the fused decode step outside head dim 128 -- prologue + mma.sync key groups
+    "gqa256_decode": ("decode", dict(B=64, Hq=16, Hkv=2, D=256, S=8192, dtype="bf16", rope_dims=64,
+                                     label="Qwen3.5-35B-A3B full-attention decode bf16 B64 ctx8192 (head_dim 256, 16/2 heads)")),
     "mla_decode": ("mla", dict(B=64, Hq=20, Hkv=1, D=576, Dv=512, S=4096, L=1, dtype="bf16", causal=False,
                                label="GLM-4.7-Flash absorbed-MLA decode bf16 B64 ctx4096 (keys 576 / values 512)")),
     "mla_prefill": ("mla", dict(B=1, Hq=20, Hkv=1, D=576, Dv=512, S=4096, L=4096, dtype="bf16", causal=True,
@@ -164,6 +168,8 @@ def workload_config(name, world):
     elif name == "c1":
         c.update(global_batch=B, per_gpu_batch=B,
                  parallelism="single GPU" if world == 1 else f"{world} independent replicas (the path does not shard)")
+    elif name == "gqa256_decode":
+        c.update(global_batch=B, per_gpu_batch=B, rope_dims=cfg["rope_dims"], parallelism="single GPU")
     elif name in ("c5", "c5_collective"):
         how = "peer stores fused into the decode kernel" if name == "c5" else "ncclAllGather"
         c.update(global_batch=B, per_gpu_batch=B,
@@ -413,7 +419,7 @@ class Bench:
         tdt = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
         es = 2 if cfg["dtype"] == "bf16" else 4
         Bl = len(rows)
-        tag = {"c1": 1, "c2": 2, "c2_weak": 2, "c2_paged": 2, "c5": 5}[name]
+        tag = {"c1": 1, "c2": 2, "c2_weak": 2, "c2_paged": 2, "c5": 5, "gqa256_decode": 8}[name]
         kv_bytes = 2 * Bl * Hkv * S * D * es
         # L2 policy: a working set below ~2x L2 is rotated through R distinct caches so every step reads HBM
         R = 1
@@ -451,7 +457,7 @@ class Bench:
         kn = self.rows_randn(tag + 20, rows, (Hkv, 1, D), tdt)
         vn = self.rows_randn(tag + 30, rows, (Hkv, 1, D), tdt)
         out = torch.empty((Bl, Hq, 1, D), dtype=tdt, device=self.dev)
-        rope = omx.nn.Rope(D, False, 1e6, 1.0)
+        rope = omx.nn.Rope(cfg.get("rope_dims", D), False, 1e6, 1.0)
         scale = D ** -0.5
 
         if paged:
@@ -942,6 +948,9 @@ class Bench:
         elif name == "c1":
             rec, st = self.run_decode(name, cfg, [0], 1, steps, warmup, False)
             rec["scaling"] = "replicas only" if W > 1 else "single GPU"
+        elif name == "gqa256_decode":
+            rec, st = self.run_decode(name, cfg, list(range(cfg["B"])), 1, steps, warmup, False)
+            rec["scaling"] = "single GPU"
         elif name == "c5":
             if W == 1:
                 rec, st = self.run_decode(name, cfg, [0], 1, steps, warmup, False)
@@ -1020,7 +1029,7 @@ def main():
     if args.workload == "all":
         names += ["c2_paged", "c1", "c5"] + (["c5_collective"] if world > 1 and 8 % world == 0 else []) + ["c3", "c4"]
         if world == 1:
-            names += ["c1_prefill", "mla_decode", "mla_prefill"]
+            names += ["c1_prefill", "gqa256_decode", "mla_decode", "mla_prefill"]
         if world > 1:
             names.append("c2_weak")
     recs = {}
