@@ -5,8 +5,10 @@
 //   * keys wider than values -- the absorbed MLA of GLM-4.7-Flash: queries [B,20,L,576], keys [B,1,S,512+64],
 //     values [B,1,S,512], ONE shared kv head (glm-4.7-flash-mlx/src/model.rs:263-299), decode and prefill;
 //   * head dims outside {64, 128}: 72 / 80 (vision towers), 256 (qwen3.5), 16 / 32 (the reference's test shapes);
+//   * single-token (decode) calls with grouped query heads at those head dims (Qwen3.5: 16 / 2 heads, head dim 256,
+//     qwen3.5-35B-mlx/src/attention.rs), which the CUDA-core split-K kernel served at 1 TB/s;
 //   * layouts / masks the specialised kernels refuse.
-// r01 / early r02 sent all of these to sdpa_generic (one warp per query row on CUDA cores).
+// r01 / early r02 sent the multi-row ones to sdpa_generic (one warp per query row on CUDA cores).
 //
 // Shape of the kernel: `mma.sync.m16n8k16` (f32 accumulate) fed by `ldmatrix` from shared memory, `cp.async`
 // double-buffered K / V tiles.  A CTA owns 64 packed query rows of one (batch, kv head): the rows of ALL query
