@@ -476,11 +476,50 @@ void decode_fused_impl(const omx_array* out, const omx_array* q, const omx_array
   kv_cache_update(c, k_new, v_new, &kview, &vview, /*skip_copy=*/true, stream);
   SdpaArgs a = make_sdpa_args(&out_local, q, &kview, &vview, sm_scale, "", nullptr, nullptr);
   const char* why = nullptr;
-  // (grouped-query heads outside head dim 128: the unfused composition with the mma.sync attention beats the one
-  // CUDA-core launch 2 - 3x at batch sizes that matter and is level at one sequence; sharded steps stay fused)
-  const bool mma_better = t_forced_kernel.empty() && !peers && !ll && sdpa_mma_preferred_for_decode(a);
   const bool fast = out->dtype == q->dtype && decode_supported(a, &why) && k_new->strides[3] == 1 &&
-                    v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic" && !mma_better;
+                    v_new->strides[3] == 1 && t_forced_kernel != "sdpa_generic";
+  // Grouped-query / narrow heads outside head dim 128: ONE prologue launch (norm + rope + row stores) and the
+  // mma.sync key-group attention beat the one CUDA-core launch 2 - 4x at batch sizes that matter and are level at one
+  // sequence (profiles/r02_mma.md section 4).  Taken only when the prologue kernel covers the layout -- the
+  // dynamic-position step decides the same way, so eager and graph replay agree bit for bit; sharded steps stay fused.
+  if (fast && t_forced_kernel.empty() && !peers && !ll && out->dtype == q->dtype && v_new->shape[3] == D &&
+      !(freqs && freqs->data) && (rope_dims == 0 || base.has_value) && sdpa_mma_preferred_for_decode(a)) {
+    const size_t es0 = dtype_size(q->dtype);
+    const size_t qb0 = ((size_t)q->shape[0] * q->shape[1] * D * es0 + 255) & ~(size_t)255;
+    PrologueCall pc;
+    pc.dims = rope_dims;
+    pc.traditional = traditional;
+    pc.mode = 1;
+    pc.eps = norm_eps;
+    if (rope_dims > 0) pc.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, position + 1, stream);
+    omx_array qt0 = *q;  // contiguous [B, H, 1, D] scratch rows
+    qt0.data = get_outer_workspace(qb0, stream);
+    qt0.strides[0] = q->shape[1] * D;
+    qt0.strides[1] = D;
+    qt0.strides[2] = D;
+    qt0.strides[3] = 1;
+    omx_array krow0 = kview, vrow0 = vview;
+    krow0.shape[2] = 1;
+    vrow0.shape[2] = 1;
+    krow0.data = (char*)kview.data + (size_t)position * kview.strides[2] * dtype_size(kview.dtype);
+    vrow0.data = (char*)vview.data + (size_t)position * vview.strides[2] * dtype_size(vview.dtype);
+    int n = 0;
+    pc.seg[n].x = q; pc.seg[n].out = qt0; pc.seg[n].w = qn ? q_norm_w : nullptr;
+    pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+    pc.seg[n].x = k_new; pc.seg[n].out = krow0; pc.seg[n].w = kn ? k_norm_w : nullptr;
+    pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = position; ++n;
+    pc.seg[n].x = v_new; pc.seg[n].out = vrow0; pc.seg[n].w = nullptr; pc.seg[n].rope = false; ++n;
+    pc.nseg = n;
+    note_launch("qkv_prologue");
+    if (qkv_prologue(pc, stream)) {
+      SdpaArgs a2 = make_sdpa_args(&out_local, &qt0, &kview, &vview, sm_scale, "", nullptr, nullptr);
+      sdpa_mma(a2, stream);
+      txn.commit();
+      if (keys_out) *keys_out = kview;
+      if (values_out) *values_out = vview;
+      return;
+    }
+  }
   OMX_CHECK(fast || (!peers && !ll), "[attn_decode_fused_sharded] layout not supported by the decode kernels: %s",
             why ? why : "strided k_new/v_new");
   if (fast) {
@@ -668,8 +707,12 @@ int omx_kv_cache_prepare_graph(omx_kv_cache c, int max_rows, int n_q_heads, omx_
     kv_cache_shape(kc, &B, &H, &Dk, &Dv, &dt);
     OMX_CHECK(n_q_heads >= H && n_q_heads % H == 0, "[KVCache] prepare_graph: %d query heads over %d kv heads",
               n_q_heads, H);
-    kv_cache_prepare_graph(kc, max_rows, decode_graph_scratch_bytes(B, H, n_q_heads, Dk, dt, max_rows),
-                           (cudaStream_t)s);
+    // scratch for whichever kernels serve the dynamic-position step: the decode kernels' split-K partials, or the
+    // prologue's q' rows + the mma.sync kernel's partials
+    const size_t qbytes = ((size_t)B * n_q_heads * Dk * dtype_size(dt) + 255) & ~(size_t)255;
+    const size_t need = std::max(decode_graph_scratch_bytes(B, H, n_q_heads, Dk, dt, max_rows),
+                                 qbytes + sdpa_mma_graph_scratch_bytes(B, H, n_q_heads, Dv));
+    kv_cache_prepare_graph(kc, max_rows, need, (cudaStream_t)s);
   });
 }
 
@@ -719,6 +762,44 @@ int omx_attn_decode_fused_dynamic(const omx_array* out, const omx_array* q, cons
     const bool fast = decode_supported(a, &why) && k_new->strides[3] == 1 && v_new->strides[3] == 1;
     OMX_CHECK(fast, "[attn_decode_fused_dynamic] layout not supported by the decode kernels: %s",
               why ? why : "strided k_new/v_new");
+    // Grouped-query / narrow heads outside head dim 128: prologue + mma.sync key groups, as the eager step does
+    // (same kernels, same split plan derived from the device position: bit-identical outputs and cache rows)
+    if (t_forced_kernel.empty() && sdpa_mma_preferred_for_decode(a) && v_new->shape[3] == D) {
+      const size_t es = dtype_size(q->dtype);
+      const size_t qbytes = ((size_t)q->shape[0] * q->shape[1] * D * es + 255) & ~(size_t)255;
+      if (f.scratch && f.scratch_bytes > qbytes) {
+        PrologueCall pc;
+        pc.dims = rope_dims;
+        pc.traditional = traditional;
+        pc.mode = 1;
+        pc.eps = norm_eps;
+        pc.pos_dev = position;
+        if (rope_dims > 0) pc.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, f.max_rows, stream);
+        omx_array qt0 = *q;  // contiguous [B, H, 1, D] rows at the head of the scratch
+        qt0.data = f.scratch;
+        qt0.strides[0] = q->shape[1] * D;
+        qt0.strides[1] = D;
+        qt0.strides[2] = D;
+        qt0.strides[3] = 1;
+        omx_array krow0 = kview, vrow0 = vview;  // row 0 of the pinned views; the kernel moves to row *position
+        krow0.shape[2] = 1;
+        vrow0.shape[2] = 1;
+        int n = 0;
+        pc.seg[n].x = q; pc.seg[n].out = qt0; pc.seg[n].w = qn ? q_norm_weight : nullptr;
+        pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = 0; ++n;
+        pc.seg[n].x = k_new; pc.seg[n].out = krow0; pc.seg[n].w = kn ? k_norm_weight : nullptr;
+        pc.seg[n].rope = rope_dims > 0; pc.seg[n].tok0 = 0; pc.seg[n].dyn_row_stride = kview.strides[2]; ++n;
+        pc.seg[n].x = v_new; pc.seg[n].out = vrow0; pc.seg[n].w = nullptr; pc.seg[n].rope = false;
+        pc.seg[n].dyn_row_stride = vview.strides[2]; ++n;
+        pc.nseg = n;
+        note_launch("qkv_prologue");
+        if (qkv_prologue(pc, stream)) {
+          SdpaArgs a2 = make_sdpa_args(out, &qt0, &kview, &vview, sm_scale, "", nullptr, nullptr);
+          sdpa_mma_dynamic(a2, position, (char*)f.scratch + qbytes, f.scratch_bytes - qbytes, stream);
+          return;
+        }
+      }
+    }
     f.enabled = true;
     f.k_new = k_new;
     f.v_new = v_new;

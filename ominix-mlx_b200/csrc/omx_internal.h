@@ -39,6 +39,7 @@ struct PrologueSeg {
   const omx_array* w = nullptr;  // RMSNorm weight [D] or null
   bool rope = false;             // rotate (true) or copy
   int tok0 = 0;                  // table row of token l == 0
+  int64_t dyn_row_stride = 0;    // graph mode: `out` moves by this many elements per position (cache rows)
 };
 struct PrologueCall {
   PrologueSeg seg[6];
@@ -50,6 +51,8 @@ struct PrologueCall {
   const omx_array *tcos = nullptr, *tsin = nullptr;  // mode 2
   int64_t tcs[3] = {0, 0, 0}, tss[3] = {0, 0, 0};    // element strides of (b, token, pair)
   float eps = 0.f;
+  // graph mode: *pos_dev (device) is added to every segment's tok0 and, times dyn_row_stride, to its destination
+  const int* pos_dev = nullptr;
 };
 // false: shape / layout outside the kernel's coverage (nothing launched) -- the caller composes the
 // standalone ops instead.
@@ -219,6 +222,10 @@ void sdpa_f32_tiled(const SdpaArgs& a, cudaStream_t stream);
 // the kv head's query group packed into the rows (absorbed MLA, head dims outside {64, 128})
 bool sdpa_mma_supported(const SdpaArgs& a, const char** why);
 void sdpa_mma(const SdpaArgs& a, cudaStream_t stream);
+// Graph mode (single-token steps): the views in `a` span the pinned rows, the key count is *pos_dev + 1 (device);
+// partials go to `scratch` (fixed address).  Same bits as sdpa_mma() on views of *pos_dev + 1 rows.
+void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t sdpa_mma_graph_scratch_bytes(int B, int Hkv, int Hq, int Dv);
 // single-token 16-bit calls outside head dim 128 with >= 2 query heads per kv head: faster here than on decode_simt
 bool sdpa_mma_preferred_for_decode(const SdpaArgs& a);
 

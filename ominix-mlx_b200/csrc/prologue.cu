@@ -44,6 +44,7 @@ struct Seg {
   int64_t row_end;       // exclusive prefix sum of rows (= B*H*L) over the segments
   int rope;              // 1: rotate, 0: copy (after the optional norm)
   int tok0;              // table row of l == 0: position (mode 1) or token index (mode 2)
+  int64_t dyn_os;        // graph mode: destination offset in elements per position
 };
 
 struct PrologueParams {
@@ -58,6 +59,7 @@ struct PrologueParams {
   int64_t cs[3], ss[3];
   int tvec;  // mode 2: table rows are contiguous and 16-byte aligned
   float eps, inv_n;
+  const int* pos_dev;  // graph mode: device-resident position added to tok0 / the destinations
 };
 
 // ---- packed 16-bit arithmetic with one rounding per primitive
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM<T>()) qkv_prologue_kern
   uint4* tiles = tile_raw + (size_t)warp * 2 * 32 * PITCH;
   const int sub = lane / NV, chunk = lane % NV;
   const int64_t stride = (int64_t)gridDim.x * (kThreads / 32);
+  const int dpos = p.pos_dev ? *p.pos_dev : 0;  // graph mode: the step's position lives in device memory
 
   struct RowRef {
     int si, b, l;  // si < 0: no row
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM<T>()) qkv_prologue_kern
         rf.l = (int)(rr % s.L);
         rf.b = (int)(rr / s.L);
         src = (unsigned long long)((const T*)s.x + rf.b * s.xs[0] + h * s.xs[1] + rf.l * s.xs[2]);
-        rf.dst = (unsigned long long)((T*)s.out + rf.b * s.os[0] + h * s.os[1] + rf.l * s.os[2]);
+        rf.dst = (unsigned long long)((T*)s.out + rf.b * s.os[0] + h * s.os[1] + rf.l * s.os[2] + dpos * s.dyn_os);
       }
     }
     uint4* tile = tiles + buf * 32 * PITCH;
@@ -319,8 +322,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM<T>()) qkv_prologue_kern
       uint4 rv[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) rv[i] = tile[lane * PITCH + i];
-      if constexpr (std::is_same<T, float>::value) transform_row32<D, DIMS>(p, s, rv, cur.b, cur.l);
-      else transform_row16<T, D, DIMS>(p, s, rv, cur.b, cur.l);
+      if constexpr (std::is_same<T, float>::value) transform_row32<D, DIMS>(p, s, rv, cur.b, cur.l + dpos);
+      else transform_row16<T, D, DIMS>(p, s, rv, cur.b, cur.l + dpos);
 #pragma unroll
       for (int i = 0; i < NV; ++i) tile[lane * PITCH + i] = rv[i];
     }
@@ -412,12 +415,15 @@ bool qkv_prologue(const PrologueCall& c, cudaStream_t stream) {
     s.row_end = rows;
     s.rope = a.rope ? 1 : 0;
     s.tok0 = a.tok0;
+    s.dyn_os = a.dyn_row_stride;
   }
   p.nseg = c.nseg;
   p.traditional = c.traditional ? 1 : 0;
   p.mode = c.mode;
   p.eps = c.eps;
   p.inv_n = 1.0f / (float)D;
+  p.pos_dev = c.pos_dev;
+  if (c.pos_dev && c.mode != 1) return false;
   if (any_rope && c.mode == 1) {
     if (!c.table.cos || c.table.half != dims / 2) return false;
     p.cos = c.table.cos;

@@ -51,7 +51,19 @@ struct MmaParams {
   int B, Hq, Hkv, G, Lq, Lk, D, Dv, R, MT, nsplit;
   float scale;
   int mask_mode, mask_is_f32, out_is_f32;
+  // graph mode (single-token steps replayed from a CUDA graph): the key count is *pos_dev + 1, read by the kernel; Lk
+  // above is the number of pinned rows, nsplit the grid's split count (sized for all of them); the kernel derives the
+  // split count an eager call at that key count would use, so both produce the same bits
+  const int* pos_dev;
+  int split_cap, min_tiles;
+  size_t part_bytes;  // graph mode: size of `part`
 };
+
+// splits of the key range a launch uses: as many as there are free CTA slots, at least min_tiles tiles each
+__host__ __device__ inline int mma_plan_splits(int lk, int bn, int split_cap, int min_tiles) {
+  const int nt = (lk + bn - 1) / bn;
+  return max(1, min(split_cap, nt / min_tiles));
+}
 
 __device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -142,16 +154,26 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   const int g = lane >> 2, t = lane & 3;
   const int mt = blockIdx.x / p.nsplit, split = blockIdx.x - mt * p.nsplit, hk = blockIdx.y, b = blockIdx.z;
   const int m0 = mt * kBM;
-  const int q_off = max(p.Lk - p.Lq, 0);
+  const int Lk = p.pos_dev ? min(*p.pos_dev + 1, p.Lk) : p.Lk;
+  const int nsplit = p.pos_dev ? mma_plan_splits(Lk, BN, p.split_cap, p.min_tiles) : p.nsplit;
+  if (split >= nsplit) {  // (graph mode, short context: this CTA's split does not exist; mark its partial empty)
+    float* part = p.part + ((((int64_t)b * p.Hkv + hk) * p.MT + mt) * p.nsplit + split) * (kBM * DVP + 2 * kBM);
+    if (tid < kBM) {
+      part[kBM * DVP + tid] = -INFINITY;
+      part[kBM * DVP + kBM + tid] = 0.f;
+    }
+    return;
+  }
+  const int q_off = max(Lk - p.Lq, 0);
 
   // keys this CTA visits: causal launches stop at the diagonal of the tile's last token
-  int lk_eff = p.Lk;
+  int lk_eff = Lk;
   if (p.mask_mode == MASK_CAUSAL) {
     const int r_last = min(m0 + kBM, p.R) - 1;
-    lk_eff = min(p.Lk, q_off + r_last / p.G + 1);
+    lk_eff = min(Lk, q_off + r_last / p.G + 1);
   }
   const int nt_all = (lk_eff + BN - 1) / BN;
-  const int t0 = (int)((int64_t)nt_all * split / p.nsplit), t1 = (int)((int64_t)nt_all * (split + 1) / p.nsplit);
+  const int t0 = (int)((int64_t)nt_all * split / nsplit), t1 = (int)((int64_t)nt_all * (split + 1) / nsplit);
 
   const T* qg = (const T*)p.q + b * p.qs[0];
   const T* kg = (const T*)p.k + b * p.ks[0] + hk * p.ks[1];
@@ -189,7 +211,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
         }
       } else {
         for (int i = 0; i < BN / NW; ++i, rp += NW * row_stride) {
-          const bool rok_ = j0 + warp + i * NW < p.Lk;
+          const bool rok_ = j0 + warp + i * NW < Lk;
 #pragma unroll
           for (int cb = 0; cb < CHK; cb += 32) {
             const bool ok = rok_ && (cb + lane) * 8 < nfeat;
@@ -209,7 +231,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       } else {
         for (int c = tid; c < BN * CHK; c += NT) {
           const int row = c / CHK, ch = c - row * CHK;
-          const bool ok = j0 + row < p.Lk && ch * 8 < nfeat;
+          const bool ok = j0 + row < Lk && ch * 8 < nfeat;
           cp_async16(smem_u32(dst + row * PITCH + ch * 8), ok ? src + (int64_t)(j0 + row) * row_stride + ch * 8 : src, ok);
         }
       }
@@ -217,7 +239,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   };
   const bool own_width = p.D == DKP && p.Dv == DVP;
   auto load_kv = [&](int tile, int stage) {
-    const bool full = own_width && (tile + 1) * BN <= p.Lk;
+    const bool full = own_width && (tile + 1) * BN <= Lk;
     load_rows(Ks + stage * BN * KP, kg, p.ks[2], tile * BN, p.D, full, std::integral_constant<int, KP>{},
               std::integral_constant<int, DKP / 8>{});
     load_rows(Vs + stage * BN * VP, vg, p.vs[2], tile * BN, p.Dv, full, std::integral_constant<int, VP>{},
@@ -252,7 +274,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
     rok[e] = r < p.R;
     const int tok = rok[e] ? r / p.G : 0, hg = rok[e] ? r - tok * p.G : 0;
     rtok[e] = tok;
-    rjmax[e] = p.mask_mode == MASK_CAUSAL ? min(p.Lk, q_off + tok + 1) : p.Lk;
+    rjmax[e] = p.mask_mode == MASK_CAUSAL ? min(Lk, q_off + tok + 1) : Lk;
     mrow[e] = b * p.ms[0] + (int64_t)(hk * p.G + hg) * p.ms[1] + (int64_t)tok * p.ms[2];
   }
   const float fill = Num<T>::lowest();
@@ -508,7 +530,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       }
     }
   }
-  if (p.nsplit == 1) {
+  if (p.nsplit == 1 && !p.pos_dev) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       if (!rok[e]) continue;
@@ -588,6 +610,7 @@ __global__ void __launch_bounds__(kCT) sdpa_mma_combine_kernel(const __grid_cons
 #pragma unroll 8
     for (int s = sg; s < p.nsplit; s += nsg) {
       const float w = ws[s];
+      if (w == 0.f) continue;  // (no visible key in that split, or -- graph mode -- no such split: nothing stored)
       const float4 v = *reinterpret_cast<const float4*>(src + s * pstride);
       a.x = fmaf(w, v.x, a.x);
       a.y = fmaf(w, v.y, a.y);
@@ -632,24 +655,29 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
   OMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // split the key range when the row tiles alone leave SMs idle: at least 2 key tiles (both stages) per split
   const int64_t base = (int64_t)p.MT * p.Hkv * p.B;
-  const int nt = (p.Lk + C::BN - 1) / C::BN;
   static const int min_tiles = [] {
     const char* e = getenv("OMX_MMA_MIN_TILES");
     return e ? std::max(1, atoi(e)) : 2;
   }();
   // as many CTAs as stay resident (the combine kernel handles up to 148 splits)
   const int64_t slots = (int64_t)sm_count() * C::MINB;
-  int nsplit = 1;
-  if (base < slots)
-    nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slots / base, 148), nt / min_tiles));
+  p.split_cap = base < slots ? (int)std::min<int64_t>(slots / base, 148) : 1;
+  p.min_tiles = min_tiles;
+  const int nsplit = mma_plan_splits(p.Lk, C::BN, p.split_cap, p.min_tiles);
   p.nsplit = nsplit;
-  if (nsplit > 1)
-    p.part = (float*)get_workspace(sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM), stream);
+  const size_t part_bytes = sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM);
+  const bool two_launches = nsplit > 1 || p.pos_dev != nullptr;
+  if (p.pos_dev) {  // graph mode: partials live in the caller's (cache-owned, fixed-address) scratch
+    OMX_CHECK(p.part && part_bytes <= p.part_bytes, "[sdpa_mma] graph-mode scratch too small (%zu > %zu bytes)",
+              part_bytes, p.part_bytes);
+  } else if (nsplit > 1) {
+    p.part = (float*)get_workspace(part_bytes, stream);
+  }
   dim3 grid(p.MT * nsplit, p.Hkv, p.B);
   kern<<<grid, C::NT, smem, stream>>>(p);
   count_launch();
   OMX_CUDA(cudaGetLastError());
-  if (nsplit > 1) {
+  if (two_launches) {
     dim3 cgrid(p.R, p.Hkv, p.B);
     sdpa_mma_combine_kernel<T><<<cgrid, kCT, 0, stream>>>(p, DVP);
     count_launch();
@@ -713,18 +741,33 @@ bool sdpa_mma_preferred_for_decode(const SdpaArgs& a) {
   const int dt = a.q->dtype;
   if (!(dt == OMX_BFLOAT16 || dt == OMX_FLOAT16) || a.Lq != 1) return false;
   if (a.D == 128 && a.Dv == 128) return false;  // decode_hmma_tma's shape
-  if (a.Hkv < 1 || a.Hq / a.Hkv < 2) return false;
+  // one query head per kv head: narrow heads still win here (B32, 16 heads, d64, ctx 4096: 245 -> 146 us), 256-wide
+  // ones do not (182 vs 258 us)
+  if (a.Hkv < 1 || (a.Hq / a.Hkv < 2 && (a.D > 64 || a.Dv > 64))) return false;
   return sdpa_mma_supported(a, nullptr);
 }
 
-void sdpa_mma(const SdpaArgs& a, cudaStream_t stream) {
+size_t sdpa_mma_graph_scratch_bytes(int B, int Hkv, int Hq, int Dv) {
+  // worst case over the width configurations: every CTA slot a split, value rows padded to the configuration's width
+  const int dvp = Dv <= 32 ? 32 : Dv <= 64 ? 64 : Dv <= 96 ? 96 : Dv <= 128 ? 128 : Dv <= 256 ? 256 : 512;
+  const int64_t base = (int64_t)B * Hkv * ((Hq / std::max(Hkv, 1) + kBM - 1) / kBM);
+  const int64_t slots = (int64_t)sm_count() * 3;
+  const int64_t nsplit = base < slots ? std::min<int64_t>(slots / base, 148) : 1;
+  return sizeof(float) * (size_t)base * (size_t)nsplit * (kBM * dvp + 2 * kBM);
+}
+
+void sdpa_mma(const SdpaArgs& a, cudaStream_t stream) { sdpa_mma_dynamic(a, nullptr, nullptr, 0, stream); }
+
+void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
   MmaParams p{};
+  p.pos_dev = pos_dev;
+  p.part_bytes = scratch_bytes;
   p.q = a.q->data;
   p.k = a.k->data;
   p.v = a.v->data;
   p.out = a.out->data;
   p.mask = a.mask ? a.mask->data : nullptr;
-  p.part = nullptr;
+  p.part = (float*)scratch;
   for (int i = 0; i < 3; ++i) {
     p.qs[i] = a.q->strides[i];
     p.ks[i] = a.k->strides[i];

@@ -68,12 +68,13 @@ def _oracle_step(oc, q, kn, vn, qw, kw, eps, dtype, rope, scale):
     ("bf16", 3, 32, 8, 128, 1000, "decode_hmma_tma"),   # Qwen3-8B geometry
     ("bf16", 1, 16, 8, 128, 4500, "decode_hmma_tma"),   # Qwen3-0.6B geometry, several splits
     ("f32", 2, 16, 8, 128, 300, "decode_simt"),         # C1 dtype
-    ("f16", 2, 4, 4, 64, 77, "decode_simt"),            # one query head per kv head, D = 64: CUDA-core split-K, fused
+    ("f16", 2, 4, 4, 256, 77, "decode_simt"),           # one query head per kv head, D = 256: CUDA-core split-K, fused
+    ("f16", 2, 4, 4, 64, 77, "sdpa_mma"),               # narrow heads: prologue + mma.sync tiles
     ("f16", 2, 8, 2, 64, 77, "sdpa_mma"),               # grouped heads outside D = 128: unfused composition, mma.sync tiles
     ("bf16", 3, 16, 2, 256, 300, "sdpa_mma"),           # Qwen3.5 full-attention geometry (qwen3.5-35B-mlx/src/attention.rs)
 ])
 def test_fused_decode_with_q_k_norm(dtype, B, Hq, Hkv, D, S, kernel):
-    rope_t = (D, False, 1e6, 1.0)
+    rope_t = (D if D < 256 else 64, False, 1e6, 1.0)  # head dim 256: Qwen3.5's partial rotary (first 64 features)
     eps = 1e-6
     k, v = randn((B, Hkv, S, D), dtype, 1), randn((B, Hkv, S, D), dtype, 2)
     q = randn((B, 1, Hq, D), dtype, 3).transpose(1, 2)       # caller layout: [B, L, H, D] viewed [B, H, L, D]

@@ -158,11 +158,13 @@ def test_validation_errors():
 @pytest.mark.parametrize("shape", [(2, 8, 2, 1, 300, 128), (1, 16, 8, 1, 2048, 128), (3, 4, 4, 1, 77, 64),
                                    (1, 32, 2, 1, 1000, 128), (2, 6, 2, 1, 513, 128), (1, 8, 8, 1, 64, 256)])
 def test_decode_dispatch_lq1(dtype, shape):
-    # Lq == 1 goes to the split-K decode kernels (mask none; "causal" is the same thing at Lq == 1)
+    # Lq == 1 goes to the split-K decode kernels (mask none; "causal" is the same thing at Lq == 1) -- except 16-bit
+    # narrow heads (D <= 64), which the key-group mma.sync tiles serve faster
+    want = "sdpa_mma" if dtype != "f32" and shape[5] <= 64 else "decode"
     _run(shape, dtype, "none")
-    assert omx.last_kernel().startswith("decode"), omx.last_kernel()
+    assert omx.last_kernel().startswith(want), omx.last_kernel()
     _run(shape, dtype, "causal")
-    assert omx.last_kernel().startswith("decode"), omx.last_kernel()
+    assert omx.last_kernel().startswith(want), omx.last_kernel()
 
 
 def test_decode_kernel_families():
@@ -173,7 +175,9 @@ def test_decode_kernel_families():
     _run((2, 8, 2, 1, 700, 64), "bf16", "none")
     assert omx.last_kernel() == "sdpa_mma"          # grouped heads outside head dim 128: key-group mma.sync tiles
     _run((2, 4, 4, 1, 700, 64), "bf16", "none")
-    assert omx.last_kernel() == "decode_simt"       # one query head per kv head stays on the CUDA-core split-K kernel
+    assert omx.last_kernel() == "sdpa_mma"          # ... and narrow heads with one query head per kv head
+    _run((2, 4, 4, 1, 700, 256), "bf16", "none")
+    assert omx.last_kernel() == "decode_simt"       # wide heads, one query head per kv head: CUDA-core split-K kernel
     _run((2, 8, 2, 1, 700, 64), "bf16", "none", force="decode_simt")
     assert omx.last_kernel() == "decode_simt"
     _run((2, 8, 2, 1, 700, 128), "bf16", "bool2d")
