@@ -77,6 +77,20 @@ def test_prefill_composite_generic_paths(dtype, D):
     _call(gc, oc, 1, 4, 2, 9, D, dtype, (D, False, 10000.0, 1.0), "array", 2, norms=True)
 
 
+def test_qwen35_geometry_prefill_chunks_then_decode_steps():
+    """Qwen3.5 full-attention layers (qwen3.5-35B-mlx/src/attention.rs): 16 q / 2 kv heads, head dim 256, rope on the first
+    64 features, q / k norm.  Prefill chunks and single-token steps through the composites: the 512-byte-row prologue
+    + mma.sync tiles; outputs vs the oracle chain, cache rows bit-exact."""
+    B, Hq, Hkv, D, dtype = 2, 16, 2, 256, "bf16"
+    rope_t = (64, False, 1e7, 1.0)
+    gc, oc = omx.KVCache(), orc.KVCache()
+    assert _call(gc, oc, B, Hq, Hkv, 150, D, dtype, rope_t, "causal", 10, True) == "sdpa_mma"
+    assert _call(gc, oc, B, Hq, Hkv, 40, D, dtype, rope_t, "array", 20, True) == "sdpa_mma"
+    for t in range(3):
+        assert _call(gc, oc, B, Hq, Hkv, 1, D, dtype, rope_t, "none", 30 + 5 * t, True) == "sdpa_mma"
+    assert gc.offset() == 193
+
+
 def test_prefill_composite_partial_traditional_rope_and_no_rope():
     # glm4: traditional, partial rotary (glm4-mlx/src/model.rs:116-136)
     gc, oc = omx.KVCache(), orc.KVCache()
