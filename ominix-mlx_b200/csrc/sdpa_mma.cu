@@ -701,6 +701,7 @@ void launch_t(MmaParams& p, cudaStream_t stream) {
   const int d = p.D, dv = p.Dv;
   if (d <= 32 && dv <= 32) launch_ks<T, 32, 32>(p, stream);
   else if (d <= 64 && dv <= 64) launch_ks<T, 64, 64>(p, stream);
+  else if (d <= 80 && dv <= 80) launch_ks<T, 80, 80>(p, stream);  // vision towers: head dim 80 (and 72, zero-padded)
   else if (d <= 96 && dv <= 96) launch_ks<T, 96, 96>(p, stream);
   else if (d <= 128 && dv <= 128) launch_ks<T, 128, 128>(p, stream);
   else if (d <= 256 && dv <= 256) launch_ks<T, 256, 256>(p, stream);
@@ -749,7 +750,7 @@ bool sdpa_mma_preferred_for_decode(const SdpaArgs& a) {
 
 size_t sdpa_mma_graph_scratch_bytes(int B, int Hkv, int Hq, int Dv) {
   // worst case over the width configurations: every CTA slot a split, value rows padded to the configuration's width
-  const int dvp = Dv <= 32 ? 32 : Dv <= 64 ? 64 : Dv <= 96 ? 96 : Dv <= 128 ? 128 : Dv <= 256 ? 256 : 512;
+  const int dvp = Dv <= 32 ? 32 : Dv <= 64 ? 64 : Dv <= 80 ? 80 : Dv <= 96 ? 96 : Dv <= 128 ? 128 : Dv <= 256 ? 256 : 512;
   const int64_t base = (int64_t)B * Hkv * ((Hq / std::max(Hkv, 1) + kBM - 1) / kBM);
   const int64_t slots = (int64_t)sm_count() * 3;
   const int64_t nsplit = base < slots ? std::min<int64_t>(slots / base, 148) : 1;
