@@ -118,7 +118,12 @@ struct MmaCfg {
   static constexpr int NC = DVP > 256 ? 2 : (KS == 4 && DVP == 256 ? 2 : 1);
   static constexpr int NT = 128 * NC;              // threads
   static constexpr int MINB = DKP <= 96 ? 3 : (DKP <= 128 ? 2 : 1);  // resident CTAs per SM the register budget aims at
-  static constexpr int BN = DKP >= 256 ? (KS == 4 ? 64 : 32) : 64;  // keys per tile (>= 16 per key group)
+#ifndef OMX_MMA_KS4_BN_NARROW
+#define OMX_MMA_KS4_BN_NARROW 128
+#endif
+  // keys per tile (>= 16 per key group); narrow heads with four key groups take longer tiles: a 64-key tile of 64-wide
+  // rows is little work per warp between two CTA barriers
+  static constexpr int BN = DKP >= 256 ? (KS == 4 ? 64 : 32) : (KS == 4 && DKP <= 96 ? OMX_MMA_KS4_BN_NARROW : 64);
   static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
