@@ -123,7 +123,9 @@ struct MmaCfg {
 #endif
   // keys per tile (>= 16 per key group); narrow heads with four key groups take longer tiles: a 64-key tile of 64-wide
   // rows is little work per warp between two CTA barriers
-  static constexpr int BN = DKP >= 256 ? (KS == 4 ? 64 : 32) : (KS == 4 && DKP <= 96 ? OMX_MMA_KS4_BN_NARROW : 64);
+  // (B32 ctx 4096, four key groups: 64 wide 35.2 -> 33.8 us, one head per kv head 146 -> 124 us; 32 wide 29.2 -> 25.6;
+  // 80 wide 64 -> 57; 96 wide LOSES, 47.7 -> 63 us -- its stages would halve the resident CTAs -- and keeps 64 keys)
+  static constexpr int BN = DKP >= 256 ? (KS == 4 ? 64 : 32) : (KS == 4 && DKP <= 80 ? OMX_MMA_KS4_BN_NARROW : 64);
   static constexpr int KP = DKP + 8;               // row pitches in elements: +16 bytes keeps ldmatrix conflict-free
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
