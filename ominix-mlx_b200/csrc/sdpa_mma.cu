@@ -14,10 +14,14 @@
 // double-buffered K / V tiles.  A CTA owns 64 packed query rows of one (batch, kv head): the rows of ALL query
 // heads of the kv head's group are packed token-major (row = token * G + head-in-group), so a key tile is read
 // once for the whole group -- for the MLA layout that is all 20 heads.  Four row groups of 16 rows; value widths
-// above 256 put a second warp on each row group (each owns half of the output columns and repeats the small S =
-// QK^T product: no cross-warp softmax exchange).  Few CTAs (decode) -> the key range is split over CTAs and a
-// second launch merges the partials.  Mask semantics are sdpa_generic's (= the MLX fallback graph): masked bool
-// entries take finfo(T).min, additive masks are added to the scaled scores, causal is bottom-right aligned.
+// above 256 put a second warp on each row group: each owns half of the output columns and multiplies half of the
+// FEATURES of QK^T, the partial score tiles cross through shared memory at a named barrier (both add them in the
+// same order: identical softmax states).  With few packed rows (decode) row groups turn into KEY groups (KS = 2 /
+// 4): each warp scores its share of a tile's keys with its own running (m, l, O), merged once at the end.  Few CTAs
+// -> the key range is split over CTAs and a second launch merges the partials; in graph mode the key count and
+// the split plan come from a device-resident position.  Mask semantics are sdpa_generic's (= the MLX fallback
+// graph): masked bool entries take finfo(T).min, additive masks are added to the scaled scores (each rounded to
+// the array dtype like the reference's op chain), causal is bottom-right aligned.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
