@@ -363,6 +363,44 @@ def test_mma_decode_key_groups_every_width(D, Hq, Hkv, L):
     _run_wide(3, Hq, Hkv, L, 1500 + 7 * L, D, D, "f16", "bool4d" if L == 1 else mask, seed=D + Hq + 1)
 
 
+def test_mma_seeded_random_sweep_vs_generic_and_oracle():
+    """60 seeded random calls over the kernel's whole domain -- widths 8 .. 576 / 512 (values never wider than keys),
+    group sizes 1 .. 20, 1 .. 70 query rows, ragged key counts, every mask mode, both 16-bit types -- forced onto
+    sdpa_mma and compared with the row-per-warp kernel (same inputs, float32 arithmetic) and, for the small ones,
+    with the oracle chain."""
+    rng = np.random.default_rng(20261018)
+    widths = [8, 16, 24, 40, 64, 72, 80, 96, 104, 128, 192, 256, 320, 576]
+    for it in range(60):
+        B, Hkv = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        G = int(rng.choice([1, 2, 3, 4, 8, 16, 20]))
+        Lq = int(rng.choice([1, 1, 2, 3, 7, 17, 33, 70]))
+        Lk = Lq + int(rng.integers(0, 300))
+        Dk = int(rng.choice(widths))
+        Dv = min(512, int(rng.choice([Dk, Dk, max(8, Dk - 8), max(8, (Dk // 16) * 8)])))
+        dtype = "bf16" if it % 2 else "f16"
+        mask = MASKS[int(rng.integers(0, len(MASKS)))]
+        Hq = Hkv * G
+        q = randn((B, Hq, Lq, Dk), dtype, 1000 + it)
+        k = randn((B, Hkv, Lk, Dk), dtype, 2000 + it)
+        v = randn((B, Hkv, Lk, Dv), dtype, 3000 + it)
+        gm, om = _mask(mask, B, Hq, Lq, Lk, dtype, 4000 + it)
+        outs = {}
+        for kern in ("sdpa_mma", "sdpa_generic"):
+            omx.force_kernel(kern)
+            try:
+                outs[kern] = omx.fast.scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), Dk ** -0.5, gm)
+                assert omx.last_kernel() == kern
+            finally:
+                omx.force_kernel("")
+        what = f"#{it} {(B, Hq, Hkv, Lq, Lk, Dk, Dv)} {dtype} {mask}"
+        a, b = outs["sdpa_mma"].float().cpu().numpy(), outs["sdpa_generic"].float().cpu().numpy()
+        assert np.isfinite(a).all(), what
+        assert np.abs(a - b).max() <= 2e-2, f"{what}: kernels differ by {np.abs(a - b).max():.3e}"
+        if B * Hq * Lq * Lk * Dk <= 4e7:
+            want = orc.sdpa(t2n(q, dtype), t2n(k, dtype), t2n(v, dtype), Dk ** -0.5, om, dtype=dtype)
+            assert_close(a, n2f(want, dtype), dtype, what)
+
+
 def test_mma_large_batch_grid():
     # the batch index rides grid.z, (row tile, key split) grid.x: batches beyond a few hundred stay on this kernel
     _run_wide(700, 2, 1, 1, 40, 80, 80, "bf16", "none")
