@@ -134,11 +134,18 @@ struct MmaCfg {
   static constexpr int VP = DVP + 8;
   static constexpr int WN = DVP / NC;
   static constexpr int QR = 16 * RG;               // query rows held in shared memory
+  // K / V stages: the key-group variants of the 128- and 256-wide configurations keep two tiles in flight behind the
+  // one being multiplied (ncu on the Qwen3.5 decode shape with two stages: 1.45 long-scoreboard stalls per issue at
+  // 22 % issue activity -- the warps waited for the next tile); the other variants have no room or no need
+#ifndef OMX_MMA_NS3
+#define OMX_MMA_NS3 1
+#endif
+  static constexpr int NS = (OMX_MMA_NS3 && KS > 1 && (DKP == 256 || DKP == 128)) ? 3 : 2;
   static_assert(BN / KS >= 16 && (KS == 1 || KS == 2 || KS == 4), "key groups");
   // several warps on a row group split the FEATURES of QK^T and exchange partial score tiles (one slot per warp:
   // BN / KS / 2 words per lane).  576 / 512 prefill: 216,064 + 16,384 = 232,448 bytes, the whole opt-in maximum.
   static constexpr bool kSplitD = NC > 1;
-  static constexpr size_t smem = sizeof(uint16_t) * ((size_t)QR * KP + 2 * (size_t)BN * KP + 2 * (size_t)BN * VP) +
+  static constexpr size_t smem = sizeof(uint16_t) * ((size_t)QR * KP + NS * (size_t)BN * KP + NS * (size_t)BN * VP) +
                                  (kSplitD ? (NT / 32) * (BN / KS / 2) * 32 * sizeof(float) : 0);
   static_assert(smem <= 232448, "shared memory per CTA");
 };
@@ -155,9 +162,10 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   constexpr bool kSplitD = C::kSplitD;
   constexpr int NC = C::NC;
   T* Qs = reinterpret_cast<T*>(smem_raw);  // [kQR][KP]
-  T* Ks = Qs + kQR * KP;                   // [2][BN][KP]
-  T* Vs = Ks + 2 * BN * KP;                // [2][BN][VP]
-  float* xbuf = reinterpret_cast<float*>(Vs + 2 * BN * VP);  // kSplitD: [warps][BNW / 2 words][32 lanes]
+  T* Ks = Qs + kQR * KP;                   // [NS][BN][KP]
+  constexpr int NS = C::NS;
+  T* Vs = Ks + NS * BN * KP;               // [NS][BN][VP]
+  float* xbuf = reinterpret_cast<float*>(Vs + NS * BN * VP);  // kSplitD: [warps][BNW / 2 words][32 lanes]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int RG = C::RG;
@@ -213,15 +221,17 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       constexpr int NW = NT / 32;
       const T* rp = src + (int64_t)(j0 + warp) * row_stride + lane * 8;
       const uint32_t d0 = smem_u32(dst + warp * PITCH + lane * 8);
+      // (pinning the stride in a register -- its constant-bank load was the hottest stall site in ncu -- measured neutral)
+      const int64_t row_step = (int64_t)NW * row_stride;
       if (full) {
 #pragma unroll
-        for (int i = 0; i < BN / NW; ++i, rp += NW * row_stride) {
+        for (int i = 0; i < BN / NW; ++i, rp += row_step) {
 #pragma unroll
           for (int cb = 0; cb < CHK; cb += 32)
             if (cb + 32 <= CHK || lane < CHK - cb) cp_async16(d0 + (i * NW * PITCH + cb * 8) * 2, rp + cb * 8, true);
         }
       } else {
-        for (int i = 0; i < BN / NW; ++i, rp += NW * row_stride) {
+        for (int i = 0; i < BN / NW; ++i, rp += row_step) {
           const bool rok_ = j0 + warp + i * NW < Lk;
 #pragma unroll
           for (int cb = 0; cb < CHK; cb += 32) {
@@ -256,11 +266,15 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
     load_rows(Vs + stage * BN * VP, vg, p.vs[2], tile * BN, p.Dv, full, std::integral_constant<int, VP>{},
               std::integral_constant<int, DVP / 8>{});
   };
-  if (t0 < t1) load_kv(t0, 0);
-  cp_async_commit();
+  // one commit group per tile slot, empty when the tile does not exist: the group count is the same on every path
+#pragma unroll
+  for (int i = 0; i < NS - 1; ++i) {
+    if (t0 + i < t1) load_kv(t0 + i, i);
+    cp_async_commit();
+  }
   // The reference scales the queries first -- T(T(scale) * q) -- and multiplies those by the keys (mlx fast.cpp
   // fallback graph; oracle/omx_oracle.c:257-275).  Every thread rescales the chunks it fetched itself.
-  cp_async_wait<1>();
+  cp_async_wait<NS - 1>();
   {
     const float sc = rnd<T>(p.scale);
     for (int c = tid; c < kQR * CH; c += NT) {
@@ -303,14 +317,11 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   const uint32_t q_base = smem_u32(Qs) + 2 * a_off;
 
   for (int tile = t0; tile < t1; ++tile) {
-    const int stage = (tile - t0) & 1;
-    if (tile + 1 < t1) {
-      load_kv(tile + 1, stage ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    const int it = tile - t0, stage = it % NS;
+    // the stage freed by the barrier that closed the previous step takes tile + NS - 1
+    if (tile + NS - 1 < t1) load_kv(tile + NS - 1, (it + NS - 1) % NS);
+    cp_async_commit();
+    cp_async_wait<NS - 1>();  // all but the NS - 1 youngest groups: this tile has landed
     __syncthreads();
     if (warp_rows) {  // (a row group past the last packed row only helps with the loads)
     const uint32_t k_base = smem_u32(Ks + stage * BN * KP) + 2 * bk_off;
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       }
     }
     }  // warp_rows
-    __syncthreads();  // the stage is free for the load issued two iterations from now
+    __syncthreads();  // the stage is free for the load issued at the top of the next step
   }
   cp_async_wait<0>();
 
@@ -506,7 +517,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
     constexpr int NW = WN / 2 + 4;  // floats per lane: O fragment + m, l of both rows
     float* xch = reinterpret_cast<float*>(Ks) + (size_t)(wc * RG + wr) * NW * 32 + lane;
     constexpr size_t kSlot = (size_t)NC * RG * NW * 32;  // floats per key group
-    static_assert((KS - 1) * kSlot * 4 <= 2 * (size_t)BN * (KP + VP) * 2, "hand-over area");
+    static_assert((KS - 1) * kSlot * 4 <= NS * (size_t)BN * (KP + VP) * 2, "hand-over area");
     __syncthreads();  // every warp is done with the stages
     if (wk > 0) {
       float* mine = xch + (size_t)(wk - 1) * kSlot;
