@@ -977,6 +977,44 @@ int omx_attn_decode_fused_paged(const omx_array* out, const omx_array* q, const 
     const bool fast = decode_supported(a, &why) && k_new->strides[3] == 1 && v_new->strides[3] == 1;
     OMX_CHECK(fast, "[attn_decode_fused_paged] layout not supported by the decode kernels: %s",
               why ? why : "strided k_new/v_new");
+    // Grouped-query / narrow heads outside head dim 128: prologue + mma.sync key groups, like the contiguous cache's
+    // step (same kernels, split plan from each sequence's own length: same bits)
+    if (t_forced_kernel.empty() && sdpa_mma_preferred_for_decode(a) && Dv == D) {
+      const size_t qbytes = ((size_t)B * q->shape[1] * D * dtype_size(dt) + 255) & ~(size_t)255;
+      if (f.scratch && f.scratch_bytes > qbytes) {
+        PrologueCall pro;
+        pro.dims = rope_dims;
+        pro.traditional = traditional;
+        pro.mode = 1;
+        pro.eps = norm_eps;
+        pro.paged = &ref;
+        if (rope_dims > 0) pro.table = get_rope_table(rope_dims, true, base.value, rope_scale, nullptr, table_rows, stream);
+        omx_array qt0 = *q;  // contiguous [B, H, 1, D] rows at the head of the scratch
+        qt0.data = f.scratch;
+        qt0.strides[0] = q->shape[1] * D;
+        qt0.strides[1] = D;
+        qt0.strides[2] = D;
+        qt0.strides[3] = 1;
+        omx_array krow0 = kview, vrow0 = vview;  // the pools: page / head / row strides; the kernel picks the page row
+        krow0.shape[2] = 1;
+        vrow0.shape[2] = 1;
+        int n = 0;
+        pro.seg[n].x = q; pro.seg[n].out = qt0; pro.seg[n].w = qn ? q_norm_weight : nullptr;
+        pro.seg[n].rope = rope_dims > 0; pro.seg[n].tok0 = 0; ++n;
+        pro.seg[n].x = k_new; pro.seg[n].out = krow0; pro.seg[n].w = kn ? k_norm_weight : nullptr;
+        pro.seg[n].rope = rope_dims > 0; pro.seg[n].tok0 = 0; pro.seg[n].paged_dst = true; ++n;
+        pro.seg[n].x = v_new; pro.seg[n].out = vrow0; pro.seg[n].w = nullptr; pro.seg[n].rope = false;
+        pro.seg[n].paged_dst = true; ++n;
+        pro.nseg = n;
+        note_launch("qkv_prologue");
+        if (qkv_prologue(pro, stream)) {
+          SdpaArgs a2 = make_sdpa_args(out, &qt0, &kview, &vview, sm_scale, "", nullptr, nullptr);
+          sdpa_mma_dynamic(a2, nullptr, (char*)f.scratch + qbytes, f.scratch_bytes - qbytes, stream, &ref);
+          paged_end_step(pc);
+          return;
+        }
+      }
+    }
     f.enabled = true;
     f.k_new = k_new;
     f.v_new = v_new;

@@ -40,6 +40,7 @@ struct PrologueSeg {
   bool rope = false;             // rotate (true) or copy
   int tok0 = 0;                  // table row of token l == 0
   int64_t dyn_row_stride = 0;    // graph mode: `out` moves by this many elements per position (cache rows)
+  bool paged_dst = false;        // paged mode: `out` is the page pool ([page][H][64][D] through strides 0 / 1 / 2)
 };
 struct PrologueCall {
   PrologueSeg seg[6];
@@ -53,6 +54,10 @@ struct PrologueCall {
   float eps = 0.f;
   // graph mode: *pos_dev (device) is added to every segment's tok0 and, times dyn_row_stride, to its destination
   const int* pos_dev = nullptr;
+  // paged mode (single-token steps on the paged cache): sequence b stands at lens_in[b] rows (< 0: released slot, its
+  // rows are skipped); that is its rope row, and the page row its k' / v go to (segments with paged_dst) comes from the
+  // block table; the k segment's head-0 rows store lens_in[b] + 1 into lens_out[b]
+  const struct PagedRef* paged = nullptr;
 };
 // false: shape / layout outside the kernel's coverage (nothing launched) -- the caller composes the
 // standalone ops instead.
@@ -224,7 +229,9 @@ bool sdpa_mma_supported(const SdpaArgs& a, const char** why);
 void sdpa_mma(const SdpaArgs& a, cudaStream_t stream);
 // Graph mode (single-token steps): the views in `a` span the pinned rows, the key count is *pos_dev + 1 (device);
 // partials go to `scratch` (fixed address).  Same bits as sdpa_mma() on views of *pos_dev + 1 rows.
-void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+// `paged`: k / v in `a` are the page pools of the paged cache; per-sequence key counts and page ids come from device memory.
+void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream,
+                      const struct PagedRef* paged = nullptr);
 size_t sdpa_mma_graph_scratch_bytes(int B, int Hkv, int Hq, int Dv);
 // single-token 16-bit calls outside head dim 128 with >= 2 query heads per kv head: faster here than on decode_simt
 bool sdpa_mma_preferred_for_decode(const SdpaArgs& a);

@@ -327,7 +327,10 @@ void paged_begin_step(PagedKVImpl* c, int n_q_heads, omx_array* kpool_view, omx_
   *max_len_after = mx;
   // rope rows a (replayed) launch may look up: every position the sequences hold pages for
   *table_rows = std::max(mx, held);
-  const size_t need = decode_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dk, c->dtype, c->max_pages * kPageRows);
+  // split-K partials of the decode kernels, or the prologue's q' rows + the mma.sync kernel's partials (omx_api.cu)
+  const size_t qbytes = ((size_t)c->B * n_q_heads * c->Dk * dtype_size(c->dtype) + 255) & ~(size_t)255;
+  const size_t need = std::max(decode_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dk, c->dtype, c->max_pages * kPageRows),
+                               qbytes + sdpa_mma_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dv));
   if (need > c->scratch_bytes) {
     if (c->scratch) OMX_CUDA(cudaFreeAsync(c->scratch, stream));
     OMX_CUDA(cudaMallocAsync(&c->scratch, need, stream));

@@ -45,6 +45,8 @@ struct Seg {
   int rope;              // 1: rotate, 0: copy (after the optional norm)
   int tok0;              // table row of l == 0: position (mode 1) or token index (mode 2)
   int64_t dyn_os;        // graph mode: destination offset in elements per position
+  int paged_dst;         // paged mode: out = page pool, os[0] = page stride
+  int writes_len;        // paged mode: this segment's head-0 rows publish lens_in[b] + 1
 };
 
 struct PrologueParams {
@@ -60,6 +62,11 @@ struct PrologueParams {
   int tvec;  // mode 2: table rows are contiguous and 16-byte aligned
   float eps, inv_n;
   const int* pos_dev;  // graph mode: device-resident position added to tok0 / the destinations
+  // paged mode: per-sequence lengths (device), block table, where the new lengths go
+  const int* lens_in;
+  int* lens_out;
+  const int* block_table;
+  int bt_stride;
 };
 
 // ---- packed 16-bit arithmetic with one rounding per primitive
@@ -296,6 +303,21 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM<T>()) qkv_prologue_kern
         rf.b = (int)(rr / s.L);
         src = (unsigned long long)((const T*)s.x + rf.b * s.xs[0] + h * s.xs[1] + rf.l * s.xs[2]);
         rf.dst = (unsigned long long)((T*)s.out + rf.b * s.os[0] + h * s.os[1] + rf.l * s.os[2] + dpos * s.dyn_os);
+        if (p.lens_in) {  // paged single-token step: the sequence's own length is its position
+          const int len = p.lens_in[rf.b];
+          if (len < 0) {  // released slot: no row
+            rf.si = -1;
+            src = 0ull;
+            rf.dst = 0ull;
+          } else {
+            if (s.paged_dst) {
+              const int page = p.block_table[(int64_t)rf.b * p.bt_stride + (len >> 6)];
+              rf.dst = (unsigned long long)((T*)s.out + (int64_t)page * s.os[0] + h * s.os[1] + (int64_t)(len & 63) * s.os[2]);
+            }
+            if (s.writes_len && h == 0) p.lens_out[rf.b] = len + 1;
+            rf.l += len;  // (the destination is settled: from here on l is the rope row)
+          }
+        }
       }
     }
     uint4* tile = tiles + buf * 32 * PITCH;
@@ -416,6 +438,8 @@ bool qkv_prologue(const PrologueCall& c, cudaStream_t stream) {
     s.rope = a.rope ? 1 : 0;
     s.tok0 = a.tok0;
     s.dyn_os = a.dyn_row_stride;
+    s.paged_dst = a.paged_dst ? 1 : 0;
+    s.writes_len = 0;
   }
   p.nseg = c.nseg;
   p.traditional = c.traditional ? 1 : 0;
@@ -424,6 +448,22 @@ bool qkv_prologue(const PrologueCall& c, cudaStream_t stream) {
   p.inv_n = 1.0f / (float)D;
   p.pos_dev = c.pos_dev;
   if (c.pos_dev && c.mode != 1) return false;
+  if (c.paged) {
+    if (c.mode != 1 || c.pos_dev) return false;
+    p.lens_in = c.paged->lens_in;
+    p.lens_out = c.paged->lens_out;
+    p.block_table = c.paged->block_table;
+    p.bt_stride = c.paged->bt_stride;
+    bool marked = false;  // the first paged segment (the keys) publishes the new lengths
+    for (int i = 0; i < c.nseg; ++i) {
+      if (c.seg[i].x->shape[2] != 1) return false;  // single-token steps only
+      if (c.seg[i].paged_dst && !marked) {
+        p.seg[i].writes_len = 1;
+        marked = true;
+      }
+    }
+    if (!marked) return false;
+  }
   if (any_rope && c.mode == 1) {
     if (!c.table.cos || c.table.half != dims / 2) return false;
     p.cos = c.table.cos;

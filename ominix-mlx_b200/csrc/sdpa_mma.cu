@@ -61,6 +61,12 @@ struct MmaParams {
   const int* pos_dev;
   int split_cap, min_tiles;
   size_t part_bytes;  // graph mode: size of `part`
+  // paged mode (single-token steps on the paged cache): k / v are the page pools ([page][Hkv][64][D]: ks[0] / vs[0] =
+  // page stride), sequence b attends lens_in[b] + 1 keys (< 0: released slot), key row j lives in page
+  // block_table[b * bt_stride + j / 64] at row j % 64
+  const int* lens_in;
+  const int* block_table;
+  int bt_stride;
 };
 
 // splits of the key range a launch uses: as many as there are free CTA slots, at least min_tiles tiles each
@@ -173,8 +179,9 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   const int g = lane >> 2, t = lane & 3;
   const int mt = blockIdx.x / p.nsplit, split = blockIdx.x - mt * p.nsplit, hk = blockIdx.y, b = blockIdx.z;
   const int m0 = mt * kBM;
-  const int Lk = p.pos_dev ? min(*p.pos_dev + 1, p.Lk) : p.Lk;
-  const int nsplit = p.pos_dev ? mma_plan_splits(Lk, BN, p.split_cap, p.min_tiles) : p.nsplit;
+  const bool dyn = p.pos_dev != nullptr || p.lens_in != nullptr;
+  const int Lk = p.lens_in ? min(p.lens_in[b] + 1, p.Lk) : (p.pos_dev ? min(*p.pos_dev + 1, p.Lk) : p.Lk);  // (<= 0: released slot)
+  const int nsplit = dyn ? (Lk > 0 ? mma_plan_splits(Lk, BN, p.split_cap, p.min_tiles) : 0) : p.nsplit;
   if (split >= nsplit) {  // (graph mode, short context: this CTA's split does not exist; mark its partial empty)
     float* part = p.part + ((((int64_t)b * p.Hkv + hk) * p.MT + mt) * p.nsplit + split) * (kBM * DVP + 2 * kBM);
     if (tid < kBM) {
@@ -195,8 +202,10 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   const int t0 = (int)((int64_t)nt_all * split / nsplit), t1 = (int)((int64_t)nt_all * (split + 1) / nsplit);
 
   const T* qg = (const T*)p.q + b * p.qs[0];
-  const T* kg = (const T*)p.k + b * p.ks[0] + hk * p.ks[1];
-  const T* vg = (const T*)p.v + b * p.vs[0] + hk * p.vs[1];
+  const bool paged = p.block_table != nullptr;
+  const int* bt = paged ? p.block_table + (int64_t)b * p.bt_stride : nullptr;
+  const T* kg = (const T*)p.k + (paged ? 0 : b * p.ks[0]) + hk * p.ks[1];
+  const T* vg = (const T*)p.v + (paged ? 0 : b * p.vs[0]) + hk * p.vs[1];
 
   // ---- Q tile (rows beyond R and features beyond D are zero-filled)
   // (Measured alternative: one cp.async.bulk per row with mbarrier completion -- 20 % slower at 1152-byte rows, 70 %
@@ -214,8 +223,8 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
   cp_async_commit();
   // `full`: every row and every chunk of the tile exists (all but a ragged last tile, widths == the configuration's)
   // -- no predicates, no selects, immediate offsets from one running pointer per row.
-  auto load_rows = [&](T* dst, const T* src, int64_t row_stride, int j0, int nfeat, bool full, auto pitch_c,
-                       auto chunks_c) {
+  auto load_rows = [&](T* dst, const T* src, int64_t row_stride, int64_t page_stride, int j0, int nfeat, bool full,
+                       auto pitch_c, auto chunks_c) {
     constexpr int PITCH = decltype(pitch_c)::value, CHK = decltype(chunks_c)::value;
     if constexpr (CHK >= 32) {  // a warp per key row, lanes over the row's chunks
       constexpr int NW = NT / 32;
@@ -232,11 +241,14 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
         }
       } else {
         for (int i = 0; i < BN / NW; ++i, rp += row_step) {
-          const bool rok_ = j0 + warp + i * NW < Lk;
+          const int j = j0 + warp + i * NW;
+          const bool rok_ = j < Lk;
+          const T* rq = rp;
+          if (paged) rq = rok_ ? src + (int64_t)bt[j >> 6] * page_stride + (int64_t)(j & 63) * row_stride + lane * 8 : src;
 #pragma unroll
           for (int cb = 0; cb < CHK; cb += 32) {
             const bool ok = rok_ && (cb + lane) * 8 < nfeat;
-            if (cb + lane < CHK) cp_async16(d0 + (i * NW * PITCH + cb * 8) * 2, ok ? rp + cb * 8 : src, ok);
+            if (cb + lane < CHK) cp_async16(d0 + (i * NW * PITCH + cb * 8) * 2, ok ? rq + cb * 8 : src, ok);
           }
         }
       }
@@ -252,18 +264,22 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       } else {
         for (int c = tid; c < BN * CHK; c += NT) {
           const int row = c / CHK, ch = c - row * CHK;
-          const bool ok = j0 + row < Lk && ch * 8 < nfeat;
-          cp_async16(smem_u32(dst + row * PITCH + ch * 8), ok ? src + (int64_t)(j0 + row) * row_stride + ch * 8 : src, ok);
+          const int j = j0 + row;
+          const bool ok = j < Lk && ch * 8 < nfeat;
+          const T* rq = src;
+          if (ok) rq = paged ? src + (int64_t)bt[j >> 6] * page_stride + (int64_t)(j & 63) * row_stride + ch * 8
+                             : src + (int64_t)j * row_stride + ch * 8;
+          cp_async16(smem_u32(dst + row * PITCH + ch * 8), rq, ok);
         }
       }
     }
   };
   const bool own_width = p.D == DKP && p.Dv == DVP;
   auto load_kv = [&](int tile, int stage) {
-    const bool full = own_width && (tile + 1) * BN <= Lk;
-    load_rows(Ks + stage * BN * KP, kg, p.ks[2], tile * BN, p.D, full, std::integral_constant<int, KP>{},
+    const bool full = own_width && (tile + 1) * BN <= Lk && !paged;
+    load_rows(Ks + stage * BN * KP, kg, p.ks[2], p.ks[0], tile * BN, p.D, full, std::integral_constant<int, KP>{},
               std::integral_constant<int, DKP / 8>{});
-    load_rows(Vs + stage * BN * VP, vg, p.vs[2], tile * BN, p.Dv, full, std::integral_constant<int, VP>{},
+    load_rows(Vs + stage * BN * VP, vg, p.vs[2], p.vs[0], tile * BN, p.Dv, full, std::integral_constant<int, VP>{},
               std::integral_constant<int, DVP / 8>{});
   };
   // one commit group per tile slot, empty when the tile does not exist: the group count is the same on every path
@@ -552,7 +568,7 @@ __global__ void __launch_bounds__(MmaCfg<DKP, DVP, KS>::NT, MmaCfg<DKP, DVP, KS>
       }
     }
   }
-  if (p.nsplit == 1 && !p.pos_dev) {
+  if (p.nsplit == 1 && !dyn) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       if (!rok[e]) continue;
@@ -612,7 +628,8 @@ __global__ void __launch_bounds__(kCT) sdpa_mma_combine_kernel(const __grid_cons
   M = red[0];
 #pragma unroll
   for (int i = 1; i < 5; ++i) M = fmaxf(M, red[i]);  // warps 0 .. 4 hold the splits
-  const float m_safe = (M == -INFINITY) ? 0.f : M;
+  if (M == -INFINITY) return;  // no key anywhere (paged mode: a released slot): the output row is left alone
+  const float m_safe = M;
   const float w0 = exp2f((m0 - m_safe) * kLog2e);
   if (tid < p.nsplit) ws[tid] = w0;
   const float lsum = warp_sum(w0 * l0);
@@ -688,8 +705,9 @@ void launch_cfg(MmaParams& p, cudaStream_t stream) {
   const int nsplit = mma_plan_splits(p.Lk, C::BN, p.split_cap, p.min_tiles);
   p.nsplit = nsplit;
   const size_t part_bytes = sizeof(float) * (size_t)base * nsplit * (kBM * DVP + 2 * kBM);
-  const bool two_launches = nsplit > 1 || p.pos_dev != nullptr;
-  if (p.pos_dev) {  // graph mode: partials live in the caller's (cache-owned, fixed-address) scratch
+  const bool dyn = p.pos_dev != nullptr || p.lens_in != nullptr;
+  const bool two_launches = nsplit > 1 || dyn;
+  if (dyn) {  // graph / paged mode: partials live in the caller's (cache-owned, fixed-address) scratch
     OMX_CHECK(p.part && part_bytes <= p.part_bytes, "[sdpa_mma] graph-mode scratch too small (%zu > %zu bytes)",
               part_bytes, p.part_bytes);
   } else if (nsplit > 1) {
@@ -781,10 +799,16 @@ size_t sdpa_mma_graph_scratch_bytes(int B, int Hkv, int Hq, int Dv) {
 
 void sdpa_mma(const SdpaArgs& a, cudaStream_t stream) { sdpa_mma_dynamic(a, nullptr, nullptr, 0, stream); }
 
-void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+void sdpa_mma_dynamic(const SdpaArgs& a, const int* pos_dev, void* scratch, size_t scratch_bytes, cudaStream_t stream,
+                      const PagedRef* paged) {
   MmaParams p{};
   p.pos_dev = pos_dev;
   p.part_bytes = scratch_bytes;
+  if (paged) {
+    p.lens_in = paged->lens_in;
+    p.block_table = paged->block_table;
+    p.bt_stride = paged->bt_stride;
+  }
   p.q = a.q->data;
   p.k = a.k->data;
   p.v = a.v->data;
