@@ -710,8 +710,10 @@ int omx_kv_cache_prepare_graph(omx_kv_cache c, int max_rows, int n_q_heads, omx_
     // scratch for whichever kernels serve the dynamic-position step: the decode kernels' split-K partials, or the
     // prologue's q' rows + the mma.sync kernel's partials
     const size_t qbytes = ((size_t)B * n_q_heads * Dk * dtype_size(dt) + 255) & ~(size_t)255;
+    // (only geometries that can take the mma.sync route pay for its scratch: 16-bit, not the 128 / 128 heads of the TMA kernel)
+    const bool mma_route = (dt == OMX_BFLOAT16 || dt == OMX_FLOAT16) && !(Dk == 128 && Dv == 128);
     const size_t need = std::max(decode_graph_scratch_bytes(B, H, n_q_heads, Dk, dt, max_rows),
-                                 qbytes + sdpa_mma_graph_scratch_bytes(B, H, n_q_heads, Dv));
+                                 mma_route ? qbytes + sdpa_mma_graph_scratch_bytes(B, H, n_q_heads, Dv) : (size_t)0);
     kv_cache_prepare_graph(kc, max_rows, need, (cudaStream_t)s);
   });
 }

@@ -329,8 +329,10 @@ void paged_begin_step(PagedKVImpl* c, int n_q_heads, omx_array* kpool_view, omx_
   *table_rows = std::max(mx, held);
   // split-K partials of the decode kernels, or the prologue's q' rows + the mma.sync kernel's partials (omx_api.cu)
   const size_t qbytes = ((size_t)c->B * n_q_heads * c->Dk * dtype_size(c->dtype) + 255) & ~(size_t)255;
+  // (only geometries that can take the mma.sync route pay for its scratch: 16-bit, not the 128 / 128 heads of the TMA kernel)
+  const bool mma_route = (c->dtype == OMX_BFLOAT16 || c->dtype == OMX_FLOAT16) && !(c->Dk == 128 && c->Dv == 128);
   const size_t need = std::max(decode_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dk, c->dtype, c->max_pages * kPageRows),
-                               qbytes + sdpa_mma_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dv));
+                               mma_route ? qbytes + sdpa_mma_graph_scratch_bytes(c->B, c->H, n_q_heads, c->Dv) : (size_t)0);
   if (need > c->scratch_bytes) {
     if (c->scratch) OMX_CUDA(cudaFreeAsync(c->scratch, stream));
     OMX_CUDA(cudaMallocAsync(&c->scratch, need, stream));
